@@ -1,0 +1,124 @@
+/* clipk - C ABI of the B200 (sm_100a) fused contrastive-loss library.
+ *
+ * This is the drop-in boundary for the ClipLoss / gather_features hot path of chen-yy20/Megatron-CLIP.
+ * The reference has no native interface for this path: it is a chain of PyTorch library calls made from
+ * open_CLIP/src/open_clip/loss.py.  Each entry point below names the reference lines it replaces; the host
+ * side that keeps the reference's Python signatures lives in megatron-clip_b200/clipk/loss.py and binds these
+ * symbols with ctypes.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (PyTorch's caching allocator); the library
+ *    allocates nothing persistent and never synchronises the device;
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it;
+ *  - return value: 0 = ok, < 0 = CLIPK_E* below, > 0 = a cudaError_t; clipk_last_error() gives a
+ *    thread-local description.  The library never throws and never aborts;
+ *  - there is no CPU path and no other GPU architecture: on anything but compute capability 10.x every
+ *    compute entry returns CLIPK_EARCH.
+ *  - matrices are row-major with a leading dimension in ELEMENTS; dtype is the element type of X and Y.
+ *
+ * Math.  For a block of `rows` local rows X [rows, d] against `cols` columns Y [cols, d],
+ *   S = logit_scale * X * Y^T   (never stored),  the positive of row i is column diag_offset + i.
+ */
+#ifndef CLIPK_H_
+#define CLIPK_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLIPK_VERSION 1
+
+#define CLIPK_OK 0
+#define CLIPK_EINVAL (-1)       /* bad argument (null pointer, non-positive size, misaligned pointer or ld) */
+#define CLIPK_EUNSUPPORTED (-2) /* shape or dtype the kernels do not handle (d % 8 != 0, ...) */
+#define CLIPK_EARCH (-3)        /* current device is not compute capability 10.x */
+#define CLIPK_EWORKSPACE (-4)   /* workspace smaller than clipk_*_workspace_bytes() */
+#define CLIPK_EDRIVER (-5)      /* cuTensorMapEncodeTiled unavailable or failed */
+
+#define CLIPK_BF16 0  /* bf16 [rows, d] */
+#define CLIPK_F32 1   /* fp32; only a source type of clipk_to_f16 and a destination type of clipk_cast */
+#define CLIPK_F16 3   /* scaled fp16, one plane  [rows, round_up(d, 64)], zero padded: value = stored * inv_scale */
+#define CLIPK_F16X2 4 /* scaled fp16, two planes [rows, 2 * round_up(d, 64)] = [hi | lo]: value = (hi + lo) * inv_scale.
+                         The kernels contract the three plane pairs lo.hi, hi.lo, hi.hi, which reproduces an fp32
+                         product to ~2^-22 on the 16-bit tensor pipe. */
+
+int clipk_version(void);
+const char* clipk_last_error(void);
+
+/* 0 when the current CUDA device can run the kernels (CC 10.x), CLIPK_EARCH otherwise. */
+int clipk_check_device(void);
+
+/* [rows, d] bf16 or fp32 (src_dtype, ld_src) -> CLIPK_F16 (planes = 1) or CLIPK_F16X2 (planes = 2) in dst, with
+ * ld_dst == planes * round_up(d, 64).  The power-of-two scale maps max|x| into [2^13, 2^14).  scale_io is two device
+ * floats: [0] scratch, [1] receives inv_scale.  bf16 -> one fp16 plane is exact (8 significant bits fit in 11); it
+ * feeds the gradient GEMMs, whose other operand (the softmax gradient G) needs more mantissa than bf16 has.
+ * fp32 -> two planes replaces the fp32 matmul of loss.py:112-119 when autocast is off. */
+int clipk_to_f16(const void* src, int src_dtype, long long rows, long long d, long long ld_src, void* dst, int planes,
+                 long long ld_dst, float* scale_io, void* stream);
+
+/* ---- forward ------------------------------------------------------------------------------------------
+ * clipk_fwd_stats replaces, for one direction, the logits GEMM and the log-softmax reduction of
+ *   loss.py:112-113 / 115-116 / 118-119 (logit_scale * a @ b.T) and loss.py:135-138 (F.cross_entropy)
+ * without materialising the [rows, cols] logits: it returns, per row i,
+ *   row_max[i] = max_j S_ij,  row_sum[i] = sum_j exp(S_ij - row_max[i]),
+ *   pos_logit[i] = S[i, diag_offset + i]   (written only when that column exists; may be NULL).
+ * Calling it with X and Y swapped gives the statistics of the other direction (logits_per_text).
+ * dtype: CLIPK_BF16, CLIPK_F16 or CLIPK_F16X2 for both operands; x/y_inv_scale are device scalars (NULL = 1).
+ */
+size_t clipk_fwd_workspace_bytes(int rows, int cols, int d, int dtype);
+int clipk_fwd_stats(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
+                    const float* x_inv_scale, const float* y_inv_scale, const float* logit_scale,
+                    long long diag_offset, float* row_max, float* row_sum, float* pos_logit, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* clipk_finalize merges statistics into log-sum-exps and the two cross-entropy sums (loss.py:135-138).
+ *   lse_row[i] = row_max[i] + log(row_sum[i])                                  i < rows
+ *   lse_col[j] = logsumexp over the nparts (max, sum) pairs of column j        j < cols
+ *   loss_sums[0] = sum_i (lse_row[i] - pos_logit[i])
+ *   loss_sums[1] = sum_i (lse_col[diag_offset + i] - pos_logit[i])
+ * col_*_parts hold nparts parts, part p of column j at [p * part_stride + j]: one part per data-parallel rank
+ * after the all-gather of the column statistics (the exchange that replaces materialising logits_per_text on every rank).
+ */
+int clipk_finalize(const float* row_max, const float* row_sum, const float* pos_logit, int rows,
+                   const float* col_max_parts, const float* col_sum_parts, int nparts, long long part_stride,
+                   int cols, long long diag_offset, float* lse_row, float* lse_col, float* loss_sums, void* stream);
+
+/* ---- backward -----------------------------------------------------------------------------------------
+ * clipk_bwd replaces autograd's backward of the same lines (softmax - onehot, the four gradient GEMMs and
+ * the dlogit_scale reduction).  It recomputes S tile by tile from X, Y (dtype as in the forward), forms
+ *   G = alpha * (P_row - Id) + beta * (P_col - Id),
+ *   P_row = exp(S - lse_row[:, None]),  P_col = exp(S - lse_col[None, :]),
+ * holds it as fp16 (x 2^14; two planes when g_dtype == CLIPK_F16X2) in an L2-sized panel of the workspace, at most
+ * 4096 x 4096 at a time, and accumulates in fp32, with Xg / Yg the CLIPK_F16 or CLIPK_F16X2 copies of the features:
+ *   dX_acc [rows, d] = logit_scale * gscale * G * Yg          (NULL to skip)
+ *   dY_acc [cols, d] = logit_scale * gscale * G^T * Xg        (NULL to skip; the caller reduce-scatters it)
+ *   ds_acc[0] = sum (P_row - Id) . (X Y^T),  ds_acc[1] = sum (P_col - Id) . (X Y^T)      (unscaled)
+ *   ds_col[j] = sum_i ((P_col - Id) . (X Y^T))_ij   (NULL to skip; needed per rank in local-loss mode)
+ * gscale is a device scalar = grad_output / (2 * num_logits).  dX_acc, dY_acc, ds_acc and ds_col are
+ * overwritten, not accumulated into.
+ */
+size_t clipk_bwd_workspace_bytes(int rows, int cols, int d, int g_dtype);
+int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
+              const float* x_inv_scale, const float* y_inv_scale, const void* Xg, const void* Yg, long long ldxg,
+              long long ldyg, int g_dtype, const float* xg_inv_scale, const float* yg_inv_scale,
+              const float* logit_scale, long long diag_offset, const float* lse_row, const float* lse_col,
+              float alpha, float beta, const float* gscale, float* dX_acc, float* dY_acc, float* ds_acc,
+              float* ds_col, void* workspace, size_t workspace_bytes, void* stream);
+
+/* dst[i] = (dtype) src[i]; the fp32 gradient accumulators are returned in the dtype of the inputs. */
+int clipk_cast(const float* src, void* dst, long long n, int dtype, void* stream);
+
+/* ---- test hook for the tensor-core mainloop: D[M, N] (fp32, ldd) (+)= A * B^T with 16-bit operands
+ *   (bf16 when f16 == 0, fp16 when f16 == 1; both operands share the format - the hardware rejects a mix).
+ *   a_mn = 0: A is [M, K] row-major (K contiguous);  a_mn = 1: A is stored [K, M] row-major (M contiguous).
+ *   b_mn likewise for B ([N, K] or [K, N]).
+ */
+int clipk_gemm16(const void* A, const void* B, float* D, int M, int N, int K, long long lda, long long ldb,
+                 long long ldd, int a_mn, int b_mn, int f16, int accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIPK_H_ */

@@ -1,0 +1,295 @@
+"""Host side of the fused contrastive loss: a torch.autograd.Function over the clipk C ABI.
+
+Data flow on rank r of W (b local rows, N = W*b), replacing open_CLIP/src/open_clip/loss.py:104-140:
+
+  forward   T_all = all_gather(T_loc)                                  (NCCL, one contiguous [N, d] buffer)
+            row stats of  S = s * I_loc @ T_all^T   [b x N]            clipk_fwd_stats      (logits_per_image rows)
+            col stats of the same block              [N]               clipk_fwd_stats with operands swapped
+            all_gather of the (max, sum) column pairs                  (2*N floats per rank)
+            lse_row[b], lse_col[N], cross-entropy sums                 clipk_finalize
+  backward  G = s*g*(alpha*(P_row-Id) + beta*(P_col-Id)) tile by tile; dI_loc = G @ T_all;
+            dT_partial[N, d] = G^T @ I_loc                             clipk_bwd
+            dT_loc = reduce_scatter(dT_partial)                        (NCCL)
+
+The [b x N] logits are never written to HBM and I_all is never gathered.  All four (local_loss,
+gather_with_grad) modes of the reference are coefficient choices of this one pipeline.
+
+The kernels are reached through `_backend()`: the CUDA library, or - in CPU unit tests of the collective
+orchestration only - an object installed with `set_backend_for_testing`.  There is no CPU fallback in the
+product: without libclipk.so or without a compute-capability-10.x device the call raises.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+_TEST_BACKEND = None
+
+
+def set_backend_for_testing(backend):
+    """Install an object exposing fwd_stats/finalize/bwd/cast/prepare (tests only; None restores CUDA)."""
+    global _TEST_BACKEND
+    _TEST_BACKEND = backend
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class Operand:
+    """A feature matrix in the layout the kernels consume (see include/clipk.h, CLIPK_BF16 / F16 / F16X2)."""
+    __slots__ = ("data", "dtype", "ld", "inv_scale", "rows", "d", "scale_io")
+
+    def __init__(self, data, dtype, ld, inv_scale, rows, d, scale_io=None):
+        self.data, self.dtype, self.ld, self.inv_scale, self.rows, self.d = data, dtype, ld, inv_scale, rows, d
+        self.scale_io = scale_io     # keeps the device scalar behind inv_scale alive
+
+    def inv_ptr(self):
+        return None if self.inv_scale is None else self.inv_scale.data_ptr()
+
+
+class CudaBackend:
+    """Calls libclipk.so on the current CUDA stream."""
+
+    def __init__(self):
+        self.lib = _lib.load()
+        self.launches = 0   # kernels launched by this library (counted for bench.py's gpu_launches)
+
+    @staticmethod
+    def _stream():
+        return torch.cuda.current_stream().cuda_stream
+
+    def _to_f16(self, x: torch.Tensor, planes: int) -> Operand:
+        rows, d = x.shape
+        dpad = (d + 63) // 64 * 64
+        out = torch.empty(rows, planes * dpad, dtype=torch.float16, device=x.device)
+        scale_io = torch.empty(2, dtype=torch.float32, device=x.device)
+        src_dt = _lib.BF16 if x.dtype == torch.bfloat16 else _lib.F32
+        _lib.check(self.lib.clipk_to_f16(x.data_ptr(), src_dt, rows, d, x.stride(0), out.data_ptr(), planes,
+                                         planes * dpad, scale_io.data_ptr(), self._stream()), "clipk_to_f16")
+        self.launches += 2
+        return Operand(out, _lib.F16 if planes == 1 else _lib.F16X2, planes * dpad, scale_io[1:2], rows, d, scale_io)
+
+    def prepare(self, x: torch.Tensor) -> Operand:
+        """Operand of the logits GEMM: bf16 as is; fp32 as two scaled fp16 planes (CLIPK_F16X2)."""
+        if x.dtype == torch.bfloat16:
+            x = x.contiguous()
+            return Operand(x, _lib.BF16, x.stride(0), None, x.shape[0], x.shape[1])
+        if x.dtype != torch.float32:
+            raise TypeError(f"clipk: unsupported feature dtype {x.dtype} (bf16 and fp32 only)")
+        return self._to_f16(x.contiguous(), 2)
+
+    def prepare_grad(self, op: Operand) -> Operand:
+        """Operand of the gradient GEMMs (fp16 x fp16): exact one-plane fp16 copy of bf16 features; the two-plane
+        fp16 form of fp32 features is reused as is."""
+        if op.dtype == _lib.BF16:
+            return self._to_f16(op.data, 1)
+        return op
+
+    def fwd_stats(self, X: Operand, Y: Operand, scale, diag_offset, want_pos, out=None):
+        dev = X.data.device
+        rows, cols, d = X.rows, Y.rows, X.d
+        if out is None:
+            out = torch.empty(2, rows, dtype=torch.float32, device=dev)
+        row_max, row_sum = out[0], out[1]
+        pos = torch.zeros(rows, dtype=torch.float32, device=dev) if want_pos else None
+        nbytes = self.lib.clipk_fwd_workspace_bytes(rows, cols, d, X.dtype)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.check(self.lib.clipk_fwd_stats(X.data.data_ptr(), Y.data.data_ptr(), rows, cols, d, X.ld, Y.ld, X.dtype,
+                                            X.inv_ptr(), Y.inv_ptr(), scale.data_ptr(), diag_offset,
+                                            row_max.data_ptr(), row_sum.data_ptr(), _ptr(pos), ws.data_ptr(), nbytes,
+                                            self._stream()), "clipk_fwd_stats")
+        self.launches += 2
+        return row_max, row_sum, pos
+
+    def finalize(self, row_max, row_sum, pos, col_parts, diag_offset):
+        """col_parts: [nparts, 2, cols] fp32 (max, sum).  Returns lse_row, lse_col, loss_sums[2]."""
+        dev = row_max.device
+        rows = row_max.numel()
+        nparts, _, cols = col_parts.shape
+        lse_row = torch.empty(rows, dtype=torch.float32, device=dev)
+        lse_col = torch.empty(cols, dtype=torch.float32, device=dev)
+        sums = torch.empty(2, dtype=torch.float32, device=dev)
+        cmax = col_parts.data_ptr()
+        csum = cmax + cols * 4
+        _lib.check(self.lib.clipk_finalize(row_max.data_ptr(), row_sum.data_ptr(), pos.data_ptr(), rows, cmax, csum,
+                                           nparts, 2 * cols, cols, diag_offset, lse_row.data_ptr(),
+                                           lse_col.data_ptr(), sums.data_ptr(), self._stream()), "clipk_finalize")
+        self.launches += 1
+        return lse_row, lse_col, sums
+
+    def bwd(self, X: Operand, Y: Operand, Xg: Operand, Yg: Operand, scale, diag_offset, lse_row, lse_col, alpha,
+            beta, gscale, want_dx, want_dy, want_ds_col):
+        dev = X.data.device
+        rows, cols, d = X.rows, Y.rows, X.d
+        dX = torch.empty(rows, d, dtype=torch.float32, device=dev) if want_dx else None
+        dY = torch.empty(cols, d, dtype=torch.float32, device=dev) if want_dy else None
+        ds_acc = torch.empty(2, dtype=torch.float32, device=dev)
+        ds_col = torch.empty(cols, dtype=torch.float32, device=dev) if want_ds_col else None
+        nbytes = self.lib.clipk_bwd_workspace_bytes(rows, cols, d, Xg.dtype)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.check(self.lib.clipk_bwd(X.data.data_ptr(), Y.data.data_ptr(), rows, cols, d, X.ld, Y.ld, X.dtype,
+                                      X.inv_ptr(), Y.inv_ptr(), Xg.data.data_ptr(), Yg.data.data_ptr(), Xg.ld, Yg.ld,
+                                      Xg.dtype, Xg.inv_ptr(), Yg.inv_ptr(), scale.data_ptr(), diag_offset,
+                                      lse_row.data_ptr(), lse_col.data_ptr(), float(alpha), float(beta),
+                                      gscale.data_ptr(), _ptr(dX), _ptr(dY), ds_acc.data_ptr(), _ptr(ds_col),
+                                      ws.data_ptr(), nbytes, self._stream()), "clipk_bwd")
+        panels = ((rows + 4095) // 4096) * ((cols + 4095) // 4096)
+        self.launches += panels * (1 + int(want_dx) + int(want_dy))
+        return dX, dY, ds_acc, ds_col
+
+    def cast(self, src: torch.Tensor, dtype: torch.dtype):
+        if dtype == torch.float32:
+            return src
+        out = torch.empty(src.shape, dtype=dtype, device=src.device)
+        _lib.check(self.lib.clipk_cast(src.data_ptr(), out.data_ptr(), src.numel(), _lib.BF16, self._stream()),
+                   "clipk_cast")
+        self.launches += 1
+        return out
+
+
+_CUDA_BACKEND = None
+
+
+def _backend():
+    global _CUDA_BACKEND
+    if _TEST_BACKEND is not None:
+        return _TEST_BACKEND
+    if _CUDA_BACKEND is None:
+        _CUDA_BACKEND = CudaBackend()
+    return _CUDA_BACKEND
+
+
+def gpu_launches() -> int:
+    """Number of clipk kernels launched so far in this process."""
+    return 0 if _CUDA_BACKEND is None else _CUDA_BACKEND.launches
+
+
+# ----------------------------------------------------------------------------------------------------- collectives
+def _all_gather_rows(x: torch.Tensor, world_size: int, group=None) -> torch.Tensor:
+    """[n, ...] per rank -> [world*n, ...], rank-major, into one contiguous buffer (no list + cat copy)."""
+    out = torch.empty((world_size * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+    return out
+
+
+def _reduce_scatter_rows(x: torch.Tensor, world_size: int, group=None) -> torch.Tensor:
+    """[world*n, ...] per rank -> SUM over ranks of chunk `rank`, [n, ...]."""
+    n = x.shape[0] // world_size
+    out = torch.empty((n,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.reduce_scatter_tensor(out, x.contiguous(), op=dist.ReduceOp.SUM, group=group)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------- autograd
+class FusedClipLoss(torch.autograd.Function):
+    """loss = ClipLoss(local_loss, gather_with_grad, rank, world_size).forward(I, T, s)   (loss.py:123-140)."""
+
+    @staticmethod
+    def forward(ctx, image_features, text_features, logit_scale, local_loss, gather_with_grad, rank, world_size,
+                group):
+        be = _backend()
+        if image_features.dim() != 2 or image_features.shape != text_features.shape:
+            raise ValueError("image_features and text_features must both be [batch, dim]")
+        if image_features.dtype != text_features.dtype:
+            raise TypeError("image_features and text_features must have the same dtype")
+        b, d = image_features.shape
+        W = int(world_size)
+        N = W * b
+        dev = image_features.device
+        in_dtype = image_features.dtype
+        scale = logit_scale.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+
+        # under torch.autocast the reference's matmuls run in the autocast dtype
+        feats_i, feats_t = image_features.detach(), text_features.detach()
+        if in_dtype == torch.float32 and dev.type == "cuda" and torch.is_autocast_enabled("cuda") and \
+                torch.get_autocast_dtype("cuda") == torch.bfloat16:
+            feats_i, feats_t = feats_i.to(torch.bfloat16), feats_t.to(torch.bfloat16)
+
+        t_all = _all_gather_rows(feats_t, W, group) if W > 1 else feats_t
+        X = be.prepare(feats_i)
+        Y = be.prepare(t_all)
+        off = rank * b if W > 1 else 0
+
+        row_max, row_sum, pos = be.fwd_stats(X, Y, scale, off, True)
+        parts = torch.empty(1, 2, N, dtype=torch.float32, device=dev)        # (max, sum) of every column
+        be.fwd_stats(Y, X, scale, 0, False, out=parts[0])
+        if W > 1:
+            parts = _all_gather_rows(parts, W, group)                        # [W, 2, N]
+        lse_row, lse_col, sums = be.finalize(row_max, row_sum, pos, parts, off)
+
+        total = sums.sum()
+        if W > 1 and not local_loss:
+            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)        # loss over the global N x N problem
+            loss = total / (2.0 * N)
+        else:
+            loss = total / (2.0 * b)
+
+        ctx.save_for_backward(scale, lse_row, lse_col)
+        ctx.operands = (X, Y)
+        ctx.cfg = (b, d, W, rank, off, bool(local_loss), bool(gather_with_grad), group, in_dtype)
+        ctx.scale_is_param = isinstance(logit_scale, torch.Tensor)
+        ctx.scale_dtype = logit_scale.dtype
+        ctx.scale_shape = logit_scale.shape
+        return loss
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        be = _backend()
+        scale, lse_row, lse_col = ctx.saved_tensors
+        X, Y = ctx.operands
+        b, d, W, rank, off, local_loss, gwg, group, in_dtype = ctx.cfg
+        Xg, Yg = be.prepare_grad(X), be.prepare_grad(Y)
+        N = W * b
+        go = grad_out.detach().to(torch.float32).reshape(1)
+        local = (W == 1) or local_loss
+        # c of SURVEY App. A: 1/(2b) for W=1, both local modes and global+gather_with_grad; 1/(2N) for global w/o it
+        c_feat = 1.0 / (2.0 * b) if (local or gwg) else 1.0 / (2.0 * N)
+        gscale = (go * c_feat).contiguous()
+
+        if W > 1 and local_loss and not gwg:
+            # loss.py:53-56 with local_loss: gathered tensors carry no gradient, so dI sees only the image->text
+            # softmax and dT only the text->image one.
+            dX, _, acc_r, _ = be.bwd(X, Y, Xg, Yg, scale, off, lse_row, lse_col, 1.0, 0.0, gscale, True, False, False)
+            _, dY, acc_c, ds_col = be.bwd(X, Y, Xg, Yg, scale, off, lse_row, lse_col, 0.0, 1.0, gscale, False, True,
+                                          True)
+            ds_row_part = acc_r[0]
+        else:
+            dX, dY, acc, ds_col = be.bwd(X, Y, Xg, Yg, scale, off, lse_row, lse_col, 1.0, 1.0, gscale, True, True,
+                                         W > 1 and local_loss)
+            ds_row_part = acc[0]
+            acc_c = acc
+
+        if W > 1:
+            dT = _reduce_scatter_rows(dY, W, group)
+        else:
+            dT = dY
+        d_image = be.cast(dX, in_dtype)
+        d_text = be.cast(dT, in_dtype)
+
+        d_scale = None
+        if ctx.scale_is_param and ctx.needs_input_grad[2]:
+            if W == 1:
+                ds = (ds_row_part + acc_c[1]) * gscale[0]
+            elif local_loss:
+                # per-rank value: rows of this rank for the image->text term, columns of this rank (summed over
+                # every rank's rows) for the text->image term
+                col_loc = _reduce_scatter_rows(ds_col, W, group).sum()
+                ds = (ds_row_part + col_loc) * gscale[0]
+            else:
+                tot = (ds_row_part + acc_c[1]).reshape(1)
+                dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+                ds = tot[0] * go[0] / (2.0 * N)
+            d_scale = ds.reshape(ctx.scale_shape).to(ctx.scale_dtype)
+        return d_image, d_text, d_scale, None, None, None, None, None
+
+
+def fused_clip_loss(image_features, text_features, logit_scale, local_loss=False, gather_with_grad=False, rank=0,
+                    world_size=1, group=None):
+    if not isinstance(logit_scale, torch.Tensor):
+        logit_scale = torch.tensor(float(logit_scale), dtype=torch.float32, device=image_features.device)
+    return FusedClipLoss.apply(image_features, text_features, logit_scale, local_loss, gather_with_grad, rank,
+                               world_size, group)
