@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py - ClipLoss fwd+bwd samples/s at global batch 32768, d=512, bf16 (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl clipk|reference]
+
+One process per GPU (under torchrun for N > 1; RANK / LOCAL_RANK / WORLD_SIZE from the environment).  The global
+batch is fixed, so the N-GPU runs are a strong-scaling series: each rank owns 32768 / N rows.
+
+A step is one ClipLoss(local_loss=True, gather_with_grad=True) forward + backward on synthetic unit-norm embeddings
+(positives at cos ~0.3).  Every step is bracketed by its own pair of CUDA events on the
+launching stream; between steps a 256 MiB buffer is overwritten to flush the 126 MB L2 (outside the event pairs).
+`value` has the inputs resident in HBM; `e2e` runs the same call from pinned host buffers (H2D of both feature
+matrices and D2H of the loss inside the timed region).  rank 0 prints ONE JSON line.
+
+--impl reference times the reference's own CPU arithmetic (torch CPU matmul + cross_entropy + autograd, restated in
+oracle/cliploss_oracle.py::TorchPort because /root/reference does not exist on the GPU box) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "megatron-clip_b200"))
+
+GLOBAL_BATCH = 32768
+DIM = 512
+LOGIT_SCALE = 1.0 / 0.07
+METRIC = "ClipLoss fwd+bwd samples/s @ global batch 32K, d=512"
+CPU_SAMPLE_BATCH = 8192   # bounded CPU sample: fwd+bwd cost grows with batch^2
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            j = json.load(f)
+        return {"tflops_sustained": j.get("bf16_tflops_sustained", 1401.9), "tflops_burst": j.get("bf16_tflops", 1661.2),
+                "hbm_gbs": j.get("hbm_gbs", 6542.7), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops_sustained": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for n, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        sm.sort()
+        # median over the busier half of the samples = clocks under load
+        load = sm[len(sm) // 2:] if sm else []
+        med = load[len(load) // 2] if load else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_port_run(steps, warmup, batch=CPU_SAMPLE_BATCH):
+    """Reference arithmetic on host cores: returns (seconds per sample-step, cores)."""
+    import numpy as np
+    import torch
+    from oracle import cliploss_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    x, t = O.synthetic_features(batch, DIM, seed=1234)
+    I, T, s = torch.from_numpy(x), torch.from_numpy(t), torch.tensor(LOGIT_SCALE)
+    port = O.TorchPort()
+    for _ in range(warmup):
+        port.fwd_bwd(I, T, s)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        port.fwd_bwd(I, T, s)
+        ts.append(time.perf_counter() - t0)
+    return float(np.mean(ts)), cores
+
+
+def cpu_baseline_obj(sec_per_step, cores, batch):
+    # cost per step grows with batch^2 (two batch x batch logit matrices); scale the sample to the 32K workload
+    full = sec_per_step * (GLOBAL_BATCH / batch) ** 2
+    return {"value": GLOBAL_BATCH / full, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": (f"torch-CPU fp32 ClipLoss fwd+bwd at batch {batch}, d={DIM} ({sec_per_step * 1e3:.0f} ms/step), "
+                       f"scaled by (32768/{batch})^2 to the global-batch-32768 step")}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    sec, cores = cpu_port_run(steps, min(args.warmup, 1))
+    cb = cpu_baseline_obj(sec, cores, CPU_SAMPLE_BATCH)
+    full_ms = GLOBAL_BATCH / cb["value"] * 1e3
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": full_ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ClipLoss fwd+bwd, global batch 32768, d=512 (BASELINE.json configs[1]), CPU arithmetic"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_clipk(args):
+    import torch
+    import torch.distributed as dist
+    from clipk import ClipLoss, ops
+    from oracle import cliploss_oracle as O   # synthetic input generator + cpu_baseline leg only
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert GLOBAL_BATCH % world == 0
+    b = GLOBAL_BATCH // world
+
+    x, t = O.synthetic_features(b, DIM, seed=1234, rank=rank)
+    I_host = torch.from_numpy(x).bfloat16().pin_memory()
+    T_host = torch.from_numpy(t).bfloat16().pin_memory()
+    I = I_host.to(dev).requires_grad_(True)
+    T = T_host.to(dev).requires_grad_(True)
+    S = torch.tensor(LOGIT_SCALE, device=dev, requires_grad=True)
+    loss_mod = ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True, rank=rank, world_size=world)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step_resident():
+        I.grad = T.grad = S.grad = None
+        loss = loss_mod(I, T, S)
+        loss.backward()
+        return loss
+
+    def step_e2e():
+        i = I_host.to(dev, non_blocking=True).requires_grad_(True)
+        tt = T_host.to(dev, non_blocking=True).requires_grad_(True)
+        S.grad = None
+        loss = loss_mod(i, tt, S)
+        loss.backward()
+        loss_host.copy_(loss.detach(), non_blocking=True)
+        return loss
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        total_ms = 0.0
+        l0 = ops.gpu_launches()
+        launches = 0
+        for _ in range(steps):
+            flush.fill_(1)                          # L2 flush, outside the event pair
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            la = ops.gpu_launches()
+            e0.record()
+            fn()
+            e1.record()
+            launches += ops.gpu_launches() - la
+            torch.cuda.synchronize()
+            total_ms += e0.elapsed_time(e1)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)   # max over ranks
+        return tt.item() / steps, launches
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, launches = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e, _ = timed(step_e2e, max(3, args.steps // 2), 3)
+
+    # ---- per-kernel breakdown of one rank's step (events around each C-ABI call), for the roofline
+    be = ops._backend()
+    N = GLOBAL_BATCH
+    breakdown = {}
+    with torch.no_grad():
+        sc = S.detach().reshape(1).float()
+        if world > 1:
+            t_all = torch.empty(N, DIM, dtype=torch.bfloat16, device=dev)
+            dist.all_gather_into_tensor(t_all, T.detach())
+        else:
+            t_all = T.detach()
+        X, Y = be.prepare(I.detach()), be.prepare(t_all)
+        off = rank * b if world > 1 else 0
+
+        def ev(fn, reps=5):
+            fn()
+            torch.cuda.synchronize()
+            tot = 0.0
+            for _ in range(reps):
+                flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = fn()
+                e1.record()
+                torch.cuda.synchronize()
+                tot += e0.elapsed_time(e1)
+            return tot / reps, out
+
+        breakdown["fwd_row_stats_ms"], (rstats, pos) = ev(lambda: be.fwd_stats(X, Y, sc, off, True))
+        parts = torch.empty(1, 3, N, dtype=torch.float32, device=dev)
+        breakdown["fwd_col_stats_ms"], _ = ev(lambda: be.fwd_stats(Y, X, sc, 0, False, out=parts[0]))
+        gparts = parts
+        if world > 1:
+            gparts = torch.empty(world, 3, N, dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(gparts, parts)
+        lse_row, lse_col, sums = be.finalize(rstats, pos, gparts, off)
+        breakdown["to_f16_ms"], (Xg, Yg) = ev(lambda: (be.prepare_grad(X), be.prepare_grad(Y)))
+        gscale = torch.tensor([1.0 / (2 * b)], device=dev)
+        breakdown["bwd_ms"], _ = ev(lambda: be.bwd(X, Y, Xg, Yg, sc, off, lse_row, lse_col, 1.0, 1.0, gscale, True, True))
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    f_alg = 6.0 * b * N * DIM                                  # three dense passes over the b x N block
+    f_exec = 10.0 * b * N * DIM                                # issued: 2 fwd sweeps + recompute + 2 gradient GEMMs
+    achieved = f_alg / (ms * 1e-3) / 1e12
+    gemm_ms = breakdown["fwd_row_stats_ms"] + breakdown["fwd_col_stats_ms"] + breakdown["bwd_ms"]
+    roofline = {
+        "bound": "tensor", "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+        "frac": achieved / pk["tflops_sustained"], "traffic": None,
+        "kernel": "clipk::gemm_kernel (tcgen05 128x256x64 tiles; STATS x2, GRAD, 2 gradient GEMMs per panel)",
+        "algorithmic_flops_per_step_per_gpu": f_alg, "executed_mma_flops_per_step_per_gpu": f_exec,
+        "executed_tflops_in_gemm_kernels": f_exec / (gemm_ms * 1e-3) / 1e12,
+        "gemm_kernels_share_of_step": gemm_ms / ms, "breakdown_ms": breakdown, "peak_source": pk["source"],
+        "peak_burst": pk["tflops_burst"],
+    }
+
+    cb = None
+    if world == 1:
+        sec, cores = cpu_port_run(2, 1)
+        cb = cpu_baseline_obj(sec, cores, CPU_SAMPLE_BATCH)
+
+    out = {
+        "metric": METRIC, "value": GLOBAL_BATCH / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "ClipLoss local_loss=True gather_with_grad=True fwd+bwd, ViT-B/32 embeddings "
+                               "(BASELINE.json configs[1])", "global_batch": GLOBAL_BATCH, "local_batch": b, "d": DIM,
+                   "logit_scale": LOGIT_SCALE, "parallelism": f"dp{world}",
+                   "l2": "256 MiB buffer overwritten between timed steps (L2 flush), outside the per-step event pairs"},
+        "clocks": clocks,
+        "e2e": {"value": GLOBAL_BATCH / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": 2 * b * DIM * 2, "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cb,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="clipk", choices=["clipk", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "clipk" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_clipk(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -62,7 +62,9 @@ int clipk_to_f16(const void* src, int src_dtype, long long rows, long long d, lo
  * clipk_fwd_stats replaces, for one direction, the logits GEMM and the log-softmax reduction of
  *   loss.py:112-113 / 115-116 / 118-119 (logit_scale * a @ b.T) and loss.py:135-138 (F.cross_entropy)
  * without materialising the [rows, cols] logits: it returns, per row i,
- *   row_max[i] = max_j S_ij,  row_sum[i] = sum_j exp(S_ij - row_max[i]),
+ *   row_max[i] = max_j S_ij,
+ *   row_sum[i] = sum_j exp(S_ij - row_max[i]),
+ *   row_dot[i] = sum_j exp(S_ij - row_max[i]) * S_ij      (gives dloss/dlogit_scale without a backward pass over S)
  *   pos_logit[i] = S[i, diag_offset + i]   (written only when that column exists; may be NULL).
  * Calling it with X and Y swapped gives the statistics of the other direction (logits_per_text).
  * dtype: CLIPK_BF16, CLIPK_F16 or CLIPK_F16X2 for both operands; x/y_inv_scale are device scalars (NULL = 1).
@@ -70,42 +72,44 @@ int clipk_to_f16(const void* src, int src_dtype, long long rows, long long d, lo
 size_t clipk_fwd_workspace_bytes(int rows, int cols, int d, int dtype);
 int clipk_fwd_stats(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
                     const float* x_inv_scale, const float* y_inv_scale, const float* logit_scale,
-                    long long diag_offset, float* row_max, float* row_sum, float* pos_logit, void* workspace,
-                    size_t workspace_bytes, void* stream);
+                    long long diag_offset, float* row_max, float* row_sum, float* row_dot, float* pos_logit,
+                    void* workspace, size_t workspace_bytes, void* stream);
 
-/* clipk_finalize merges statistics into log-sum-exps and the two cross-entropy sums (loss.py:135-138).
+/* clipk_finalize merges statistics into log-sum-exps, the two cross-entropy sums (loss.py:135-138) and the two
+ * sums that make up dloss/dlogit_scale:
  *   lse_row[i] = row_max[i] + log(row_sum[i])                                  i < rows
  *   lse_col[j] = logsumexp over the nparts (max, sum) pairs of column j        j < cols
- *   loss_sums[0] = sum_i (lse_row[i] - pos_logit[i])
- *   loss_sums[1] = sum_i (lse_col[diag_offset + i] - pos_logit[i])
+ *   sums[0] = sum_i (lse_row[i] - pos_logit[i])            sums[1] = sum_i (lse_col[diag_offset + i] - pos_logit[i])
+ *   sums[2] = sum_i (E_row[i] - pos_logit[i])              sums[3] = sum_i (E_col[diag_offset + i] - pos_logit[i])
+ * where E is the expected logit under the row / column softmax (dot / sum), so that
+ *   dloss/dlogit_scale = (sums[2] + sums[3]) / (2 * num_logits * logit_scale).
  * col_*_parts hold nparts parts, part p of column j at [p * part_stride + j]: one part per data-parallel rank
  * after the all-gather of the column statistics (the exchange that replaces materialising logits_per_text on every rank).
  */
-int clipk_finalize(const float* row_max, const float* row_sum, const float* pos_logit, int rows,
-                   const float* col_max_parts, const float* col_sum_parts, int nparts, long long part_stride,
-                   int cols, long long diag_offset, float* lse_row, float* lse_col, float* loss_sums, void* stream);
+int clipk_finalize(const float* row_max, const float* row_sum, const float* row_dot, const float* pos_logit, int rows,
+                   const float* col_max_parts, const float* col_sum_parts, const float* col_dot_parts, int nparts,
+                   long long part_stride, int cols, long long diag_offset, float* lse_row, float* lse_col, float* sums,
+                   void* stream);
 
 /* ---- backward -----------------------------------------------------------------------------------------
- * clipk_bwd replaces autograd's backward of the same lines (softmax - onehot, the four gradient GEMMs and
- * the dlogit_scale reduction).  It recomputes S tile by tile from X, Y (dtype as in the forward), forms
+ * clipk_bwd replaces autograd's backward of the same lines (softmax - onehot and the four gradient GEMMs).  It
+ * recomputes S tile by tile from X, Y (dtype as in the forward), forms
  *   G = alpha * (P_row - Id) + beta * (P_col - Id),
  *   P_row = exp(S - lse_row[:, None]),  P_col = exp(S - lse_col[None, :]),
- * holds it as fp16 (x 2^14; two planes when g_dtype == CLIPK_F16X2) in an L2-sized panel of the workspace, at most
- * 4096 x 4096 at a time, and accumulates in fp32, with Xg / Yg the CLIPK_F16 or CLIPK_F16X2 copies of the features:
+ * holds it as fp16 (x 2^14; two planes when g_dtype == CLIPK_F16X2) in an L2-sized panel of the workspace (about
+ * 4736 x 4736 at a time), and accumulates in fp32, with Xg / Yg the CLIPK_F16 or CLIPK_F16X2 copies of the features:
  *   dX_acc [rows, d] = logit_scale * gscale * G * Yg          (NULL to skip)
  *   dY_acc [cols, d] = logit_scale * gscale * G^T * Xg        (NULL to skip; the caller reduce-scatters it)
- *   ds_acc[0] = sum (P_row - Id) . (X Y^T),  ds_acc[1] = sum (P_col - Id) . (X Y^T)      (unscaled)
- *   ds_col[j] = sum_i ((P_col - Id) . (X Y^T))_ij   (NULL to skip; needed per rank in local-loss mode)
- * gscale is a device scalar = grad_output / (2 * num_logits).  dX_acc, dY_acc, ds_acc and ds_col are
- * overwritten, not accumulated into.
+ * Per panel: one launch recomputes and writes G, one launch runs the dX tiles and the dY tiles together.
+ * gscale is a device scalar = grad_output / (2 * num_logits).  dX_acc and dY_acc are overwritten.
  */
 size_t clipk_bwd_workspace_bytes(int rows, int cols, int d, int g_dtype);
 int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
               const float* x_inv_scale, const float* y_inv_scale, const void* Xg, const void* Yg, long long ldxg,
               long long ldyg, int g_dtype, const float* xg_inv_scale, const float* yg_inv_scale,
               const float* logit_scale, long long diag_offset, const float* lse_row, const float* lse_col,
-              float alpha, float beta, const float* gscale, float* dX_acc, float* dY_acc, float* ds_acc,
-              float* ds_col, void* workspace, size_t workspace_bytes, void* stream);
+              float alpha, float beta, const float* gscale, float* dX_acc, float* dY_acc, void* workspace,
+              size_t workspace_bytes, void* stream);
 
 /* dst[i] = (dtype) src[i]; the fp32 gradient accumulators are returned in the dtype of the inputs. */
 int clipk_cast(const float* src, void* dst, long long n, int dtype, void* stream);

@@ -89,56 +89,54 @@ class CudaBackend:
         return op
 
     def fwd_stats(self, X: Operand, Y: Operand, scale, diag_offset, want_pos, out=None):
+        """(max, sum, dot) per row of s * X @ Y^T, written into out[0..2] ([3, rows] fp32), plus the positive logit."""
         dev = X.data.device
         rows, cols, d = X.rows, Y.rows, X.d
         if out is None:
-            out = torch.empty(2, rows, dtype=torch.float32, device=dev)
-        row_max, row_sum = out[0], out[1]
+            out = torch.empty(3, rows, dtype=torch.float32, device=dev)
         pos = torch.zeros(rows, dtype=torch.float32, device=dev) if want_pos else None
         nbytes = self.lib.clipk_fwd_workspace_bytes(rows, cols, d, X.dtype)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         _lib.check(self.lib.clipk_fwd_stats(X.data.data_ptr(), Y.data.data_ptr(), rows, cols, d, X.ld, Y.ld, X.dtype,
                                             X.inv_ptr(), Y.inv_ptr(), scale.data_ptr(), diag_offset,
-                                            row_max.data_ptr(), row_sum.data_ptr(), _ptr(pos), ws.data_ptr(), nbytes,
-                                            self._stream()), "clipk_fwd_stats")
+                                            out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), _ptr(pos),
+                                            ws.data_ptr(), nbytes, self._stream()), "clipk_fwd_stats")
         self.launches += 2
-        return row_max, row_sum, pos
+        return out, pos
 
-    def finalize(self, row_max, row_sum, pos, col_parts, diag_offset):
-        """col_parts: [nparts, 2, cols] fp32 (max, sum).  Returns lse_row, lse_col, loss_sums[2]."""
-        dev = row_max.device
-        rows = row_max.numel()
+    def finalize(self, row_stats, pos, col_parts, diag_offset):
+        """row_stats [3, rows]; col_parts [nparts, 3, cols] fp32 (max, sum, dot).
+        Returns lse_row, lse_col, sums[4] = (CE row sum, CE col sum, dscale row sum, dscale col sum)."""
+        dev = row_stats.device
+        rows = row_stats.shape[1]
         nparts, _, cols = col_parts.shape
         lse_row = torch.empty(rows, dtype=torch.float32, device=dev)
         lse_col = torch.empty(cols, dtype=torch.float32, device=dev)
-        sums = torch.empty(2, dtype=torch.float32, device=dev)
-        cmax = col_parts.data_ptr()
-        csum = cmax + cols * 4
-        _lib.check(self.lib.clipk_finalize(row_max.data_ptr(), row_sum.data_ptr(), pos.data_ptr(), rows, cmax, csum,
-                                           nparts, 2 * cols, cols, diag_offset, lse_row.data_ptr(),
-                                           lse_col.data_ptr(), sums.data_ptr(), self._stream()), "clipk_finalize")
+        sums = torch.empty(4, dtype=torch.float32, device=dev)
+        cbase = col_parts.data_ptr()
+        _lib.check(self.lib.clipk_finalize(row_stats[0].data_ptr(), row_stats[1].data_ptr(), row_stats[2].data_ptr(),
+                                           pos.data_ptr(), rows, cbase, cbase + cols * 4, cbase + 2 * cols * 4, nparts,
+                                           3 * cols, cols, diag_offset, lse_row.data_ptr(), lse_col.data_ptr(),
+                                           sums.data_ptr(), self._stream()), "clipk_finalize")
         self.launches += 1
         return lse_row, lse_col, sums
 
     def bwd(self, X: Operand, Y: Operand, Xg: Operand, Yg: Operand, scale, diag_offset, lse_row, lse_col, alpha,
-            beta, gscale, want_dx, want_dy, want_ds_col):
+            beta, gscale, want_dx, want_dy):
         dev = X.data.device
         rows, cols, d = X.rows, Y.rows, X.d
         dX = torch.empty(rows, d, dtype=torch.float32, device=dev) if want_dx else None
         dY = torch.empty(cols, d, dtype=torch.float32, device=dev) if want_dy else None
-        ds_acc = torch.empty(2, dtype=torch.float32, device=dev)
-        ds_col = torch.empty(cols, dtype=torch.float32, device=dev) if want_ds_col else None
         nbytes = self.lib.clipk_bwd_workspace_bytes(rows, cols, d, Xg.dtype)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         _lib.check(self.lib.clipk_bwd(X.data.data_ptr(), Y.data.data_ptr(), rows, cols, d, X.ld, Y.ld, X.dtype,
                                       X.inv_ptr(), Y.inv_ptr(), Xg.data.data_ptr(), Yg.data.data_ptr(), Xg.ld, Yg.ld,
                                       Xg.dtype, Xg.inv_ptr(), Yg.inv_ptr(), scale.data_ptr(), diag_offset,
                                       lse_row.data_ptr(), lse_col.data_ptr(), float(alpha), float(beta),
-                                      gscale.data_ptr(), _ptr(dX), _ptr(dY), ds_acc.data_ptr(), _ptr(ds_col),
-                                      ws.data_ptr(), nbytes, self._stream()), "clipk_bwd")
-        panels = ((rows + 4095) // 4096) * ((cols + 4095) // 4096)
-        self.launches += panels * (1 + int(want_dx) + int(want_dy))
-        return dX, dY, ds_acc, ds_col
+                                      gscale.data_ptr(), _ptr(dX), _ptr(dY), ws.data_ptr(), nbytes, self._stream()),
+                   "clipk_bwd")
+        self.launches += 2 * ((rows + 4735) // 4736) * ((cols + 4863) // 4864)   # approximate: 2 launches per panel
+        return dX, dY
 
     def cast(self, src: torch.Tensor, dtype: torch.dtype):
         if dtype == torch.float32:
@@ -213,77 +211,63 @@ class FusedClipLoss(torch.autograd.Function):
         Y = be.prepare(t_all)
         off = rank * b if W > 1 else 0
 
-        row_max, row_sum, pos = be.fwd_stats(X, Y, scale, off, True)
-        parts = torch.empty(1, 2, N, dtype=torch.float32, device=dev)        # (max, sum) of every column
+        row_stats, pos = be.fwd_stats(X, Y, scale, off, True)
+        parts = torch.empty(1, 3, N, dtype=torch.float32, device=dev)        # (max, sum, dot) of every column
         be.fwd_stats(Y, X, scale, 0, False, out=parts[0])
         if W > 1:
-            parts = _all_gather_rows(parts, W, group)                        # [W, 2, N]
-        lse_row, lse_col, sums = be.finalize(row_max, row_sum, pos, parts, off)
+            parts = _all_gather_rows(parts, W, group)                        # [W, 3, N]
+        lse_row, lse_col, sums = be.finalize(row_stats, pos, parts, off)
 
-        total = sums.sum()
+        # sums[0:2] -> loss, sums[2:4] -> s * dloss/ds; the global (local_loss=False) loss is the same N x N problem
+        # on every rank, so both are all-reduced there.  dlogit_scale is never reduced by the loss in local mode
+        # (DDP averages it later), exactly like the reference.
+        pair = torch.stack((sums[0] + sums[1], sums[2] + sums[3]))
         if W > 1 and not local_loss:
-            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)        # loss over the global N x N problem
-            loss = total / (2.0 * N)
+            dist.all_reduce(pair, op=dist.ReduceOp.SUM, group=group)
+            pair = pair / (2.0 * N)
         else:
-            loss = total / (2.0 * b)
+            pair = pair / (2.0 * b)
+        loss = pair[0]
 
-        ctx.save_for_backward(scale, lse_row, lse_col)
+        ctx.save_for_backward(scale, lse_row, lse_col, pair)
         ctx.operands = (X, Y)
         ctx.cfg = (b, d, W, rank, off, bool(local_loss), bool(gather_with_grad), group, in_dtype)
         ctx.scale_is_param = isinstance(logit_scale, torch.Tensor)
         ctx.scale_dtype = logit_scale.dtype
         ctx.scale_shape = logit_scale.shape
-        return loss
+        return loss.clone()
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
         be = _backend()
-        scale, lse_row, lse_col = ctx.saved_tensors
+        scale, lse_row, lse_col, pair = ctx.saved_tensors
         X, Y = ctx.operands
         b, d, W, rank, off, local_loss, gwg, group, in_dtype = ctx.cfg
-        Xg, Yg = be.prepare_grad(X), be.prepare_grad(Y)
         N = W * b
         go = grad_out.detach().to(torch.float32).reshape(1)
-        local = (W == 1) or local_loss
-        # c of SURVEY App. A: 1/(2b) for W=1, both local modes and global+gather_with_grad; 1/(2N) for global w/o it
-        c_feat = 1.0 / (2.0 * b) if (local or gwg) else 1.0 / (2.0 * N)
-        gscale = (go * c_feat).contiguous()
-
-        if W > 1 and local_loss and not gwg:
-            # loss.py:53-56 with local_loss: gathered tensors carry no gradient, so dI sees only the image->text
-            # softmax and dT only the text->image one.
-            dX, _, acc_r, _ = be.bwd(X, Y, Xg, Yg, scale, off, lse_row, lse_col, 1.0, 0.0, gscale, True, False, False)
-            _, dY, acc_c, ds_col = be.bwd(X, Y, Xg, Yg, scale, off, lse_row, lse_col, 0.0, 1.0, gscale, False, True,
-                                          True)
-            ds_row_part = acc_r[0]
-        else:
-            dX, dY, acc, ds_col = be.bwd(X, Y, Xg, Yg, scale, off, lse_row, lse_col, 1.0, 1.0, gscale, True, True,
-                                         W > 1 and local_loss)
-            ds_row_part = acc[0]
-            acc_c = acc
-
-        if W > 1:
-            dT = _reduce_scatter_rows(dY, W, group)
-        else:
-            dT = dY
-        d_image = be.cast(dX, in_dtype)
-        d_text = be.cast(dT, in_dtype)
+        d_image = d_text = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            Xg, Yg = be.prepare_grad(X), be.prepare_grad(Y)
+            local = (W == 1) or local_loss
+            # c of SURVEY App. A: 1/(2b) for W=1, both local modes and global+gather_with_grad; 1/(2N) otherwise
+            c_feat = 1.0 / (2.0 * b) if (local or gwg) else 1.0 / (2.0 * N)
+            gscale = (go * c_feat).contiguous()
+            if W > 1 and local_loss and not gwg:
+                # loss.py:53-56 with local_loss: gathered tensors carry no gradient, so dI sees only the image->text
+                # softmax and dT only the text->image one.
+                dX, _ = be.bwd(X, Y, Xg, Yg, scale, off, lse_row, lse_col, 1.0, 0.0, gscale, True, False)
+                _, dY = be.bwd(X, Y, Xg, Yg, scale, off, lse_row, lse_col, 0.0, 1.0, gscale, False, True)
+            else:
+                dX, dY = be.bwd(X, Y, Xg, Yg, scale, off, lse_row, lse_col, 1.0, 1.0, gscale, True, True)
+            dT = _reduce_scatter_rows(dY, W, group) if W > 1 else dY
+            d_image = be.cast(dX, in_dtype)
+            d_text = be.cast(dT, in_dtype)
 
         d_scale = None
         if ctx.scale_is_param and ctx.needs_input_grad[2]:
-            if W == 1:
-                ds = (ds_row_part + acc_c[1]) * gscale[0]
-            elif local_loss:
-                # per-rank value: rows of this rank for the image->text term, columns of this rank (summed over
-                # every rank's rows) for the text->image term
-                col_loc = _reduce_scatter_rows(ds_col, W, group).sum()
-                ds = (ds_row_part + col_loc) * gscale[0]
-            else:
-                tot = (ds_row_part + acc_c[1]).reshape(1)
-                dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
-                ds = tot[0] * go[0] / (2.0 * N)
-            d_scale = ds.reshape(ctx.scale_shape).to(ctx.scale_dtype)
+            # pair[1] = s * dloss/ds, already normalised (and all-reduced in global mode) by the forward
+            d_scale = (pair[1] * go[0] / scale[0]).reshape(ctx.scale_shape).to(ctx.scale_dtype)
         return d_image, d_text, d_scale, None, None, None, None, None
 
 

@@ -97,70 +97,96 @@ static int tmap_mnmajor(CUtensorMap* m, const void* base, long long mn, long lon
 }
 
 // ------------------------------------------------------------------------------------------------ small kernels
-// merge the per-unit partial row statistics (log2-scaled domain) into natural-log (max, sum).
+// merge the per-unit partial row statistics (log2-scaled domain) into natural-log (max, sum, dot):
+//   row_max = max_j S_ij,  row_sum = sum_j exp(S_ij - row_max),  row_dot = sum_j exp(S_ij - row_max) * S_ij
 __global__ void merge_row_parts_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,
-                                       int nparts, int rows, float* __restrict__ row_max, float* __restrict__ row_sum) {
+                                       const float* __restrict__ part_dot, int nparts, int rows,
+                                       float* __restrict__ row_max, float* __restrict__ row_sum,
+                                       float* __restrict__ row_dot) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows) return;
     float m = -CUDART_INF_F;
     for (int p = 0; p < nparts; ++p) m = fmaxf(m, part_max[(size_t)p * rows + i]);
-    float l = 0.f;
+    float l = 0.f, t = 0.f;
     for (int p = 0; p < nparts; ++p) {
         const float pm = part_max[(size_t)p * rows + i];
-        if (pm > -CUDART_INF_F) l += part_sum[(size_t)p * rows + i] * exp2f(pm - m);
+        if (pm > -CUDART_INF_F) {
+            const float w = exp2f(pm - m);
+            l += part_sum[(size_t)p * rows + i] * w;
+            t += part_dot[(size_t)p * rows + i] * w;
+        }
     }
     row_max[i] = m * LN2;
     row_sum[i] = l;
+    row_dot[i] = t * LN2;
 }
 
-__device__ __forceinline__ float merge_col(const float* __restrict__ cmax, const float* __restrict__ csum, int nparts,
-                                           long long stride, long long j) {
+// column j: merge nparts (max, sum, dot) triples -> (lse, expected logit under the column softmax)
+__device__ __forceinline__ void merge_col(const float* __restrict__ cmax, const float* __restrict__ csum,
+                                          const float* __restrict__ cdot, int nparts, long long stride, long long j,
+                                          float* lse, float* expect) {
     float m = -CUDART_INF_F;
     for (int p = 0; p < nparts; ++p) m = fmaxf(m, cmax[(size_t)p * stride + j]);
-    float l = 0.f;
+    float l = 0.f, t = 0.f;
     for (int p = 0; p < nparts; ++p) {
         const float pm = cmax[(size_t)p * stride + j];
-        if (pm > -CUDART_INF_F) l += csum[(size_t)p * stride + j] * expf(pm - m);
+        if (pm > -CUDART_INF_F) {
+            const float w = expf(pm - m);
+            l += csum[(size_t)p * stride + j] * w;
+            t += cdot[(size_t)p * stride + j] * w;
+        }
     }
-    return m + logf(l);
+    *lse = m + logf(l);
+    *expect = t / l;
 }
 
+// sums[0] = sum_i (lse_row_i - pos_i)          sums[1] = sum_i (lse_col_{off+i} - pos_i)        (cross-entropy sums)
+// sums[2] = sum_i (E_row_i - pos_i)            sums[3] = sum_i (E_col_{off+i} - pos_i)          (s * dloss/ds sums)
+// with E = expected logit under the row / column softmax.
 __global__ void finalize_kernel(const float* __restrict__ row_max, const float* __restrict__ row_sum,
-                                const float* __restrict__ pos, int rows, const float* __restrict__ cmax,
-                                const float* __restrict__ csum, int nparts, long long stride, int cols,
-                                long long diag_offset,
-                                float* __restrict__ lse_row, float* __restrict__ lse_col, float* __restrict__ loss_sums) {
+                                const float* __restrict__ row_dot, const float* __restrict__ pos, int rows,
+                                const float* __restrict__ cmax, const float* __restrict__ csum,
+                                const float* __restrict__ cdot, int nparts, long long stride, int cols,
+                                long long diag_offset, float* __restrict__ lse_row, float* __restrict__ lse_col,
+                                float* __restrict__ sums) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    float a = 0.f, b = 0.f;
-    if (i < cols) lse_col[i] = merge_col(cmax, csum, nparts, stride, i);
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (i < cols) {
+        float lse, e;
+        merge_col(cmax, csum, cdot, nparts, stride, i, &lse, &e);
+        lse_col[i] = lse;
+    }
     if (i < rows) {
-        const float lr = row_max[i] + logf(row_sum[i]);
+        const float rs = row_sum[i];
+        const float lr = row_max[i] + logf(rs);
         lse_row[i] = lr;
         const float p = pos[i];
-        a = lr - p;
+        v[0] = lr - p;
+        v[2] = row_dot[i] / rs - p;
         const long long j = diag_offset + i;
-        if (j >= 0 && j < cols) b = merge_col(cmax, csum, nparts, stride, j) - p;
+        if (j >= 0 && j < cols) {
+            float lse, e;
+            merge_col(cmax, csum, cdot, nparts, stride, j, &lse, &e);
+            v[1] = lse - p;
+            v[3] = e - p;
+        }
     }
-    __shared__ float sa[32], sb[32];
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        a += __shfl_xor_sync(0xffffffffu, a, off);
-        b += __shfl_xor_sync(0xffffffffu, b, off);
-    }
+    __shared__ float sh[4][32];
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    if (l == 0) { sa[w] = a; sb[w] = b; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+        if (l == 0) sh[k][w] = v[k];
+    }
     __syncthreads();
     if (w == 0) {
-        a = (l < (blockDim.x >> 5)) ? sa[l] : 0.f;
-        b = (l < (blockDim.x >> 5)) ? sb[l] : 0.f;
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            a += __shfl_xor_sync(0xffffffffu, a, off);
-            b += __shfl_xor_sync(0xffffffffu, b, off);
-        }
-        if (l == 0) {
-            atomicAdd(loss_sums + 0, a);
-            atomicAdd(loss_sums + 1, b);
+        for (int k = 0; k < 4; ++k) {
+            float x = (l < (blockDim.x >> 5)) ? sh[k][l] : 0.f;
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+            if (l == 0) atomicAdd(sums + k, x);
         }
     }
 }
@@ -234,8 +260,8 @@ static inline int cdiv(long long a, long long b) { return int((a + b - 1) / b); 
 static inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
 
 constexpr int MAX_SPLIT = 32;
-constexpr long long PANEL_ROWS = 4096;
-constexpr long long PANEL_COLS = 4096;
+constexpr int MAX_PARTS = MAX_SPLIT * PARTS_PER_UNIT;
+constexpr long long G_PANEL_BYTES = 48ll << 20;     // the fp16 G panel must stay L2 resident (126 MB L2)
 
 // How many CTAs share the column sweep of one 128-row block: fill the SMs in as few equal waves as possible.
 static int choose_split(int m_blocks, int n_tiles, int sms) {
@@ -251,14 +277,56 @@ static int choose_split(int m_blocks, int n_tiles, int sms) {
     return best;
 }
 
-template <int MODE, int A_MN, int B_MN, int F16>
+// Panel of the backward: G[rp x cp] is produced once and consumed by the dX tiles (rp/128 * nt CTAs, K = cp) and the
+// dY tiles (cp/128 * nt CTAs, K = rp) of ONE launch; pick rp, cp so that launch is close to a whole number of waves
+// with long K, and the panel fits the L2 budget.  Then even the panels out over the problem.
+static void choose_panel(int rows, int cols, int d, int gplanes, int sms, long long* rp_out, long long* cp_out) {
+    const int nt = cdiv(d, BN);
+    const int R = cdiv(rows, BM), C = cdiv(cols, BN) * 2;       // available 128-row / 128-col blocks (cp multiple of 256)
+    double best = 1e30;
+    int best_rb = 1, best_cb = 2;
+    for (int waves = 1; waves <= 3; ++waves) {
+        const int total = sms * waves / nt;                      // 128-blocks (rows + cols) per launch
+        if (total < 3) continue;
+        int rb = total / 2 < R ? total / 2 : R;
+        int cb = (total - rb) & ~1;
+        if (cb > C) { cb = C; rb = total - cb < R ? total - cb : R; }
+        if (cb < 2) cb = 2;
+        while ((long long)rb * BM * cb * BM * 2 * gplanes > G_PANEL_BYTES && (rb > 1 || cb > 2)) {
+            if (rb >= cb && rb > 1) --rb; else cb -= 2;
+        }
+        const int jobs = (rb + cb) * nt;
+        const int w = cdiv(jobs, sms);
+        const int kmax = (rb > cb ? rb : cb) * BM;
+        const double t = w * (8.0 + kmax * (6.0 / 1024.0));      // us: ~8 us per CTA lifetime + 6 us per 1024 of K
+        const double per_area = t / ((double)rb * cb);
+        if (per_area < best) { best = per_area; best_rb = rb; best_cb = cb; }
+    }
+    const int nrp = cdiv(R, best_rb), ncp = cdiv(C, best_cb);
+    *rp_out = (long long)cdiv(R, nrp) * BM;
+    *cp_out = (long long)((cdiv(C, ncp) + 1) & ~1) * BM;
+}
+
+template <int MODE, int F16>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const KArgs& a, dim3 grid, cudaStream_t st) {
-    auto kfn = gemm_kernel<MODE, A_MN, B_MN, F16>;
+    auto kfn = gemm_kernel<MODE, F16>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); });
     if (attr_err != cudaSuccess) return fail(int(attr_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
     kfn<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, a);
+    CK_CUDA(cudaGetLastError());
+    return CLIPK_OK;
+}
+
+static int launch_pair(const CUtensorMap& ta0, const CUtensorMap& tb0, const KArgs& a0, int jobs0, const CUtensorMap& ta1,
+                       const CUtensorMap& tb1, const KArgs& a1, int jobs1, cudaStream_t st) {
+    auto kfn = gemm_pair_kernel<1>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); });
+    if (attr_err != cudaSuccess) return fail(int(attr_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+    kfn<<<jobs0 + jobs1, NUM_THREADS, SMEM_BYTES, st>>>(ta0, tb0, a0, ta1, tb1, a1, jobs0);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
 }
@@ -276,7 +344,7 @@ static void set_segments(KArgs& a, int planes, int k_extent, long long a_plane, 
     a.kb_per_seg = cdiv(k_extent, BK);
     a.nseg = (planes == 2) ? 3 : 1;
     a.num_kb = a.nseg * a.kb_per_seg;
-    for (int i = 0; i < 6; ++i) { a.a_off[i] = 0; a.b_off[i] = 0; }
+    for (int i = 0; i < 3; ++i) { a.a_off[i] = 0; a.b_off[i] = 0; }
     if (planes == 2)
         for (int i = 0; i < 3; ++i) {
             a.a_off[i] = int(kPairA[i] * a_plane);
@@ -342,16 +410,16 @@ int clipk_to_f16(const void* src, int src_dtype, long long rows, long long d, lo
 size_t clipk_fwd_workspace_bytes(int rows, int cols, int d, int dtype) {
     (void)cols; (void)d; (void)dtype;
     if (rows <= 0) return 0;
-    return size_t(2) * MAX_SPLIT * size_t(rows) * sizeof(float) + 256;
+    return size_t(3) * MAX_PARTS * size_t(rows) * sizeof(float) + 256;
 }
 
 int clipk_fwd_stats(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
                     const float* x_inv_scale, const float* y_inv_scale, const float* logit_scale,
-                    long long diag_offset, float* row_max, float* row_sum, float* pos_logit, void* workspace,
-                    size_t workspace_bytes, void* stream) {
+                    long long diag_offset, float* row_max, float* row_sum, float* row_dot, float* pos_logit,
+                    void* workspace, size_t workspace_bytes, void* stream) {
     int rc = check_common(X, Y, rows, cols, d, ldx, ldy, dtype);
     if (rc) return rc;
-    if (!logit_scale || !row_max || !row_sum || !workspace) return fail(CLIPK_EINVAL, "null pointer argument");
+    if (!logit_scale || !row_max || !row_sum || !row_dot || !workspace) return fail(CLIPK_EINVAL, "null pointer argument");
     if (workspace_bytes < clipk_fwd_workspace_bytes(rows, cols, d, dtype)) return fail(CLIPK_EWORKSPACE, "workspace too small");
     DevInfo di;
     if ((rc = device_info(&di))) return rc;
@@ -372,21 +440,25 @@ int clipk_fwd_stats(const void* X, const void* Y, int rows, int cols, int d, lon
     const int units = cdiv(a.n_tiles, a.tiles_per_unit);
     a.scale = logit_scale; a.xs = x_inv_scale; a.ys = y_inv_scale; a.diag_offset = diag_offset;
     a.part_max = static_cast<float*>(workspace);
-    a.part_sum = a.part_max + size_t(MAX_SPLIT) * rows;
+    a.part_sum = a.part_max + size_t(MAX_PARTS) * rows;
+    a.part_dot = a.part_sum + size_t(MAX_PARTS) * rows;
     a.pos = pos_logit;
     if (!pos_logit) a.diag_offset = -(1LL << 40);   // no row has a positive inside [0, cols)
-    if (is_f16(dtype)) rc = launch_gemm<MODE_STATS, 0, 0, 1>(ta, tb, a, dim3(units, m_blocks), st);
-    else rc = launch_gemm<MODE_STATS, 0, 0, 0>(ta, tb, a, dim3(units, m_blocks), st);
+    if (is_f16(dtype)) rc = launch_gemm<MODE_STATS, 1>(ta, tb, a, dim3(units, m_blocks), st);
+    else rc = launch_gemm<MODE_STATS, 0>(ta, tb, a, dim3(units, m_blocks), st);
     if (rc) return rc;
-    merge_row_parts_kernel<<<cdiv(rows, 256), 256, 0, st>>>(a.part_max, a.part_sum, units, rows, row_max, row_sum);
+    merge_row_parts_kernel<<<cdiv(rows, 256), 256, 0, st>>>(a.part_max, a.part_sum, a.part_dot, units * PARTS_PER_UNIT,
+                                                            rows, row_max, row_sum, row_dot);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
 }
 
-int clipk_finalize(const float* row_max, const float* row_sum, const float* pos_logit, int rows,
-                   const float* col_max_parts, const float* col_sum_parts, int nparts, long long part_stride,
-                   int cols, long long diag_offset, float* lse_row, float* lse_col, float* loss_sums, void* stream) {
-    if (!row_max || !row_sum || !pos_logit || !col_max_parts || !col_sum_parts || !lse_row || !lse_col || !loss_sums)
+int clipk_finalize(const float* row_max, const float* row_sum, const float* row_dot, const float* pos_logit, int rows,
+                   const float* col_max_parts, const float* col_sum_parts, const float* col_dot_parts, int nparts,
+                   long long part_stride, int cols, long long diag_offset, float* lse_row, float* lse_col, float* sums,
+                   void* stream) {
+    if (!row_max || !row_sum || !row_dot || !pos_logit || !col_max_parts || !col_sum_parts || !col_dot_parts || !lse_row ||
+        !lse_col || !sums)
         return fail(CLIPK_EINVAL, "null pointer argument");
     if (rows <= 0 || cols <= 0 || nparts <= 0) return fail(CLIPK_EINVAL, "rows, cols and nparts must be positive");
     if (part_stride < cols) return fail(CLIPK_EINVAL, "part_stride smaller than cols");
@@ -394,33 +466,36 @@ int clipk_finalize(const float* row_max, const float* row_sum, const float* pos_
     int rc = device_info(&di);
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    CK_CUDA(cudaMemsetAsync(loss_sums, 0, 2 * sizeof(float), st));
+    CK_CUDA(cudaMemsetAsync(sums, 0, 4 * sizeof(float), st));
     const int n = rows > cols ? rows : cols;
-    finalize_kernel<<<cdiv(n, 256), 256, 0, st>>>(row_max, row_sum, pos_logit, rows, col_max_parts, col_sum_parts, nparts,
-                                                  part_stride, cols, diag_offset, lse_row, lse_col, loss_sums);
+    finalize_kernel<<<cdiv(n, 256), 256, 0, st>>>(row_max, row_sum, row_dot, pos_logit, rows, col_max_parts, col_sum_parts,
+                                                  col_dot_parts, nparts, part_stride, cols, diag_offset, lse_row, lse_col,
+                                                  sums);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
 }
 
 size_t clipk_bwd_workspace_bytes(int rows, int cols, int d, int g_dtype) {
-    (void)d;
-    if (rows <= 0 || cols <= 0) return 0;
-    const long long rp = round_up(rows < PANEL_ROWS ? rows : PANEL_ROWS, BM);
-    const long long cp = round_up(cols < PANEL_COLS ? cols : PANEL_COLS, BN);
-    return size_t(rp) * size_t(cp) * 2 * planes_of(g_dtype) + 1024;
+    if (rows <= 0 || cols <= 0 || d <= 0) return 0;
+    long long rp, cp;
+    choose_panel(rows, cols, d, planes_of(g_dtype), 148, &rp, &cp);
+    // the SM count only nudges the split; size for the L2 budget so any device fits
+    (void)rp; (void)cp;
+    return size_t(G_PANEL_BYTES) + size_t(2) * 1024 * 1024;
 }
 
 int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
               const float* x_inv_scale, const float* y_inv_scale, const void* Xg, const void* Yg, long long ldxg,
               long long ldyg, int g_dtype, const float* xg_inv_scale, const float* yg_inv_scale,
               const float* logit_scale, long long diag_offset, const float* lse_row, const float* lse_col,
-              float alpha, float beta, const float* gscale, float* dX_acc, float* dY_acc, float* ds_acc,
-              float* ds_col, void* workspace, size_t workspace_bytes, void* stream) {
+              float alpha, float beta, const float* gscale, float* dX_acc, float* dY_acc, void* workspace,
+              size_t workspace_bytes, void* stream) {
     int rc = check_common(X, Y, rows, cols, d, ldx, ldy, dtype);
     if (rc) return rc;
     if (g_dtype != CLIPK_F16 && g_dtype != CLIPK_F16X2) return fail(CLIPK_EUNSUPPORTED, "g_dtype must be CLIPK_F16 or CLIPK_F16X2");
     if ((rc = check_common(Xg, Yg, rows, cols, d, ldxg, ldyg, g_dtype))) return rc;
-    if (!logit_scale || !lse_row || !lse_col || !gscale || !ds_acc || !workspace) return fail(CLIPK_EINVAL, "null pointer argument");
+    if (!logit_scale || !lse_row || !lse_col || !gscale || !workspace) return fail(CLIPK_EINVAL, "null pointer argument");
+    if (!dX_acc && !dY_acc) return fail(CLIPK_EINVAL, "nothing to compute: dX_acc and dY_acc are both NULL");
     if (workspace_bytes < clipk_bwd_workspace_bytes(rows, cols, d, g_dtype)) return fail(CLIPK_EWORKSPACE, "workspace too small");
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail(CLIPK_EINVAL, "workspace must be 256-byte aligned");
     DevInfo di;
@@ -432,25 +507,24 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
     const long long dpad = round_up(d, BK);
     const long long kext = (dtype == CLIPK_BF16) ? d : planes * dpad;   // inner extent of X / Y rows
     const long long gext = gplanes * dpad;                              // inner extent of Xg / Yg rows
-    const long long rp_max = rows < PANEL_ROWS ? rows : PANEL_ROWS;
-    const long long cp_max = cols < PANEL_COLS ? cols : PANEL_COLS;
-    const int ncp = int(round_up(cp_max, BN));          // padded panel width = G plane stride
+    long long rp_max, cp_max;
+    choose_panel(rows, cols, d, gplanes, di.sms, &rp_max, &cp_max);
+    const int ncp = int(cp_max);                        // panel width (multiple of BN) = G plane stride
     const int ldg = gplanes * ncp;
+    if ((unsigned long long)round_up(rp_max, BM) * ldg * 2 > workspace_bytes) return fail(CLIPK_EWORKSPACE, "panel does not fit the workspace");
     __half* G = static_cast<__half*>(workspace);
     const size_t esz = 2;
     const char* Xb = static_cast<const char*>(X);
     const char* Yb = static_cast<const char*>(Y);
     const char* Xgb = static_cast<const char*>(Xg);
     const char* Ygb = static_cast<const char*>(Yg);
-
-    CK_CUDA(cudaMemsetAsync(ds_acc, 0, 2 * sizeof(float), st));
-    if (ds_col) CK_CUDA(cudaMemsetAsync(ds_col, 0, size_t(cols) * sizeof(float), st));
+    const int nt = cdiv(d, BN);
 
     for (long long r0 = 0; r0 < rows; r0 += rp_max) {
         const int nr = int(rows - r0 < rp_max ? rows - r0 : rp_max);
         for (long long c0 = 0; c0 < cols; c0 += cp_max) {
             const int nc = int(cols - c0 < cp_max ? cols - c0 : cp_max);
-            // ---- A: recompute S on the panel, write G (fp16, x 2^14) and the dlogit_scale sums
+            // ---- recompute S on the panel, write G (fp16, x 2^14)
             {
                 CUtensorMap ta, tb;
                 if ((rc = tmap_kmajor(&ta, Xb + r0 * ldx * esz, nr, kext, ldx, BM))) return rc;
@@ -465,37 +539,39 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
                 a.scale = logit_scale; a.xs = x_inv_scale; a.ys = y_inv_scale;
                 a.diag_offset = diag_offset + r0 - c0;
                 a.lse_row = lse_row + r0; a.lse_col = lse_col + c0;
-                a.alpha = alpha; a.beta = beta; a.gscale = gscale;
+                a.alpha = alpha; a.beta = beta;
                 a.G = G; a.ldg = ldg; a.g_planes = gplanes; a.g_plane_stride = ncp;
-                a.ds_acc = ds_acc; a.ds_col = ds_col ? ds_col + c0 : nullptr;
-                if (is_f16(dtype)) rc = launch_gemm<MODE_GRAD, 0, 0, 1>(ta, tb, a, dim3(units, m_blocks), st);
-                else rc = launch_gemm<MODE_GRAD, 0, 0, 0>(ta, tb, a, dim3(units, m_blocks), st);
+                if (is_f16(dtype)) rc = launch_gemm<MODE_GRAD, 1>(ta, tb, a, dim3(units, m_blocks), st);
+                else rc = launch_gemm<MODE_GRAD, 0>(ta, tb, a, dim3(units, m_blocks), st);
                 if (rc) return rc;
             }
-            // ---- B: dX[r0:r0+nr, :] (+)= G[nr, nc] * Yg[c0:c0+nc, :]      (A K-major, B MN-major, fp16 x fp16)
+            // ---- job 0: dX[r0:r0+nr, :] (+)= G[nr, nc] * Yg[c0:c0+nc, :]      (A K-major, B MN-major, fp16 x fp16)
+            // ---- job 1: dY[c0:c0+nc, :] (+)= G^T[nc, nr] * Xg[r0:r0+nr, :]    (A MN-major, B MN-major, fp16 x fp16)
+            CUtensorMap ta0, tb0, ta1, tb1;
+            KArgs a0{}, a1{};
+            int jobs0 = 0, jobs1 = 0;
             if (dX_acc) {
-                CUtensorMap ta, tb;
-                if ((rc = tmap_kmajor(&ta, G, nr, gplanes == 2 ? ldg : nc, ldg, BM))) return rc;
-                if ((rc = tmap_mnmajor(&tb, Ygb + c0 * ldyg * esz, gext, nc, ldyg))) return rc;
-                KArgs a{};
-                a.M = nr; a.N = d; a.n_tiles = cdiv(d, BN); a.tiles_per_unit = 1;
-                set_segments(a, gplanes, nc, ncp, dpad);
-                a.out = dX_acc + r0 * d; a.ldo = d; a.accumulate = (c0 > 0);
-                a.oscale0 = logit_scale; a.oscale1 = gscale; a.oscale2 = yg_inv_scale; a.oconst = 1.f / 16384.f;
-                if ((rc = launch_gemm<MODE_OUT, 0, 1, 1>(ta, tb, a, dim3(a.n_tiles, cdiv(nr, BM)), st))) return rc;
+                if ((rc = tmap_kmajor(&ta0, G, nr, gplanes == 2 ? ldg : nc, ldg, BM))) return rc;
+                if ((rc = tmap_mnmajor(&tb0, Ygb + c0 * ldyg * esz, gext, nc, ldyg))) return rc;
+                a0.M = nr; a0.N = d; a0.n_tiles = nt; a0.tiles_per_unit = 1; a0.a_mn = 0; a0.b_mn = 1;
+                set_segments(a0, gplanes, nc, ncp, dpad);
+                a0.out = dX_acc + r0 * d; a0.ldo = d; a0.accumulate = (c0 > 0);
+                a0.oscale0 = logit_scale; a0.oscale1 = gscale; a0.oscale2 = yg_inv_scale; a0.oconst = 1.f / 16384.f;
+                jobs0 = cdiv(nr, BM) * nt;
             }
-            // ---- C: dY[c0:c0+nc, :] (+)= G^T[nc, nr] * Xg[r0:r0+nr, :]    (A MN-major, B MN-major, fp16 x fp16)
             if (dY_acc) {
-                CUtensorMap ta, tb;
-                if ((rc = tmap_mnmajor(&ta, G, gplanes == 2 ? ldg : nc, nr, ldg))) return rc;
-                if ((rc = tmap_mnmajor(&tb, Xgb + r0 * ldxg * esz, gext, nr, ldxg))) return rc;
-                KArgs a{};
-                a.M = nc; a.N = d; a.n_tiles = cdiv(d, BN); a.tiles_per_unit = 1;
-                set_segments(a, gplanes, nr, ncp, dpad);
-                a.out = dY_acc + c0 * d; a.ldo = d; a.accumulate = (r0 > 0);
-                a.oscale0 = logit_scale; a.oscale1 = gscale; a.oscale2 = xg_inv_scale; a.oconst = 1.f / 16384.f;
-                if ((rc = launch_gemm<MODE_OUT, 1, 1, 1>(ta, tb, a, dim3(a.n_tiles, cdiv(nc, BM)), st))) return rc;
+                if ((rc = tmap_mnmajor(&ta1, G, gplanes == 2 ? ldg : nc, nr, ldg))) return rc;
+                if ((rc = tmap_mnmajor(&tb1, Xgb + r0 * ldxg * esz, gext, nr, ldxg))) return rc;
+                a1.M = nc; a1.N = d; a1.n_tiles = nt; a1.tiles_per_unit = 1; a1.a_mn = 1; a1.b_mn = 1;
+                set_segments(a1, gplanes, nr, ncp, dpad);
+                a1.out = dY_acc + c0 * d; a1.ldo = d; a1.accumulate = (r0 > 0);
+                a1.oscale0 = logit_scale; a1.oscale1 = gscale; a1.oscale2 = xg_inv_scale; a1.oconst = 1.f / 16384.f;
+                jobs1 = cdiv(nc, BM) * nt;
             }
+            if (dX_acc && dY_acc) rc = launch_pair(ta0, tb0, a0, jobs0, ta1, tb1, a1, jobs1, st);
+            else if (dX_acc) rc = launch_gemm<MODE_OUT, 1>(ta0, tb0, a0, dim3(nt, cdiv(nr, BM)), st);
+            else rc = launch_gemm<MODE_OUT, 1>(ta1, tb1, a1, dim3(nt, cdiv(nc, BM)), st);
+            if (rc) return rc;
         }
     }
     return CLIPK_OK;
@@ -524,20 +600,12 @@ int clipk_gemm16(const void* A, const void* B, float* D, int M, int N, int K, lo
     if (b_mn) rc = tmap_mnmajor(&tb, B, N, K, ldb); else rc = tmap_kmajor(&tb, B, N, K, ldb, BN);
     if (rc) return rc;
     KArgs a{};
-    a.M = M; a.N = N; a.n_tiles = cdiv(N, BN); a.tiles_per_unit = 1;
+    a.M = M; a.N = N; a.n_tiles = cdiv(N, BN); a.tiles_per_unit = 1; a.a_mn = a_mn ? 1 : 0; a.b_mn = b_mn ? 1 : 0;
     set_segments(a, 1, K, 0, 0);
     a.out = D; a.ldo = int(ldd); a.accumulate = accumulate; a.oconst = 1.f;
     dim3 grid(a.n_tiles, cdiv(M, BM));
-    if (f16) {
-        if (!a_mn && !b_mn) return launch_gemm<MODE_OUT, 0, 0, 1>(ta, tb, a, grid, st);
-        if (!a_mn && b_mn) return launch_gemm<MODE_OUT, 0, 1, 1>(ta, tb, a, grid, st);
-        if (a_mn && b_mn) return launch_gemm<MODE_OUT, 1, 1, 1>(ta, tb, a, grid, st);
-        return fail(CLIPK_EUNSUPPORTED, "fp16 operands: (a_mn=1, b_mn=0) is not built");
-    }
-    if (!a_mn && !b_mn) return launch_gemm<MODE_OUT, 0, 0, 0>(ta, tb, a, grid, st);
-    if (!a_mn && b_mn) return launch_gemm<MODE_OUT, 0, 1, 0>(ta, tb, a, grid, st);
-    if (a_mn && b_mn) return launch_gemm<MODE_OUT, 1, 1, 0>(ta, tb, a, grid, st);
-    return launch_gemm<MODE_OUT, 1, 0, 0>(ta, tb, a, grid, st);
+    if (f16) return launch_gemm<MODE_OUT, 1>(ta, tb, a, grid, st);
+    return launch_gemm<MODE_OUT, 0>(ta, tb, a, grid, st);
 }
 
 }  // extern "C"

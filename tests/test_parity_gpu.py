@@ -156,7 +156,9 @@ def test_large_properties_c2_shape():
     X = be.prepare(I.detach()[:256])
     Y = be.prepare(T.detach())
     sc = torch.tensor([s], device="cuda")
-    rmax, rsum, p = be.fwd_stats(X, Y, sc, 0, True)
+    stats, p = be.fwd_stats(X, Y, sc, 0, True)
     torch.cuda.synchronize()
-    assert torch.allclose(rmax + rsum.log(), lse, rtol=0, atol=2e-3)
+    assert torch.allclose(stats[0] + stats[1].log(), lse, rtol=0, atol=2e-3)
+    expect = (torch.softmax(rows, dim=1) * rows).sum(dim=1)
+    assert torch.allclose(stats[2] / stats[1], expect, rtol=0, atol=2e-3)
     assert torch.allclose(p, pos, rtol=0, atol=2e-3)
