@@ -1,6 +1,7 @@
 // clipk - C ABI implementation (see include/clipk.h).  sm_100a only; no CPU path, no other backend.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -70,22 +71,33 @@ static EncodeTiledFn encode_fn() {
     return g_encode;
 }
 
-// 2D bf16 tensor map, SWIZZLE_128B, zero fill out of bounds.  inner = contiguous extent (elements).
-static int make_tmap_bf16(CUtensorMap* m, const void* base, long long inner, long long outer, long long ld_elems,
-                          int box_inner, int box_outer) {
+// 2D tensor map, SWIZZLE_128B, zero fill out of bounds.  inner = contiguous extent (elements of esize bytes).
+static int make_tmap(CUtensorMap* m, const void* base, long long inner, long long outer, long long ld_elems,
+                     int box_inner, int box_outer, int esize) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(CLIPK_EDRIVER, "cuTensorMapEncodeTiled entry point not available");
     if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(CLIPK_EINVAL, "operand pointer not 16-byte aligned");
-    if ((ld_elems * 2) % 16 != 0) return fail(CLIPK_EINVAL, "leading dimension %lld not a multiple of 8 elements", ld_elems);
+    if ((ld_elems * esize) % 16 != 0) return fail(CLIPK_EINVAL, "leading dimension %lld is not a multiple of 16 bytes", ld_elems);
     cuuint64_t dims[2] = {cuuint64_t(inner), cuuint64_t(outer)};
-    cuuint64_t strides[1] = {cuuint64_t(ld_elems) * 2};
+    cuuint64_t strides[1] = {cuuint64_t(ld_elems) * esize};
     cuuint32_t box[2] = {cuuint32_t(box_inner), cuuint32_t(box_outer)};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(m, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(CLIPK_EDRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", int(r));
     return CLIPK_OK;
+}
+static int make_tmap_bf16(CUtensorMap* m, const void* base, long long inner, long long outer, long long ld_elems,
+                          int box_inner, int box_outer) {
+    return make_tmap(m, base, inner, outer, ld_elems, box_inner, box_outer, 2);
+}
+// epilogue stores: fp32 output tile pieces of 32 columns x 32 rows, fp16 G tile pieces of 64 columns x 32 rows
+static int tmap_out_f32(CUtensorMap* m, const float* base, long long rows, long long cols, long long ld) {
+    return make_tmap(m, base, cols, rows, ld, 32, 32, 4);
+}
+static int tmap_g_store(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld) {
+    return make_tmap(m, base, cols, rows, ld, 64, 32, 2);
 }
 // operand [rows, K] row-major, consumed K-major: box = 64 (K) x box_rows
 static int tmap_kmajor(CUtensorMap* m, const void* base, long long rows, long long K, long long ld, int box_rows) {
@@ -261,7 +273,18 @@ static inline long long round_up(long long a, long long b) { return (a + b - 1) 
 
 constexpr int MAX_SPLIT = 32;
 constexpr int MAX_PARTS = MAX_SPLIT * PARTS_PER_UNIT;
-constexpr long long G_PANEL_BYTES = 48ll << 20;     // the fp16 G panel must stay L2 resident (126 MB L2)
+// Budget of the fp16 G panel.  48 MB keeps it L2 resident (126 MB L2) next to the operands; CLIPK_PANEL_MB overrides
+// it for experiments (a larger panel spills to HBM but amortises the per-launch fill/drain over longer kernels).
+static long long panel_bytes() {
+    static long long v = [] {
+        const char* e = getenv("CLIPK_PANEL_MB");
+        long long mb = e ? atoll(e) : 48;
+        if (mb < 8) mb = 8;
+        if (mb > 1024) mb = 1024;
+        return mb << 20;
+    }();
+    return v;
+}
 
 // How many CTAs share the column sweep of one 128-row block: fill the SMs in as few equal waves as possible.
 static int choose_split(int m_blocks, int n_tiles, int sms) {
@@ -285,14 +308,14 @@ static void choose_panel(int rows, int cols, int d, int gplanes, int sms, long l
     const int R = cdiv(rows, BM), C = cdiv(cols, BN) * 2;       // available 128-row / 128-col blocks (cp multiple of 256)
     double best = 1e30;
     int best_rb = 1, best_cb = 2;
-    for (int waves = 1; waves <= 3; ++waves) {
+    for (int waves = 1; waves <= 4; ++waves) {
         const int total = sms * waves / nt;                      // 128-blocks (rows + cols) per launch
         if (total < 3) continue;
         int rb = total / 2 < R ? total / 2 : R;
         int cb = (total - rb) & ~1;
         if (cb > C) { cb = C; rb = total - cb < R ? total - cb : R; }
         if (cb < 2) cb = 2;
-        while ((long long)rb * BM * cb * BM * 2 * gplanes > G_PANEL_BYTES && (rb > 1 || cb > 2)) {
+        while ((long long)rb * BM * cb * BM * 2 * gplanes > panel_bytes() && (rb > 1 || cb > 2)) {
             if (rb >= cb && rb > 1) --rb; else cb -= 2;
         }
         const int jobs = (rb + cb) * nt;
@@ -307,26 +330,31 @@ static void choose_panel(int rows, int cols, int d, int gplanes, int sms, long l
     *cp_out = (long long)((cdiv(C, ncp) + 1) & ~1) * BM;
 }
 
+// tc = epilogue store map (G panel for GRAD, fp32 output for OUT; unused by STATS - pass ta)
 template <int MODE, int F16>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const KArgs& a, dim3 grid, cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const KArgs& a, dim3 grid,
+                       cudaStream_t st) {
     auto kfn = gemm_kernel<MODE, F16>;
+    constexpr int smem = smem_bytes_of(MODE);
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); });
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
     if (attr_err != cudaSuccess) return fail(int(attr_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-    kfn<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, a);
+    kfn<<<grid, NUM_THREADS, smem, st>>>(ta, tb, tc, a);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
 }
 
-static int launch_pair(const CUtensorMap& ta0, const CUtensorMap& tb0, const KArgs& a0, int jobs0, const CUtensorMap& ta1,
-                       const CUtensorMap& tb1, const KArgs& a1, int jobs1, cudaStream_t st) {
+static int launch_pair(const CUtensorMap& ta0, const CUtensorMap& tb0, const CUtensorMap& tc0, const KArgs& a0, int jobs0,
+                       const CUtensorMap& ta1, const CUtensorMap& tb1, const CUtensorMap& tc1, const KArgs& a1, int jobs1,
+                       cudaStream_t st) {
     auto kfn = gemm_pair_kernel<1>;
+    constexpr int smem = smem_bytes_of(MODE_OUT);
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); });
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
     if (attr_err != cudaSuccess) return fail(int(attr_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-    kfn<<<jobs0 + jobs1, NUM_THREADS, SMEM_BYTES, st>>>(ta0, tb0, a0, ta1, tb1, a1, jobs0);
+    kfn<<<jobs0 + jobs1, NUM_THREADS, smem, st>>>(ta0, tb0, tc0, a0, ta1, tb1, tc1, a1, jobs0);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
 }
@@ -444,8 +472,8 @@ int clipk_fwd_stats(const void* X, const void* Y, int rows, int cols, int d, lon
     a.part_dot = a.part_sum + size_t(MAX_PARTS) * rows;
     a.pos = pos_logit;
     if (!pos_logit) a.diag_offset = -(1LL << 40);   // no row has a positive inside [0, cols)
-    if (is_f16(dtype)) rc = launch_gemm<MODE_STATS, 1>(ta, tb, a, dim3(units, m_blocks), st);
-    else rc = launch_gemm<MODE_STATS, 0>(ta, tb, a, dim3(units, m_blocks), st);
+    if (is_f16(dtype)) rc = launch_gemm<MODE_STATS, 1>(ta, tb, ta, a, dim3(units, m_blocks), st);
+    else rc = launch_gemm<MODE_STATS, 0>(ta, tb, ta, a, dim3(units, m_blocks), st);
     if (rc) return rc;
     merge_row_parts_kernel<<<cdiv(rows, 256), 256, 0, st>>>(a.part_max, a.part_sum, a.part_dot, units * PARTS_PER_UNIT,
                                                             rows, row_max, row_sum, row_dot);
@@ -481,7 +509,7 @@ size_t clipk_bwd_workspace_bytes(int rows, int cols, int d, int g_dtype) {
     choose_panel(rows, cols, d, planes_of(g_dtype), 148, &rp, &cp);
     // the SM count only nudges the split; size for the L2 budget so any device fits
     (void)rp; (void)cp;
-    return size_t(G_PANEL_BYTES) + size_t(2) * 1024 * 1024;
+    return size_t(panel_bytes()) + size_t(2) * 1024 * 1024;
 }
 
 int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
@@ -526,9 +554,10 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
             const int nc = int(cols - c0 < cp_max ? cols - c0 : cp_max);
             // ---- recompute S on the panel, write G (fp16, x 2^14)
             {
-                CUtensorMap ta, tb;
+                CUtensorMap ta, tb, tc;
                 if ((rc = tmap_kmajor(&ta, Xb + r0 * ldx * esz, nr, kext, ldx, BM))) return rc;
                 if ((rc = tmap_kmajor(&tb, Yb + c0 * ldy * esz, nc, kext, ldy, BN))) return rc;
+                if ((rc = tmap_g_store(&tc, G, round_up(nr, BM), ldg, ldg))) return rc;
                 KArgs a{};
                 a.M = nr; a.N = nc; a.n_tiles = cdiv(nc, BN);
                 set_segments(a, planes, d, dpad, dpad);
@@ -541,18 +570,19 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
                 a.lse_row = lse_row + r0; a.lse_col = lse_col + c0;
                 a.alpha = alpha; a.beta = beta;
                 a.G = G; a.ldg = ldg; a.g_planes = gplanes; a.g_plane_stride = ncp;
-                if (is_f16(dtype)) rc = launch_gemm<MODE_GRAD, 1>(ta, tb, a, dim3(units, m_blocks), st);
-                else rc = launch_gemm<MODE_GRAD, 0>(ta, tb, a, dim3(units, m_blocks), st);
+                if (is_f16(dtype)) rc = launch_gemm<MODE_GRAD, 1>(ta, tb, tc, a, dim3(units, m_blocks), st);
+                else rc = launch_gemm<MODE_GRAD, 0>(ta, tb, tc, a, dim3(units, m_blocks), st);
                 if (rc) return rc;
             }
             // ---- job 0: dX[r0:r0+nr, :] (+)= G[nr, nc] * Yg[c0:c0+nc, :]      (A K-major, B MN-major, fp16 x fp16)
             // ---- job 1: dY[c0:c0+nc, :] (+)= G^T[nc, nr] * Xg[r0:r0+nr, :]    (A MN-major, B MN-major, fp16 x fp16)
-            CUtensorMap ta0, tb0, ta1, tb1;
+            CUtensorMap ta0, tb0, tc0, ta1, tb1, tc1;
             KArgs a0{}, a1{};
             int jobs0 = 0, jobs1 = 0;
             if (dX_acc) {
                 if ((rc = tmap_kmajor(&ta0, G, nr, gplanes == 2 ? ldg : nc, ldg, BM))) return rc;
                 if ((rc = tmap_mnmajor(&tb0, Ygb + c0 * ldyg * esz, gext, nc, ldyg))) return rc;
+                if ((rc = tmap_out_f32(&tc0, dX_acc + r0 * d, nr, d, d))) return rc;
                 a0.M = nr; a0.N = d; a0.n_tiles = nt; a0.tiles_per_unit = 1; a0.a_mn = 0; a0.b_mn = 1;
                 set_segments(a0, gplanes, nc, ncp, dpad);
                 a0.out = dX_acc + r0 * d; a0.ldo = d; a0.accumulate = (c0 > 0);
@@ -562,15 +592,16 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
             if (dY_acc) {
                 if ((rc = tmap_mnmajor(&ta1, G, gplanes == 2 ? ldg : nc, nr, ldg))) return rc;
                 if ((rc = tmap_mnmajor(&tb1, Xgb + r0 * ldxg * esz, gext, nr, ldxg))) return rc;
+                if ((rc = tmap_out_f32(&tc1, dY_acc + c0 * d, nc, d, d))) return rc;
                 a1.M = nc; a1.N = d; a1.n_tiles = nt; a1.tiles_per_unit = 1; a1.a_mn = 1; a1.b_mn = 1;
                 set_segments(a1, gplanes, nr, ncp, dpad);
                 a1.out = dY_acc + c0 * d; a1.ldo = d; a1.accumulate = (r0 > 0);
                 a1.oscale0 = logit_scale; a1.oscale1 = gscale; a1.oscale2 = xg_inv_scale; a1.oconst = 1.f / 16384.f;
                 jobs1 = cdiv(nc, BM) * nt;
             }
-            if (dX_acc && dY_acc) rc = launch_pair(ta0, tb0, a0, jobs0, ta1, tb1, a1, jobs1, st);
-            else if (dX_acc) rc = launch_gemm<MODE_OUT, 1>(ta0, tb0, a0, dim3(nt, cdiv(nr, BM)), st);
-            else rc = launch_gemm<MODE_OUT, 1>(ta1, tb1, a1, dim3(nt, cdiv(nc, BM)), st);
+            if (dX_acc && dY_acc) rc = launch_pair(ta0, tb0, tc0, a0, jobs0, ta1, tb1, tc1, a1, jobs1, st);
+            else if (dX_acc) rc = launch_gemm<MODE_OUT, 1>(ta0, tb0, tc0, a0, dim3(nt, cdiv(nr, BM)), st);
+            else rc = launch_gemm<MODE_OUT, 1>(ta1, tb1, tc1, a1, dim3(nt, cdiv(nc, BM)), st);
             if (rc) return rc;
         }
     }
@@ -594,18 +625,19 @@ int clipk_gemm16(const void* A, const void* B, float* D, int M, int N, int K, lo
     int rc = device_info(&di);
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, tc;
     if (a_mn) rc = tmap_mnmajor(&ta, A, M, K, lda); else rc = tmap_kmajor(&ta, A, M, K, lda, BM);
     if (rc) return rc;
     if (b_mn) rc = tmap_mnmajor(&tb, B, N, K, ldb); else rc = tmap_kmajor(&tb, B, N, K, ldb, BN);
     if (rc) return rc;
+    if ((rc = tmap_out_f32(&tc, D, M, N, ldd))) return rc;
     KArgs a{};
     a.M = M; a.N = N; a.n_tiles = cdiv(N, BN); a.tiles_per_unit = 1; a.a_mn = a_mn ? 1 : 0; a.b_mn = b_mn ? 1 : 0;
     set_segments(a, 1, K, 0, 0);
     a.out = D; a.ldo = int(ldd); a.accumulate = accumulate; a.oconst = 1.f;
     dim3 grid(a.n_tiles, cdiv(M, BM));
-    if (f16) return launch_gemm<MODE_OUT, 1>(ta, tb, a, grid, st);
-    return launch_gemm<MODE_OUT, 0>(ta, tb, a, grid, st);
+    if (f16) return launch_gemm<MODE_OUT, 1>(ta, tb, tc, a, grid, st);
+    return launch_gemm<MODE_OUT, 0>(ta, tb, tc, a, grid, st);
 }
 
 }  // extern "C"

@@ -15,6 +15,8 @@
 //   MODE_GRAD  : recompute the tile and write G = 2^14 * (alpha*(P_row - Id) + beta*(P_col - Id)) as fp16 into an
 //                L2-resident panel.
 //   MODE_OUT   : plain fp32 output (optionally accumulating) - the two gradient GEMMs dX = G*Y and dY = G^T*X.
+// GRAD and OUT tiles leave the SM through swizzled shared-memory staging and TMA (store / reduce-add), so the global
+// writes are full 128-byte lines issued by the copy engine, not 32 scattered 16-byte stores per warp instruction.
 // Operands may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]); the latter lets the gradient
 // GEMMs read Y, X and the G panel in place, without transposes.
 #pragma once
@@ -29,14 +31,22 @@ namespace clipk {
 constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;
-constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;               // 2 accumulator stages x 256 fp32 columns
 constexpr int MISC_BYTES = 4096;
-constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + MISC_BYTES;
+// Epilogue staging: every epilogue warp owns two 4 KB buffers (32 rows x 128 B, SWIZZLE_128B) from which its part of
+// the tile leaves through TMA (store of the fp16 G tile, store / reduce-add of the fp32 gradient tile).  The STATS
+// kernel writes nothing per tile, so it spends that shared memory on a fourth pipeline stage instead.
+constexpr int STG_BYTES = 4096;
+constexpr int STG_TOTAL = NUM_EPI_WARPS * 2 * STG_BYTES;   // 64 KB
+__host__ __device__ constexpr int stages_of(int mode) { return mode == 0 ? 4 : 3; }
+__host__ __device__ constexpr int smem_bytes_of(int mode) {
+    return 1024 /*align slack*/ + stages_of(mode) * STAGE_BYTES + 256 + MISC_BYTES + (mode == 0 ? 0 : STG_TOTAL);
+}
 constexpr int PARTS_PER_UNIT = 2;            // each 128-column half of a tile keeps its own row statistics
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
@@ -128,10 +138,20 @@ __device__ __forceinline__ void stats_chunk(const uint32_t (&r)[32], float sc, i
     }
 }
 
+// 16-byte piece `piece` (0..7) of row `row` (0..31) inside a 32 x 128 B SWIZZLE_128B staging buffer
+__device__ __forceinline__ uint32_t stg_addr(uint32_t stg, int row, int piece) {
+    return stg + row * 128 + ((piece ^ (row & 7)) << 4);
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// One 32-column chunk of the G tile: 64 B of fp16 per row go to pieces [piece0, piece0 + 4) of the row's 128 B line in
+// `stg` (plane hi) and, for two-plane G, of `stg_lo`.
 template <bool EDGE>
 __device__ __forceinline__ void grad_chunk(const uint32_t (&r)[32], float sc, float Lr, const float* __restrict__ lc,
-                                           float ga, float gb, int col0, int ncols, long long dcol, __half* gp,
-                                           int g_planes, int g_plane_stride) {
+                                           float ga, float gb, int col0, int ncols, long long dcol, uint32_t stg,
+                                           uint32_t stg_lo, int lane, int piece0, int g_planes) {
     uint32_t packed[16];
     const int didx = (EDGE && dcol >= col0 && dcol < (long long)col0 + 32) ? int(dcol - col0) : -1;
     auto g_of = [&](int kk, float lcv) -> float {
@@ -150,10 +170,9 @@ __device__ __forceinline__ void grad_chunk(const uint32_t (&r)[32], float sc, fl
         packed[k >> 1] = ptx::pack_f16x2(g_of(k, l4.x), g_of(k + 1, l4.y));
         packed[(k >> 1) + 1] = ptx::pack_f16x2(g_of(k + 2, l4.z), g_of(k + 3, l4.w));
     }
-    // G panel rows are padded to BM and columns to BN, so no bounds checks on the store.
-    uint4* gq = reinterpret_cast<uint4*>(gp);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) gq[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+    for (int j = 0; j < 4; ++j)
+        st_shared_v4(stg_addr(stg, lane, piece0 + j), packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
     if (g_planes == 2) {
         // residual plane: g = hi + lo, each piece exactly representable in fp16 (22 bits together).  g is recomputed
         // from the accumulator so the one-plane path carries no extra registers.
@@ -164,33 +183,36 @@ __device__ __forceinline__ void grad_chunk(const uint32_t (&r)[32], float sc, fl
             const float lo1 = g_of(k + 1, lc[k + 1]) - __half2float(__ushort_as_half((unsigned short)(prev >> 16)));
             packed[k >> 1] = ptx::pack_f16x2(lo0, lo1);
         }
-        uint4* gl = reinterpret_cast<uint4*>(gp + g_plane_stride);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-            gl[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            st_shared_v4(stg_addr(stg_lo, lane, piece0 + j), packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------- CTA body
 // a_mn / b_mn come from args: the branches on them are warp-uniform and outside the hot loops.
 template <int MODE, int F16>
-__device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensorMap* tmB, const KArgs& args, int m_blk,
-                                          int unit) {
+__device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensorMap* tmB, const CUtensorMap* tmC,
+                                          const KArgs& args, int m_blk, int unit) {
+    constexpr int STAGES = stages_of(MODE);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
     const uint32_t base = (raw_u32 + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - raw_u32);
     const uint32_t sA = base;
     const uint32_t sB = sA + STAGES * A_STAGE_BYTES;
-    const uint32_t sBar = sB + STAGES * B_STAGE_BYTES;
+    // layout (all 1024-byte aligned up to the barriers): A stages | B stages | epilogue staging | barriers | misc
+    constexpr uint32_t kStg = (MODE == MODE_STATS) ? 0u : uint32_t(STG_TOTAL);
+    const uint32_t sStg = sB + STAGES * B_STAGE_BYTES;      // epilogue staging (GRAD / OUT only)
+    const uint32_t sBar = sStg + kStg;
     const uint32_t bar_full = sBar;
     const uint32_t bar_empty = sBar + STAGES * 8;
     const uint32_t bar_tfull = sBar + 2 * STAGES * 8;
     const uint32_t bar_tempty = bar_tfull + 16;
     const uint32_t sTmemPtr = bar_tempty + 16;
-    volatile uint32_t* tmem_ptr_gen =
-        reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + (2 * STAGES + 4) * 8);
-    float* misc = reinterpret_cast<float*>(base_ptr + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256);
+    uint8_t* bar_ptr = base_ptr + STAGES * STAGE_BYTES + kStg;
+    volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(bar_ptr + (2 * STAGES + 4) * 8);
+    float* misc = reinterpret_cast<float*>(bar_ptr + 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -213,6 +235,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(tmA);
         ptx::prefetch_tmap(tmB);
+        if (MODE != MODE_STATS) ptx::prefetch_tmap(tmC);
     }
     if (warp == 1) {
         ptx::tmem_alloc(sTmemPtr, TMEM_COLS);
@@ -325,6 +348,21 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
             gb = 16384.f * args.beta;
         }
 
+        const uint32_t stg0 = sStg + (warp - 2) * 2 * STG_BYTES;   // this warp's two staging buffers
+        int stg_use = 0;                                           // TMA stores issued so far by this warp
+        // before (re)writing a staging buffer: at most one older bulk store may still be reading shared memory
+        auto stg_acquire = [&]() -> uint32_t {
+            if (lane == 0) ptx::tma_store_wait_read<1>();
+            __syncwarp();
+            return stg0 + (stg_use & 1) * STG_BYTES;
+        };
+        // after the warp filled a staging buffer: publish it to the async proxy and let one lane issue the TMA
+        auto stg_commit = [&]() {
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            ++stg_use;
+        };
+
         int it = 0;
         for (int t = t0; t < t1; ++t, ++it) {
             const int a = it & 1;
@@ -343,44 +381,79 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
             const long long d_lo = args.diag_offset + (long long)m_blk * BM;
             const bool edge = (MODE != MODE_OUT) &&
                               (((d_lo + BM - 1 >= n0) && (d_lo < (long long)n0 + BN)) || (n0 + BN > args.N));
+            const int colh = n0 + half * (BN / 2);          // first column of this warp's half tile
+            const int row0 = m_blk * BM + q * 32;           // first row of this warp
 
-#pragma unroll 1
-            for (int c = 0; c < BN / 64; ++c) {
-                uint32_t r[32];
-                ptx::tmem_ld_32x32(taddr + c * 32, r);
-                ptx::tmem_ld_wait();
-                const int col0 = n0 + half * (BN / 2) + c * 32;
-
+            auto process = [&](const uint32_t (&r)[32], int c) {
+                const int col0 = colh + c * 32;
                 if (MODE == MODE_STATS) {
                     if (edge) stats_chunk<true>(r, sc, col0, args.N, dcol, st);
                     else stats_chunk<false>(r, sc, col0, args.N, dcol, st);
                 } else if (MODE == MODE_GRAD) {
-                    __half* gp = args.G + (size_t)row * args.ldg + (col0 - 0);
-                    const float* lc = lc_s + half * (BN / 2) + c * 32;
-                    if (edge) grad_chunk<true>(r, sc, Lr, lc, ga, gb, col0, args.N, dcol, gp, args.g_planes, args.g_plane_stride);
-                    else grad_chunk<false>(r, sc, Lr, lc, ga, gb, col0, args.N, dcol, gp, args.g_planes, args.g_plane_stride);
-                } else {  // MODE_OUT
-                    if (row_ok) {
-                        float* op = args.out + (size_t)row * args.ldo + col0;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            if (col0 + 4 * j < args.N) {
-                                float4 o = make_float4(__uint_as_float(r[4 * j]) * oscale, __uint_as_float(r[4 * j + 1]) * oscale,
-                                                       __uint_as_float(r[4 * j + 2]) * oscale, __uint_as_float(r[4 * j + 3]) * oscale);
-                                if (args.accumulate) {
-                                    const float4 old = *reinterpret_cast<const float4*>(op + 4 * j);
-                                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                                }
-                                *reinterpret_cast<float4*>(op + 4 * j) = o;
-                            }
+                    // two chunks (64 columns = 128 B of fp16 per row) share one staging buffer and one TMA store
+                    uint32_t stg = stg0 + (stg_use & 1) * STG_BYTES;
+                    uint32_t stg_lo = stg0 + ((stg_use + 1) & 1) * STG_BYTES;
+                    if ((c & 1) == 0) {
+                        stg = stg_acquire();
+                        if (args.g_planes == 2) {
+                            // the second plane takes the other buffer: nothing of this warp may still be in flight
+                            if (lane == 0) ptx::tma_store_wait_read<0>();
+                            __syncwarp();
                         }
                     }
+                    const float* lc = lc_s + half * (BN / 2) + c * 32;
+                    if (edge) grad_chunk<true>(r, sc, Lr, lc, ga, gb, col0, args.N, dcol, stg, stg_lo, lane, (c & 1) * 4, args.g_planes);
+                    else grad_chunk<false>(r, sc, Lr, lc, ga, gb, col0, args.N, dcol, stg, stg_lo, lane, (c & 1) * 4, args.g_planes);
+                    if (c & 1) {
+                        ptx::fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            ptx::tma_store_2d(tmC, stg, col0 - 32, row0);
+                            if (args.g_planes == 2) ptx::tma_store_2d(tmC, stg_lo, args.g_plane_stride + col0 - 32, row0);
+                            ptx::tma_store_commit();
+                        }
+                        stg_use += (args.g_planes == 2) ? 2 : 1;
+                    }
+                } else {  // MODE_OUT: 32 fp32 columns = 128 B per row = one staging buffer and one TMA store / reduce
+                    const uint32_t stg = stg_acquire();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        st_shared_v4(stg_addr(stg, lane, j), __float_as_uint(__uint_as_float(r[4 * j]) * oscale),
+                                     __float_as_uint(__uint_as_float(r[4 * j + 1]) * oscale),
+                                     __float_as_uint(__uint_as_float(r[4 * j + 2]) * oscale),
+                                     __float_as_uint(__uint_as_float(r[4 * j + 3]) * oscale));
+                    stg_commit();
+                    if (lane == 0) {
+                        // the tensor map clips rows >= M and columns >= N
+                        if (args.accumulate) ptx::tma_reduce_add_2d(tmC, stg, col0, row0);
+                        else ptx::tma_store_2d(tmC, stg, col0, row0);
+                        ptx::tma_store_commit();
+                    }
                 }
-            }
-            // accumulator stage drained: hand it back to the MMA warp
+            };
+
+            // TMEM loads are double buffered: the load of chunk c+1 is in flight while chunk c is processed, and the
+            // accumulator stage goes back to the MMA warp as soon as the last load has landed in registers.
+            uint32_t ra[32], rb[32];
+            ptx::tmem_ld_32x32(taddr, ra);
+            ptx::tmem_ld_wait();
+            ptx::tmem_ld_32x32(taddr + 32, rb);
+            process(ra, 0);
+            ptx::tmem_ld_wait();
+            ptx::tmem_ld_32x32(taddr + 64, ra);
+            process(rb, 1);
+            ptx::tmem_ld_wait();
+            ptx::tmem_ld_32x32(taddr + 96, rb);
+            process(ra, 2);
+            ptx::tmem_ld_wait();
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * a);
+            process(rb, 3);
+        }
+        if (MODE != MODE_STATS) {
+            if (lane == 0) ptx::tma_store_wait<0>();   // all bulk stores of this warp complete before the CTA exits
+            __syncwarp();
         }
 
         if (MODE == MODE_STATS) {
@@ -405,23 +478,25 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
 
 template <int MODE, int F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KArgs args) {
-    gemm_body<MODE, F16>(&tmA, &tmB, args, blockIdx.y, blockIdx.x);
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmC, const KArgs args) {
+    gemm_body<MODE, F16>(&tmA, &tmB, &tmC, args, blockIdx.y, blockIdx.x);
 }
 
 // The two gradient GEMMs of one panel in ONE launch, so that their tiles together fill the SMs:
 // CTAs [0, jobs0) run job 0 (dX = G * Yg), the rest run job 1 (dY = G^T * Xg).  A CTA is one 128 x 256 output tile.
 template <int F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0, const KArgs args0,
-                 const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, const KArgs args1,
-                 const int jobs0) {
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+                 const __grid_constant__ CUtensorMap tmC0, const KArgs args0,
+                 const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                 const __grid_constant__ CUtensorMap tmC1, const KArgs args1, const int jobs0) {
     const int j = blockIdx.x;
     if (j < jobs0) {
-        gemm_body<MODE_OUT, F16>(&tmA0, &tmB0, args0, j / args0.n_tiles, j % args0.n_tiles);
+        gemm_body<MODE_OUT, F16>(&tmA0, &tmB0, &tmC0, args0, j / args0.n_tiles, j % args0.n_tiles);
     } else {
         const int k = j - jobs0;
-        gemm_body<MODE_OUT, F16>(&tmA1, &tmB1, args1, k / args1.n_tiles, k % args1.n_tiles);
+        gemm_body<MODE_OUT, F16>(&tmA1, &tmB1, &tmC1, args1, k / args1.n_tiles, k % args1.n_tiles);
     }
 }
 
