@@ -275,6 +275,10 @@ constexpr int MAX_SPLIT = 32;
 constexpr int MAX_PARTS = MAX_SPLIT * PARTS_PER_UNIT;
 // Budget of the fp16 G panel.  48 MB keeps it L2 resident (126 MB L2) next to the operands; CLIPK_PANEL_MB overrides
 // it for experiments (a larger panel spills to HBM but amortises the per-launch fill/drain over longer kernels).
+static int dbg_flags() {
+    static int v = [] { const char* e = getenv("CLIPK_DBG"); return e ? atoi(e) : 0; }();
+    return v;
+}
 static long long panel_bytes() {
     static long long v = [] {
         const char* e = getenv("CLIPK_PANEL_MB");
@@ -340,7 +344,9 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
     if (attr_err != cudaSuccess) return fail(int(attr_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-    kfn<<<grid, NUM_THREADS, smem, st>>>(ta, tb, tc, a);
+    KArgs aa = a;
+    aa.dbg = dbg_flags();
+    kfn<<<grid, NUM_THREADS, smem, st>>>(ta, tb, tc, aa);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
 }
@@ -354,7 +360,9 @@ static int launch_pair(const CUtensorMap& ta0, const CUtensorMap& tb0, const CUt
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
     if (attr_err != cudaSuccess) return fail(int(attr_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-    kfn<<<jobs0 + jobs1, NUM_THREADS, smem, st>>>(ta0, tb0, tc0, a0, ta1, tb1, tc1, a1, jobs0);
+    KArgs b0 = a0, b1 = a1;
+    b0.dbg = b1.dbg = dbg_flags();
+    kfn<<<jobs0 + jobs1, NUM_THREADS, smem, st>>>(ta0, tb0, tc0, b0, ta1, tb1, tc1, b1, jobs0);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
 }

@@ -37,7 +37,7 @@ constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;               // 2 accumulator stages x 256 fp32 columns
-constexpr int MISC_BYTES = 4096;
+constexpr int MISC_BYTES = 8192;
 // Epilogue staging: every epilogue warp owns two 4 KB buffers (32 rows x 128 B, SWIZZLE_128B) from which its part of
 // the tile leaves through TMA (store of the fp16 G tile, store / reduce-add of the fp32 gradient tile).  The STATS
 // kernel writes nothing per tile, so it spends that shared memory on a fourth pipeline stage instead.
@@ -89,6 +89,7 @@ struct KArgs {
     const float* oscale1;
     const float* oscale2;
     float oconst;
+    int dbg;                   // CLIPK_DBG experiment bits: 1 = skip epilogue math+staging, 2 = skip TMA stores, 4 = skip tile barriers
 };
 
 // ---------------------------------------------------------------------------------------------------- epilogues
@@ -148,25 +149,36 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 
 // One 32-column chunk of the G tile: 64 B of fp16 per row go to pieces [piece0, piece0 + 4) of the row's 128 B line in
 // `stg` (plane hi) and, for two-plane G, of `stg_lo`.
-template <bool EDGE>
+//   PATH 0 (interior tile, LSE spread of the tile <= 100 in log2 units): ONE ex2 per element.  With the tile
+//          reference c = min of the tile's row and column LSEs,  E = 2^(v - c),  g = E * (A_i + B_j),
+//          A_i = ga * 2^(c - Lr_i) (a register), B_j = gb * 2^(c - Lc_j) (staged in shared memory per tile).
+//          v <= min(Lr_i, Lc_j) and the spread bound keep every factor inside fp32 range; whatever underflows is
+//          below 2^-126 of a probability.  MUFU runs at 16 ex2/clk/SM, so two per element would cost exactly the
+//          MMA time of the tile - this path halves it.
+//   PATH 1 (tile with positives, columns beyond N, or a wide LSE spread): two ex2 per element, exact masking.
+template <int PATH>
 __device__ __forceinline__ void grad_chunk(const uint32_t (&r)[32], float sc, float Lr, const float* __restrict__ lc,
-                                           float ga, float gb, int col0, int ncols, long long dcol, uint32_t stg,
-                                           uint32_t stg_lo, int lane, int piece0, int g_planes) {
+                                           float ga, float gb, float cref, float Ai, const float* __restrict__ bj,
+                                           int col0, int ncols, long long dcol, uint32_t stg, uint32_t stg_lo, int lane,
+                                           int piece0, int g_planes) {
     uint32_t packed[16];
-    const int didx = (EDGE && dcol >= col0 && dcol < (long long)col0 + 32) ? int(dcol - col0) : -1;
-    auto g_of = [&](int kk, float lcv) -> float {
+    const int didx = (PATH == 1 && dcol >= col0 && dcol < (long long)col0 + 32) ? int(dcol - col0) : -1;
+    auto g_of = [&](int kk, float cv) -> float {   // cv = B_j (PATH 0) or Lc_j (PATH 1)
         const float sraw = __uint_as_float(r[kk]);
-        float pr = ptx::ex2(fmaf(sraw, sc, -Lr));
-        float pc = ptx::ex2(fmaf(sraw, sc, -lcv));
-        if (EDGE) {
+        if (PATH == 0) {
+            return ptx::ex2(fmaf(sraw, sc, -cref)) * (Ai + cv);
+        } else {
+            float pr = ptx::ex2(fmaf(sraw, sc, -Lr));
+            float pc = ptx::ex2(fmaf(sraw, sc, -cv));
             if (kk == didx) { pr -= 1.f; pc -= 1.f; }
             if (col0 + kk >= ncols) { pr = 0.f; pc = 0.f; }
+            return ga * pr + gb * pc;
         }
-        return ga * pr + gb * pc;
     };
+    const float* cvec = (PATH == 0) ? bj : lc;
 #pragma unroll
     for (int k = 0; k < 32; k += 4) {
-        const float4 l4 = *reinterpret_cast<const float4*>(lc + k);
+        const float4 l4 = *reinterpret_cast<const float4*>(cvec + k);
         packed[k >> 1] = ptx::pack_f16x2(g_of(k, l4.x), g_of(k + 1, l4.y));
         packed[(k >> 1) + 1] = ptx::pack_f16x2(g_of(k + 2, l4.z), g_of(k + 3, l4.w));
     }
@@ -179,8 +191,8 @@ __device__ __forceinline__ void grad_chunk(const uint32_t (&r)[32], float sc, fl
 #pragma unroll
         for (int k = 0; k < 32; k += 2) {
             const uint32_t prev = packed[k >> 1];
-            const float lo0 = g_of(k, lc[k]) - __half2float(__ushort_as_half((unsigned short)(prev & 0xffffu)));
-            const float lo1 = g_of(k + 1, lc[k + 1]) - __half2float(__ushort_as_half((unsigned short)(prev >> 16)));
+            const float lo0 = g_of(k, cvec[k]) - __half2float(__ushort_as_half((unsigned short)(prev & 0xffffu)));
+            const float lo1 = g_of(k + 1, cvec[k + 1]) - __half2float(__ushort_as_half((unsigned short)(prev >> 16)));
             packed[k >> 1] = ptx::pack_f16x2(lo0, lo1);
         }
 #pragma unroll
@@ -339,7 +351,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
             if (args.oscale2) oscale *= __ldg(args.oscale2);
         }
         StatsState st{-CUDART_INF_F, 0.f, 0.f, 0.f, false};
-        float Lr = 0.f, ga = 0.f, gb = 0.f;
+        float Lr = CUDART_INF_F, ga = 0.f, gb = 0.f;   // rows beyond M: every probability is 0
         if (MODE == MODE_GRAD) {
             if (row_ok) Lr = __ldg(args.lse_row + row) * LOG2E;
             // G is stored as 2^14 * (alpha*(P_row-Id) + beta*(P_col-Id)) in fp16: |.| <= 2^15 and entries down to
@@ -368,10 +380,32 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
             const int a = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             const int n0 = t * BN;
-            float* lc_s = misc + a * BN;   // staged column LSE (log2 units) for this tile
-            if (MODE == MODE_GRAD) {
+            float* lc_s = misc + a * (2 * BN);   // staged column LSE (log2 units) for this tile
+            float* bj_s = lc_s + BN;             // staged B_j = gb * 2^(c - Lc_j) (fast path)
+            float* red_s = misc + 4 * BN + a * 16;
+            float cref = 0.f, Ai = 0.f;
+            bool fast = false;
+            if (MODE == MODE_GRAD && !(args.dbg & 4)) {
                 const int c = n0 + epi_tid;
-                lc_s[epi_tid] = (c < args.N) ? __ldg(args.lse_col + c) * LOG2E : CUDART_INF_F;
+                const float lcv = (c < args.N) ? __ldg(args.lse_col + c) * LOG2E : CUDART_INF_F;
+                lc_s[epi_tid] = lcv;
+                // tile reference: min / max over the valid row and column LSEs of this tile
+                float lo = fminf(Lr, lcv);
+                float hi = fmaxf(Lr < CUDART_INF_F ? Lr : -CUDART_INF_F, lcv < CUDART_INF_F ? lcv : -CUDART_INF_F);
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+                    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+                }
+                if (lane == 0) { red_s[warp - 2] = lo; red_s[8 + warp - 2] = hi; }
+                ptx::named_bar_sync(1, NUM_EPI_WARPS * 32);
+                lo = red_s[0]; hi = red_s[8];
+#pragma unroll
+                for (int w = 1; w < NUM_EPI_WARPS; ++w) { lo = fminf(lo, red_s[w]); hi = fmaxf(hi, red_s[8 + w]); }
+                cref = lo;
+                fast = (hi - lo <= 100.f) && (lo > -CUDART_INF_F) && (hi < CUDART_INF_F);
+                bj_s[epi_tid] = gb * ptx::ex2(cref - lcv);
+                Ai = ga * ptx::ex2(cref - Lr);
                 ptx::named_bar_sync(1, NUM_EPI_WARPS * 32);
             }
             ptx::mbar_wait(bar_tfull + 8 * a, aph);
@@ -386,6 +420,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
 
             auto process = [&](const uint32_t (&r)[32], int c) {
                 const int col0 = colh + c * 32;
+                if (args.dbg & 1) return;
                 if (MODE == MODE_STATS) {
                     if (edge) stats_chunk<true>(r, sc, col0, args.N, dcol, st);
                     else stats_chunk<false>(r, sc, col0, args.N, dcol, st);
@@ -402,12 +437,13 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
                         }
                     }
                     const float* lc = lc_s + half * (BN / 2) + c * 32;
-                    if (edge) grad_chunk<true>(r, sc, Lr, lc, ga, gb, col0, args.N, dcol, stg, stg_lo, lane, (c & 1) * 4, args.g_planes);
-                    else grad_chunk<false>(r, sc, Lr, lc, ga, gb, col0, args.N, dcol, stg, stg_lo, lane, (c & 1) * 4, args.g_planes);
+                    const float* bj = bj_s + half * (BN / 2) + c * 32;
+                    if (fast && !edge) grad_chunk<0>(r, sc, Lr, lc, ga, gb, cref, Ai, bj, col0, args.N, dcol, stg, stg_lo, lane, (c & 1) * 4, args.g_planes);
+                    else grad_chunk<1>(r, sc, Lr, lc, ga, gb, cref, Ai, bj, col0, args.N, dcol, stg, stg_lo, lane, (c & 1) * 4, args.g_planes);
                     if (c & 1) {
                         ptx::fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0) {
+                        if (lane == 0 && !(args.dbg & 2)) {
                             ptx::tma_store_2d(tmC, stg, col0 - 32, row0);
                             if (args.g_planes == 2) ptx::tma_store_2d(tmC, stg_lo, args.g_plane_stride + col0 - 32, row0);
                             ptx::tma_store_commit();
@@ -423,7 +459,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
                                      __float_as_uint(__uint_as_float(r[4 * j + 2]) * oscale),
                                      __float_as_uint(__uint_as_float(r[4 * j + 3]) * oscale));
                     stg_commit();
-                    if (lane == 0) {
+                    if (lane == 0 && !(args.dbg & 2)) {
                         // the tensor map clips rows >= M and columns >= N
                         if (args.accumulate) ptx::tma_reduce_add_2d(tmC, stg, col0, row0);
                         else ptx::tma_store_2d(tmC, stg, col0, row0);
