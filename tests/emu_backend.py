@@ -1,0 +1,68 @@
+"""CPU emulation of the clipk kernel entry points, for tests of the HOST logic only (collectives, mode coefficients,
+autograd plumbing) under gloo.  Same method signatures and return conventions as clipk.ops.CudaBackend; plain torch
+float64 arithmetic.  Never used by the product: clipk.ops._backend() only returns it after a test called
+set_backend_for_testing()."""
+import torch
+
+
+class EmuOperand:
+    def __init__(self, x):
+        self.data = x.detach().to(torch.float64)
+        self.rows, self.d = x.shape
+        self.dtype = -1
+
+
+class EmuBackend:
+    launches = 0
+
+    def prepare(self, x):
+        return EmuOperand(x)
+
+    def prepare_grad(self, op):
+        return op
+
+    def fwd_stats(self, X, Y, scale, diag_offset, want_pos, out=None):
+        S = float(scale[0]) * X.data @ Y.data.T
+        m = S.max(dim=1).values
+        e = torch.exp(S - m[:, None])
+        stats = torch.stack((m, e.sum(1), (e * S).sum(1))).to(torch.float32)
+        if out is not None:
+            out.copy_(stats)
+            stats = out
+        pos = None
+        if want_pos:
+            idx = torch.arange(X.rows) + diag_offset
+            pos = S[torch.arange(X.rows), idx].to(torch.float32)
+        return stats, pos
+
+    def finalize(self, row_stats, pos, col_parts, diag_offset):
+        rs = row_stats.double()
+        cp = col_parts.double()
+        lse_row = rs[0] + rs[1].log()
+        M = cp[:, 0].max(dim=0).values
+        w = torch.exp(cp[:, 0] - M)
+        L = (cp[:, 1] * w).sum(0)
+        Tt = (cp[:, 2] * w).sum(0)
+        lse_col = M + L.log()
+        e_col = Tt / L
+        rows = rs.shape[1]
+        idx = torch.arange(rows) + diag_offset
+        p = pos.double()
+        sums = torch.stack(((lse_row - p).sum(), (lse_col[idx] - p).sum(), (rs[2] / rs[1] - p).sum(),
+                            (e_col[idx] - p).sum()))
+        return lse_row.float(), lse_col.float(), sums.float()
+
+    def bwd(self, X, Y, Xg, Yg, scale, diag_offset, lse_row, lse_col, alpha, beta, gscale, want_dx, want_dy):
+        s = float(scale[0])
+        S = s * X.data @ Y.data.T
+        Pr = torch.exp(S - lse_row.double()[:, None])
+        Pc = torch.exp(S - lse_col.double()[None, :])
+        eye = torch.zeros_like(S)
+        eye[torch.arange(X.rows), torch.arange(X.rows) + diag_offset] = 1.0
+        G = s * float(gscale[0]) * (alpha * (Pr - eye) + beta * (Pc - eye))
+        dX = (G @ Y.data).float() if want_dx else None
+        dY = (G.T @ X.data).float() if want_dy else None
+        return dX, dY
+
+    def cast(self, src, dtype):
+        return src.to(dtype)

@@ -1,0 +1,117 @@
+"""Host-side checks that need no GPU: the C-ABI library loads and exports every symbol include/clipk.h declares, the
+drop-in module mirrors the reference's names and label semantics bit-exactly, and the product refuses to run without
+a GPU instead of falling back."""
+import ctypes
+import os
+import re
+import types
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from clipk import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "clipk.h")).read()
+    declared = set(re.findall(r"\b(clipk_[a-z0-9_]+)\s*\(", header))
+    assert {"clipk_fwd_stats", "clipk_finalize", "clipk_bwd", "clipk_to_f16", "clipk_cast", "clipk_gemm16"} <= declared
+    for name in declared:
+        assert hasattr(lib, name), name                 # dlsym resolves it
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    assert lib.clipk_version() == 1
+
+
+def test_abi_reports_errors_without_a_gpu():
+    from clipk import _lib
+    lib = _lib.load()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    rc = lib.clipk_check_device()
+    assert rc != 0
+    assert len(lib.clipk_last_error()) > 0
+    # argument validation comes before any CUDA call
+    assert lib.clipk_cast(None, None, 4, 0, None) == -1
+    assert lib.clipk_fwd_workspace_bytes(128, 128, 64, 0) > 0
+    assert lib.clipk_bwd_workspace_bytes(128, 128, 64, 3) > 0
+
+
+def test_no_cpu_fallback():
+    from clipk import ClipLoss
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    I = torch.randn(8, 16, requires_grad=True)
+    T = torch.randn(8, 16, requires_grad=True)
+    with pytest.raises(Exception):
+        ClipLoss()(I, T, torch.tensor(10.0))
+
+
+def test_module_surface_matches_reference():
+    import clipk
+    from clipk import loss as L
+    for name in ("ClipLoss", "CoCaLoss", "DistillClipLoss", "create_loss", "gather_features"):
+        assert hasattr(clipk, name)
+    import inspect
+    sig = inspect.signature(L.ClipLoss.__init__)
+    assert list(sig.parameters)[1:] == ["local_loss", "gather_with_grad", "cache_labels", "rank", "world_size", "use_horovod"]
+    assert [p.default for p in list(sig.parameters.values())[1:]] == [False, False, False, 0, 1, False]
+    assert list(inspect.signature(L.ClipLoss.forward).parameters)[1:] == ["image_features", "text_features", "logit_scale", "output_dict"]
+    assert list(inspect.signature(L.gather_features).parameters) == ["image_features", "text_features", "local_loss", "gather_with_grad", "rank", "world_size", "use_horovod"]
+    with pytest.raises(NotImplementedError):
+        L.ClipLoss(use_horovod=True)
+
+
+def test_labels_bit_exact_and_cache_semantics():
+    from clipk import ClipLoss
+    from oracle import cliploss_oracle as O
+    dev = torch.device("cpu")
+    for (ll, W, r, n) in [(False, 1, 0, 16), (True, 4, 2, 8), (False, 4, 3, 32), (True, 2, 1, 100)]:
+        m = ClipLoss(local_loss=ll, cache_labels=True, rank=r, world_size=W)
+        lab = m.get_ground_truth(dev, n)
+        assert lab.dtype == torch.long
+        assert np.array_equal(lab.numpy(), O.ground_truth(n, r, W, ll))
+        assert m.get_ground_truth(dev, n) is lab                  # cached
+        lab2 = m.get_ground_truth(dev, n + 4)                      # accum-freq changes num_logits: cache invalidated
+        assert lab2.numel() == n + 4 and m.prev_num_logits == n + 4
+    m = ClipLoss(cache_labels=False)
+    assert m.get_ground_truth(dev, 4) is not m.get_ground_truth(dev, 4) and m.labels == {}
+
+
+def test_create_loss_plumbing():
+    from clipk import create_loss, ClipLoss, CoCaLoss, DistillClipLoss
+    a = types.SimpleNamespace(distill=False, model="ViT-B-32", local_loss=True, gather_with_grad=True, rank=3,
+                              world_size=8, horovod=False)
+    m = create_loss(a)
+    assert type(m) is ClipLoss and m.local_loss and m.gather_with_grad and m.cache_labels and m.rank == 3 and m.world_size == 8
+    a.model = "coca_ViT-B-32"
+    a.coca_caption_loss_weight, a.coca_contrastive_loss_weight = 2.0, 1.0
+    assert type(create_loss(a)) is CoCaLoss
+    a.distill = True
+    assert type(create_loss(a)) is DistillClipLoss
+
+
+def test_single_process_host_logic_with_emulated_kernels():
+    """W = 1 autograd plumbing (output_dict, float scale, grad_output) with the kernel calls emulated on CPU."""
+    from clipk import ClipLoss, ops
+    from oracle import cliploss_oracle as O
+    from tests.emu_backend import EmuBackend
+    ops.set_backend_for_testing(EmuBackend())
+    try:
+        x, t = O.synthetic_features(24, 32, seed=3)
+        I = torch.from_numpy(x).requires_grad_(True)
+        T = torch.from_numpy(t).requires_grad_(True)
+        s = torch.tensor(12.5, requires_grad=True)
+        out = ClipLoss()(I, T, s, output_dict=True)
+        (out["contrastive_loss"] * 2.0).backward()
+        ref = O.clip_loss_single(x, t, 12.5, grad_output=2.0)
+        assert abs(out["contrastive_loss"].item() - ref.loss) < 1e-5 * ref.loss
+        assert np.linalg.norm(I.grad.numpy() - ref.d_image) < 1e-5 * np.linalg.norm(ref.d_image)
+        assert np.linalg.norm(T.grad.numpy() - ref.d_text) < 1e-5 * np.linalg.norm(ref.d_text)
+        assert abs(s.grad.item() - ref.d_scale) < 1e-5 * abs(ref.d_scale)
+        l2 = ClipLoss()(I.detach(), T.detach(), 12.5)              # python-float scale, no grads
+        assert abs(l2.item() - ref.loss) < 1e-5 * ref.loss
+    finally:
+        ops.set_backend_for_testing(None)
