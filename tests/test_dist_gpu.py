@@ -1,0 +1,86 @@
+"""Multi-GPU parity (NCCL, real kernels): every (local_loss, gather_with_grad) mode against the reference goldens and
+against the oracle on bf16 inputs.  Needs >= 2 GPUs on one box; skipped otherwise (run with `gpurun --gpus 2`)."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import golden_files, load_golden, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, tmp, case):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "megatron-clip_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    from clipk import ClipLoss
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"file://{tmp}/store", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    kind = case["kind"]
+    if kind == "golden":
+        z, W, ranks = load_golden(case["path"])
+        g = ranks[rank]
+        x, t = g["image"].astype(np.float32), g["text"].astype(np.float32)
+        s, go, ll, gwg, dtype = float(z["scale"]), float(z["grad_output"]), bool(z["local_loss"]), bool(z["gather_with_grad"]), torch.float32
+    else:
+        from oracle import cliploss_oracle as O
+        x, t = O.synthetic_features(case["b"], case["d"], seed=77, rank=rank)
+        s, go, ll, gwg, dtype = 1 / 0.07, 1.0, case["ll"], case["gwg"], torch.bfloat16
+    I = torch.from_numpy(x).cuda().to(dtype).requires_grad_(True)
+    T = torch.from_numpy(t).cuda().to(dtype).requires_grad_(True)
+    S = torch.tensor(s, device="cuda", requires_grad=True)
+    mod = ClipLoss(local_loss=ll, gather_with_grad=gwg, cache_labels=True, rank=rank, world_size=world)
+    loss = mod(I, T, S)
+    (loss * go).backward()
+    torch.cuda.synchronize()
+    np.savez(f"{tmp}/out{rank}.npz", loss=loss.item(), d_image=I.grad.float().cpu().numpy(),
+             d_text=T.grad.float().cpu().numpy(), d_scale=S.grad.item(), image=I.detach().float().cpu().numpy(),
+             text=T.detach().float().cpu().numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run(world, case):
+    import torch.multiprocessing as mp
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(_worker, args=(world, tmp, case), nprocs=world, join=True)
+        return [dict(np.load(f"{tmp}/out{r}.npz")) for r in range(world)]
+
+
+def _need(n):
+    if torch.cuda.device_count() < n:
+        pytest.skip(f"needs {n} GPUs")
+
+
+@pytest.mark.parametrize("path", [p for p in golden_files(world=2)], ids=lambda p: os.path.basename(p)[:-4])
+def test_two_gpus_match_reference_goldens(path):
+    _need(2)
+    z, W, ranks = load_golden(path)
+    outs = _run(2, {"kind": "golden", "path": path})
+    tol = 1e-5 if float(z["scale"]) < 50 else 2e-4
+    for r in range(2):
+        g, o = ranks[r], outs[r]
+        assert abs(float(o["loss"]) - float(g["loss"])) <= tol * abs(float(g["loss"]))
+        assert rel(o["d_image"], g["d_image"]) <= tol and rel(o["d_text"], g["d_text"]) <= tol
+        assert abs(float(o["d_scale"]) - float(g["d_scale"])) <= tol * max(abs(float(g["d_scale"])), float(z["grad_output"]) / float(z["scale"]))
+
+
+@pytest.mark.parametrize("ll,gwg", [(True, True), (True, False), (False, True), (False, False)])
+@pytest.mark.parametrize("world", [2, 4])
+def test_bf16_modes_against_oracle(world, ll, gwg):
+    _need(world)
+    from oracle import cliploss_oracle as O
+    outs = _run(world, {"kind": "oracle", "b": 640, "d": 256, "ll": ll, "gwg": gwg})
+    ref = O.clip_loss_world([o["image"] for o in outs], [o["text"] for o in outs], 1 / 0.07, ll, gwg)
+    for r in range(world):
+        o, g = outs[r], ref[r]
+        assert abs(float(o["loss"]) - g.loss) <= 2e-3 * abs(g.loss)
+        assert rel(o["d_image"], g.d_image) <= 2e-3 and rel(o["d_text"], g.d_text) <= 2e-3
+        assert abs(float(o["d_scale"]) - g.d_scale) <= 2e-3 * max(abs(g.d_scale), 0.07)
