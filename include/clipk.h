@@ -114,6 +114,10 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
 /* dst[i] = (dtype) src[i]; the fp32 gradient accumulators are returned in the dtype of the inputs. */
 int clipk_cast(const float* src, void* dst, long long n, int dtype, void* stream);
 
+/* Experiments only: a device buffer of 3 * 3 * 64 int64 that CTA (0,0) of every following launch fills with clock64
+ * stamps of its producer / MMA / epilogue roles; NULL switches it off (the default). */
+int clipk_debug_set_trace(long long* device_buffer);
+
 /* ---- test hook for the tensor-core mainloop: D[M, N] (fp32, ldd) (+)= A * B^T with 16-bit operands
  *   (bf16 when f16 == 0, fp16 when f16 == 1; both operands share the format - the hardware rejects a mix).
  *   a_mn = 0: A is [M, K] row-major (K contiguous);  a_mn = 1: A is stored [K, M] row-major (M contiguous).

@@ -34,6 +34,7 @@ PROTOTYPES = {
     "clipk_bwd": (_i, [_vp, _vp, _i, _i, _i, _ll, _ll, _i, _vp, _vp, _vp, _vp, _ll, _ll, _i, _vp, _vp,
                        _vp, _ll, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "clipk_cast": (_i, [_vp, _vp, _ll, _i, _vp]),
+    "clipk_debug_set_trace": (_i, [_vp]),
     "clipk_gemm16": (_i, [_vp, _vp, _vp, _i, _i, _i, _ll, _ll, _ll, _i, _i, _i, _i, _vp]),
 }
 

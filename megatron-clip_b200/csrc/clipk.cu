@@ -279,6 +279,7 @@ static int dbg_flags() {
     static int v = [] { const char* e = getenv("CLIPK_DBG"); return e ? atoi(e) : 0; }();
     return v;
 }
+static long long* g_trace = nullptr;   // set by clipk_debug_set_trace (experiments only)
 static long long panel_bytes() {
     static long long v = [] {
         const char* e = getenv("CLIPK_PANEL_MB");
@@ -291,7 +292,8 @@ static long long panel_bytes() {
 }
 
 // How many CTAs share the column sweep of one 128-row block: fill the SMs in as few equal waves as possible.
-static int choose_split(int m_blocks, int n_tiles, int sms) {
+static int choose_split(int m_pairs, int n_tiles, int sms) {
+    const int m_blocks = 2 * m_pairs;   // CTAs per unit
     int best = 1;
     double best_cost = 1e30;
     const int lim = n_tiles < MAX_SPLIT ? n_tiles : MAX_SPLIT;
@@ -309,35 +311,56 @@ static int choose_split(int m_blocks, int n_tiles, int sms) {
 // with long K, and the panel fits the L2 budget.  Then even the panels out over the problem.
 static void choose_panel(int rows, int cols, int d, int gplanes, int sms, long long* rp_out, long long* cp_out) {
     const int nt = cdiv(d, BN);
-    const int R = cdiv(rows, BM), C = cdiv(cols, BN) * 2;       // available 128-row / 128-col blocks (cp multiple of 256)
+    const int R = cdiv(rows, 2 * BM), C = cdiv(cols, BN);       // available 256-row / 256-col blocks
+    const int pairs = sms / 2;
     double best = 1e30;
-    int best_rb = 1, best_cb = 2;
+    int best_rb = 1, best_cb = 1;
     for (int waves = 1; waves <= 4; ++waves) {
-        const int total = sms * waves / nt;                      // 128-blocks (rows + cols) per launch
-        if (total < 3) continue;
+        const int total = pairs * waves / nt;                    // 256-blocks (rows + cols) per launch
+        if (total < 2) continue;
         int rb = total / 2 < R ? total / 2 : R;
-        int cb = (total - rb) & ~1;
+        int cb = total - rb;
         if (cb > C) { cb = C; rb = total - cb < R ? total - cb : R; }
-        if (cb < 2) cb = 2;
-        while ((long long)rb * BM * cb * BM * 2 * gplanes > panel_bytes() && (rb > 1 || cb > 2)) {
-            if (rb >= cb && rb > 1) --rb; else cb -= 2;
+        if (cb < 1) cb = 1;
+        while ((long long)rb * cb * 4 * BM * BM * 2 * gplanes > panel_bytes() && (rb > 1 || cb > 1)) {
+            if (rb >= cb && rb > 1) --rb; else --cb;
         }
         const int jobs = (rb + cb) * nt;
-        const int w = cdiv(jobs, sms);
-        const int kmax = (rb > cb ? rb : cb) * BM;
+        const int w = cdiv(jobs, pairs);
+        const int kmax = (rb > cb ? rb : cb) * 2 * BM;
         const double t = w * (8.0 + kmax * (6.0 / 1024.0));      // us: ~8 us per CTA lifetime + 6 us per 1024 of K
         const double per_area = t / ((double)rb * cb);
         if (per_area < best) { best = per_area; best_rb = rb; best_cb = cb; }
     }
     const int nrp = cdiv(R, best_rb), ncp = cdiv(C, best_cb);
-    *rp_out = (long long)cdiv(R, nrp) * BM;
-    *cp_out = (long long)((cdiv(C, ncp) + 1) & ~1) * BM;
+    *rp_out = (long long)cdiv(R, nrp) * 2 * BM;
+    *cp_out = (long long)cdiv(C, ncp) * BN;
 }
 
-// tc = epilogue store map (G panel for GRAD, fp32 output for OUT; unused by STATS - pass ta)
+// Launch with a thread-block cluster of two CTAs (the tcgen05 cta_group::2 pair).
+template <typename... Args>
+static int launch_clustered(void (*kfn)(Args...), dim3 grid, dim3 cluster, int smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = size_t(smem);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster.x;
+    attr[0].val.clusterDim.y = cluster.y;
+    attr[0].val.clusterDim.z = cluster.z;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CK_CUDA(cudaLaunchKernelEx(&cfg, kfn, args...));
+    return CLIPK_OK;
+}
+
+// tc = epilogue store map (G panel for GRAD, fp32 output for OUT; unused by STATS - pass ta).
+// grid = (units, m_pairs): every unit is run by a PAIR of CTAs covering 256 rows.
 template <int MODE, int F16>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const KArgs& a, dim3 grid,
-                       cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const KArgs& a, int units,
+                       int m_pairs, cudaStream_t st) {
     auto kfn = gemm_kernel<MODE, F16>;
     constexpr int smem = smem_bytes_of(MODE);
     static std::once_flag once;
@@ -346,11 +369,11 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     if (attr_err != cudaSuccess) return fail(int(attr_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
     KArgs aa = a;
     aa.dbg = dbg_flags();
-    kfn<<<grid, NUM_THREADS, smem, st>>>(ta, tb, tc, aa);
-    CK_CUDA(cudaGetLastError());
-    return CLIPK_OK;
+    aa.trace = g_trace;
+    return launch_clustered(kfn, dim3(2 * m_pairs, units), dim3(2, 1, 1), smem, st, ta, tb, tc, aa);
 }
 
+// jobs0 / jobs1 are counted in PAIRS (256 x 256 output tiles)
 static int launch_pair(const CUtensorMap& ta0, const CUtensorMap& tb0, const CUtensorMap& tc0, const KArgs& a0, int jobs0,
                        const CUtensorMap& ta1, const CUtensorMap& tb1, const CUtensorMap& tc1, const KArgs& a1, int jobs1,
                        cudaStream_t st) {
@@ -362,9 +385,9 @@ static int launch_pair(const CUtensorMap& ta0, const CUtensorMap& tb0, const CUt
     if (attr_err != cudaSuccess) return fail(int(attr_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
     KArgs b0 = a0, b1 = a1;
     b0.dbg = b1.dbg = dbg_flags();
-    kfn<<<jobs0 + jobs1, NUM_THREADS, smem, st>>>(ta0, tb0, tc0, b0, ta1, tb1, tc1, b1, jobs0);
-    CK_CUDA(cudaGetLastError());
-    return CLIPK_OK;
+    b0.trace = g_trace;
+    return launch_clustered(kfn, dim3(2 * (jobs0 + jobs1)), dim3(2, 1, 1), smem, st, ta0, tb0, tc0, b0, ta1, tb1, tc1, b1,
+                            jobs0);
 }
 
 // plane pairs of the split-precision product, SMALLEST terms first: the tensor core truncates when it adds into the
@@ -466,12 +489,12 @@ int clipk_fwd_stats(const void* X, const void* Y, int rows, int cols, int d, lon
     const long long kext = (dtype == CLIPK_BF16) ? d : planes * dpad;
     CUtensorMap ta, tb;
     if ((rc = tmap_kmajor(&ta, X, rows, kext, ldx, BM))) return rc;
-    if ((rc = tmap_kmajor(&tb, Y, cols, kext, ldy, BN))) return rc;
+    if ((rc = tmap_kmajor(&tb, Y, cols, kext, ldy, BN / 2))) return rc;
     KArgs a{};
     a.M = rows; a.N = cols; a.n_tiles = cdiv(cols, BN);
     set_segments(a, planes, d, dpad, dpad);
-    const int m_blocks = cdiv(rows, BM);
-    const int split = choose_split(m_blocks, a.n_tiles, di.sms);
+    const int m_pairs = cdiv(rows, 2 * BM);
+    const int split = choose_split(m_pairs, a.n_tiles, di.sms);
     a.tiles_per_unit = cdiv(a.n_tiles, split);
     const int units = cdiv(a.n_tiles, a.tiles_per_unit);
     a.scale = logit_scale; a.xs = x_inv_scale; a.ys = y_inv_scale; a.diag_offset = diag_offset;
@@ -480,8 +503,8 @@ int clipk_fwd_stats(const void* X, const void* Y, int rows, int cols, int d, lon
     a.part_dot = a.part_sum + size_t(MAX_PARTS) * rows;
     a.pos = pos_logit;
     if (!pos_logit) a.diag_offset = -(1LL << 40);   // no row has a positive inside [0, cols)
-    if (is_f16(dtype)) rc = launch_gemm<MODE_STATS, 1>(ta, tb, ta, a, dim3(units, m_blocks), st);
-    else rc = launch_gemm<MODE_STATS, 0>(ta, tb, ta, a, dim3(units, m_blocks), st);
+    if (is_f16(dtype)) rc = launch_gemm<MODE_STATS, 1>(ta, tb, ta, a, units, m_pairs, st);
+    else rc = launch_gemm<MODE_STATS, 0>(ta, tb, ta, a, units, m_pairs, st);
     if (rc) return rc;
     merge_row_parts_kernel<<<cdiv(rows, 256), 256, 0, st>>>(a.part_max, a.part_sum, a.part_dot, units * PARTS_PER_UNIT,
                                                             rows, row_max, row_sum, row_dot);
@@ -547,7 +570,7 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
     choose_panel(rows, cols, d, gplanes, di.sms, &rp_max, &cp_max);
     const int ncp = int(cp_max);                        // panel width (multiple of BN) = G plane stride
     const int ldg = gplanes * ncp;
-    if ((unsigned long long)round_up(rp_max, BM) * ldg * 2 > workspace_bytes) return fail(CLIPK_EWORKSPACE, "panel does not fit the workspace");
+    if ((unsigned long long)round_up(rp_max, 2 * BM) * ldg * 2 > workspace_bytes) return fail(CLIPK_EWORKSPACE, "panel does not fit the workspace");
     __half* G = static_cast<__half*>(workspace);
     const size_t esz = 2;
     const char* Xb = static_cast<const char*>(X);
@@ -564,13 +587,13 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
             {
                 CUtensorMap ta, tb, tc;
                 if ((rc = tmap_kmajor(&ta, Xb + r0 * ldx * esz, nr, kext, ldx, BM))) return rc;
-                if ((rc = tmap_kmajor(&tb, Yb + c0 * ldy * esz, nc, kext, ldy, BN))) return rc;
-                if ((rc = tmap_g_store(&tc, G, round_up(nr, BM), ldg, ldg))) return rc;
+                if ((rc = tmap_kmajor(&tb, Yb + c0 * ldy * esz, nc, kext, ldy, BN / 2))) return rc;
+                if ((rc = tmap_g_store(&tc, G, round_up(nr, 2 * BM), ldg, ldg))) return rc;
                 KArgs a{};
                 a.M = nr; a.N = nc; a.n_tiles = cdiv(nc, BN);
                 set_segments(a, planes, d, dpad, dpad);
-                const int m_blocks = cdiv(nr, BM);
-                const int split = choose_split(m_blocks, a.n_tiles, di.sms);
+                const int m_pairs = cdiv(nr, 2 * BM);
+                const int split = choose_split(m_pairs, a.n_tiles, di.sms);
                 a.tiles_per_unit = cdiv(a.n_tiles, split);
                 const int units = cdiv(a.n_tiles, a.tiles_per_unit);
                 a.scale = logit_scale; a.xs = x_inv_scale; a.ys = y_inv_scale;
@@ -578,8 +601,8 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
                 a.lse_row = lse_row + r0; a.lse_col = lse_col + c0;
                 a.alpha = alpha; a.beta = beta;
                 a.G = G; a.ldg = ldg; a.g_planes = gplanes; a.g_plane_stride = ncp;
-                if (is_f16(dtype)) rc = launch_gemm<MODE_GRAD, 1>(ta, tb, tc, a, dim3(units, m_blocks), st);
-                else rc = launch_gemm<MODE_GRAD, 0>(ta, tb, tc, a, dim3(units, m_blocks), st);
+                if (is_f16(dtype)) rc = launch_gemm<MODE_GRAD, 1>(ta, tb, tc, a, units, m_pairs, st);
+                else rc = launch_gemm<MODE_GRAD, 0>(ta, tb, tc, a, units, m_pairs, st);
                 if (rc) return rc;
             }
             // ---- job 0: dX[r0:r0+nr, :] (+)= G[nr, nc] * Yg[c0:c0+nc, :]      (A K-major, B MN-major, fp16 x fp16)
@@ -595,7 +618,7 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
                 set_segments(a0, gplanes, nc, ncp, dpad);
                 a0.out = dX_acc + r0 * d; a0.ldo = d; a0.accumulate = (c0 > 0);
                 a0.oscale0 = logit_scale; a0.oscale1 = gscale; a0.oscale2 = yg_inv_scale; a0.oconst = 1.f / 16384.f;
-                jobs0 = cdiv(nr, BM) * nt;
+                jobs0 = cdiv(nr, 2 * BM) * nt;
             }
             if (dY_acc) {
                 if ((rc = tmap_mnmajor(&ta1, G, gplanes == 2 ? ldg : nc, nr, ldg))) return rc;
@@ -605,14 +628,20 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
                 set_segments(a1, gplanes, nr, ncp, dpad);
                 a1.out = dY_acc + c0 * d; a1.ldo = d; a1.accumulate = (r0 > 0);
                 a1.oscale0 = logit_scale; a1.oscale1 = gscale; a1.oscale2 = xg_inv_scale; a1.oconst = 1.f / 16384.f;
-                jobs1 = cdiv(nc, BM) * nt;
+                jobs1 = cdiv(nc, 2 * BM) * nt;
             }
             if (dX_acc && dY_acc) rc = launch_pair(ta0, tb0, tc0, a0, jobs0, ta1, tb1, tc1, a1, jobs1, st);
-            else if (dX_acc) rc = launch_gemm<MODE_OUT, 1>(ta0, tb0, tc0, a0, dim3(nt, cdiv(nr, BM)), st);
-            else rc = launch_gemm<MODE_OUT, 1>(ta1, tb1, tc1, a1, dim3(nt, cdiv(nc, BM)), st);
+            else if (dX_acc) rc = launch_gemm<MODE_OUT, 1>(ta0, tb0, tc0, a0, nt, cdiv(nr, 2 * BM), st);
+            else rc = launch_gemm<MODE_OUT, 1>(ta1, tb1, tc1, a1, nt, cdiv(nc, 2 * BM), st);
             if (rc) return rc;
         }
     }
+    return CLIPK_OK;
+}
+
+// Experiments only: device buffer of 3*64 int64 that CTA (0,0) of every following launch fills with clock64 stamps.
+int clipk_debug_set_trace(long long* device_buffer) {
+    g_trace = device_buffer;
     return CLIPK_OK;
 }
 
@@ -636,16 +665,15 @@ int clipk_gemm16(const void* A, const void* B, float* D, int M, int N, int K, lo
     CUtensorMap ta, tb, tc;
     if (a_mn) rc = tmap_mnmajor(&ta, A, M, K, lda); else rc = tmap_kmajor(&ta, A, M, K, lda, BM);
     if (rc) return rc;
-    if (b_mn) rc = tmap_mnmajor(&tb, B, N, K, ldb); else rc = tmap_kmajor(&tb, B, N, K, ldb, BN);
+    if (b_mn) rc = tmap_mnmajor(&tb, B, N, K, ldb); else rc = tmap_kmajor(&tb, B, N, K, ldb, BN / 2);
     if (rc) return rc;
     if ((rc = tmap_out_f32(&tc, D, M, N, ldd))) return rc;
     KArgs a{};
     a.M = M; a.N = N; a.n_tiles = cdiv(N, BN); a.tiles_per_unit = 1; a.a_mn = a_mn ? 1 : 0; a.b_mn = b_mn ? 1 : 0;
     set_segments(a, 1, K, 0, 0);
     a.out = D; a.ldo = int(ldd); a.accumulate = accumulate; a.oconst = 1.f;
-    dim3 grid(a.n_tiles, cdiv(M, BM));
-    if (f16) return launch_gemm<MODE_OUT, 1>(ta, tb, tc, a, grid, st);
-    return launch_gemm<MODE_OUT, 0>(ta, tb, tc, a, grid, st);
+    if (f16) return launch_gemm<MODE_OUT, 1>(ta, tb, tc, a, a.n_tiles, cdiv(M, 2 * BM), st);
+    return launch_gemm<MODE_OUT, 0>(ta, tb, tc, a, a.n_tiles, cdiv(M, 2 * BM), st);
 }
 
 }  // extern "C"

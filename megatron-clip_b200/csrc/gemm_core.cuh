@@ -2,11 +2,15 @@
 //
 //   D[M, N] = A[M, K] * B[N, K]^T      16-bit operands (bf16 or fp16), fp32 accumulation in TMEM
 //
-// One CTA = 10 warps: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
-// warps 2..9 = epilogue (two warps per TMEM lane quarter, one per 128-column half of the tile).  Three pipelines:
-// a 4-stage shared-memory ring (TMA -> MMA, mbarrier full/empty), a 2-stage TMEM accumulator ring (MMA -> epilogue)
-// and the unit's tile loop.  A CTA tile is 128 x 256 (UMMA M=128, N=256, K=16); K is streamed in 64-element
-// (128-byte, SWIZZLE_128B) blocks.
+// CTAs work in PAIRS (cluster of 2, tcgen05 cta_group::2): a pair computes a 256 x 256 tile with UMMA M=256, N=256,
+// K=16.  Each CTA loads its own 128 rows of A and HALF of the B tile, so a pipeline stage is 32 KB per CTA instead of
+// 48 KB: the measured refill round trip of a stage is ~1900 cycles against 512 cycles of MMA per K block, so the ring
+// needs >= 5 stages to keep the tensor pipe busy, which only fits with the halved B (6 stages STATS, 4 + staging
+// otherwise).  One CTA = 10 warps: warp 0 = TMA producer, warp 1 = TMEM allocator and, in the even (leader) CTA, the
+// single-thread tcgen05.mma issuer for the pair, warps 2..9 = epilogue for the CTA's own 128 accumulator rows (two
+// warps per TMEM lane quarter, one per 128-column half).  Three pipelines: the shared-memory ring (TMA -> MMA, full
+// barriers in the leader, empty barriers in both CTAs via multicast commit), a 2-stage TMEM accumulator ring
+// (MMA -> epilogue) and the unit's tile loop.  K is streamed in 64-element (128-byte, SWIZZLE_128B) blocks.
 //
 // Epilogue modes (all read the accumulator with tcgen05.ld, thread == one row of the tile):
 //   MODE_STATS : online row max / sum-of-exp / sum-of-exp-times-logit of s*A*B^T over a run of column tiles, plus the
@@ -32,7 +36,7 @@ constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
+constexpr int B_STAGE_BYTES = (BN / 2) * BK * 2;   // 16 KB: this CTA's half of the pair's 256-column B tile
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
@@ -40,10 +44,10 @@ constexpr int TMEM_COLS = 512;               // 2 accumulator stages x 256 fp32 
 constexpr int MISC_BYTES = 8192;
 // Epilogue staging: every epilogue warp owns two 4 KB buffers (32 rows x 128 B, SWIZZLE_128B) from which its part of
 // the tile leaves through TMA (store of the fp16 G tile, store / reduce-add of the fp32 gradient tile).  The STATS
-// kernel writes nothing per tile, so it spends that shared memory on a fourth pipeline stage instead.
+// kernel writes nothing per tile, so it spends that shared memory on two more pipeline stages instead.
 constexpr int STG_BYTES = 4096;
 constexpr int STG_TOTAL = NUM_EPI_WARPS * 2 * STG_BYTES;   // 64 KB
-__host__ __device__ constexpr int stages_of(int mode) { return mode == 0 ? 4 : 3; }
+__host__ __device__ constexpr int stages_of(int mode) { return mode == 0 ? 6 : 4; }
 __host__ __device__ constexpr int smem_bytes_of(int mode) {
     return 1024 /*align slack*/ + stages_of(mode) * STAGE_BYTES + 256 + MISC_BYTES + (mode == 0 ? 0 : STG_TOTAL);
 }
@@ -89,6 +93,7 @@ struct KArgs {
     const float* oscale1;
     const float* oscale2;
     float oconst;
+    long long* trace;          // optional clock64 trace of CTA (0,0): [3 modes][3 roles][64] (nullptr in production)
     int dbg;                   // CLIPK_DBG experiment bits: 1 = skip epilogue math+staging, 2 = skip TMA stores, 4 = skip tile barriers
 };
 
@@ -205,8 +210,11 @@ __device__ __forceinline__ void grad_chunk(const uint32_t (&r)[32], float sc, fl
 // a_mn / b_mn come from args: the branches on them are warp-uniform and outside the hot loops.
 template <int MODE, int F16>
 __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensorMap* tmB, const CUtensorMap* tmC,
-                                          const KArgs& args, int m_blk, int unit) {
+                                          const KArgs& args, int m_pair, int unit) {
     constexpr int STAGES = stages_of(MODE);
+    const uint32_t cta_rank = ptx::cluster_ctarank();   // 0 = leader (issues the pair's MMAs), 1 = peer
+    const bool leader = (cta_rank == 0);
+    const int m_blk = 2 * m_pair + int(cta_rank);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
     const uint32_t base = (raw_u32 + 1023u) & ~1023u;
@@ -240,7 +248,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(bar_tfull + 8 * a, 1);
-            ptx::mbar_init(bar_tempty + 8 * a, NUM_EPI_WARPS);
+            ptx::mbar_init(bar_tempty + 8 * a, 2 * NUM_EPI_WARPS);   // epilogue warps of both CTAs (leader's copy is used)
         }
         ptx::fence_barrier_init();
     }
@@ -250,13 +258,18 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
         if (MODE != MODE_STATS) ptx::prefetch_tmap(tmC);
     }
     if (warp == 1) {
-        ptx::tmem_alloc(sTmemPtr, TMEM_COLS);
-        ptx::tmem_relinquish();
+        ptx::tmem_alloc_pair(sTmemPtr, TMEM_COLS);
+        ptx::tmem_relinquish_pair();
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    ptx::cluster_sync();          // barriers of both CTAs initialised, TMEM allocated, before any remote arrive / TMA
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
+    const bool tracing = (args.trace != nullptr) && m_blk == 0 && unit == 0;
+    int tr_n = 0;
+    auto TR = [&](int role) {
+        if (tracing && tr_n < 64) args.trace[MODE * 192 + role * 64 + tr_n++] = clock64();
+    };
 
     if (warp == 0) {
         // ================================ TMA producer ================================
@@ -264,37 +277,41 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
             int s = 0;
             uint32_t ph = 0;
             for (int t = t0; t < t1; ++t) {
+                TR(0);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     const int seg = kb / args.kb_per_seg;
                     const int kw = (kb - seg * args.kb_per_seg) * BK;
                     const int ao = args.a_off[seg], bo = args.b_off[seg];
                     ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of the pair
                     const uint32_t full = bar_full + 8 * s;
-                    ptx::mbar_arrive_expect_tx(full, A_STAGE_BYTES + B_STAGE_BYTES);
+                    if (leader) ptx::mbar_arrive_expect_tx(full, 2 * STAGE_BYTES);
                     const uint32_t a_dst = sA + s * A_STAGE_BYTES;
                     const uint32_t b_dst = sB + s * B_STAGE_BYTES;
+                    const int bn0 = t * BN + int(cta_rank) * (BN / 2);   // this CTA's half of the B tile
                     if (a_mn) {
 #pragma unroll
                         for (int i = 0; i < BM / 64; ++i)
-                            ptx::tma_load_2d(a_dst + i * 8192, tmA, ao + m_blk * BM + i * 64, kw, full);
+                            ptx::tma_load_2d_pair(a_dst + i * 8192, tmA, ao + m_blk * BM + i * 64, kw, full);
                     } else {
-                        ptx::tma_load_2d(a_dst, tmA, ao + kw, m_blk * BM, full);
+                        ptx::tma_load_2d_pair(a_dst, tmA, ao + kw, m_blk * BM, full);
                     }
                     if (b_mn) {
 #pragma unroll
-                        for (int i = 0; i < BN / 64; ++i)
-                            ptx::tma_load_2d(b_dst + i * 8192, tmB, bo + t * BN + i * 64, kw, full);
+                        for (int i = 0; i < BN / 128; ++i)
+                            ptx::tma_load_2d_pair(b_dst + i * 8192, tmB, bo + bn0 + i * 64, kw, full);
                     } else {
-                        ptx::tma_load_2d(b_dst, tmB, bo + kw, t * BN, full);
+                        ptx::tma_load_2d_pair(b_dst, tmB, bo + kw, bn0, full);
                     }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
+            TR(0);
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
-        if (lane == 0) {
-            const uint32_t idesc = ptx::make_idesc_16bit(BM, BN, a_mn, b_mn, /*a_is_bf16=*/!F16, /*b_is_bf16=*/!F16);
+        if (lane == 0 && leader) {
+            const uint32_t idesc = ptx::make_idesc_16bit(2 * BM, BN, a_mn, b_mn, /*a_is_bf16=*/!F16, /*b_is_bf16=*/!F16);
             // K-major SW128: 8-row groups 1024 B apart (SBO); MN-major SW128: 64-wide MN blocks 8192 B apart (LBO),
             // 8-row K groups 1024 B apart (SBO).
             const uint64_t adesc_hi = a_mn ? ptx::make_smem_desc_sw128(8192, 1024) : ptx::make_smem_desc_sw128(16, 1024);
@@ -307,8 +324,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
             for (int t = t0; t < t1; ++t, ++it) {
                 const int a = it & 1;
                 const uint32_t aph = (it >> 1) & 1;
+                TR(1);
                 ptx::mbar_wait(bar_tempty + 8 * a, aph ^ 1);
                 ptx::tc_fence_after();
+                TR(1);
                 const uint32_t d_tmem = tmem_base + a * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     ptx::mbar_wait(bar_full + 8 * s, ph);
@@ -317,13 +336,14 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
                     const uint32_t b_src = sB + s * B_STAGE_BYTES;
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
-                        ptx::mma_f16_ss(d_tmem, ptx::desc_with_addr(adesc_hi, a_src + k * a_kstep),
+                        ptx::mma_f16_ss_pair(d_tmem, ptx::desc_with_addr(adesc_hi, a_src + k * a_kstep),
                                         ptx::desc_with_addr(bdesc_hi, b_src + k * b_kstep), idesc, (kb | k) != 0);
                     }
-                    ptx::mma_commit(bar_empty + 8 * s);
+                    ptx::mma_commit_pair(bar_empty + 8 * s);
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
-                ptx::mma_commit(bar_tfull + 8 * a);
+                ptx::mma_commit_pair(bar_tfull + 8 * a);
+                TR(1);
             }
         }
     } else {
@@ -380,6 +400,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
             const int a = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             const int n0 = t * BN;
+            if (warp == 2 && lane == 0) TR(2);
             float* lc_s = misc + a * (2 * BN);   // staged column LSE (log2 units) for this tile
             float* bj_s = lc_s + BN;             // staged B_j = gb * 2^(c - Lc_j) (fast path)
             float* red_s = misc + 4 * BN + a * 16;
@@ -408,8 +429,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
                 Ai = ga * ptx::ex2(cref - Lr);
                 ptx::named_bar_sync(1, NUM_EPI_WARPS * 32);
             }
+            if (warp == 2 && lane == 0) TR(2);
             ptx::mbar_wait(bar_tfull + 8 * a, aph);
             ptx::tc_fence_after();
+            if (warp == 2 && lane == 0) TR(2);
             const uint32_t taddr = tmem_base + a * BN + half * (BN / 2) + (uint32_t(q * 32) << 16);
             // edge tile: contains positives (diagonal entries) of this CTA's rows, or columns beyond N
             const long long d_lo = args.diag_offset + (long long)m_blk * BM;
@@ -484,8 +507,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
             ptx::tmem_ld_wait();
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * a);
+            if (lane == 0) ptx::mbar_arrive_leader(bar_tempty + 8 * a);
+            if (warp == 2 && lane == 0) TR(2);
             process(rb, 3);
+            if (warp == 2 && lane == 0) TR(2);
         }
         if (MODE != MODE_STATS) {
             if (lane == 0) ptx::tma_store_wait<0>();   // all bulk stores of this warp complete before the CTA exits
@@ -504,11 +529,12 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
     }
 
     // ================================ teardown ================================
+    // neither CTA may exit (or free TMEM) while its peer can still read its shared memory or signal its barriers
     ptx::tc_fence_before();
-    __syncthreads();
+    ptx::cluster_sync();
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+        ptx::tmem_dealloc_pair(tmem_base, TMEM_COLS);
     }
 }
 
@@ -516,18 +542,18 @@ template <int MODE, int F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const KArgs args) {
-    gemm_body<MODE, F16>(&tmA, &tmB, &tmC, args, blockIdx.y, blockIdx.x);
+    gemm_body<MODE, F16>(&tmA, &tmB, &tmC, args, blockIdx.x >> 1, blockIdx.y);   // cluster (2, 1, 1): pair = two m blocks
 }
 
 // The two gradient GEMMs of one panel in ONE launch, so that their tiles together fill the SMs:
-// CTAs [0, jobs0) run job 0 (dX = G * Yg), the rest run job 1 (dY = G^T * Xg).  A CTA is one 128 x 256 output tile.
+// pairs [0, jobs0) run job 0 (dX = G * Yg), the rest run job 1 (dY = G^T * Xg).  A pair is one 256 x 256 output tile.
 template <int F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                  const __grid_constant__ CUtensorMap tmC0, const KArgs args0,
                  const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                  const __grid_constant__ CUtensorMap tmC1, const KArgs args1, const int jobs0) {
-    const int j = blockIdx.x;
+    const int j = blockIdx.x >> 1;   // cluster (2, 1, 1): one job per CTA pair = a 256 x 256 output tile
     if (j < jobs0) {
         gemm_body<MODE_OUT, F16>(&tmA0, &tmB0, &tmC0, args0, j / args0.n_tiles, j % args0.n_tiles);
     } else {
