@@ -203,6 +203,46 @@ __global__ void finalize_kernel(const float* __restrict__ row_max, const float* 
     }
 }
 
+// ---- backward preparation: one reference for every exponential of this backward (see grad_chunk PATH 0)
+__device__ __forceinline__ int float_to_ordered(float f) {
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+// mm[0] = min, mm[1] = max (ordered-int encoding) over both LSE vectors
+__global__ void lse_minmax_kernel(const float* __restrict__ a, int na, const float* __restrict__ b, int nb, int* mm) {
+    int lo = 0x7fffffff, hi = int(0x80000000);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < na + nb; i += gridDim.x * blockDim.x) {
+        const int v = float_to_ordered(i < na ? a[i] : b[i - na]);
+        lo = min(lo, v);
+        hi = max(hi, v);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(mm, lo);
+        atomicMax(mm + 1, hi);
+    }
+}
+
+// c = min LSE (log2 units); avec[i] = 2^(c - Lr_i), bvec[j] = 2^(c - Lc_j); gref = {c, fast flag}
+__global__ void grad_prep_kernel(const float* __restrict__ lse_row, int rows, const float* __restrict__ lse_col, int cols,
+                                 const int* __restrict__ mm, float* __restrict__ avec, float* __restrict__ bvec,
+                                 float* __restrict__ gref) {
+    const float lo = ordered_to_float(mm[0]) * LOG2E, hi = ordered_to_float(mm[1]) * LOG2E;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        gref[0] = lo;
+        gref[1] = (hi - lo <= 100.f && lo > -CUDART_INF_F && hi < CUDART_INF_F) ? 1.f : 0.f;
+    }
+    if (i < rows) avec[i] = exp2f(lo - lse_row[i] * LOG2E);
+    if (i < cols) bvec[i] = exp2f(lo - lse_col[i] * LOG2E);
+}
+
 __global__ void cast_kernel(const float* __restrict__ src, void* __restrict__ dst, long long n, int dtype) {
     const long long i = (long long)(blockIdx.x) * blockDim.x + threadIdx.x;
     const long long base = i * 4;
@@ -345,13 +385,17 @@ static int launch_clustered(void (*kfn)(Args...), dim3 grid, dim3 cluster, int s
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = size_t(smem);
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cluster.x;
     attr[0].val.clusterDim.y = cluster.y;
     attr[0].val.clusterDim.z = cluster.z;
+    // programmatic dependent launch: this kernel's CTAs may be scheduled (and run their prologue up to
+    // griddepcontrol.wait) while the previous kernel of the stream drains
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = (dbg_flags() & 32) ? 1 : 2;
     CK_CUDA(cudaLaunchKernelEx(&cfg, kfn, args...));
     return CLIPK_OK;
 }
@@ -540,7 +584,7 @@ size_t clipk_bwd_workspace_bytes(int rows, int cols, int d, int g_dtype) {
     choose_panel(rows, cols, d, planes_of(g_dtype), 148, &rp, &cp);
     // the SM count only nudges the split; size for the L2 budget so any device fits
     (void)rp; (void)cp;
-    return size_t(panel_bytes()) + size_t(2) * 1024 * 1024;
+    return size_t(panel_bytes()) + size_t(2) * 1024 * 1024 + (size_t(rows) + size_t(cols)) * sizeof(float) + 4096;
 }
 
 int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
@@ -572,6 +616,25 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
     const int ldg = gplanes * ncp;
     if ((unsigned long long)round_up(rp_max, 2 * BM) * ldg * 2 > workspace_bytes) return fail(CLIPK_EWORKSPACE, "panel does not fit the workspace");
     __half* G = static_cast<__half*>(workspace);
+    // after the panel: avec[rows], bvec[cols], gref[2], minmax[2]
+    const size_t g_bytes = size_t(round_up(round_up(rp_max, 2 * BM) * ldg * 2, 256));
+    float* avec = reinterpret_cast<float*>(static_cast<char*>(workspace) + g_bytes);
+    float* bvec = avec + round_up(rows, 64);
+    float* gref = bvec + round_up(cols, 64);
+    int* mm = reinterpret_cast<int*>(gref + 4);
+    if (g_bytes + (round_up(rows, 64) + round_up(cols, 64) + 8) * sizeof(float) > workspace_bytes)
+        return fail(CLIPK_EWORKSPACE, "workspace too small for the panel and the reference vectors");
+    CK_CUDA(cudaMemsetAsync(mm, 0x7f, sizeof(int), st));
+    CK_CUDA(cudaMemsetAsync(mm + 1, 0x80, sizeof(int), st));
+    {
+        const int n = rows + cols;
+        int blocks = cdiv(n, 256);
+        if (blocks > 4 * di.sms) blocks = 4 * di.sms;
+        lse_minmax_kernel<<<blocks, 256, 0, st>>>(lse_row, rows, lse_col, cols, mm);
+        const int m = rows > cols ? rows : cols;
+        grad_prep_kernel<<<cdiv(m, 256), 256, 0, st>>>(lse_row, rows, lse_col, cols, mm, avec, bvec, gref);
+        CK_CUDA(cudaGetLastError());
+    }
     const size_t esz = 2;
     const char* Xb = static_cast<const char*>(X);
     const char* Yb = static_cast<const char*>(Y);
@@ -600,6 +663,7 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
                 a.diag_offset = diag_offset + r0 - c0;
                 a.lse_row = lse_row + r0; a.lse_col = lse_col + c0;
                 a.alpha = alpha; a.beta = beta;
+                a.avec = avec + r0; a.bvec = bvec + c0; a.gref = gref;
                 a.G = G; a.ldg = ldg; a.g_planes = gplanes; a.g_plane_stride = ncp;
                 if (is_f16(dtype)) rc = launch_gemm<MODE_GRAD, 1>(ta, tb, tc, a, units, m_pairs, st);
                 else rc = launch_gemm<MODE_GRAD, 0>(ta, tb, tc, a, units, m_pairs, st);

@@ -5,7 +5,7 @@
 // CTAs work in PAIRS (cluster of 2, tcgen05 cta_group::2): a pair computes a 256 x 256 tile with UMMA M=256, N=256,
 // K=16.  Each CTA loads its own 128 rows of A and HALF of the B tile, so a pipeline stage is 32 KB per CTA instead of
 // 48 KB: the measured refill round trip of a stage is ~1900 cycles against 512 cycles of MMA per K block, so the ring
-// needs >= 5 stages to keep the tensor pipe busy, which only fits with the halved B (6 stages STATS, 4 + staging
+// needs >= 5 stages to keep the tensor pipe busy, which only fits with the halved B (7 stages STATS, 5 + staging
 // otherwise).  One CTA = 10 warps: warp 0 = TMA producer, warp 1 = TMEM allocator and, in the even (leader) CTA, the
 // single-thread tcgen05.mma issuer for the pair, warps 2..9 = epilogue for the CTA's own 128 accumulator rows (two
 // warps per TMEM lane quarter, one per 128-column half).  Three pipelines: the shared-memory ring (TMA -> MMA, full
@@ -41,13 +41,13 @@ constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;               // 2 accumulator stages x 256 fp32 columns
-constexpr int MISC_BYTES = 8192;
+constexpr int MISC_BYTES = 1024;
 // Epilogue staging: every epilogue warp owns two 4 KB buffers (32 rows x 128 B, SWIZZLE_128B) from which its part of
 // the tile leaves through TMA (store of the fp16 G tile, store / reduce-add of the fp32 gradient tile).  The STATS
 // kernel writes nothing per tile, so it spends that shared memory on two more pipeline stages instead.
 constexpr int STG_BYTES = 4096;
 constexpr int STG_TOTAL = NUM_EPI_WARPS * 2 * STG_BYTES;   // 64 KB
-__host__ __device__ constexpr int stages_of(int mode) { return mode == 0 ? 6 : 4; }
+__host__ __device__ constexpr int stages_of(int mode) { return mode == 0 ? 7 : 5; }
 __host__ __device__ constexpr int smem_bytes_of(int mode) {
     return 1024 /*align slack*/ + stages_of(mode) * STAGE_BYTES + 256 + MISC_BYTES + (mode == 0 ? 0 : STG_TOTAL);
 }
@@ -80,6 +80,9 @@ struct KArgs {
     // GRAD
     const float* lse_row;      // [M] natural log
     const float* lse_col;      // [N] natural log
+    const float* avec;         // [M] 2^(c - Lr_i), c = global reference of this backward (log2 units), from grad_prep
+    const float* bvec;         // [N] 2^(c - Lc_j)
+    const float* gref;         // [2]: c, fast-path flag (1 = LSE spread small enough for the one-ex2 path)
     float alpha, beta;
     __half* G;                 // panel of G * 2^14 in fp16, row-major, rows padded to BM and ldg to BN
     int ldg;
@@ -119,17 +122,21 @@ __device__ __forceinline__ void stats_chunk(const uint32_t (&r)[32], float sc, i
     for (int k = 1; k < 32; ++k) cmax = fmaxf(cmax, v[k]);
     const float m_new = fmaxf(st.m, cmax);
     if (m_new > -CUDART_INF_F) {
-        float acc = 0.f, dot = 0.f;
+        // all 32 ex2 are issued back to back (MUFU latency is paid once, not per element), then reduced with four
+        // independent accumulators
+        float e[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) e[k] = ptx::ex2(v[k] - m_new);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f}, dot[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
-            const float e = ptx::ex2(v[k] - m_new);
-            acc += e;
+            acc[k & 3] += e[k];
             // masked columns have e == 0 but v == -inf: keep 0 * -inf out of the sum
-            dot = fmaf(e, (EDGE && col0 + k >= ncols) ? 0.f : v[k], dot);
+            dot[k & 3] = fmaf(e[k], (EDGE && col0 + k >= ncols) ? 0.f : v[k], dot[k & 3]);
         }
         const float corr = ptx::ex2(st.m - m_new);
-        st.l = st.l * corr + acc;
-        st.t = st.t * corr + dot;
+        st.l = st.l * corr + ((acc[0] + acc[1]) + (acc[2] + acc[3]));
+        st.t = st.t * corr + ((dot[0] + dot[1]) + (dot[2] + dot[3]));
         st.m = m_new;
     }
     if (EDGE) {
@@ -154,38 +161,55 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 
 // One 32-column chunk of the G tile: 64 B of fp16 per row go to pieces [piece0, piece0 + 4) of the row's 128 B line in
 // `stg` (plane hi) and, for two-plane G, of `stg_lo`.
-//   PATH 0 (interior tile, LSE spread of the tile <= 100 in log2 units): ONE ex2 per element.  With the tile
-//          reference c = min of the tile's row and column LSEs,  E = 2^(v - c),  g = E * (A_i + B_j),
-//          A_i = ga * 2^(c - Lr_i) (a register), B_j = gb * 2^(c - Lc_j) (staged in shared memory per tile).
-//          v <= min(Lr_i, Lc_j) and the spread bound keep every factor inside fp32 range; whatever underflows is
-//          below 2^-126 of a probability.  MUFU runs at 16 ex2/clk/SM, so two per element would cost exactly the
-//          MMA time of the tile - this path halves it.
+//   PATH 0 (interior tile and the LSE spread of this backward <= 100 in log2 units): ONE ex2 per element.  With the
+//          reference c = min over all row and column LSEs,  E = 2^(v - c),  g = E * (A_i + B_j),
+//          A_i = ga * 2^(c - Lr_i) (a register), B_j = gb * 2^(c - Lc_j) (a vector prepared once per backward, read
+//          through L1 as warp-uniform float4 loads).  v <= min(Lr_i, Lc_j) and the spread bound keep every factor in
+//          fp32 range; what underflows is below 2^-126 of a probability.  MUFU runs 16 ex2/clk/SM, so two per element
+//          would cost exactly the tile's MMA time - this path halves it and needs no per-tile staging or barrier.
 //   PATH 1 (tile with positives, columns beyond N, or a wide LSE spread): two ex2 per element, exact masking.
 template <int PATH>
-__device__ __forceinline__ void grad_chunk(const uint32_t (&r)[32], float sc, float Lr, const float* __restrict__ lc,
-                                           float ga, float gb, float cref, float Ai, const float* __restrict__ bj,
-                                           int col0, int ncols, long long dcol, uint32_t stg, uint32_t stg_lo, int lane,
-                                           int piece0, int g_planes) {
+__device__ __forceinline__ void grad_chunk(const uint32_t (&r)[32], float sc, float Lr, float ga, float gb, float cref,
+                                           float Ai, const float* __restrict__ cvec, int col0, int ncols, long long dcol,
+                                           uint32_t stg, uint32_t stg_lo, int lane, int piece0, int g_planes) {
     uint32_t packed[16];
     const int didx = (PATH == 1 && dcol >= col0 && dcol < (long long)col0 + 32) ? int(dcol - col0) : -1;
-    auto g_of = [&](int kk, float cv) -> float {   // cv = B_j (PATH 0) or Lc_j (PATH 1)
+    // cvec = bvec + col0 (PATH 0, pre-scaled by gb below) or lse_col + col0 (PATH 1, natural log)
+    auto g_of = [&](int kk, float cv) -> float {
         const float sraw = __uint_as_float(r[kk]);
         if (PATH == 0) {
-            return ptx::ex2(fmaf(sraw, sc, -cref)) * (Ai + cv);
+            return ptx::ex2(fmaf(sraw, sc, -cref)) * fmaf(gb, cv, Ai);
         } else {
             float pr = ptx::ex2(fmaf(sraw, sc, -Lr));
-            float pc = ptx::ex2(fmaf(sraw, sc, -cv));
+            float pc = ptx::ex2(fmaf(sraw, sc, -cv * LOG2E));
             if (kk == didx) { pr -= 1.f; pc -= 1.f; }
             if (col0 + kk >= ncols) { pr = 0.f; pc = 0.f; }
             return ga * pr + gb * pc;
         }
     };
-    const float* cvec = (PATH == 0) ? bj : lc;
+    auto cv_at = [&](int kk) -> float {
+        if (PATH == 0) return __ldg(cvec + kk);
+        return (col0 + kk < ncols) ? __ldg(cvec + kk) : CUDART_INF_F;
+    };
+    if (PATH == 0) {
+        // loads and all 32 ex2 first (MUFU latency paid once per chunk, not per element), then scale and pack
+        float4 l4[8];
 #pragma unroll
-    for (int k = 0; k < 32; k += 4) {
-        const float4 l4 = *reinterpret_cast<const float4*>(cvec + k);
-        packed[k >> 1] = ptx::pack_f16x2(g_of(k, l4.x), g_of(k + 1, l4.y));
-        packed[(k >> 1) + 1] = ptx::pack_f16x2(g_of(k + 2, l4.z), g_of(k + 3, l4.w));
+        for (int j = 0; j < 8; ++j) l4[j] = __ldg(reinterpret_cast<const float4*>(cvec) + j);
+        float e[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) e[k] = ptx::ex2(fmaf(__uint_as_float(r[k]), sc, -cref));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            packed[2 * j] = ptx::pack_f16x2(e[4 * j] * fmaf(gb, l4[j].x, Ai), e[4 * j + 1] * fmaf(gb, l4[j].y, Ai));
+            packed[2 * j + 1] = ptx::pack_f16x2(e[4 * j + 2] * fmaf(gb, l4[j].z, Ai), e[4 * j + 3] * fmaf(gb, l4[j].w, Ai));
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 32; k += 4) {
+            packed[k >> 1] = ptx::pack_f16x2(g_of(k, cv_at(k)), g_of(k + 1, cv_at(k + 1)));
+            packed[(k >> 1) + 1] = ptx::pack_f16x2(g_of(k + 2, cv_at(k + 2)), g_of(k + 3, cv_at(k + 3)));
+        }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -196,8 +220,8 @@ __device__ __forceinline__ void grad_chunk(const uint32_t (&r)[32], float sc, fl
 #pragma unroll
         for (int k = 0; k < 32; k += 2) {
             const uint32_t prev = packed[k >> 1];
-            const float lo0 = g_of(k, cvec[k]) - __half2float(__ushort_as_half((unsigned short)(prev & 0xffffu)));
-            const float lo1 = g_of(k + 1, cvec[k + 1]) - __half2float(__ushort_as_half((unsigned short)(prev >> 16)));
+            const float lo0 = g_of(k, cv_at(k)) - __half2float(__ushort_as_half((unsigned short)(prev & 0xffffu)));
+            const float lo1 = g_of(k + 1, cv_at(k + 1)) - __half2float(__ushort_as_half((unsigned short)(prev >> 16)));
             packed[k >> 1] = ptx::pack_f16x2(lo0, lo1);
         }
 #pragma unroll
@@ -232,7 +256,6 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
     const uint32_t sTmemPtr = bar_tempty + 16;
     uint8_t* bar_ptr = base_ptr + STAGES * STAGE_BYTES + kStg;
     volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(bar_ptr + (2 * STAGES + 4) * 8);
-    float* misc = reinterpret_cast<float*>(bar_ptr + 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -264,6 +287,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
     ptx::tc_fence_before();
     ptx::cluster_sync();          // barriers of both CTAs initialised, TMEM allocated, before any remote arrive / TMA
     ptx::tc_fence_after();
+    // Programmatic dependent launch: everything above overlapped the tail of the previous kernel in the stream; from
+    // here on global memory written by it is read (and memory it reads is overwritten), so wait for it to finish.
+    ptx::pdl_launch_dependents();
+    ptx::pdl_wait();
     const uint32_t tmem_base = *tmem_ptr_gen;
     const bool tracing = (args.trace != nullptr) && m_blk == 0 && unit == 0;
     int tr_n = 0;
@@ -352,7 +379,6 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
         const int half = (warp - 2) >> 2;             // which 128-column half of the tile this warp drains
         const int row_in_tile = q * 32 + lane;
         const int row = m_blk * BM + row_in_tile;
-        const int epi_tid = (warp - 2) * 32 + lane;   // 0..255
         const bool row_ok = row < args.M;
         const long long dcol = args.diag_offset + row;
 
@@ -371,20 +397,24 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
             if (args.oscale2) oscale *= __ldg(args.oscale2);
         }
         StatsState st{-CUDART_INF_F, 0.f, 0.f, 0.f, false};
-        float Lr = CUDART_INF_F, ga = 0.f, gb = 0.f;   // rows beyond M: every probability is 0
+        float Lr = CUDART_INF_F, ga = 0.f, gb = 0.f, cref = 0.f, Ai = 0.f;   // rows beyond M: every probability is 0
+        bool fast = false;
         if (MODE == MODE_GRAD) {
             if (row_ok) Lr = __ldg(args.lse_row + row) * LOG2E;
             // G is stored as 2^14 * (alpha*(P_row-Id) + beta*(P_col-Id)) in fp16: |.| <= 2^15 and entries down to
             // ~4e-9 keep the full 11-bit mantissa; logit_scale * gscale * 2^-14 is applied by the gradient GEMMs.
             ga = 16384.f * args.alpha;
             gb = 16384.f * args.beta;
+            cref = __ldg(args.gref);
+            fast = __ldg(args.gref + 1) != 0.f;
+            Ai = row_ok ? ga * __ldg(args.avec + row) : 0.f;
         }
 
         const uint32_t stg0 = sStg + (warp - 2) * 2 * STG_BYTES;   // this warp's two staging buffers
         int stg_use = 0;                                           // TMA stores issued so far by this warp
         // before (re)writing a staging buffer: at most one older bulk store may still be reading shared memory
         auto stg_acquire = [&]() -> uint32_t {
-            if (lane == 0) ptx::tma_store_wait_read<1>();
+            if (lane == 0 && !(args.dbg & 16)) ptx::tma_store_wait_read<1>();
             __syncwarp();
             return stg0 + (stg_use & 1) * STG_BYTES;
         };
@@ -401,33 +431,17 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
             const uint32_t aph = (it >> 1) & 1;
             const int n0 = t * BN;
             if (warp == 2 && lane == 0) TR(2);
-            float* lc_s = misc + a * (2 * BN);   // staged column LSE (log2 units) for this tile
-            float* bj_s = lc_s + BN;             // staged B_j = gb * 2^(c - Lc_j) (fast path)
-            float* red_s = misc + 4 * BN + a * 16;
-            float cref = 0.f, Ai = 0.f;
-            bool fast = false;
-            if (MODE == MODE_GRAD && !(args.dbg & 4)) {
-                const int c = n0 + epi_tid;
-                const float lcv = (c < args.N) ? __ldg(args.lse_col + c) * LOG2E : CUDART_INF_F;
-                lc_s[epi_tid] = lcv;
-                // tile reference: min / max over the valid row and column LSEs of this tile
-                float lo = fminf(Lr, lcv);
-                float hi = fmaxf(Lr < CUDART_INF_F ? Lr : -CUDART_INF_F, lcv < CUDART_INF_F ? lcv : -CUDART_INF_F);
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
-                    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
-                    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+            if (MODE == MODE_GRAD && lane < 4) {
+                // pull the B_j / LSE values of this warp's half of the NEXT tile (512 B) into L1 ahead of their use
+                const int cn = (t + 1) * BN + half * (BN / 2) + lane * 32;
+                if (t + 1 < t1 && cn + 32 <= args.N) {
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(args.bvec + cn));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(args.lse_col + cn));
                 }
-                if (lane == 0) { red_s[warp - 2] = lo; red_s[8 + warp - 2] = hi; }
-                ptx::named_bar_sync(1, NUM_EPI_WARPS * 32);
-                lo = red_s[0]; hi = red_s[8];
-#pragma unroll
-                for (int w = 1; w < NUM_EPI_WARPS; ++w) { lo = fminf(lo, red_s[w]); hi = fmaxf(hi, red_s[8 + w]); }
-                cref = lo;
-                fast = (hi - lo <= 100.f) && (lo > -CUDART_INF_F) && (hi < CUDART_INF_F);
-                bj_s[epi_tid] = gb * ptx::ex2(cref - lcv);
-                Ai = ga * ptx::ex2(cref - Lr);
-                ptx::named_bar_sync(1, NUM_EPI_WARPS * 32);
+                if (it == 0) {
+                    const int c0 = t * BN + half * (BN / 2) + lane * 32;
+                    if (c0 + 32 <= args.N) asm volatile("prefetch.global.L1 [%0];" ::"l"(args.bvec + c0));
+                }
             }
             if (warp == 2 && lane == 0) TR(2);
             ptx::mbar_wait(bar_tfull + 8 * a, aph);
@@ -459,12 +473,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
                             __syncwarp();
                         }
                     }
-                    const float* lc = lc_s + half * (BN / 2) + c * 32;
-                    const float* bj = bj_s + half * (BN / 2) + c * 32;
-                    if (fast && !edge) grad_chunk<0>(r, sc, Lr, lc, ga, gb, cref, Ai, bj, col0, args.N, dcol, stg, stg_lo, lane, (c & 1) * 4, args.g_planes);
-                    else grad_chunk<1>(r, sc, Lr, lc, ga, gb, cref, Ai, bj, col0, args.N, dcol, stg, stg_lo, lane, (c & 1) * 4, args.g_planes);
+                    if (fast && !edge) grad_chunk<0>(r, sc, Lr, ga, gb, cref, Ai, args.bvec + col0, col0, args.N, dcol, stg, stg_lo, lane, (c & 1) * 4, args.g_planes);
+                    else grad_chunk<1>(r, sc, Lr, ga, gb, cref, Ai, args.lse_col + col0, col0, args.N, dcol, stg, stg_lo, lane, (c & 1) * 4, args.g_planes);
                     if (c & 1) {
-                        ptx::fence_proxy_async_smem();
+                        if (!(args.dbg & 8)) ptx::fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0 && !(args.dbg & 2)) {
                             ptx::tma_store_2d(tmC, stg, col0 - 32, row0);

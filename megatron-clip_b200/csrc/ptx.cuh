@@ -189,6 +189,12 @@ __host__ __device__ constexpr uint32_t make_idesc_16bit(int m, int n, int a_mn_m
            (uint32_t(b_mn_major) << 16) | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// launch_dependents: the next kernel in the stream may start its CTAs (prologue only) as SMs free up;
+// grid_dep_wait: block until the previous kernel has completed and its memory is visible.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------ misc
 __device__ __forceinline__ float ex2(float x) {
     float y;
