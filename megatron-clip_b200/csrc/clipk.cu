@@ -456,6 +456,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     KArgs aa = a;
     aa.dbg = dbg_flags();
     aa.trace = g_trace;
+    aa.f16 = F16;
     return launch_clustered(kfn, dim3(2 * m_pairs, units), dim3(2, 1, 1), smem, st, ta, tb, tc, aa);
 }
 
@@ -472,6 +473,7 @@ static int launch_pair(const CUtensorMap& ta0, const CUtensorMap& tb0, const CUt
     KArgs b0 = a0, b1 = a1;
     b0.dbg = b1.dbg = dbg_flags();
     b0.trace = g_trace;
+    b0.f16 = b1.f16 = 1;
     return launch_clustered(kfn, dim3(2 * (jobs0 + jobs1)), dim3(2, 1, 1), smem, st, ta0, tb0, tc0, b0, ta1, tb1, tc1, b1,
                             jobs0);
 }

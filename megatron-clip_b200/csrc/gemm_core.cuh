@@ -66,6 +66,9 @@ struct KArgs {
     int nseg, kb_per_seg;
     int a_off[3], b_off[3];
     int a_mn, b_mn;       // operand majors (1 = MN-major)
+    int f16;              // operands are fp16 (1) or bf16 (0)
+    int a_outer_off, b_outer_off;   // added to the OUTER TMA coordinate (row of a K-major operand, K of an MN-major one)
+    int c_col_off, c_row_off;       // added to the epilogue's TMA store coordinates
     int n_tiles;          // ceil(N / BN)
     int tiles_per_unit;   // column tiles swept by one CTA (STATS / GRAD); 1 for OUT
     // STATS / GRAD
@@ -192,17 +195,20 @@ __device__ __forceinline__ void grad_chunk(const uint32_t (&r)[32], float sc, fl
         return (col0 + kk < ncols) ? __ldg(cvec + kk) : CUDART_INF_F;
     };
     if (PATH == 0) {
-        // loads and all 32 ex2 first (MUFU latency paid once per chunk, not per element), then scale and pack
-        float4 l4[8];
+        // per half chunk: loads and 16 ex2 first (MUFU latency paid once per batch, not per element), then scale + pack
 #pragma unroll
-        for (int j = 0; j < 8; ++j) l4[j] = __ldg(reinterpret_cast<const float4*>(cvec) + j);
-        float e[32];
+        for (int h = 0; h < 2; ++h) {
+            float4 l4[4];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) e[k] = ptx::ex2(fmaf(__uint_as_float(r[k]), sc, -cref));
+            for (int j = 0; j < 4; ++j) l4[j] = __ldg(reinterpret_cast<const float4*>(cvec) + 4 * h + j);
+            float e[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            packed[2 * j] = ptx::pack_f16x2(e[4 * j] * fmaf(gb, l4[j].x, Ai), e[4 * j + 1] * fmaf(gb, l4[j].y, Ai));
-            packed[2 * j + 1] = ptx::pack_f16x2(e[4 * j + 2] * fmaf(gb, l4[j].z, Ai), e[4 * j + 3] * fmaf(gb, l4[j].w, Ai));
+            for (int k = 0; k < 16; ++k) e[k] = ptx::ex2(fmaf(__uint_as_float(r[16 * h + k]), sc, -cref));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                packed[8 * h + 2 * j] = ptx::pack_f16x2(e[4 * j] * fmaf(gb, l4[j].x, Ai), e[4 * j + 1] * fmaf(gb, l4[j].y, Ai));
+                packed[8 * h + 2 * j + 1] = ptx::pack_f16x2(e[4 * j + 2] * fmaf(gb, l4[j].z, Ai), e[4 * j + 3] * fmaf(gb, l4[j].w, Ai));
+            }
         }
     } else {
 #pragma unroll
@@ -231,56 +237,59 @@ __device__ __forceinline__ void grad_chunk(const uint32_t (&r)[32], float sc, fl
 }
 
 // ---------------------------------------------------------------------------------------------------- CTA body
-// a_mn / b_mn come from args: the branches on them are warp-uniform and outside the hot loops.
-template <int MODE, int F16>
-__device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensorMap* tmB, const CUtensorMap* tmC,
-                                          const KArgs& args, int m_pair, int unit) {
-    constexpr int STAGES = stages_of(MODE);
-    const uint32_t cta_rank = ptx::cluster_ctarank();   // 0 = leader (issues the pair's MMAs), 1 = peer
-    const bool leader = (cta_rank == 0);
-    const int m_blk = 2 * m_pair + int(cta_rank);
+// The body is split into per-role "unit" functions that carry their pipeline state (ring stage / phase, accumulator
+// stage, staging-buffer use) across calls, so the same code serves the one-unit-per-CTA kernels and the persistent
+// backward kernel that walks many units per CTA.
+struct Cta {
+    uint32_t sA, sB, sStg, bar_full, bar_empty, bar_tfull, bar_tempty, tmem_base;
+    uint32_t cta_rank;
+    bool leader;
+    int warp, lane;
+};
+struct Pipe {
+    int s = 0;          // shared-memory ring stage (producer / MMA)
+    uint32_t ph = 0;    // its phase
+    int it = 0;         // tiles processed so far (MMA / epilogue): accumulator stage = it & 1
+    int stg_use = 0;    // TMA stores issued so far by this epilogue warp
+};
+
+template <int STAGES, bool HAS_STG>
+__device__ __forceinline__ Cta cta_setup() {
+    Cta c;
+    c.cta_rank = ptx::cluster_ctarank();   // 0 = leader (issues the pair's MMAs), 1 = peer
+    c.leader = (c.cta_rank == 0);
+    c.warp = threadIdx.x >> 5;
+    c.lane = threadIdx.x & 31;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
     const uint32_t base = (raw_u32 + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - raw_u32);
-    const uint32_t sA = base;
-    const uint32_t sB = sA + STAGES * A_STAGE_BYTES;
-    // layout (all 1024-byte aligned up to the barriers): A stages | B stages | epilogue staging | barriers | misc
-    constexpr uint32_t kStg = (MODE == MODE_STATS) ? 0u : uint32_t(STG_TOTAL);
-    const uint32_t sStg = sB + STAGES * B_STAGE_BYTES;      // epilogue staging (GRAD / OUT only)
-    const uint32_t sBar = sStg + kStg;
-    const uint32_t bar_full = sBar;
-    const uint32_t bar_empty = sBar + STAGES * 8;
-    const uint32_t bar_tfull = sBar + 2 * STAGES * 8;
-    const uint32_t bar_tempty = bar_tfull + 16;
-    const uint32_t sTmemPtr = bar_tempty + 16;
-    uint8_t* bar_ptr = base_ptr + STAGES * STAGE_BYTES + kStg;
-    volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(bar_ptr + (2 * STAGES + 4) * 8);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int t0 = unit * args.tiles_per_unit;
-    const int t1 = min(args.n_tiles, t0 + args.tiles_per_unit);
-    const int num_kb = args.num_kb;
-    const int a_mn = args.a_mn, b_mn = args.b_mn;
+    // layout (1024-byte aligned up to the barriers): A stages | B stages | epilogue staging | barriers
+    constexpr uint32_t kStg = HAS_STG ? uint32_t(STG_TOTAL) : 0u;
+    c.sA = base;
+    c.sB = c.sA + STAGES * A_STAGE_BYTES;
+    c.sStg = c.sB + STAGES * B_STAGE_BYTES;
+    const uint32_t sBar = c.sStg + kStg;
+    c.bar_full = sBar;
+    c.bar_empty = sBar + STAGES * 8;
+    c.bar_tfull = sBar + 2 * STAGES * 8;
+    c.bar_tempty = c.bar_tfull + 16;
+    const uint32_t sTmemPtr = c.bar_tempty + 16;
+    volatile uint32_t* tmem_ptr_gen =
+        reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * STAGE_BYTES + kStg + (2 * STAGES + 4) * 8);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            ptx::mbar_init(bar_full + 8 * s, 1);
-            ptx::mbar_init(bar_empty + 8 * s, 1);
+            ptx::mbar_init(c.bar_full + 8 * s, 1);
+            ptx::mbar_init(c.bar_empty + 8 * s, 1);
         }
         for (int a = 0; a < 2; ++a) {
-            ptx::mbar_init(bar_tfull + 8 * a, 1);
-            ptx::mbar_init(bar_tempty + 8 * a, 2 * NUM_EPI_WARPS);   // epilogue warps of both CTAs (leader's copy is used)
+            ptx::mbar_init(c.bar_tfull + 8 * a, 1);
+            ptx::mbar_init(c.bar_tempty + 8 * a, 2 * NUM_EPI_WARPS);   // epilogue warps of both CTAs (leader's copy is used)
         }
         ptx::fence_barrier_init();
     }
-    if (warp == 0 && lane == 0) {
-        ptx::prefetch_tmap(tmA);
-        ptx::prefetch_tmap(tmB);
-        if (MODE != MODE_STATS) ptx::prefetch_tmap(tmC);
-    }
-    if (warp == 1) {
+    if (c.warp == 1) {
         ptx::tmem_alloc_pair(sTmemPtr, TMEM_COLS);
         ptx::tmem_relinquish_pair();
     }
@@ -291,270 +300,286 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
     // here on global memory written by it is read (and memory it reads is overwritten), so wait for it to finish.
     ptx::pdl_launch_dependents();
     ptx::pdl_wait();
-    const uint32_t tmem_base = *tmem_ptr_gen;
-    const bool tracing = (args.trace != nullptr) && m_blk == 0 && unit == 0;
-    int tr_n = 0;
-    auto TR = [&](int role) {
-        if (tracing && tr_n < 64) args.trace[MODE * 192 + role * 64 + tr_n++] = clock64();
-    };
+    c.tmem_base = *tmem_ptr_gen;
+    return c;
+}
 
-    if (warp == 0) {
-        // ================================ TMA producer ================================
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
-            for (int t = t0; t < t1; ++t) {
-                TR(0);
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    const int seg = kb / args.kb_per_seg;
-                    const int kw = (kb - seg * args.kb_per_seg) * BK;
-                    const int ao = args.a_off[seg], bo = args.b_off[seg];
-                    ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);
-                    // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of the pair
-                    const uint32_t full = bar_full + 8 * s;
-                    if (leader) ptx::mbar_arrive_expect_tx(full, 2 * STAGE_BYTES);
-                    const uint32_t a_dst = sA + s * A_STAGE_BYTES;
-                    const uint32_t b_dst = sB + s * B_STAGE_BYTES;
-                    const int bn0 = t * BN + int(cta_rank) * (BN / 2);   // this CTA's half of the B tile
-                    if (a_mn) {
-#pragma unroll
-                        for (int i = 0; i < BM / 64; ++i)
-                            ptx::tma_load_2d_pair(a_dst + i * 8192, tmA, ao + m_blk * BM + i * 64, kw, full);
-                    } else {
-                        ptx::tma_load_2d_pair(a_dst, tmA, ao + kw, m_blk * BM, full);
-                    }
-                    if (b_mn) {
-#pragma unroll
-                        for (int i = 0; i < BN / 128; ++i)
-                            ptx::tma_load_2d_pair(b_dst + i * 8192, tmB, bo + bn0 + i * 64, kw, full);
-                    } else {
-                        ptx::tma_load_2d_pair(b_dst, tmB, bo + kw, bn0, full);
-                    }
-                    if (++s == STAGES) { s = 0; ph ^= 1; }
-                }
-            }
-            TR(0);
-        }
-    } else if (warp == 1) {
-        // ================================ MMA issuer ================================
-        if (lane == 0 && leader) {
-            const uint32_t idesc = ptx::make_idesc_16bit(2 * BM, BN, a_mn, b_mn, /*a_is_bf16=*/!F16, /*b_is_bf16=*/!F16);
-            // K-major SW128: 8-row groups 1024 B apart (SBO); MN-major SW128: 64-wide MN blocks 8192 B apart (LBO),
-            // 8-row K groups 1024 B apart (SBO).
-            const uint64_t adesc_hi = a_mn ? ptx::make_smem_desc_sw128(8192, 1024) : ptx::make_smem_desc_sw128(16, 1024);
-            const uint64_t bdesc_hi = b_mn ? ptx::make_smem_desc_sw128(8192, 1024) : ptx::make_smem_desc_sw128(16, 1024);
-            const uint32_t a_kstep = a_mn ? 2048 : 32;   // bytes per UMMA_K = 16 elements
-            const uint32_t b_kstep = b_mn ? 2048 : 32;
-            int s = 0;
-            uint32_t ph = 0;
-            int it = 0;
-            for (int t = t0; t < t1; ++t, ++it) {
-                const int a = it & 1;
-                const uint32_t aph = (it >> 1) & 1;
-                TR(1);
-                ptx::mbar_wait(bar_tempty + 8 * a, aph ^ 1);
-                ptx::tc_fence_after();
-                TR(1);
-                const uint32_t d_tmem = tmem_base + a * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    ptx::mbar_wait(bar_full + 8 * s, ph);
-                    ptx::tc_fence_after();
-                    const uint32_t a_src = sA + s * A_STAGE_BYTES;
-                    const uint32_t b_src = sB + s * B_STAGE_BYTES;
-#pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        ptx::mma_f16_ss_pair(d_tmem, ptx::desc_with_addr(adesc_hi, a_src + k * a_kstep),
-                                        ptx::desc_with_addr(bdesc_hi, b_src + k * b_kstep), idesc, (kb | k) != 0);
-                    }
-                    ptx::mma_commit_pair(bar_empty + 8 * s);
-                    if (++s == STAGES) { s = 0; ph ^= 1; }
-                }
-                ptx::mma_commit_pair(bar_tfull + 8 * a);
-                TR(1);
-            }
-        }
-    } else {
-        // ================================ epilogue warps ================================
-        const int q = warp & 3;                       // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;             // which 128-column half of the tile this warp drains
-        const int row_in_tile = q * 32 + lane;
-        const int row = m_blk * BM + row_in_tile;
-        const bool row_ok = row < args.M;
-        const long long dcol = args.diag_offset + row;
-
-        // acc holds the dot product of the STORED operands; dequant = xs*ys turns it into the true x.y
-        float sc = 0.f, s_nat = 0.f, oscale = 1.f;
-        if (MODE != MODE_OUT) {
-            float dequant = 1.f;
-            if (args.xs) dequant *= __ldg(args.xs);
-            if (args.ys) dequant *= __ldg(args.ys);
-            s_nat = __ldg(args.scale) * dequant;      // S = s_nat * acc
-            sc = s_nat * LOG2E;
-        } else {
-            oscale = args.oconst;
-            if (args.oscale0) oscale *= __ldg(args.oscale0);
-            if (args.oscale1) oscale *= __ldg(args.oscale1);
-            if (args.oscale2) oscale *= __ldg(args.oscale2);
-        }
-        StatsState st{-CUDART_INF_F, 0.f, 0.f, 0.f, false};
-        float Lr = CUDART_INF_F, ga = 0.f, gb = 0.f, cref = 0.f, Ai = 0.f;   // rows beyond M: every probability is 0
-        bool fast = false;
-        if (MODE == MODE_GRAD) {
-            if (row_ok) Lr = __ldg(args.lse_row + row) * LOG2E;
-            // G is stored as 2^14 * (alpha*(P_row-Id) + beta*(P_col-Id)) in fp16: |.| <= 2^15 and entries down to
-            // ~4e-9 keep the full 11-bit mantissa; logit_scale * gscale * 2^-14 is applied by the gradient GEMMs.
-            ga = 16384.f * args.alpha;
-            gb = 16384.f * args.beta;
-            cref = __ldg(args.gref);
-            fast = __ldg(args.gref + 1) != 0.f;
-            Ai = row_ok ? ga * __ldg(args.avec + row) : 0.f;
-        }
-
-        const uint32_t stg0 = sStg + (warp - 2) * 2 * STG_BYTES;   // this warp's two staging buffers
-        int stg_use = 0;                                           // TMA stores issued so far by this warp
-        // before (re)writing a staging buffer: at most one older bulk store may still be reading shared memory
-        auto stg_acquire = [&]() -> uint32_t {
-            if (lane == 0 && !(args.dbg & 16)) ptx::tma_store_wait_read<1>();
-            __syncwarp();
-            return stg0 + (stg_use & 1) * STG_BYTES;
-        };
-        // after the warp filled a staging buffer: publish it to the async proxy and let one lane issue the TMA
-        auto stg_commit = [&]() {
-            ptx::fence_proxy_async_smem();
-            __syncwarp();
-            ++stg_use;
-        };
-
-        int it = 0;
-        for (int t = t0; t < t1; ++t, ++it) {
-            const int a = it & 1;
-            const uint32_t aph = (it >> 1) & 1;
-            const int n0 = t * BN;
-            if (warp == 2 && lane == 0) TR(2);
-            if (MODE == MODE_GRAD && lane < 4) {
-                // pull the B_j / LSE values of this warp's half of the NEXT tile (512 B) into L1 ahead of their use
-                const int cn = (t + 1) * BN + half * (BN / 2) + lane * 32;
-                if (t + 1 < t1 && cn + 32 <= args.N) {
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(args.bvec + cn));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(args.lse_col + cn));
-                }
-                if (it == 0) {
-                    const int c0 = t * BN + half * (BN / 2) + lane * 32;
-                    if (c0 + 32 <= args.N) asm volatile("prefetch.global.L1 [%0];" ::"l"(args.bvec + c0));
-                }
-            }
-            if (warp == 2 && lane == 0) TR(2);
-            ptx::mbar_wait(bar_tfull + 8 * a, aph);
-            ptx::tc_fence_after();
-            if (warp == 2 && lane == 0) TR(2);
-            const uint32_t taddr = tmem_base + a * BN + half * (BN / 2) + (uint32_t(q * 32) << 16);
-            // edge tile: contains positives (diagonal entries) of this CTA's rows, or columns beyond N
-            const long long d_lo = args.diag_offset + (long long)m_blk * BM;
-            const bool edge = (MODE != MODE_OUT) &&
-                              (((d_lo + BM - 1 >= n0) && (d_lo < (long long)n0 + BN)) || (n0 + BN > args.N));
-            const int colh = n0 + half * (BN / 2);          // first column of this warp's half tile
-            const int row0 = m_blk * BM + q * 32;           // first row of this warp
-
-            auto process = [&](const uint32_t (&r)[32], int c) {
-                const int col0 = colh + c * 32;
-                if (args.dbg & 1) return;
-                if (MODE == MODE_STATS) {
-                    if (edge) stats_chunk<true>(r, sc, col0, args.N, dcol, st);
-                    else stats_chunk<false>(r, sc, col0, args.N, dcol, st);
-                } else if (MODE == MODE_GRAD) {
-                    // two chunks (64 columns = 128 B of fp16 per row) share one staging buffer and one TMA store
-                    uint32_t stg = stg0 + (stg_use & 1) * STG_BYTES;
-                    uint32_t stg_lo = stg0 + ((stg_use + 1) & 1) * STG_BYTES;
-                    if ((c & 1) == 0) {
-                        stg = stg_acquire();
-                        if (args.g_planes == 2) {
-                            // the second plane takes the other buffer: nothing of this warp may still be in flight
-                            if (lane == 0) ptx::tma_store_wait_read<0>();
-                            __syncwarp();
-                        }
-                    }
-                    if (fast && !edge) grad_chunk<0>(r, sc, Lr, ga, gb, cref, Ai, args.bvec + col0, col0, args.N, dcol, stg, stg_lo, lane, (c & 1) * 4, args.g_planes);
-                    else grad_chunk<1>(r, sc, Lr, ga, gb, cref, Ai, args.lse_col + col0, col0, args.N, dcol, stg, stg_lo, lane, (c & 1) * 4, args.g_planes);
-                    if (c & 1) {
-                        if (!(args.dbg & 8)) ptx::fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0 && !(args.dbg & 2)) {
-                            ptx::tma_store_2d(tmC, stg, col0 - 32, row0);
-                            if (args.g_planes == 2) ptx::tma_store_2d(tmC, stg_lo, args.g_plane_stride + col0 - 32, row0);
-                            ptx::tma_store_commit();
-                        }
-                        stg_use += (args.g_planes == 2) ? 2 : 1;
-                    }
-                } else {  // MODE_OUT: 32 fp32 columns = 128 B per row = one staging buffer and one TMA store / reduce
-                    const uint32_t stg = stg_acquire();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        st_shared_v4(stg_addr(stg, lane, j), __float_as_uint(__uint_as_float(r[4 * j]) * oscale),
-                                     __float_as_uint(__uint_as_float(r[4 * j + 1]) * oscale),
-                                     __float_as_uint(__uint_as_float(r[4 * j + 2]) * oscale),
-                                     __float_as_uint(__uint_as_float(r[4 * j + 3]) * oscale));
-                    stg_commit();
-                    if (lane == 0 && !(args.dbg & 2)) {
-                        // the tensor map clips rows >= M and columns >= N
-                        if (args.accumulate) ptx::tma_reduce_add_2d(tmC, stg, col0, row0);
-                        else ptx::tma_store_2d(tmC, stg, col0, row0);
-                        ptx::tma_store_commit();
-                    }
-                }
-            };
-
-            // TMEM loads are double buffered: the load of chunk c+1 is in flight while chunk c is processed, and the
-            // accumulator stage goes back to the MMA warp as soon as the last load has landed in registers.
-            uint32_t ra[32], rb[32];
-            ptx::tmem_ld_32x32(taddr, ra);
-            ptx::tmem_ld_wait();
-            ptx::tmem_ld_32x32(taddr + 32, rb);
-            process(ra, 0);
-            ptx::tmem_ld_wait();
-            ptx::tmem_ld_32x32(taddr + 64, ra);
-            process(rb, 1);
-            ptx::tmem_ld_wait();
-            ptx::tmem_ld_32x32(taddr + 96, rb);
-            process(ra, 2);
-            ptx::tmem_ld_wait();
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive_leader(bar_tempty + 8 * a);
-            if (warp == 2 && lane == 0) TR(2);
-            process(rb, 3);
-            if (warp == 2 && lane == 0) TR(2);
-        }
-        if (MODE != MODE_STATS) {
-            if (lane == 0) ptx::tma_store_wait<0>();   // all bulk stores of this warp complete before the CTA exits
-            __syncwarp();
-        }
-
-        if (MODE == MODE_STATS) {
-            if (row_ok) {
-                const size_t slot = (size_t)(unit * PARTS_PER_UNIT + half) * args.M + row;
-                args.part_max[slot] = st.m;
-                args.part_sum[slot] = st.l;
-                args.part_dot[slot] = st.t;
-                if (st.have_pos) args.pos[row] = st.pos_raw * s_nat;
-            }
-        }
-    }
-
-    // ================================ teardown ================================
+__device__ __forceinline__ void cta_teardown(const Cta& c) {
     // neither CTA may exit (or free TMEM) while its peer can still read its shared memory or signal its barriers
     ptx::tc_fence_before();
     ptx::cluster_sync();
-    if (warp == 1) {
+    if (c.warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc_pair(tmem_base, TMEM_COLS);
+        ptx::tmem_dealloc_pair(c.tmem_base, TMEM_COLS);
     }
 }
 
+// ------------------------------------------------------------------ TMA producer (one lane of warp 0, both CTAs)
+template <int STAGES>
+__device__ __forceinline__ void produce_unit(const Cta& c, Pipe& p, const CUtensorMap* tmA, const CUtensorMap* tmB,
+                                             const KArgs& args, int m_blk, int t0, int t1) {
+    const int a_mn = args.a_mn, b_mn = args.b_mn;
+    for (int t = t0; t < t1; ++t) {
+        for (int kb = 0; kb < args.num_kb; ++kb) {
+            const int seg = kb / args.kb_per_seg;
+            const int kw = (kb - seg * args.kb_per_seg) * BK;
+            const int ao = args.a_off[seg], bo = args.b_off[seg];
+            ptx::mbar_wait(c.bar_empty + 8 * p.s, p.ph ^ 1);
+            // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of the pair
+            const uint32_t full = c.bar_full + 8 * p.s;
+            if (c.leader) ptx::mbar_arrive_expect_tx(full, 2 * STAGE_BYTES);
+            const uint32_t a_dst = c.sA + p.s * A_STAGE_BYTES;
+            const uint32_t b_dst = c.sB + p.s * B_STAGE_BYTES;
+            const int bn0 = t * BN + int(c.cta_rank) * (BN / 2);   // this CTA's half of the B tile
+            if (a_mn) {
+#pragma unroll
+                for (int i = 0; i < BM / 64; ++i)
+                    ptx::tma_load_2d_pair(a_dst + i * 8192, tmA, ao + m_blk * BM + i * 64, args.a_outer_off + kw, full);
+            } else {
+                ptx::tma_load_2d_pair(a_dst, tmA, ao + kw, args.a_outer_off + m_blk * BM, full);
+            }
+            if (b_mn) {
+#pragma unroll
+                for (int i = 0; i < BN / 128; ++i)
+                    ptx::tma_load_2d_pair(b_dst + i * 8192, tmB, bo + bn0 + i * 64, args.b_outer_off + kw, full);
+            } else {
+                ptx::tma_load_2d_pair(b_dst, tmB, bo + kw, args.b_outer_off + bn0, full);
+            }
+            if (++p.s == STAGES) { p.s = 0; p.ph ^= 1; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ MMA issuer (one lane of warp 1, leader CTA only)
+template <int STAGES>
+__device__ __forceinline__ void mma_unit(const Cta& c, Pipe& p, const KArgs& args, int ntiles) {
+    const int a_mn = args.a_mn, b_mn = args.b_mn;
+    const uint32_t idesc = ptx::make_idesc_16bit(2 * BM, BN, a_mn, b_mn, /*a_is_bf16=*/!args.f16, /*b_is_bf16=*/!args.f16);
+    // K-major SW128: 8-row groups 1024 B apart (SBO); MN-major SW128: 64-wide MN blocks 8192 B apart (LBO),
+    // 8-row K groups 1024 B apart (SBO).
+    const uint64_t adesc_hi = a_mn ? ptx::make_smem_desc_sw128(8192, 1024) : ptx::make_smem_desc_sw128(16, 1024);
+    const uint64_t bdesc_hi = b_mn ? ptx::make_smem_desc_sw128(8192, 1024) : ptx::make_smem_desc_sw128(16, 1024);
+    const uint32_t a_kstep = a_mn ? 2048 : 32;   // bytes per UMMA_K = 16 elements
+    const uint32_t b_kstep = b_mn ? 2048 : 32;
+    for (int t = 0; t < ntiles; ++t, ++p.it) {
+        const int a = p.it & 1;
+        const uint32_t aph = (p.it >> 1) & 1;
+        ptx::mbar_wait(c.bar_tempty + 8 * a, aph ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = c.tmem_base + a * BN;
+        for (int kb = 0; kb < args.num_kb; ++kb) {
+            ptx::mbar_wait(c.bar_full + 8 * p.s, p.ph);
+            ptx::tc_fence_after();
+            const uint32_t a_src = c.sA + p.s * A_STAGE_BYTES;
+            const uint32_t b_src = c.sB + p.s * B_STAGE_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+                ptx::mma_f16_ss_pair(d_tmem, ptx::desc_with_addr(adesc_hi, a_src + k * a_kstep),
+                                     ptx::desc_with_addr(bdesc_hi, b_src + k * b_kstep), idesc, (kb | k) != 0);
+            }
+            ptx::mma_commit_pair(c.bar_empty + 8 * p.s);
+            if (++p.s == STAGES) { p.s = 0; p.ph ^= 1; }
+        }
+        ptx::mma_commit_pair(c.bar_tfull + 8 * a);
+    }
+}
+
+// ------------------------------------------------------------------ epilogue (warps 2..9, both CTAs)
+template <int MODE>
+__device__ __forceinline__ void epilogue_unit(const Cta& c, Pipe& p, const CUtensorMap* tmC, const KArgs& args, int m_blk,
+                                              int unit, int t0, int t1) {
+    const int warp = c.warp, lane = c.lane;
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;             // which 128-column half of the tile this warp drains
+    const int row = m_blk * BM + q * 32 + lane;
+    const bool row_ok = row < args.M;
+    const long long dcol = args.diag_offset + row;
+
+    // acc holds the dot product of the STORED operands; dequant = xs*ys turns it into the true x.y
+    float sc = 0.f, s_nat = 0.f, oscale = 1.f;
+    if (MODE != MODE_OUT) {
+        float dequant = 1.f;
+        if (args.xs) dequant *= __ldg(args.xs);
+        if (args.ys) dequant *= __ldg(args.ys);
+        s_nat = __ldg(args.scale) * dequant;      // S = s_nat * acc
+        sc = s_nat * LOG2E;
+    } else {
+        oscale = args.oconst;
+        if (args.oscale0) oscale *= __ldg(args.oscale0);
+        if (args.oscale1) oscale *= __ldg(args.oscale1);
+        if (args.oscale2) oscale *= __ldg(args.oscale2);
+    }
+    StatsState st{-CUDART_INF_F, 0.f, 0.f, 0.f, false};
+    float Lr = CUDART_INF_F, ga = 0.f, gb = 0.f, cref = 0.f, Ai = 0.f;   // rows beyond M: every probability is 0
+    bool fast = false;
+    if (MODE == MODE_GRAD) {
+        if (row_ok) Lr = __ldg(args.lse_row + row) * LOG2E;
+        // G is stored as 2^14 * (alpha*(P_row-Id) + beta*(P_col-Id)) in fp16: |.| <= 2^15 and entries down to
+        // ~4e-9 keep the full 11-bit mantissa; logit_scale * gscale * 2^-14 is applied by the gradient GEMMs.
+        ga = 16384.f * args.alpha;
+        gb = 16384.f * args.beta;
+        cref = __ldg(args.gref);
+        fast = __ldg(args.gref + 1) != 0.f;
+        Ai = row_ok ? ga * __ldg(args.avec + row) : 0.f;
+    }
+    const bool tracing = (args.trace != nullptr) && m_blk == 0 && unit == 0 && warp == 2 && lane == 0;
+    int tr_n = 0;
+    auto TR = [&]() {
+        if (tracing && tr_n < 64) args.trace[MODE * 192 + 128 + tr_n++] = clock64();
+    };
+
+    const uint32_t stg0 = c.sStg + (warp - 2) * 2 * STG_BYTES;   // this warp's two staging buffers
+    // before (re)writing a staging buffer: at most one older bulk store may still be reading shared memory
+    auto stg_acquire = [&]() -> uint32_t {
+        if (lane == 0) ptx::tma_store_wait_read<1>();
+        __syncwarp();
+        return stg0 + (p.stg_use & 1) * STG_BYTES;
+    };
+
+    for (int t = t0; t < t1; ++t, ++p.it) {
+        const int a = p.it & 1;
+        const uint32_t aph = (p.it >> 1) & 1;
+        const int n0 = t * BN;
+        TR();
+        if (MODE == MODE_GRAD && lane < 4) {
+            // pull the B_j / LSE values of this warp's half of the NEXT tile (512 B) into L1 ahead of their use
+            const int cn = (t + 1) * BN + half * (BN / 2) + lane * 32;
+            if (t + 1 < t1 && cn + 32 <= args.N) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(args.bvec + cn));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(args.lse_col + cn));
+            }
+            if (t == t0) {
+                const int c0 = t * BN + half * (BN / 2) + lane * 32;
+                if (c0 + 32 <= args.N) asm volatile("prefetch.global.L1 [%0];" ::"l"(args.bvec + c0));
+            }
+        }
+        ptx::mbar_wait(c.bar_tfull + 8 * a, aph);
+        ptx::tc_fence_after();
+        TR();
+        const uint32_t taddr = c.tmem_base + a * BN + half * (BN / 2) + (uint32_t(q * 32) << 16);
+        // edge tile: contains positives (diagonal entries) of this CTA's rows, or columns beyond N
+        const long long d_lo = args.diag_offset + (long long)m_blk * BM;
+        const bool edge = (MODE != MODE_OUT) &&
+                          (((d_lo + BM - 1 >= n0) && (d_lo < (long long)n0 + BN)) || (n0 + BN > args.N));
+        const int colh = n0 + half * (BN / 2);          // first column of this warp's half tile
+        const int row0 = m_blk * BM + q * 32;           // first row of this warp
+
+        auto process = [&](const uint32_t (&r)[32], int cidx) {
+            const int col0 = colh + cidx * 32;
+            if (args.dbg & 1) return;
+            if (MODE == MODE_STATS) {
+                if (edge) stats_chunk<true>(r, sc, col0, args.N, dcol, st);
+                else stats_chunk<false>(r, sc, col0, args.N, dcol, st);
+            } else if (MODE == MODE_GRAD) {
+                // two chunks (64 columns = 128 B of fp16 per row) share one staging buffer and one TMA store
+                uint32_t stg = stg0 + (p.stg_use & 1) * STG_BYTES;
+                uint32_t stg_lo = stg0 + ((p.stg_use + 1) & 1) * STG_BYTES;
+                if ((cidx & 1) == 0) {
+                    stg = stg_acquire();
+                    if (args.g_planes == 2) {
+                        // the second plane takes the other buffer: nothing of this warp may still be in flight
+                        if (lane == 0) ptx::tma_store_wait_read<0>();
+                        __syncwarp();
+                    }
+                }
+                if (fast && !edge) grad_chunk<0>(r, sc, Lr, ga, gb, cref, Ai, args.bvec + col0, col0, args.N, dcol, stg, stg_lo, lane, (cidx & 1) * 4, args.g_planes);
+                else grad_chunk<1>(r, sc, Lr, ga, gb, cref, Ai, args.lse_col + col0, col0, args.N, dcol, stg, stg_lo, lane, (cidx & 1) * 4, args.g_planes);
+                if (cidx & 1) {
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0 && !(args.dbg & 2)) {
+                        ptx::tma_store_2d(tmC, stg, args.c_col_off + col0 - 32, args.c_row_off + row0);
+                        if (args.g_planes == 2)
+                            ptx::tma_store_2d(tmC, stg_lo, args.c_col_off + args.g_plane_stride + col0 - 32, args.c_row_off + row0);
+                        ptx::tma_store_commit();
+                    }
+                    p.stg_use += (args.g_planes == 2) ? 2 : 1;
+                }
+            } else {  // MODE_OUT: 32 fp32 columns = 128 B per row = one staging buffer and one TMA store / reduce
+                const uint32_t stg = stg_acquire();
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    st_shared_v4(stg_addr(stg, lane, j), __float_as_uint(__uint_as_float(r[4 * j]) * oscale),
+                                 __float_as_uint(__uint_as_float(r[4 * j + 1]) * oscale),
+                                 __float_as_uint(__uint_as_float(r[4 * j + 2]) * oscale),
+                                 __float_as_uint(__uint_as_float(r[4 * j + 3]) * oscale));
+                ptx::fence_proxy_async_smem();
+                __syncwarp();
+                ++p.stg_use;
+                if (lane == 0 && !(args.dbg & 2)) {
+                    // the tensor map clips rows and columns beyond the output matrix
+                    if (args.accumulate) ptx::tma_reduce_add_2d(tmC, stg, args.c_col_off + col0, args.c_row_off + row0);
+                    else ptx::tma_store_2d(tmC, stg, args.c_col_off + col0, args.c_row_off + row0);
+                    ptx::tma_store_commit();
+                }
+            }
+        };
+
+        // TMEM loads are double buffered: the load of chunk c+1 is in flight while chunk c is processed, and the
+        // accumulator stage goes back to the MMA warp as soon as the last load has landed in registers.
+        uint32_t ra[32], rb[32];
+        ptx::tmem_ld_32x32(taddr, ra);
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_32x32(taddr + 32, rb);
+        process(ra, 0);
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_32x32(taddr + 64, ra);
+        process(rb, 1);
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_32x32(taddr + 96, rb);
+        process(ra, 2);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_leader(c.bar_tempty + 8 * a);
+        TR();
+        process(rb, 3);
+        TR();
+    }
+
+    if (MODE == MODE_STATS) {
+        if (row_ok) {
+            const size_t slot = (size_t)(unit * PARTS_PER_UNIT + half) * args.M + row;
+            args.part_max[slot] = st.m;
+            args.part_sum[slot] = st.l;
+            args.part_dot[slot] = st.t;
+            if (st.have_pos) args.pos[row] = st.pos_raw * s_nat;
+        }
+    }
+}
+
+// all bulk stores of this epilogue warp complete (writes performed) - before the CTA exits or a grid barrier
+__device__ __forceinline__ void epilogue_drain(const Cta& c) {
+    if (c.lane == 0) ptx::tma_store_wait<0>();
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------- kernels
+// One unit per CTA pair: grid = (2 * m_pairs, units), cluster (2, 1, 1).
 template <int MODE, int F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const KArgs args) {
-    gemm_body<MODE, F16>(&tmA, &tmB, &tmC, args, blockIdx.x >> 1, blockIdx.y);   // cluster (2, 1, 1): pair = two m blocks
+    constexpr int STAGES = stages_of(MODE);
+    const Cta c = cta_setup<STAGES, MODE != MODE_STATS>();
+    const int m_blk = int(blockIdx.x);          // = 2 * m_pair + cta_rank
+    const int unit = int(blockIdx.y);
+    const int t0 = unit * args.tiles_per_unit;
+    const int t1 = min(args.n_tiles, t0 + args.tiles_per_unit);
+    Pipe p;
+    if (c.warp == 0) {
+        if (c.lane == 0) {
+            ptx::prefetch_tmap(&tmA);
+            ptx::prefetch_tmap(&tmB);
+            produce_unit<STAGES>(c, p, &tmA, &tmB, args, m_blk, t0, t1);
+        }
+    } else if (c.warp == 1) {
+        if (c.lane == 0 && c.leader) mma_unit<STAGES>(c, p, args, t1 - t0);
+    } else {
+        epilogue_unit<MODE>(c, p, &tmC, args, m_blk, unit, t0, t1);
+        if (MODE != MODE_STATS) epilogue_drain(c);
+    }
+    cta_teardown(c);
 }
 
 // The two gradient GEMMs of one panel in ONE launch, so that their tiles together fill the SMs:
@@ -565,13 +590,31 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                  const __grid_constant__ CUtensorMap tmC0, const KArgs args0,
                  const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                  const __grid_constant__ CUtensorMap tmC1, const KArgs args1, const int jobs0) {
+    constexpr int STAGES = stages_of(MODE_OUT);
+    const Cta c = cta_setup<STAGES, true>();
     const int j = blockIdx.x >> 1;   // cluster (2, 1, 1): one job per CTA pair = a 256 x 256 output tile
-    if (j < jobs0) {
-        gemm_body<MODE_OUT, F16>(&tmA0, &tmB0, &tmC0, args0, j / args0.n_tiles, j % args0.n_tiles);
+    const bool first = j < jobs0;
+    const KArgs& args = first ? args0 : args1;
+    const CUtensorMap* tmA = first ? &tmA0 : &tmA1;
+    const CUtensorMap* tmB = first ? &tmB0 : &tmB1;
+    const CUtensorMap* tmC = first ? &tmC0 : &tmC1;
+    const int k = first ? j : j - jobs0;
+    const int m_blk = 2 * (k / args.n_tiles) + int(c.cta_rank);
+    const int t0 = k % args.n_tiles;
+    Pipe p;
+    if (c.warp == 0) {
+        if (c.lane == 0) {
+            ptx::prefetch_tmap(tmA);
+            ptx::prefetch_tmap(tmB);
+            produce_unit<STAGES>(c, p, tmA, tmB, args, m_blk, t0, t0 + 1);
+        }
+    } else if (c.warp == 1) {
+        if (c.lane == 0 && c.leader) mma_unit<STAGES>(c, p, args, 1);
     } else {
-        const int k = j - jobs0;
-        gemm_body<MODE_OUT, F16>(&tmA1, &tmB1, &tmC1, args1, k / args1.n_tiles, k % args1.n_tiles);
+        epilogue_unit<MODE_OUT>(c, p, tmC, args, m_blk, t0, t0, t0 + 1);
+        epilogue_drain(c);
     }
+    cta_teardown(c);
 }
 
 }  // namespace clipk
