@@ -357,6 +357,10 @@ constexpr int MAX_SPLIT = 32;
 constexpr int MAX_PARTS = MAX_SPLIT * PARTS_PER_UNIT;
 // Budget of the fp16 G panel.  48 MB keeps it L2 resident (126 MB L2) next to the operands; CLIPK_PANEL_MB overrides
 // it for experiments (a larger panel spills to HBM but amortises the per-launch fill/drain over longer kernels).
+static int use_persistent() {
+    static int v = [] { const char* e = getenv("CLIPK_PERSISTENT"); return e ? atoi(e) : 0; }();
+    return v;
+}
 static int dbg_flags() {
     static int v = [] { const char* e = getenv("CLIPK_DBG"); return e ? atoi(e) : 0; }();
     return v;
@@ -632,7 +636,7 @@ size_t clipk_bwd_workspace_bytes(int rows, int cols, int d, int g_dtype) {
     choose_panel(rows, cols, d, planes_of(g_dtype), 148, &rp, &cp);
     // the SM count only nudges the split; size for the L2 budget so any device fits
     (void)rp; (void)cp;
-    return size_t(panel_bytes()) + size_t(2) * 1024 * 1024 + (size_t(rows) + size_t(cols)) * sizeof(float) + 4096;
+    return size_t(2) * size_t(panel_bytes()) + size_t(4) * 1024 * 1024 + (size_t(rows) + size_t(cols)) * sizeof(float) + 4096;
 }
 
 int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
@@ -664,6 +668,93 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
     const int ldg = gplanes * ncp;
     if ((unsigned long long)round_up(rp_max, 2 * BM) * ldg * 2 > workspace_bytes) return fail(CLIPK_EWORKSPACE, "panel does not fit the workspace");
     __half* G = static_cast<__half*>(workspace);
+    if (use_persistent()) {
+        // ---- one persistent launch over all panels (see bwd_persistent_kernel)
+        const int gbuf_rows = int(round_up(rp_max, 2 * BM));
+        const size_t g2_bytes = size_t(round_up((long long)2 * gbuf_rows * ldg * 2, 256));
+        float* avec2 = reinterpret_cast<float*>(static_cast<char*>(workspace) + g2_bytes);
+        // the reference vectors were placed after ONE panel above; the persistent path needs two, so redo the carve
+        float* bvec2 = avec2 + round_up(rows, 64);
+        float* gref2 = bvec2 + round_up(cols, 64);
+        int* mm2 = reinterpret_cast<int*>(gref2 + 4);
+        unsigned int* barrier = reinterpret_cast<unsigned int*>(mm2 + 2);
+        if (g2_bytes + (round_up(rows, 64) + round_up(cols, 64) + 16) * sizeof(float) > workspace_bytes)
+            return fail(CLIPK_EWORKSPACE, "workspace too small for two panels and the reference vectors");
+        CK_CUDA(cudaMemsetAsync(mm2, 0x7f, sizeof(int), st));
+        CK_CUDA(cudaMemsetAsync(mm2 + 1, 0x80, sizeof(int), st));
+        CK_CUDA(cudaMemsetAsync(barrier, 0, sizeof(unsigned int), st));
+        if (dbg_flags() & 256) CK_CUDA(cudaMemsetAsync(G, 0, g2_bytes, st));
+        {
+            const int n = rows + cols;
+            int blocks = cdiv(n, 256);
+            if (blocks > 4 * di.sms) blocks = 4 * di.sms;
+            lse_minmax_kernel<<<blocks, 256, 0, st>>>(lse_row, rows, lse_col, cols, mm2);
+            const int m = rows > cols ? rows : cols;
+            grad_prep_kernel<<<cdiv(m, 256), 256, 0, st>>>(lse_row, rows, lse_col, cols, mm2, avec2, bvec2, gref2);
+            CK_CUDA(cudaGetLastError());
+        }
+        CUtensorMap tmX, tmY, tmGst, tmGk, tmGmn, tmYg, tmXg, tmDX, tmDY;
+        if ((rc = tmap_kmajor(&tmX, X, rows, kext, ldx, BM))) return rc;
+        if ((rc = tmap_kmajor(&tmY, Y, cols, kext, ldy, BN / 2))) return rc;
+        if ((rc = tmap_g_store(&tmGst, G, 2 * gbuf_rows, ldg, ldg))) return rc;
+        if ((rc = tmap_kmajor(&tmGk, G, 2 * gbuf_rows, ldg, ldg, BM))) return rc;
+        if ((rc = tmap_mnmajor(&tmGmn, G, ldg, 2 * gbuf_rows, ldg))) return rc;
+        if ((rc = tmap_mnmajor(&tmYg, Yg, gext, cols, ldyg))) return rc;
+        if ((rc = tmap_mnmajor(&tmXg, Xg, gext, rows, ldxg))) return rc;
+        // a skipped gradient still needs a valid descriptor: point it at the other output
+        float* dx_ptr = dX_acc ? dX_acc : dY_acc;
+        float* dy_ptr = dY_acc ? dY_acc : dX_acc;
+        if ((rc = tmap_out_f32(&tmDX, dx_ptr, dX_acc ? rows : cols, d, d))) return rc;
+        if ((rc = tmap_out_f32(&tmDY, dy_ptr, dY_acc ? cols : rows, d, d))) return rc;
+
+        if (getenv("CLIPK_VERBOSE")) fprintf(stderr, "[clipk] persistent bwd rows=%d cols=%d rp=%lld cp=%lld ldg=%d gbuf_rows=%d\n", rows, cols, rp_max, cp_max, ldg, gbuf_rows);
+        BwdP P{};
+        P.rows = rows; P.cols = cols; P.d = d; P.diag_offset = diag_offset;
+        P.rp = int(rp_max); P.cp = int(cp_max);
+        P.n_rp = cdiv(rows, rp_max); P.n_cp = cdiv(cols, cp_max);
+        P.nt = cdiv(d, BN); P.gbuf_rows = gbuf_rows;
+        P.want_dx = dX_acc != nullptr; P.want_dy = dY_acc != nullptr;
+        P.s_f16 = is_f16(dtype) ? 1 : 0;
+        {
+            KArgs t{};
+            set_segments(t, planes, d, dpad, dpad);
+            P.s_nseg = t.nseg; P.s_kb_per_seg = t.kb_per_seg;
+            for (int i = 0; i < 3; ++i) { P.s_a_off[i] = t.a_off[i]; P.s_b_off[i] = t.b_off[i]; }
+            set_segments(t, gplanes, 64, ncp, dpad);
+            P.g_nseg = t.nseg;
+            for (int i = 0; i < 3; ++i) { P.g_a_off[i] = t.a_off[i]; P.g_b_off[i] = t.b_off[i]; }
+        }
+        P.barrier = barrier; P.xg_inv = xg_inv_scale; P.yg_inv = yg_inv_scale;
+        KArgs& b = P.base;
+        b.scale = logit_scale; b.xs = x_inv_scale; b.ys = y_inv_scale;
+        b.lse_row = lse_row; b.lse_col = lse_col; b.avec = avec2; b.bvec = bvec2; b.gref = gref2;
+        b.alpha = alpha; b.beta = beta;
+        b.g_planes = gplanes; b.g_plane_stride = ncp; b.ldg = ldg;
+        b.oscale0 = logit_scale; b.oscale1 = gscale; b.oconst = 1.f / 16384.f;
+        b.tiles_per_unit = 1; b.dbg = dbg_flags(); b.trace = g_trace;
+
+        auto kfn = bwd_persistent_kernel;
+        constexpr int smem = smem_bytes_of(MODE_GRAD);
+        static std::once_flag once;
+        static cudaError_t attr_err = cudaSuccess;
+        static int max_clusters = 0;
+        std::call_once(once, [&] {
+            attr_err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (attr_err != cudaSuccess) return;
+            cudaLaunchConfig_t q{};
+            q.gridDim = dim3(2 * di.sms); q.blockDim = dim3(NUM_THREADS); q.dynamicSmemBytes = smem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            q.attrs = at; q.numAttrs = 1;
+            attr_err = cudaOccupancyMaxActiveClusters(&max_clusters, kfn, &q);
+        });
+        if (attr_err != cudaSuccess) return fail(int(attr_err), "persistent backward setup: %s", cudaGetErrorString(attr_err));
+        int n_clusters = max_clusters < di.sms / 2 ? max_clusters : di.sms / 2;
+        if (n_clusters < 1) return fail(CLIPK_EUNSUPPORTED, "no CTA pair of the persistent backward fits this device");
+        return launch_clustered(kfn, dim3(2 * n_clusters), dim3(2, 1, 1), smem, st, tmX, tmY, tmGst, tmGk, tmGmn, tmYg,
+                                tmXg, tmDX, tmDY, P);
+    }
     // after the panel: avec[rows], bvec[cols], gref[2], minmax[2]
     const size_t g_bytes = size_t(round_up(round_up(rp_max, 2 * BM) * ldg * 2, 256));
     float* avec = reinterpret_cast<float*>(static_cast<char*>(workspace) + g_bytes);

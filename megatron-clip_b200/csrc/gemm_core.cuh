@@ -617,4 +617,179 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     cta_teardown(c);
 }
 
+// ---------------------------------------------------------------------------------------------------- persistent backward
+// ONE launch for the whole backward.  The [rows x cols] block is cut into panels (rp x cp, both multiples of 256); the
+// fp16 G of a panel lives in one of two L2-sized buffers.  Phase p = { gradient-GEMM tiles of panel p-1 (read G[(p-1)&1]),
+// recompute tiles of panel p (write G[p&1]) }: everything inside a phase is independent, so a CTA pair runs its share
+// back to back through the same smem / TMEM pipelines - the epilogue of one tile overlaps the MMAs of the next across
+// job types - and phases are separated by one grid barrier (an atomic counter; all CTAs are co-resident).  Launch
+// latency, prologue, pipeline fill and the non-overlapped last epilogue are paid once per phase instead of once per
+// kernel per panel.
+struct BwdP {
+    int rows, cols, d;
+    long long diag_offset;
+    int rp, cp, n_rp, n_cp;      // panel extents and counts
+    int nt;                      // 256-wide tiles of d (output tiles of the gradient GEMMs per 256 rows)
+    int gbuf_rows;               // rows of one G buffer (multiple of 256); buffer b starts at row b * gbuf_rows
+    int want_dx, want_dy;
+    int s_f16;                   // operand format of the recompute GEMM
+    int s_nseg, s_kb_per_seg, s_a_off[3], s_b_off[3];       // K segments of the recompute GEMM
+    int g_nseg, g_a_off[3], g_b_off[3];                     // plane pairs of the gradient GEMMs (K extent varies per panel)
+    unsigned int* barrier;       // grid barrier counter, zero at launch
+    const float* xg_inv;         // dequant scalars of the fp16 feature copies used by the gradient GEMMs (null = 1)
+    const float* yg_inv;
+    KArgs base;                  // everything that does not depend on the panel
+};
+
+__device__ __forceinline__ void grid_barrier_arrive(unsigned int* counter) {
+    asm volatile("fence.proxy.async;" ::: "memory");   // bulk (async proxy) stores of this CTA before the generic release
+    __threadfence();
+    atomicAdd(counter, 1u);
+}
+__device__ __forceinline__ void grid_barrier_wait(unsigned int* counter, unsigned int target) {
+    unsigned int v;
+    do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < target);
+    asm volatile("fence.proxy.async;" ::: "memory");   // following TMA loads see what the other CTAs stored
+}
+
+// geometry of panel q
+struct Panel { int r0, c0, nr, nc, ri, ci; };
+__device__ __forceinline__ Panel panel_of(const BwdP& P, int q) {
+    Panel x;
+    x.ri = q / P.n_cp;
+    x.ci = q - x.ri * P.n_cp;
+    x.r0 = x.ri * P.rp;
+    x.c0 = x.ci * P.cp;
+    x.nr = min(P.rp, P.rows - x.r0);
+    x.nc = min(P.cp, P.cols - x.c0);
+    return x;
+}
+__device__ __forceinline__ int cdiv_d(int a, int b) { return (a + b - 1) / b; }
+
+// recompute (GRAD) unit of panel q: row pair m_pair, column tiles [t0, t1)
+__device__ __forceinline__ void make_grad_args(const BwdP& P, int q, KArgs& a) {
+    const Panel x = panel_of(P, q);
+    a = P.base;
+    a.M = x.nr; a.N = x.nc;
+    a.nseg = P.s_nseg; a.kb_per_seg = P.s_kb_per_seg; a.num_kb = P.s_nseg * P.s_kb_per_seg;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { a.a_off[i] = P.s_a_off[i]; a.b_off[i] = P.s_b_off[i]; }
+    a.a_mn = 0; a.b_mn = 0; a.f16 = P.s_f16;
+    a.a_outer_off = x.r0; a.b_outer_off = x.c0;
+    a.n_tiles = cdiv_d(x.nc, BN);
+    a.diag_offset = P.diag_offset + x.r0 - x.c0;
+    a.lse_row = P.base.lse_row + x.r0; a.lse_col = P.base.lse_col + x.c0;
+    a.avec = P.base.avec + x.r0; a.bvec = P.base.bvec + x.c0;
+    a.c_col_off = 0; a.c_row_off = (q & 1) * P.gbuf_rows;
+}
+// gradient-GEMM job of panel q: which = 0: dX[r0.., :] (+)= G * Yg[c0.., :]; which = 1: dY[c0.., :] (+)= G^T * Xg[r0.., :]
+__device__ __forceinline__ void make_out_args(const BwdP& P, int q, int which, KArgs& a) {
+    const Panel x = panel_of(P, q);
+    a = P.base;
+    const int kext = which == 0 ? x.nc : x.nr;
+    a.M = which == 0 ? x.nr : x.nc;
+    a.N = P.d;
+    a.nseg = P.g_nseg; a.kb_per_seg = cdiv_d(kext, BK); a.num_kb = a.nseg * a.kb_per_seg;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { a.a_off[i] = P.g_a_off[i]; a.b_off[i] = P.g_b_off[i]; }
+    a.a_mn = which; a.b_mn = 1; a.f16 = 1;
+    // A = G: K-major rows of the buffer (job 0) or its transpose, K = buffer rows (job 1); B = features, K = their rows
+    a.a_outer_off = (q & 1) * P.gbuf_rows;
+    a.b_outer_off = which == 0 ? x.c0 : x.r0;
+    a.n_tiles = P.nt;
+    a.c_col_off = 0; a.c_row_off = which == 0 ? x.r0 : x.c0;
+    a.accumulate = which == 0 ? (x.ci > 0) : (x.ri > 0);
+    a.oscale2 = which == 0 ? P.yg_inv : P.xg_inv;   // dequant of the feature operand: Yg for dX, Xg for dY
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+                      const __grid_constant__ CUtensorMap tmGst, const __grid_constant__ CUtensorMap tmGk,
+                      const __grid_constant__ CUtensorMap tmGmn, const __grid_constant__ CUtensorMap tmYg,
+                      const __grid_constant__ CUtensorMap tmXg, const __grid_constant__ CUtensorMap tmDX,
+                      const __grid_constant__ CUtensorMap tmDY, const BwdP P) {
+    constexpr int STAGES = stages_of(MODE_GRAD);
+    static_assert(stages_of(MODE_GRAD) == stages_of(MODE_OUT), "GRAD and OUT share one shared-memory layout");
+    const Cta c = cta_setup<STAGES, true>();
+    const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int n_panels = P.n_rp * P.n_cp;
+    Pipe p;
+    if (c.warp == 0 && c.lane == 0) {
+        ptx::prefetch_tmap(&tmX); ptx::prefetch_tmap(&tmY); ptx::prefetch_tmap(&tmGk); ptx::prefetch_tmap(&tmGmn);
+        ptx::prefetch_tmap(&tmYg); ptx::prefetch_tmap(&tmXg);
+    }
+    const bool active = (c.warp == 0 && c.lane == 0) || (c.warp == 1 && c.lane == 0 && c.leader) || c.warp >= 2;
+
+    for (int ph = 0; ph <= n_panels; ++ph) {
+        if (active) {
+            // producer: loads of this phase may only start once every CTA finished the previous phase
+            if (c.warp == 0 && P.base.trace && blockIdx.x == 0 && ph < 20) P.base.trace[3 * ph] = clock64();
+            if (c.warp == 0 && ph > 0) grid_barrier_wait(P.barrier, gridDim.x * (unsigned int)ph);
+            if (c.warp == 0 && P.base.trace && blockIdx.x == 0 && ph < 20) P.base.trace[3 * ph + 1] = clock64();
+            // ---- gradient-GEMM tiles of panel ph-1 (long K: first, so that they start early)
+            if (ph >= 1 && !(P.base.dbg & 64)) {
+                const int q = ph - 1;
+                const Panel x = panel_of(P, q);
+                const int jobs0 = P.want_dx ? cdiv_d(x.nr, 2 * BM) * P.nt : 0;
+                const int jobs1 = P.want_dy ? cdiv_d(x.nc, 2 * BM) * P.nt : 0;
+                for (int j = cluster; j < jobs0 + jobs1; j += n_clusters) {
+                    const int which = j < jobs0 ? 0 : 1;
+                    const int k = which == 0 ? j : j - jobs0;
+                    KArgs a;
+                    make_out_args(P, q, which, a);
+                    const int m_blk = 2 * (k / P.nt) + int(c.cta_rank);
+                    const int t = k % P.nt;
+                    if (c.warp == 0) {
+                        produce_unit<STAGES>(c, p, which == 0 ? &tmGk : &tmGmn, which == 0 ? &tmYg : &tmXg, a, m_blk, t, t + 1);
+                    } else if (c.warp == 1) {
+                        mma_unit<STAGES>(c, p, a, 1);
+                    } else {
+                        epilogue_unit<MODE_OUT>(c, p, which == 0 ? &tmDX : &tmDY, a, m_blk, t, t, t + 1);
+                    }
+                }
+            }
+            // ---- recompute tiles of panel ph: the flat list (row pair, column tile) is cut evenly over the clusters
+            if (ph < n_panels && !(P.base.dbg & 128)) {
+                const int q = ph;
+                const Panel x = panel_of(P, q);
+                const int m_pairs = cdiv_d(x.nr, 2 * BM), n_tiles = cdiv_d(x.nc, BN);
+                const long long total = (long long)m_pairs * n_tiles;
+                int f0 = int(total * cluster / n_clusters), f1 = int(total * (cluster + 1) / n_clusters);
+                KArgs a;
+                make_grad_args(P, q, a);
+                while (f0 < f1) {
+                    const int m_pair = f0 / n_tiles;
+                    const int t0 = f0 - m_pair * n_tiles;
+                    const int t1 = min(n_tiles, t0 + (f1 - f0));
+                    const int m_blk = 2 * m_pair + int(c.cta_rank);
+                    if (c.warp == 0) {
+                        produce_unit<STAGES>(c, p, &tmX, &tmY, a, m_blk, t0, t1);
+                    } else if (c.warp == 1) {
+                        mma_unit<STAGES>(c, p, a, t1 - t0);
+                    } else {
+                        epilogue_unit<MODE_GRAD>(c, p, &tmGst, a, m_blk, 1 + f0, t0, t1);
+                    }
+                    f0 += t1 - t0;
+                }
+            }
+        }
+        // ---- end of phase: this CTA's stores are complete and visible, then it arrives at the grid barrier
+        if (c.warp >= 2 && ph < n_panels) {
+            epilogue_drain(c);
+            ptx::named_bar_sync(1, NUM_EPI_WARPS * 32);
+            if (c.warp == 2 && c.lane == 0) {
+                if (P.base.trace && blockIdx.x == 0 && ph < 20) P.base.trace[3 * ph + 2] = clock64();
+                // a CTA without work in this phase must not run ahead: its arrival for phase ph may only be counted
+                // once every CTA arrived for phase ph-1, or the counter would reach a target early
+                if (ph > 0) grid_barrier_wait(P.barrier, gridDim.x * (unsigned int)ph);
+                grid_barrier_arrive(P.barrier);
+            }
+        }
+    }
+    if (c.warp >= 2) epilogue_drain(c);
+    cta_teardown(c);
+}
+
 }  // namespace clipk

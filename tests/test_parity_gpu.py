@@ -44,7 +44,8 @@ def check(x, t, s, dtype, grad_output=1.0, tol=None):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
-@pytest.mark.parametrize("b,d", [(16, 1024), (100, 512), (257, 640), (256, 512), (1000, 128), (2048, 256)])
+@pytest.mark.parametrize("b,d", [(16, 1024), (100, 512), (257, 640), (256, 512), (1000, 128), (2048, 256), (520, 768),
+                                 (768, 1024), (300, 1280)])
 def test_single_gpu_unit_inputs(b, d, dtype):
     x, t = make_inputs(b, d, seed=b + d)
     check(x, t, 1 / 0.07, dtype)
@@ -162,3 +163,27 @@ def test_large_properties_c2_shape():
     expect = (torch.softmax(rows, dim=1) * rows).sum(dim=1)
     assert torch.allclose(stats[2] / stats[1], expect, rtol=0, atol=2e-3)
     assert torch.allclose(p, pos, rtol=0, atol=2e-3)
+
+
+def test_persistent_backward_path_matches():
+    """The opt-in single-launch backward (CLIPK_PERSISTENT=1) gives the same gradients as the default per-panel path."""
+    import os, subprocess, sys, json
+    code = (
+        "import sys, json, torch, numpy as np\n"
+        "sys.path.insert(0, 'megatron-clip_b200'); sys.path.insert(0, '.')\n"
+        "from clipk import ClipLoss\n"
+        "from oracle import cliploss_oracle as O\n"
+        "x, t = O.synthetic_features(4700, 128, seed=21)\n"
+        "I = torch.from_numpy(x).cuda().bfloat16().requires_grad_(True)\n"
+        "T = torch.from_numpy(t).cuda().bfloat16().requires_grad_(True)\n"
+        "S = torch.tensor(1 / 0.07, device='cuda', requires_grad=True)\n"
+        "ClipLoss()(I, T, S).backward(); torch.cuda.synchronize()\n"
+        "ref = O.clip_loss_single(I.detach().float().cpu().numpy(), T.detach().float().cpu().numpy(), 1 / 0.07)\n"
+        "r = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))\n"
+        "print(json.dumps([r(I.grad.float().cpu().numpy(), ref.d_image), r(T.grad.float().cpu().numpy(), ref.d_text)]))\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CLIPK_PERSISTENT="1", CLIPK_PANEL_MB="8")     # small panels: several phases and barriers
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    e = json.loads(out.stdout.strip().splitlines()[-1])
+    assert e[0] <= 2e-3 and e[1] <= 2e-3, e
