@@ -114,8 +114,8 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
 /* dst[i] = (dtype) src[i]; the fp32 gradient accumulators are returned in the dtype of the inputs. */
 int clipk_cast(const float* src, void* dst, long long n, int dtype, void* stream);
 
-/* Experiments only: a device buffer of 3 * 3 * 64 int64 that CTA (0,0) of every following launch fills with clock64
- * stamps of its producer / MMA / epilogue roles; NULL switches it off (the default). */
+/* Experiments only: a device buffer of 3 * 512 int64 that CTA 0 of every following launch fills with clock64
+ * stamps of its producer / MMA / epilogue roles ([role][stamp]); NULL switches it off (the default). */
 int clipk_debug_set_trace(long long* device_buffer);
 
 /* ---- test hook for the tensor-core mainloop: D[M, N] (fp32, ldd) (+)= A * B^T with 16-bit operands

@@ -3,7 +3,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <mutex>
+#include <vector>
 
 #include "../../include/clipk.h"
 #include "gemm_core.cuh"
@@ -460,8 +462,25 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     KArgs aa = a;
     aa.dbg = dbg_flags();
     aa.trace = g_trace;
+    aa.trace_on = 1;
     aa.f16 = F16;
     return launch_clustered(kfn, dim3(2 * m_pairs, units), dim3(2, 1, 1), smem, st, ta, tb, tc, aa);
+}
+
+template <int F16>
+static int launch_ares(const CUtensorMap& ta, const CUtensorMap& tb, const KArgs& a, int units, int m_pairs, cudaStream_t st) {
+    auto kfn = stats_ares_kernel<F16>;
+    constexpr int smem = smem_bytes_ares();
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
+    if (attr_err != cudaSuccess) return fail(int(attr_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+    KArgs aa = a;
+    aa.dbg = dbg_flags();
+    aa.trace = g_trace;
+    aa.trace_on = 1;
+    aa.f16 = F16;
+    return launch_clustered(kfn, dim3(2 * m_pairs, units), dim3(2, 1, 1), smem, st, ta, tb, aa);
 }
 
 // jobs0 / jobs1 are counted in PAIRS (256 x 256 output tiles)
@@ -477,6 +496,7 @@ static int launch_pair(const CUtensorMap& ta0, const CUtensorMap& tb0, const CUt
     KArgs b0 = a0, b1 = a1;
     b0.dbg = b1.dbg = dbg_flags();
     b0.trace = g_trace;
+    b0.trace_on = 1;
     b0.f16 = b1.f16 = 1;
     return launch_clustered(kfn, dim3(2 * (jobs0 + jobs1)), dim3(2, 1, 1), smem, st, ta0, tb0, tc0, b0, ta1, tb1, tc1, b1,
                             jobs0);
@@ -501,6 +521,107 @@ static void set_segments(KArgs& a, int planes, int k_extent, long long a_plane, 
             a.a_off[i] = int(kPairA[i] * a_plane);
             a.b_off[i] = int(kPairB[i] * b_plane);
         }
+}
+
+// ---- work plan of the dataflow backward (see bwd_dataflow_kernel) ----------------------------------------------
+// Per panel q the virtual cluster v = (cluster + shift[q]) % n runs the gradient-GEMM jobs v, v + n, ... and the
+// recompute tiles [start[q][v], start[q][v + 1]).  Work is counted in K blocks (64 wide): a recompute tile costs its
+// K blocks plus `tile_extra` (its epilogue is the expensive one), a job costs its K blocks; every cluster gets the
+// same total, so clusters with a long job (or any job) recompute fewer tiles.  The shift rotates the roles from
+// panel to panel.  The plan depends only on the shapes: it is built once per shape on the host and kept on the device.
+struct BwdPlanDev {
+    int* shift;
+    int* start;
+    unsigned char* pos;
+};
+struct BwdPlanKey {
+    int dev, rows, cols, d, rp, cp, nt, want_dx, want_dy, s_kb, g_nseg, n_clusters, tile_extra;
+    bool operator==(const BwdPlanKey& o) const { return memcmp(this, &o, sizeof(*this)) == 0; }
+};
+struct BwdPlanEntry {
+    BwdPlanKey key;
+    BwdPlanDev dev;
+    void* block;
+};
+static std::mutex g_plan_mu;
+static BwdPlanEntry g_plans[64];
+static int g_nplans = 0;
+
+static int tile_extra_cost() {
+    static int v = [] { const char* e = getenv("CLIPK_TILE_EXTRA"); return e ? atoi(e) : 3; }();
+    return v;
+}
+
+static int get_bwd_plan(const BwdP& P, int n_clusters, const BwdPlanDev** out) {
+    BwdPlanKey key;
+    memset(&key, 0, sizeof(key));
+    CK_CUDA(cudaGetDevice(&key.dev));
+    key.rows = P.rows; key.cols = P.cols; key.d = P.d; key.rp = P.rp; key.cp = P.cp; key.nt = P.nt;
+    key.want_dx = P.want_dx; key.want_dy = P.want_dy; key.s_kb = P.s_nseg * P.s_kb_per_seg; key.g_nseg = P.g_nseg;
+    key.n_clusters = n_clusters; key.tile_extra = tile_extra_cost();
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    for (int i = 0; i < g_nplans; ++i)
+        if (g_plans[i].key == key) { *out = &g_plans[i].dev; return CLIPK_OK; }
+    if (g_nplans == 64) {
+        // shapes keep changing: drop every cached plan (no kernel may still be reading them)
+        CK_CUDA(cudaDeviceSynchronize());
+        for (int i = 0; i < g_nplans; ++i) cudaFree(g_plans[i].block);
+        g_nplans = 0;
+    }
+    const int n = n_clusters, n_panels = P.n_rp * P.n_cp, max_tiles = P.max_tiles;
+    const size_t n_int = size_t(n_panels) + size_t(n_panels) * 2 * n;
+    const size_t bytes = n_int * 4 + size_t(n_panels) * max_tiles;
+    std::vector<unsigned char> host(bytes, 0);
+    int* shift = reinterpret_cast<int*>(host.data());
+    int* start = shift + n_panels;            // [q][cluster] = {first tile, end tile}
+    unsigned char* pos = host.data() + n_int * 4;
+    // A cluster's sequence is G(0) O(0) G(1) O(1) ...: the tiles of panel q are needed by every job right after they
+    // are produced, so what has to take equally long on every cluster is O(q - 1) followed by G(q).
+    std::vector<double> prev_work(n, 0.0), work(n);
+    for (int q = 0; q < n_panels; ++q) {
+        const int ri = q / P.n_cp, ci = q - ri * P.n_cp;
+        const int nr = std::min(P.rp, P.rows - ri * P.rp), nc = std::min(P.cp, P.cols - ci * P.cp);
+        const int m_pairs = cdiv(nr, 2 * BM), n_tiles = cdiv(nc, BN), tiles = m_pairs * n_tiles;
+        const int jobs0 = P.want_dx ? m_pairs * P.nt : 0, jobs1 = P.want_dy ? cdiv(nc, 2 * BM) * P.nt : 0;
+        const double k0 = double(P.g_nseg) * cdiv(nc, BK), k1 = double(P.g_nseg) * cdiv(nr, BK);
+        const double tile_cost = double(key.s_kb + key.tile_extra);
+        shift[q] = int((long long)q * 17 % n);
+        double total = tiles * tile_cost;
+        for (int c = 0; c < n; ++c) total += prev_work[c];
+        const double target = total / n;
+        double cap_total = 0;
+        for (int c = 0; c < n; ++c) cap_total += std::max(0.0, target - prev_work[c]);
+        int* st = start + size_t(q) * 2 * n;
+        double prefix = 0;
+        int f = 0;
+        for (int i = 0; i < n; ++i) {
+            const int c = (i + shift[q]) % n;     // rotate which clusters get the first rows of the panel
+            prefix += std::max(0.0, target - prev_work[c]);
+            int f1 = cap_total > 0 ? int(tiles * (prefix / cap_total) + 0.5) : int((long long)tiles * (i + 1) / n);
+            if (i == n - 1) f1 = tiles;
+            if (f1 < f) f1 = f;
+            st[2 * c] = f; st[2 * c + 1] = f1;
+            for (int t = f; t < f1; ++t) pos[size_t(q) * max_tiles + t] = (unsigned char)std::min(t - f, 255);
+            f = f1;
+        }
+        for (int c = 0; c < n; ++c) {
+            const int v = (c + shift[q]) % n;
+            work[c] = 0;
+            for (int j = v; j < jobs0 + jobs1; j += n) work[c] += (j < jobs0) ? k0 : k1;
+        }
+        prev_work = work;
+    }
+    void* block = nullptr;
+    CK_CUDA(cudaMalloc(&block, bytes));
+    cudaError_t e = cudaMemcpy(block, host.data(), bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(block); return fail(int(e), "plan upload: %s", cudaGetErrorString(e)); }
+    BwdPlanEntry& en = g_plans[g_nplans++];
+    en.key = key; en.block = block;
+    en.dev.shift = static_cast<int*>(block);
+    en.dev.start = en.dev.shift + n_panels;
+    en.dev.pos = static_cast<unsigned char*>(block) + n_int * 4;
+    *out = &en.dev;
+    return CLIPK_OK;
 }
 
 static int check_common(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype) {
@@ -599,8 +720,16 @@ int clipk_fwd_stats(const void* X, const void* Y, int rows, int cols, int d, lon
     a.part_dot = a.part_sum + size_t(MAX_PARTS) * rows;
     a.pos = pos_logit;
     if (!pos_logit) a.diag_offset = -(1LL << 40);   // no row has a positive inside [0, cols)
-    if (is_f16(dtype)) rc = launch_gemm<MODE_STATS, 1>(ta, tb, ta, a, units, m_pairs, st);
-    else rc = launch_gemm<MODE_STATS, 0>(ta, tb, ta, a, units, m_pairs, st);
+    const bool ares = a.nseg == 1 && a.num_kb <= ARES_KB && !(dbg_flags() & 512);
+    if (ares) {
+        // rows of X resident in shared memory, only Y streams (see stats_ares_kernel)
+        if ((rc = tmap_kmajor(&tb, Y, cols, kext, ldy, BN / 2))) return rc;
+        rc = is_f16(dtype) ? launch_ares<1>(ta, tb, a, units, m_pairs, st) : launch_ares<0>(ta, tb, a, units, m_pairs, st);
+    } else if (is_f16(dtype)) {
+        rc = launch_gemm<MODE_STATS, 1>(ta, tb, ta, a, units, m_pairs, st);
+    } else {
+        rc = launch_gemm<MODE_STATS, 0>(ta, tb, ta, a, units, m_pairs, st);
+    }
     if (rc) return rc;
     merge_row_parts_kernel<<<cdiv(rows, 256), 256, 0, st>>>(a.part_max, a.part_sum, a.part_dot, units * PARTS_PER_UNIT,
                                                             rows, row_max, row_sum, row_dot);
@@ -636,7 +765,9 @@ size_t clipk_bwd_workspace_bytes(int rows, int cols, int d, int g_dtype) {
     choose_panel(rows, cols, d, planes_of(g_dtype), 148, &rp, &cp);
     // the SM count only nudges the split; size for the L2 budget so any device fits
     (void)rp; (void)cp;
-    return size_t(2) * size_t(panel_bytes()) + size_t(4) * 1024 * 1024 + (size_t(rows) + size_t(cols)) * sizeof(float) + 4096;
+    // two G panels, slack for their padding, the reference vectors, and the per-tile / per-panel counters of the dataflow schedule
+    const size_t counters = (size_t(cdiv(rows, 2 * BM)) + 64) * (size_t(cdiv(cols, BN)) + 64) * 2 * sizeof(int);
+    return size_t(2) * size_t(panel_bytes()) + size_t(4) * 1024 * 1024 + (size_t(rows) + size_t(cols)) * sizeof(float) + counters + 4096;
 }
 
 int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
@@ -669,21 +800,68 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
     if ((unsigned long long)round_up(rp_max, 2 * BM) * ldg * 2 > workspace_bytes) return fail(CLIPK_EWORKSPACE, "panel does not fit the workspace");
     __half* G = static_cast<__half*>(workspace);
     if (use_persistent()) {
-        // ---- one persistent launch over all panels (see bwd_persistent_kernel)
+        // ---- one dataflow launch over all panels (see bwd_dataflow_kernel)
+        auto kfn = bwd_dataflow_kernel;
+        constexpr int smem = smem_bytes_of(MODE_GRAD);
+        static std::once_flag once;
+        static cudaError_t attr_err = cudaSuccess;
+        static int max_clusters = 0;
+        std::call_once(once, [&] {
+            attr_err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (attr_err != cudaSuccess) return;
+            cudaLaunchConfig_t q{};
+            q.gridDim = dim3(2 * di.sms); q.blockDim = dim3(NUM_THREADS); q.dynamicSmemBytes = smem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            q.attrs = at; q.numAttrs = 1;
+            attr_err = cudaOccupancyMaxActiveClusters(&max_clusters, kfn, &q);
+        });
+        if (attr_err != cudaSuccess) return fail(int(attr_err), "dataflow backward setup: %s", cudaGetErrorString(attr_err));
+        const int n_clusters = max_clusters < di.sms / 2 ? max_clusters : di.sms / 2;
+        if (n_clusters < 1) return fail(CLIPK_EUNSUPPORTED, "no CTA pair of the dataflow backward fits this device");
+
+        BwdP P{};
+        P.rows = rows; P.cols = cols; P.d = d; P.diag_offset = diag_offset;
+        P.rp = int(rp_max); P.cp = int(cp_max);
+        P.n_rp = cdiv(rows, rp_max); P.n_cp = cdiv(cols, cp_max);
+        P.nt = cdiv(d, BN);
+        P.want_dx = dX_acc != nullptr; P.want_dy = dY_acc != nullptr;
+        P.s_f16 = is_f16(dtype) ? 1 : 0;
+        {
+            KArgs t{};
+            set_segments(t, planes, d, dpad, dpad);
+            P.s_nseg = t.nseg; P.s_kb_per_seg = t.kb_per_seg;
+            for (int i = 0; i < 3; ++i) { P.s_a_off[i] = t.a_off[i]; P.s_b_off[i] = t.b_off[i]; }
+            set_segments(t, gplanes, 64, ncp, dpad);
+            P.g_nseg = t.nseg;
+            for (int i = 0; i < 3; ++i) { P.g_a_off[i] = t.a_off[i]; P.g_b_off[i] = t.b_off[i]; }
+        }
+        const int n_panels = P.n_rp * P.n_cp;
+        P.max_tiles = cdiv(P.rp, 2 * BM) * cdiv(P.cp, BN);
+        const BwdPlanDev* plan = nullptr;
+        if ((rc = get_bwd_plan(P, n_clusters, &plan))) return rc;
+        P.plan_shift = plan->shift; P.plan_start = plan->start; P.plan_pos = plan->pos;
+
+        // workspace: two G buffers | avec | bvec | gref[4] | minmax[2] | out_done[n_panels] | tile_flags[n_panels][max_tiles]
         const int gbuf_rows = int(round_up(rp_max, 2 * BM));
+        P.gbuf_rows = gbuf_rows;
         const size_t g2_bytes = size_t(round_up((long long)2 * gbuf_rows * ldg * 2, 256));
         float* avec2 = reinterpret_cast<float*>(static_cast<char*>(workspace) + g2_bytes);
-        // the reference vectors were placed after ONE panel above; the persistent path needs two, so redo the carve
         float* bvec2 = avec2 + round_up(rows, 64);
         float* gref2 = bvec2 + round_up(cols, 64);
         int* mm2 = reinterpret_cast<int*>(gref2 + 4);
-        unsigned int* barrier = reinterpret_cast<unsigned int*>(mm2 + 2);
-        if (g2_bytes + (round_up(rows, 64) + round_up(cols, 64) + 16) * sizeof(float) > workspace_bytes)
-            return fail(CLIPK_EWORKSPACE, "workspace too small for two panels and the reference vectors");
+        unsigned int* out_done = reinterpret_cast<unsigned int*>(mm2 + 4);
+        unsigned int* tile_flags = out_done + round_up(n_panels, 4);
+        const size_t ctl_words = size_t(round_up(n_panels, 4)) + size_t(n_panels) * P.max_tiles;
+        const size_t need = g2_bytes + (round_up(rows, 64) + round_up(cols, 64) + 8) * sizeof(float) + ctl_words * 4;
+        if (need > workspace_bytes) return fail(CLIPK_EWORKSPACE, "workspace too small for two G panels, the reference vectors and the flags (%zu > %zu)", need, workspace_bytes);
+        P.out_done = out_done; P.tile_flags = tile_flags;
         CK_CUDA(cudaMemsetAsync(mm2, 0x7f, sizeof(int), st));
         CK_CUDA(cudaMemsetAsync(mm2 + 1, 0x80, sizeof(int), st));
-        CK_CUDA(cudaMemsetAsync(barrier, 0, sizeof(unsigned int), st));
-        if (dbg_flags() & 256) CK_CUDA(cudaMemsetAsync(G, 0, g2_bytes, st));
+        CK_CUDA(cudaMemsetAsync(out_done, 0, ctl_words * 4, st));
+        if (dX_acc) CK_CUDA(cudaMemsetAsync(dX_acc, 0, size_t(rows) * d * sizeof(float), st));
+        if (dY_acc) CK_CUDA(cudaMemsetAsync(dY_acc, 0, size_t(cols) * d * sizeof(float), st));
         {
             const int n = rows + cols;
             int blocks = cdiv(n, 256);
@@ -707,24 +885,8 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
         if ((rc = tmap_out_f32(&tmDX, dx_ptr, dX_acc ? rows : cols, d, d))) return rc;
         if ((rc = tmap_out_f32(&tmDY, dy_ptr, dY_acc ? cols : rows, d, d))) return rc;
 
-        if (getenv("CLIPK_VERBOSE")) fprintf(stderr, "[clipk] persistent bwd rows=%d cols=%d rp=%lld cp=%lld ldg=%d gbuf_rows=%d\n", rows, cols, rp_max, cp_max, ldg, gbuf_rows);
-        BwdP P{};
-        P.rows = rows; P.cols = cols; P.d = d; P.diag_offset = diag_offset;
-        P.rp = int(rp_max); P.cp = int(cp_max);
-        P.n_rp = cdiv(rows, rp_max); P.n_cp = cdiv(cols, cp_max);
-        P.nt = cdiv(d, BN); P.gbuf_rows = gbuf_rows;
-        P.want_dx = dX_acc != nullptr; P.want_dy = dY_acc != nullptr;
-        P.s_f16 = is_f16(dtype) ? 1 : 0;
-        {
-            KArgs t{};
-            set_segments(t, planes, d, dpad, dpad);
-            P.s_nseg = t.nseg; P.s_kb_per_seg = t.kb_per_seg;
-            for (int i = 0; i < 3; ++i) { P.s_a_off[i] = t.a_off[i]; P.s_b_off[i] = t.b_off[i]; }
-            set_segments(t, gplanes, 64, ncp, dpad);
-            P.g_nseg = t.nseg;
-            for (int i = 0; i < 3; ++i) { P.g_a_off[i] = t.a_off[i]; P.g_b_off[i] = t.b_off[i]; }
-        }
-        P.barrier = barrier; P.xg_inv = xg_inv_scale; P.yg_inv = yg_inv_scale;
+        if (getenv("CLIPK_VERBOSE")) fprintf(stderr, "[clipk] dataflow bwd rows=%d cols=%d rp=%lld cp=%lld ldg=%d gbuf_rows=%d panels=%d clusters=%d\n", rows, cols, rp_max, cp_max, ldg, gbuf_rows, n_panels, n_clusters);
+        P.xg_inv = xg_inv_scale; P.yg_inv = yg_inv_scale;
         KArgs& b = P.base;
         b.scale = logit_scale; b.xs = x_inv_scale; b.ys = y_inv_scale;
         b.lse_row = lse_row; b.lse_col = lse_col; b.avec = avec2; b.bvec = bvec2; b.gref = gref2;
@@ -732,26 +894,6 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
         b.g_planes = gplanes; b.g_plane_stride = ncp; b.ldg = ldg;
         b.oscale0 = logit_scale; b.oscale1 = gscale; b.oconst = 1.f / 16384.f;
         b.tiles_per_unit = 1; b.dbg = dbg_flags(); b.trace = g_trace;
-
-        auto kfn = bwd_persistent_kernel;
-        constexpr int smem = smem_bytes_of(MODE_GRAD);
-        static std::once_flag once;
-        static cudaError_t attr_err = cudaSuccess;
-        static int max_clusters = 0;
-        std::call_once(once, [&] {
-            attr_err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (attr_err != cudaSuccess) return;
-            cudaLaunchConfig_t q{};
-            q.gridDim = dim3(2 * di.sms); q.blockDim = dim3(NUM_THREADS); q.dynamicSmemBytes = smem;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            q.attrs = at; q.numAttrs = 1;
-            attr_err = cudaOccupancyMaxActiveClusters(&max_clusters, kfn, &q);
-        });
-        if (attr_err != cudaSuccess) return fail(int(attr_err), "persistent backward setup: %s", cudaGetErrorString(attr_err));
-        int n_clusters = max_clusters < di.sms / 2 ? max_clusters : di.sms / 2;
-        if (n_clusters < 1) return fail(CLIPK_EUNSUPPORTED, "no CTA pair of the persistent backward fits this device");
         return launch_clustered(kfn, dim3(2 * n_clusters), dim3(2, 1, 1), smem, st, tmX, tmY, tmGst, tmGk, tmGmn, tmYg,
                                 tmXg, tmDX, tmDY, P);
     }

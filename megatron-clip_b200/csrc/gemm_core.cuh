@@ -52,6 +52,7 @@ __host__ __device__ constexpr int smem_bytes_of(int mode) {
     return 1024 /*align slack*/ + stages_of(mode) * STAGE_BYTES + 256 + MISC_BYTES + (mode == 0 ? 0 : STG_TOTAL);
 }
 constexpr int PARTS_PER_UNIT = 2;            // each 128-column half of a tile keeps its own row statistics
+constexpr int TRACE_N = 512;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 
@@ -99,7 +100,8 @@ struct KArgs {
     const float* oscale1;
     const float* oscale2;
     float oconst;
-    long long* trace;          // optional clock64 trace of CTA (0,0): [3 modes][3 roles][64] (nullptr in production)
+    long long* trace;          // optional clock64 trace (nullptr in production): [3 roles][TRACE_N] stamps of one CTA
+    int trace_on;              // set by the kernel for the CTA that records
     int dbg;                   // CLIPK_DBG experiment bits: 1 = skip epilogue math+staging, 2 = skip TMA stores, 4 = skip tile barriers
 };
 
@@ -162,77 +164,63 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// One 32-column chunk of the G tile: 64 B of fp16 per row go to pieces [piece0, piece0 + 4) of the row's 128 B line in
-// `stg` (plane hi) and, for two-plane G, of `stg_lo`.
-//   PATH 0 (interior tile and the LSE spread of this backward <= 100 in log2 units): ONE ex2 per element.  With the
-//          reference c = min over all row and column LSEs,  E = 2^(v - c),  g = E * (A_i + B_j),
-//          A_i = ga * 2^(c - Lr_i) (a register), B_j = gb * 2^(c - Lc_j) (a vector prepared once per backward, read
-//          through L1 as warp-uniform float4 loads).  v <= min(Lr_i, Lc_j) and the spread bound keep every factor in
-//          fp32 range; what underflows is below 2^-126 of a probability.  MUFU runs 16 ex2/clk/SM, so two per element
-//          would cost exactly the tile's MMA time - this path halves it and needs no per-tile staging or barrier.
-//   PATH 1 (tile with positives, columns beyond N, or a wide LSE spread): two ex2 per element, exact masking.
-template <int PATH>
-__device__ __forceinline__ void grad_chunk(const uint32_t (&r)[32], float sc, float Lr, float ga, float gb, float cref,
-                                           float Ai, const float* __restrict__ cvec, int col0, int ncols, long long dcol,
-                                           uint32_t stg, uint32_t stg_lo, int lane, int piece0, int g_planes) {
-    uint32_t packed[16];
-    const int didx = (PATH == 1 && dcol >= col0 && dcol < (long long)col0 + 32) ? int(dcol - col0) : -1;
-    // cvec = bvec + col0 (PATH 0, pre-scaled by gb below) or lse_col + col0 (PATH 1, natural log)
-    auto g_of = [&](int kk, float cv) -> float {
-        const float sraw = __uint_as_float(r[kk]);
-        if (PATH == 0) {
-            return ptx::ex2(fmaf(sraw, sc, -cref)) * fmaf(gb, cv, Ai);
-        } else {
-            float pr = ptx::ex2(fmaf(sraw, sc, -Lr));
-            float pc = ptx::ex2(fmaf(sraw, sc, -cv * LOG2E));
-            if (kk == didx) { pr -= 1.f; pc -= 1.f; }
-            if (col0 + kk >= ncols) { pr = 0.f; pc = 0.f; }
-            return ga * pr + gb * pc;
-        }
-    };
-    auto cv_at = [&](int kk) -> float {
-        if (PATH == 0) return __ldg(cvec + kk);
-        return (col0 + kk < ncols) ? __ldg(cvec + kk) : CUDART_INF_F;
-    };
-    if (PATH == 0) {
-        // per half chunk: loads and 16 ex2 first (MUFU latency paid once per batch, not per element), then scale + pack
+// 16 columns of the G tile as fp32 values g[16] (still to be packed).
+//   FAST (interior tile and the LSE spread of this backward <= 100 in log2 units): ONE ex2 per element.  With the
+//        reference c = min over all row and column LSEs,  E = 2^(v - c),  g = E * (A_i + B_j),
+//        A_i = ga * 2^(c - Lr_i) (a register), B_j = gb * 2^(c - Lc_j) (a vector prepared once per backward, read
+//        through L1 as warp-uniform float4 loads).  v <= min(Lr_i, Lc_j) and the spread bound keep every factor in
+//        fp32 range; what underflows is below 2^-126 of a probability.  MUFU runs 16 ex2/clk/SM, so two per element
+//        would cost exactly the tile's MMA time - this path halves it and needs no per-tile staging or barrier.
+//   exact (tile with positives, columns beyond N, or a wide LSE spread): two ex2 per element, exact masking.
+__device__ __forceinline__ void grad16_fast(const uint32_t (&r)[16], float sc, float cref, float Ai, float gb,
+                                            const float* __restrict__ bv, float (&g)[16]) {
+    float4 l4[4];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            float4 l4[4];
+    for (int j = 0; j < 4; ++j) l4[j] = __ldg(reinterpret_cast<const float4*>(bv) + j);
+    float e[16];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) l4[j] = __ldg(reinterpret_cast<const float4*>(cvec) + 4 * h + j);
-            float e[16];
+    for (int k = 0; k < 16; ++k) e[k] = ptx::ex2(fmaf(__uint_as_float(r[k]), sc, -cref));
 #pragma unroll
-            for (int k = 0; k < 16; ++k) e[k] = ptx::ex2(fmaf(__uint_as_float(r[16 * h + k]), sc, -cref));
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                packed[8 * h + 2 * j] = ptx::pack_f16x2(e[4 * j] * fmaf(gb, l4[j].x, Ai), e[4 * j + 1] * fmaf(gb, l4[j].y, Ai));
-                packed[8 * h + 2 * j + 1] = ptx::pack_f16x2(e[4 * j + 2] * fmaf(gb, l4[j].z, Ai), e[4 * j + 3] * fmaf(gb, l4[j].w, Ai));
-            }
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < 32; k += 4) {
-            packed[k >> 1] = ptx::pack_f16x2(g_of(k, cv_at(k)), g_of(k + 1, cv_at(k + 1)));
-            packed[(k >> 1) + 1] = ptx::pack_f16x2(g_of(k + 2, cv_at(k + 2)), g_of(k + 3, cv_at(k + 3)));
-        }
+    for (int j = 0; j < 4; ++j) {
+        g[4 * j] = e[4 * j] * fmaf(gb, l4[j].x, Ai);
+        g[4 * j + 1] = e[4 * j + 1] * fmaf(gb, l4[j].y, Ai);
+        g[4 * j + 2] = e[4 * j + 2] * fmaf(gb, l4[j].z, Ai);
+        g[4 * j + 3] = e[4 * j + 3] * fmaf(gb, l4[j].w, Ai);
     }
+}
+__device__ __forceinline__ void grad16_exact(const uint32_t (&r)[16], float sc, float Lr, float ga, float gb,
+                                             const float* __restrict__ lse_col, int col0, int ncols, long long dcol,
+                                             float (&g)[16]) {
+    const int didx = (dcol >= col0 && dcol < (long long)col0 + 16) ? int(dcol - col0) : -1;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-        st_shared_v4(stg_addr(stg, lane, piece0 + j), packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-    if (g_planes == 2) {
-        // residual plane: g = hi + lo, each piece exactly representable in fp16 (22 bits together).  g is recomputed
-        // from the accumulator so the one-plane path carries no extra registers.
+    for (int k = 0; k < 16; ++k) {
+        const bool inside = col0 + k < ncols;
+        const float lc = inside ? __ldg(lse_col + k) * LOG2E : CUDART_INF_F;
+        const float v = __uint_as_float(r[k]) * sc;
+        float pr = ptx::ex2(v - Lr), pc = ptx::ex2(v - lc);
+        if (k == didx) { pr -= 1.f; pc -= 1.f; }
+        g[k] = inside ? ga * pr + gb * pc : 0.f;
+    }
+}
+// g[16] -> fp16, into 16-byte pieces [piece0, piece0 + 2) of this row's 128 B line of the staging buffer(s)
+template <bool TWO_PLANES>
+__device__ __forceinline__ void grad16_store(const float (&g)[16], uint32_t stg, uint32_t stg_lo, int lane, int piece0) {
+    uint32_t pk[8];
 #pragma unroll
-        for (int k = 0; k < 32; k += 2) {
-            const uint32_t prev = packed[k >> 1];
-            const float lo0 = g_of(k, cv_at(k)) - __half2float(__ushort_as_half((unsigned short)(prev & 0xffffu)));
-            const float lo1 = g_of(k + 1, cv_at(k + 1)) - __half2float(__ushort_as_half((unsigned short)(prev >> 16)));
-            packed[k >> 1] = ptx::pack_f16x2(lo0, lo1);
+    for (int k = 0; k < 8; ++k) pk[k] = ptx::pack_f16x2(g[2 * k], g[2 * k + 1]);
+    st_shared_v4(stg_addr(stg, lane, piece0), pk[0], pk[1], pk[2], pk[3]);
+    st_shared_v4(stg_addr(stg, lane, piece0 + 1), pk[4], pk[5], pk[6], pk[7]);
+    if (TWO_PLANES) {
+        // residual plane: g = hi + lo, each piece exactly representable in fp16 (22 bits together)
+        uint32_t lo[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float h0 = __half2float(__ushort_as_half((unsigned short)(pk[k] & 0xffffu)));
+            const float h1 = __half2float(__ushort_as_half((unsigned short)(pk[k] >> 16)));
+            lo[k] = ptx::pack_f16x2(g[2 * k] - h0, g[2 * k + 1] - h1);
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            st_shared_v4(stg_addr(stg_lo, lane, piece0 + j), packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        st_shared_v4(stg_addr(stg_lo, lane, piece0), lo[0], lo[1], lo[2], lo[3]);
+        st_shared_v4(stg_addr(stg_lo, lane, piece0 + 1), lo[4], lo[5], lo[6], lo[7]);
     }
 }
 
@@ -241,7 +229,7 @@ __device__ __forceinline__ void grad_chunk(const uint32_t (&r)[32], float sc, fl
 // stage, staging-buffer use) across calls, so the same code serves the one-unit-per-CTA kernels and the persistent
 // backward kernel that walks many units per CTA.
 struct Cta {
-    uint32_t sA, sB, sStg, bar_full, bar_empty, bar_tfull, bar_tempty, tmem_base;
+    uint32_t sA, sB, sStg, bar_full, bar_empty, bar_tfull, bar_tempty, bar_afull, tmem_base;
     uint32_t cta_rank;
     bool leader;
     int warp, lane;
@@ -251,9 +239,20 @@ struct Pipe {
     uint32_t ph = 0;    // its phase
     int it = 0;         // tiles processed so far (MMA / epilogue): accumulator stage = it & 1
     int stg_use = 0;    // TMA stores issued so far by this epilogue warp
+    int tr = 0;         // clock64 stamps recorded so far by this role (experiments)
+    unsigned int* pend = nullptr;   // dataflow backward: completion counter of the G tile whose stores may still be in flight
 };
 
-template <int STAGES, bool HAS_STG>
+// experiments: stamp number p.tr of `role` (0 producer, 1 MMA, 2 first epilogue warp)
+__device__ __forceinline__ void trace_stamp(const KArgs& args, Pipe& p, int role) {
+    // trace_on: 1 = CTA (0, 0) of the grid records (set by the host), 2 = this CTA records (set by the kernel)
+    if (args.trace && (args.trace_on == 2 || (args.trace_on == 1 && blockIdx.x == 0 && blockIdx.y == 0)) && p.tr < TRACE_N)
+        args.trace[role * TRACE_N + p.tr++] = clock64();
+}
+
+// Shared memory: A region (A_BYTES) | NB B stages | epilogue staging | barriers.  The streaming kernels use one A slot
+// per stage (A_BYTES = STAGES * A_STAGE_BYTES, NB = STAGES); the A-resident forward keeps all K blocks of its rows.
+template <int STAGES, bool HAS_STG, int A_BYTES = STAGES * A_STAGE_BYTES>
 __device__ __forceinline__ Cta cta_setup() {
     Cta c;
     c.cta_rank = ptx::cluster_ctarank();   // 0 = leader (issues the pair's MMAs), 1 = peer
@@ -267,16 +266,17 @@ __device__ __forceinline__ Cta cta_setup() {
     // layout (1024-byte aligned up to the barriers): A stages | B stages | epilogue staging | barriers
     constexpr uint32_t kStg = HAS_STG ? uint32_t(STG_TOTAL) : 0u;
     c.sA = base;
-    c.sB = c.sA + STAGES * A_STAGE_BYTES;
+    c.sB = c.sA + A_BYTES;
     c.sStg = c.sB + STAGES * B_STAGE_BYTES;
     const uint32_t sBar = c.sStg + kStg;
     c.bar_full = sBar;
     c.bar_empty = sBar + STAGES * 8;
     c.bar_tfull = sBar + 2 * STAGES * 8;
     c.bar_tempty = c.bar_tfull + 16;
-    const uint32_t sTmemPtr = c.bar_tempty + 16;
+    c.bar_afull = c.bar_tempty + 16;
+    const uint32_t sTmemPtr = c.bar_afull + 8;
     volatile uint32_t* tmem_ptr_gen =
-        reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * STAGE_BYTES + kStg + (2 * STAGES + 4) * 8);
+        reinterpret_cast<volatile uint32_t*>(base_ptr + A_BYTES + STAGES * B_STAGE_BYTES + kStg + (2 * STAGES + 5) * 8);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -287,6 +287,7 @@ __device__ __forceinline__ Cta cta_setup() {
             ptx::mbar_init(c.bar_tfull + 8 * a, 1);
             ptx::mbar_init(c.bar_tempty + 8 * a, 2 * NUM_EPI_WARPS);   // epilogue warps of both CTAs (leader's copy is used)
         }
+        ptx::mbar_init(c.bar_afull, 1);
         ptx::fence_barrier_init();
     }
     if (c.warp == 1) {
@@ -315,39 +316,87 @@ __device__ __forceinline__ void cta_teardown(const Cta& c) {
 }
 
 // ------------------------------------------------------------------ TMA producer (one lane of warp 0, both CTAs)
+// loads of K block `kb` of segment `seg` for output tile (m_blk, t) into the next ring stage
+template <int STAGES>
+__device__ __forceinline__ void load_kblock(const Cta& c, Pipe& p, const CUtensorMap* tmA, const CUtensorMap* tmB,
+                                            const KArgs& args, int m_blk, int t, int seg, int kb) {
+    const int kw = kb * BK;
+    const int ao = args.a_off[seg], bo = args.b_off[seg];
+    ptx::mbar_wait(c.bar_empty + 8 * p.s, p.ph ^ 1);
+    // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of the pair
+    const uint32_t full = c.bar_full + 8 * p.s;
+    if (c.leader) ptx::mbar_arrive_expect_tx(full, 2 * STAGE_BYTES);
+    const uint32_t a_dst = c.sA + p.s * A_STAGE_BYTES;
+    const uint32_t b_dst = c.sB + p.s * B_STAGE_BYTES;
+    const int bn0 = t * BN + int(c.cta_rank) * (BN / 2);   // this CTA's half of the B tile
+    if (args.a_mn) {
+#pragma unroll
+        for (int i = 0; i < BM / 64; ++i)
+            ptx::tma_load_2d_pair(a_dst + i * 8192, tmA, ao + m_blk * BM + i * 64, args.a_outer_off + kw, full);
+    } else {
+        ptx::tma_load_2d_pair(a_dst, tmA, ao + kw, args.a_outer_off + m_blk * BM, full);
+    }
+    if (args.b_mn) {
+#pragma unroll
+        for (int i = 0; i < BN / 128; ++i)
+            ptx::tma_load_2d_pair(b_dst + i * 8192, tmB, bo + bn0 + i * 64, args.b_outer_off + kw, full);
+    } else {
+        ptx::tma_load_2d_pair(b_dst, tmB, bo + kw, args.b_outer_off + bn0, full);
+    }
+    if (++p.s == STAGES) { p.s = 0; p.ph ^= 1; }
+}
+
 template <int STAGES>
 __device__ __forceinline__ void produce_unit(const Cta& c, Pipe& p, const CUtensorMap* tmA, const CUtensorMap* tmB,
                                              const KArgs& args, int m_blk, int t0, int t1) {
-    const int a_mn = args.a_mn, b_mn = args.b_mn;
     for (int t = t0; t < t1; ++t) {
+        trace_stamp(args, p, 0);
         for (int kb = 0; kb < args.num_kb; ++kb) {
             const int seg = kb / args.kb_per_seg;
-            const int kw = (kb - seg * args.kb_per_seg) * BK;
-            const int ao = args.a_off[seg], bo = args.b_off[seg];
-            ptx::mbar_wait(c.bar_empty + 8 * p.s, p.ph ^ 1);
-            // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of the pair
-            const uint32_t full = c.bar_full + 8 * p.s;
-            if (c.leader) ptx::mbar_arrive_expect_tx(full, 2 * STAGE_BYTES);
-            const uint32_t a_dst = c.sA + p.s * A_STAGE_BYTES;
-            const uint32_t b_dst = c.sB + p.s * B_STAGE_BYTES;
-            const int bn0 = t * BN + int(c.cta_rank) * (BN / 2);   // this CTA's half of the B tile
-            if (a_mn) {
-#pragma unroll
-                for (int i = 0; i < BM / 64; ++i)
-                    ptx::tma_load_2d_pair(a_dst + i * 8192, tmA, ao + m_blk * BM + i * 64, args.a_outer_off + kw, full);
-            } else {
-                ptx::tma_load_2d_pair(a_dst, tmA, ao + kw, args.a_outer_off + m_blk * BM, full);
+            load_kblock<STAGES>(c, p, tmA, tmB, args, m_blk, t, seg, kb - seg * args.kb_per_seg);
+        }
+        trace_stamp(args, p, 0);
+    }
+}
+
+// spin until a counter written by other CTAs reaches `target`; what they stored before (also through TMA) is then
+// visible to this thread's following TMA loads / stores
+__device__ __forceinline__ void flag_wait(const unsigned int* flag, unsigned int target) {
+    unsigned int v;
+    do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    } while (v < target);
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+// publish: this thread's completed bulk stores (cp.async.bulk.wait_group done) and generic stores, then count
+__device__ __forceinline__ void flag_signal(unsigned int* flag) {
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __threadfence();
+    atomicAdd(flag, 1u);
+}
+
+// Gradient-GEMM job of the dataflow backward: the K extent is made of `nkt` 256-wide pieces, piece i being one G tile
+// whose completion counter is flags[i * fstride].  Pieces are loaded in the order they were produced (`pos` = rank
+// of the tile in its producer's list), so the job starts on the oldest tiles while the newest are still being written.
+template <int STAGES>
+__device__ __forceinline__ void produce_job(const Cta& c, Pipe& p, const CUtensorMap* tmA, const CUtensorMap* tmB,
+                                            const KArgs& args, int m_blk, int t, int nkt, const unsigned int* flags,
+                                            const unsigned char* pos, int fstride, unsigned int target) {
+    constexpr int KB_PER_TILE = BN / BK;
+    trace_stamp(args, p, 0);
+    for (int seg = 0; seg < args.nseg; ++seg) {
+        int done = 0;
+        for (int pass = 0; done < nkt; ++pass) {
+            for (int i = 0; i < nkt; ++i) {
+                if (int(pos[i * fstride]) != pass) continue;
+                if (seg == 0) flag_wait(flags + i * fstride, target);
+                const int kb1 = min(args.kb_per_seg, (i + 1) * KB_PER_TILE);
+                for (int kb = i * KB_PER_TILE; kb < kb1; ++kb) load_kblock<STAGES>(c, p, tmA, tmB, args, m_blk, t, seg, kb);
+                ++done;
             }
-            if (b_mn) {
-#pragma unroll
-                for (int i = 0; i < BN / 128; ++i)
-                    ptx::tma_load_2d_pair(b_dst + i * 8192, tmB, bo + bn0 + i * 64, args.b_outer_off + kw, full);
-            } else {
-                ptx::tma_load_2d_pair(b_dst, tmB, bo + kw, args.b_outer_off + bn0, full);
-            }
-            if (++p.s == STAGES) { p.s = 0; p.ph ^= 1; }
         }
     }
+    trace_stamp(args, p, 0);
 }
 
 // ------------------------------------------------------------------ MMA issuer (one lane of warp 1, leader CTA only)
@@ -364,12 +413,15 @@ __device__ __forceinline__ void mma_unit(const Cta& c, Pipe& p, const KArgs& arg
     for (int t = 0; t < ntiles; ++t, ++p.it) {
         const int a = p.it & 1;
         const uint32_t aph = (p.it >> 1) & 1;
+        trace_stamp(args, p, 1);
         ptx::mbar_wait(c.bar_tempty + 8 * a, aph ^ 1);
         ptx::tc_fence_after();
+        trace_stamp(args, p, 1);
         const uint32_t d_tmem = c.tmem_base + a * BN;
         for (int kb = 0; kb < args.num_kb; ++kb) {
             ptx::mbar_wait(c.bar_full + 8 * p.s, p.ph);
             ptx::tc_fence_after();
+            if (kb == 0) trace_stamp(args, p, 1);
             const uint32_t a_src = c.sA + p.s * A_STAGE_BYTES;
             const uint32_t b_src = c.sB + p.s * B_STAGE_BYTES;
 #pragma unroll
@@ -381,13 +433,16 @@ __device__ __forceinline__ void mma_unit(const Cta& c, Pipe& p, const KArgs& arg
             if (++p.s == STAGES) { p.s = 0; p.ph ^= 1; }
         }
         ptx::mma_commit_pair(c.bar_tfull + 8 * a);
+        trace_stamp(args, p, 1);
     }
 }
 
 // ------------------------------------------------------------------ epilogue (warps 2..9, both CTAs)
+// STATS and OUT tiles (the recompute tiles have their own epilogue below)
 template <int MODE>
 __device__ __forceinline__ void epilogue_unit(const Cta& c, Pipe& p, const CUtensorMap* tmC, const KArgs& args, int m_blk,
-                                              int unit, int t0, int t1) {
+                                              int unit, int t0, int t1, unsigned int* done_ctr = nullptr) {
+    static_assert(MODE == MODE_STATS || MODE == MODE_OUT, "GRAD tiles go through grad_epilogue_unit");
     const int warp = c.warp, lane = c.lane;
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;             // which 128-column half of the tile this warp drains
@@ -397,7 +452,7 @@ __device__ __forceinline__ void epilogue_unit(const Cta& c, Pipe& p, const CUten
 
     // acc holds the dot product of the STORED operands; dequant = xs*ys turns it into the true x.y
     float sc = 0.f, s_nat = 0.f, oscale = 1.f;
-    if (MODE != MODE_OUT) {
+    if (MODE == MODE_STATS) {
         float dequant = 1.f;
         if (args.xs) dequant *= __ldg(args.xs);
         if (args.ys) dequant *= __ldg(args.ys);
@@ -410,93 +465,42 @@ __device__ __forceinline__ void epilogue_unit(const Cta& c, Pipe& p, const CUten
         if (args.oscale2) oscale *= __ldg(args.oscale2);
     }
     StatsState st{-CUDART_INF_F, 0.f, 0.f, 0.f, false};
-    float Lr = CUDART_INF_F, ga = 0.f, gb = 0.f, cref = 0.f, Ai = 0.f;   // rows beyond M: every probability is 0
-    bool fast = false;
-    if (MODE == MODE_GRAD) {
-        if (row_ok) Lr = __ldg(args.lse_row + row) * LOG2E;
-        // G is stored as 2^14 * (alpha*(P_row-Id) + beta*(P_col-Id)) in fp16: |.| <= 2^15 and entries down to
-        // ~4e-9 keep the full 11-bit mantissa; logit_scale * gscale * 2^-14 is applied by the gradient GEMMs.
-        ga = 16384.f * args.alpha;
-        gb = 16384.f * args.beta;
-        cref = __ldg(args.gref);
-        fast = __ldg(args.gref + 1) != 0.f;
-        Ai = row_ok ? ga * __ldg(args.avec + row) : 0.f;
-    }
-    const bool tracing = (args.trace != nullptr) && m_blk == 0 && unit == 0 && warp == 2 && lane == 0;
-    int tr_n = 0;
     auto TR = [&]() {
-        if (tracing && tr_n < 64) args.trace[MODE * 192 + 128 + tr_n++] = clock64();
+        if (warp == 2 && lane == 0) trace_stamp(args, p, 2);
     };
-
     const uint32_t stg0 = c.sStg + (warp - 2) * 2 * STG_BYTES;   // this warp's two staging buffers
-    // before (re)writing a staging buffer: at most one older bulk store may still be reading shared memory
-    auto stg_acquire = [&]() -> uint32_t {
-        if (lane == 0) ptx::tma_store_wait_read<1>();
-        __syncwarp();
-        return stg0 + (p.stg_use & 1) * STG_BYTES;
-    };
+    const int dbg = args.dbg, accumulate = args.accumulate, ncols = args.N;
+    const int c_col_off = args.c_col_off, c_row_off = args.c_row_off;
 
     for (int t = t0; t < t1; ++t, ++p.it) {
         const int a = p.it & 1;
         const uint32_t aph = (p.it >> 1) & 1;
         const int n0 = t * BN;
         TR();
-        if (MODE == MODE_GRAD && lane < 4) {
-            // pull the B_j / LSE values of this warp's half of the NEXT tile (512 B) into L1 ahead of their use
-            const int cn = (t + 1) * BN + half * (BN / 2) + lane * 32;
-            if (t + 1 < t1 && cn + 32 <= args.N) {
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(args.bvec + cn));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(args.lse_col + cn));
-            }
-            if (t == t0) {
-                const int c0 = t * BN + half * (BN / 2) + lane * 32;
-                if (c0 + 32 <= args.N) asm volatile("prefetch.global.L1 [%0];" ::"l"(args.bvec + c0));
-            }
-        }
         ptx::mbar_wait(c.bar_tfull + 8 * a, aph);
         ptx::tc_fence_after();
         TR();
+        // dataflow backward: every MMA of this job has completed, so nothing reads its G panel any more
+        if (MODE == MODE_OUT && done_ctr && warp == 2 && lane == 0 && c.leader) atomicAdd(done_ctr, 1u);
         const uint32_t taddr = c.tmem_base + a * BN + half * (BN / 2) + (uint32_t(q * 32) << 16);
         // edge tile: contains positives (diagonal entries) of this CTA's rows, or columns beyond N
         const long long d_lo = args.diag_offset + (long long)m_blk * BM;
-        const bool edge = (MODE != MODE_OUT) &&
-                          (((d_lo + BM - 1 >= n0) && (d_lo < (long long)n0 + BN)) || (n0 + BN > args.N));
+        const bool edge = (MODE == MODE_STATS) &&
+                          (((d_lo + BM - 1 >= n0) && (d_lo < (long long)n0 + BN)) || (n0 + BN > ncols));
         const int colh = n0 + half * (BN / 2);          // first column of this warp's half tile
         const int row0 = m_blk * BM + q * 32;           // first row of this warp
 
         auto process = [&](const uint32_t (&r)[32], int cidx) {
             const int col0 = colh + cidx * 32;
-            if (args.dbg & 1) return;
+            if (dbg & 1) return;
             if (MODE == MODE_STATS) {
-                if (edge) stats_chunk<true>(r, sc, col0, args.N, dcol, st);
-                else stats_chunk<false>(r, sc, col0, args.N, dcol, st);
-            } else if (MODE == MODE_GRAD) {
-                // two chunks (64 columns = 128 B of fp16 per row) share one staging buffer and one TMA store
-                uint32_t stg = stg0 + (p.stg_use & 1) * STG_BYTES;
-                uint32_t stg_lo = stg0 + ((p.stg_use + 1) & 1) * STG_BYTES;
-                if ((cidx & 1) == 0) {
-                    stg = stg_acquire();
-                    if (args.g_planes == 2) {
-                        // the second plane takes the other buffer: nothing of this warp may still be in flight
-                        if (lane == 0) ptx::tma_store_wait_read<0>();
-                        __syncwarp();
-                    }
-                }
-                if (fast && !edge) grad_chunk<0>(r, sc, Lr, ga, gb, cref, Ai, args.bvec + col0, col0, args.N, dcol, stg, stg_lo, lane, (cidx & 1) * 4, args.g_planes);
-                else grad_chunk<1>(r, sc, Lr, ga, gb, cref, Ai, args.lse_col + col0, col0, args.N, dcol, stg, stg_lo, lane, (cidx & 1) * 4, args.g_planes);
-                if (cidx & 1) {
-                    ptx::fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0 && !(args.dbg & 2)) {
-                        ptx::tma_store_2d(tmC, stg, args.c_col_off + col0 - 32, args.c_row_off + row0);
-                        if (args.g_planes == 2)
-                            ptx::tma_store_2d(tmC, stg_lo, args.c_col_off + args.g_plane_stride + col0 - 32, args.c_row_off + row0);
-                        ptx::tma_store_commit();
-                    }
-                    p.stg_use += (args.g_planes == 2) ? 2 : 1;
-                }
+                if (edge) stats_chunk<true>(r, sc, col0, ncols, dcol, st);
+                else stats_chunk<false>(r, sc, col0, ncols, dcol, st);
             } else {  // MODE_OUT: 32 fp32 columns = 128 B per row = one staging buffer and one TMA store / reduce
-                const uint32_t stg = stg_acquire();
+                // before rewriting a staging buffer: at most one older bulk store may still be reading shared memory
+                if (lane == 0) ptx::tma_store_wait_read<1>();
+                __syncwarp();
+                const uint32_t stg = stg0 + (p.stg_use & 1) * STG_BYTES;
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     st_shared_v4(stg_addr(stg, lane, j), __float_as_uint(__uint_as_float(r[4 * j]) * oscale),
@@ -506,10 +510,10 @@ __device__ __forceinline__ void epilogue_unit(const Cta& c, Pipe& p, const CUten
                 ptx::fence_proxy_async_smem();
                 __syncwarp();
                 ++p.stg_use;
-                if (lane == 0 && !(args.dbg & 2)) {
+                if (lane == 0 && !(dbg & 2)) {
                     // the tensor map clips rows and columns beyond the output matrix
-                    if (args.accumulate) ptx::tma_reduce_add_2d(tmC, stg, args.c_col_off + col0, args.c_row_off + row0);
-                    else ptx::tma_store_2d(tmC, stg, args.c_col_off + col0, args.c_row_off + row0);
+                    if (accumulate) ptx::tma_reduce_add_2d(tmC, stg, c_col_off + col0, c_row_off + row0);
+                    else ptx::tma_store_2d(tmC, stg, c_col_off + col0, c_row_off + row0);
                     ptx::tma_store_commit();
                 }
             }
@@ -548,9 +552,137 @@ __device__ __forceinline__ void epilogue_unit(const Cta& c, Pipe& p, const CUten
     }
 }
 
-// all bulk stores of this epilogue warp complete (writes performed) - before the CTA exits or a grid barrier
+// Recompute tiles: S tile -> G tile (fp16, x 2^14) -> swizzled staging -> TMA store into the L2-resident panel.
+// The tile is drained in 16-column pieces (tcgen05.ld x16, double buffered) to keep the live registers well under the
+// 168 a 10-warp CTA allows; four pieces (64 columns = 128 B of fp16 per row) fill one staging buffer = one TMA store.
+template <bool TWO_PLANES>
+__device__ __forceinline__ void grad_epilogue_unit(const Cta& c, Pipe& p, const CUtensorMap* tmC, const KArgs& args,
+                                                   int m_blk, int t0, int t1, unsigned int* tile_flags = nullptr) {
+    const int warp = c.warp, lane = c.lane;
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = m_blk * BM + q * 32 + lane;
+    const bool row_ok = row < args.M;
+    const long long dcol = args.diag_offset + row;
+    float dequant = 1.f;
+    if (args.xs) dequant *= __ldg(args.xs);
+    if (args.ys) dequant *= __ldg(args.ys);
+    const float sc = __ldg(args.scale) * dequant * LOG2E;
+    // G is stored as 2^14 * (alpha*(P_row-Id) + beta*(P_col-Id)) in fp16: |.| <= 2^15 and entries down to
+    // ~4e-9 keep the full 11-bit mantissa; logit_scale * gscale * 2^-14 is applied by the gradient GEMMs.
+    const float ga = 16384.f * args.alpha, gb = 16384.f * args.beta;
+    const float Lr = row_ok ? __ldg(args.lse_row + row) * LOG2E : CUDART_INF_F;   // rows beyond M: every probability is 0
+    const float cref = __ldg(args.gref);
+    const bool fast = __ldg(args.gref + 1) != 0.f;
+    const float Ai = row_ok ? ga * __ldg(args.avec + row) : 0.f;
+    const float* __restrict__ bvec = args.bvec;
+    const float* __restrict__ lse_col = args.lse_col;
+    const int dbg = args.dbg, ncols = args.N, plane_stride = args.g_plane_stride;
+    const int c_col_off = args.c_col_off, c_row_off = args.c_row_off + m_blk * BM + q * 32;
+    const long long d_lo = args.diag_offset + (long long)m_blk * BM;
+    const uint32_t stg0 = c.sStg + (warp - 2) * 2 * STG_BYTES;   // this warp's two staging buffers
+    auto TR = [&]() {
+        if (warp == 2 && lane == 0) trace_stamp(args, p, 2);
+    };
+
+    for (int t = t0; t < t1; ++t, ++p.it) {
+        const int a = p.it & 1;
+        const uint32_t aph = (p.it >> 1) & 1;
+        const int n0 = t * BN;
+        const int colh = n0 + half * (BN / 2);          // first column of this warp's half tile
+        TR();
+        if (lane < 4 && t + 1 < t1) {
+            // pull the B_j / LSE values of this warp's half of the NEXT tile (512 B) into L1 ahead of their use
+            const int cn = colh + BN + lane * 32;
+            if (cn + 32 <= ncols) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(bvec + cn));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(lse_col + cn));
+            }
+        }
+        ptx::mbar_wait(c.bar_tfull + 8 * a, aph);
+        ptx::tc_fence_after();
+        TR();
+        const uint32_t taddr = c.tmem_base + a * BN + half * (BN / 2) + (uint32_t(q * 32) << 16);
+        // edge tile: contains positives (diagonal entries) of this CTA's rows, or columns beyond N
+        const bool exact = !fast || ((d_lo + BM - 1 >= n0) && (d_lo < (long long)n0 + BN)) || (n0 + BN > ncols);
+
+        uint32_t stg = 0, stg_lo = 0;
+        auto piece = [&](const uint32_t (&r)[16], int pi) {
+            if (dbg & 1) return;
+            const int col0 = colh + pi * 16;
+            if ((pi & 3) == 0) {
+                // (re)use of a staging buffer: at most one older bulk store may still be reading shared memory; with
+                // two planes both buffers are written, so nothing of this warp may still be in flight
+                if (lane == 0) {
+                    if (TWO_PLANES) ptx::tma_store_wait_read<0>();
+                    else ptx::tma_store_wait_read<1>();
+                }
+                __syncwarp();
+                stg = stg0 + (p.stg_use & 1) * STG_BYTES;
+                stg_lo = stg0 + ((p.stg_use + 1) & 1) * STG_BYTES;
+            }
+            float g[16];
+            if (exact) grad16_exact(r, sc, Lr, ga, gb, lse_col + col0, col0, ncols, dcol, g);
+            else grad16_fast(r, sc, cref, Ai, gb, bvec + col0, g);
+            grad16_store<TWO_PLANES>(g, stg, stg_lo, lane, (pi & 3) * 2);
+            if ((pi & 3) == 3) {
+                ptx::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0 && !(dbg & 2)) {
+                    ptx::tma_store_2d(tmC, stg, c_col_off + col0 - 48, c_row_off);
+                    if (TWO_PLANES) ptx::tma_store_2d(tmC, stg_lo, c_col_off + plane_stride + col0 - 48, c_row_off);
+                    ptx::tma_store_commit();
+                }
+                p.stg_use += TWO_PLANES ? 2 : 1;
+            }
+        };
+
+        uint32_t ra[16], rb[16];
+        ptx::tmem_ld_32x16(taddr, ra);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int pi = 0; pi < 8; pi += 2) {
+            ptx::tmem_ld_32x16(taddr + (pi + 1) * 16, rb);
+            piece(ra, pi);
+            ptx::tmem_ld_wait();
+            if (pi + 2 < 8) {
+                ptx::tmem_ld_32x16(taddr + (pi + 2) * 16, ra);
+            } else {
+                // the last load has landed: the accumulator stage goes back to the MMA warp
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive_leader(c.bar_tempty + 8 * a);
+                TR();
+            }
+            piece(rb, pi + 1);
+            if (pi + 2 < 8) ptx::tmem_ld_wait();
+        }
+        TR();
+        if (tile_flags && lane == 0) {
+            // the stores of the PREVIOUS tile were committed a whole tile ago: wait for them (the two groups of this
+            // tile may stay in flight) and publish that tile
+            if (p.pend) {
+                if (dbg & 8192) atomicAdd(p.pend, 1u);
+                else { ptx::tma_store_wait<2>(); flag_signal(p.pend); }
+            }
+            p.pend = tile_flags + t;
+        }
+        if (dbg & 2048) TR();
+    }
+}
+
+// all bulk stores of this epilogue warp complete (writes performed) - before the CTA exits
 __device__ __forceinline__ void epilogue_drain(const Cta& c) {
     if (c.lane == 0) ptx::tma_store_wait<0>();
+    __syncwarp();
+}
+// dataflow backward: publish the last G tile this warp wrote
+__device__ __forceinline__ void epilogue_flush_flag(const Cta& c, Pipe& p) {
+    if (c.lane == 0 && p.pend) {
+        ptx::tma_store_wait<0>();
+        flag_signal(p.pend);
+        p.pend = nullptr;
+    }
     __syncwarp();
 }
 
@@ -576,8 +708,89 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     } else if (c.warp == 1) {
         if (c.lane == 0 && c.leader) mma_unit<STAGES>(c, p, args, t1 - t0);
     } else {
-        epilogue_unit<MODE>(c, p, &tmC, args, m_blk, unit, t0, t1);
+        if (MODE == MODE_GRAD) {
+            if (args.g_planes == 2) grad_epilogue_unit<true>(c, p, &tmC, args, m_blk, t0, t1);
+            else grad_epilogue_unit<false>(c, p, &tmC, args, m_blk, t0, t1);
+        } else {
+            epilogue_unit<MODE == MODE_GRAD ? MODE_OUT : MODE>(c, p, &tmC, args, m_blk, unit, t0, t1);
+        }
         if (MODE != MODE_STATS) epilogue_drain(c);
+    }
+    cta_teardown(c);
+}
+
+// ---------------------------------------------------------------------------------------------------- A-resident forward
+// The mainloop of the streaming kernels is bound by L2 -> SM bandwidth, not by the tensor pipe: 148 CTAs x 32 KB per K
+// block against ~6300 B/clk of L2 is ~770 clk for 512 clk of MMA.  A forward unit sweeps MANY column tiles with the same
+// 128 rows of A per CTA, so for K <= ARES_KB * 64 those rows are loaded ONCE and stay in shared memory (128 KB); only the
+// B half-tiles stream (16 KB per K block and CTA, 6 stages), which halves the L2 traffic and leaves the tensor pipe as
+// the limit.
+constexpr int ARES_KB = 8;                       // resident K blocks (K <= 512)
+constexpr int ARES_STAGES = 6;
+__host__ __device__ constexpr int smem_bytes_ares() {
+    return 1024 + ARES_KB * A_STAGE_BYTES + ARES_STAGES * B_STAGE_BYTES + 256 + MISC_BYTES;
+}
+
+template <int F16>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+stats_ares_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KArgs args) {
+    constexpr int STAGES = ARES_STAGES;
+    const Cta c = cta_setup<STAGES, false, ARES_KB * A_STAGE_BYTES>();
+    const int m_blk = int(blockIdx.x);          // = 2 * m_pair + cta_rank
+    const int unit = int(blockIdx.y);
+    const int t0 = unit * args.tiles_per_unit;
+    const int t1 = min(args.n_tiles, t0 + args.tiles_per_unit);
+    const int num_kb = args.num_kb;             // <= ARES_KB, one segment, both operands K-major
+    Pipe p;
+    if (c.warp == 0) {
+        if (c.lane == 0) {
+            ptx::prefetch_tmap(&tmA);
+            ptx::prefetch_tmap(&tmB);
+            // the rows of A, all K blocks, once: both CTAs' loads complete on the leader's barrier
+            if (c.leader) ptx::mbar_arrive_expect_tx(c.bar_afull, 2 * num_kb * A_STAGE_BYTES);
+            for (int kb = 0; kb < num_kb; ++kb)
+                ptx::tma_load_2d_pair(c.sA + kb * A_STAGE_BYTES, &tmA, kb * BK, args.a_outer_off + m_blk * BM, c.bar_afull);
+            for (int t = t0; t < t1; ++t) {
+                const int bn0 = t * BN + int(c.cta_rank) * (BN / 2);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(c.bar_empty + 8 * p.s, p.ph ^ 1);
+                    const uint32_t full = c.bar_full + 8 * p.s;
+                    if (c.leader) ptx::mbar_arrive_expect_tx(full, 2 * B_STAGE_BYTES);
+                    ptx::tma_load_2d_pair(c.sB + p.s * B_STAGE_BYTES, &tmB, kb * BK, args.b_outer_off + bn0, full);
+                    if (++p.s == STAGES) { p.s = 0; p.ph ^= 1; }
+                }
+            }
+        }
+    } else if (c.warp == 1) {
+        if (c.lane == 0 && c.leader) {
+            const uint32_t idesc = ptx::make_idesc_16bit(2 * BM, BN, 0, 0, !F16, !F16);
+            const uint64_t desc_hi = ptx::make_smem_desc_sw128(16, 1024);
+            ptx::mbar_wait(c.bar_afull, 0);
+            ptx::tc_fence_after();
+            for (int t = t0; t < t1; ++t, ++p.it) {
+                const int a = p.it & 1;
+                const uint32_t aph = (p.it >> 1) & 1;
+                ptx::mbar_wait(c.bar_tempty + 8 * a, aph ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = c.tmem_base + a * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(c.bar_full + 8 * p.s, p.ph);
+                    ptx::tc_fence_after();
+                    const uint32_t a_src = c.sA + kb * A_STAGE_BYTES;
+                    const uint32_t b_src = c.sB + p.s * B_STAGE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        ptx::mma_f16_ss_pair(d_tmem, ptx::desc_with_addr(desc_hi, a_src + k * 32),
+                                             ptx::desc_with_addr(desc_hi, b_src + k * 32), idesc, (kb | k) != 0);
+                    }
+                    ptx::mma_commit_pair(c.bar_empty + 8 * p.s);
+                    if (++p.s == STAGES) { p.s = 0; p.ph ^= 1; }
+                }
+                ptx::mma_commit_pair(c.bar_tfull + 8 * a);
+            }
+        }
+    } else {
+        epilogue_unit<MODE_STATS>(c, p, &tmA, args, m_blk, unit, t0, t1);
     }
     cta_teardown(c);
 }
@@ -617,14 +830,20 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     cta_teardown(c);
 }
 
-// ---------------------------------------------------------------------------------------------------- persistent backward
-// ONE launch for the whole backward.  The [rows x cols] block is cut into panels (rp x cp, both multiples of 256); the
-// fp16 G of a panel lives in one of two L2-sized buffers.  Phase p = { gradient-GEMM tiles of panel p-1 (read G[(p-1)&1]),
-// recompute tiles of panel p (write G[p&1]) }: everything inside a phase is independent, so a CTA pair runs its share
-// back to back through the same smem / TMEM pipelines - the epilogue of one tile overlaps the MMAs of the next across
-// job types - and phases are separated by one grid barrier (an atomic counter; all CTAs are co-resident).  Launch
-// latency, prologue, pipeline fill and the non-overlapped last epilogue are paid once per phase instead of once per
-// kernel per panel.
+// ---------------------------------------------------------------------------------------------------- dataflow backward
+// ONE launch for the whole backward, one CTA pair per SM pair, no grid-wide barrier.  The [rows x cols] block is cut
+// into panels (rp x cp, both multiples of 256); the fp16 G of panel q lives in L2-sized buffer q & 1.  Every pair
+// walks the panels in order and runs, per panel, its share of the recompute (GRAD) tiles and then its gradient-GEMM
+// job(s) on the SAME panel, back to back through one set of smem / TMEM pipelines - so the epilogue of one item
+// overlaps the MMAs of the next across item types.  Dependencies are tracked per G tile:
+//   * an epilogue warp counts a tile as done (tile_flags[q][tile] += 1; 16 per tile) once its bulk stores of the
+//     tile have completed; the TMA producer of a gradient-GEMM job waits for the flag of the tile behind each
+//     256-wide piece of its K extent, visiting the pieces in the order they were produced;
+//   * a job counts itself done (out_done[q] += 1) once its last MMA has completed; the first G store of panel q + 2
+//     (same buffer) waits until all jobs of panel q are done.
+// Every pair executes GRAD(0) < OUT(0) < GRAD(1) < ... in this order and every dependency points backwards in it,
+// so with all pairs co-resident the schedule cannot deadlock.  The share of GRAD tiles of a pair is weighted by the
+// length of its job (plan computed on the host, see build_bwd_plan), which evens out the work per panel.
 struct BwdP {
     int rows, cols, d;
     long long diag_offset;
@@ -635,24 +854,18 @@ struct BwdP {
     int s_f16;                   // operand format of the recompute GEMM
     int s_nseg, s_kb_per_seg, s_a_off[3], s_b_off[3];       // K segments of the recompute GEMM
     int g_nseg, g_a_off[3], g_b_off[3];                     // plane pairs of the gradient GEMMs (K extent varies per panel)
-    unsigned int* barrier;       // grid barrier counter, zero at launch
+    // plan (read only): shift[q] (cluster c runs jobs v, v + n, ... with v = (c + shift[q]) % n); start[q][c] = {first,
+    // end} recompute tile of cluster c; pos[q][tile] = rank of the tile in its producer's list
+    const int* plan_shift;
+    const int* plan_start;
+    const unsigned char* plan_pos;
+    int max_tiles;               // stride of the per-panel tile arrays
+    unsigned int* tile_flags;    // [n_panels][max_tiles], zero at launch
+    unsigned int* out_done;      // [n_panels], zero at launch
     const float* xg_inv;         // dequant scalars of the fp16 feature copies used by the gradient GEMMs (null = 1)
     const float* yg_inv;
     KArgs base;                  // everything that does not depend on the panel
 };
-
-__device__ __forceinline__ void grid_barrier_arrive(unsigned int* counter) {
-    asm volatile("fence.proxy.async;" ::: "memory");   // bulk (async proxy) stores of this CTA before the generic release
-    __threadfence();
-    atomicAdd(counter, 1u);
-}
-__device__ __forceinline__ void grid_barrier_wait(unsigned int* counter, unsigned int target) {
-    unsigned int v;
-    do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-    } while (v < target);
-    asm volatile("fence.proxy.async;" ::: "memory");   // following TMA loads see what the other CTAs stored
-}
 
 // geometry of panel q
 struct Panel { int r0, c0, nr, nc, ri, ci; };
@@ -667,6 +880,9 @@ __device__ __forceinline__ Panel panel_of(const BwdP& P, int q) {
     return x;
 }
 __device__ __forceinline__ int cdiv_d(int a, int b) { return (a + b - 1) / b; }
+__device__ __forceinline__ int jobs_of(const BwdP& P, const Panel& x) {
+    return (P.want_dx ? cdiv_d(x.nr, 2 * BM) * P.nt : 0) + (P.want_dy ? cdiv_d(x.nc, 2 * BM) * P.nt : 0);
+}
 
 // recompute (GRAD) unit of panel q: row pair m_pair, column tiles [t0, t1)
 __device__ __forceinline__ void make_grad_args(const BwdP& P, int q, KArgs& a) {
@@ -700,65 +916,62 @@ __device__ __forceinline__ void make_out_args(const BwdP& P, int q, int which, K
     a.b_outer_off = which == 0 ? x.c0 : x.r0;
     a.n_tiles = P.nt;
     a.c_col_off = 0; a.c_row_off = which == 0 ? x.r0 : x.c0;
-    a.accumulate = which == 0 ? (x.ci > 0) : (x.ri > 0);
+    // jobs of different panels that hit the same output rows are not ordered against each other: every job adds
+    // (TMA reduce) into an accumulator the host zeroed before the launch
+    a.accumulate = 1;
     a.oscale2 = which == 0 ? P.yg_inv : P.xg_inv;   // dequant of the feature operand: Yg for dX, Xg for dY
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
-                      const __grid_constant__ CUtensorMap tmGst, const __grid_constant__ CUtensorMap tmGk,
-                      const __grid_constant__ CUtensorMap tmGmn, const __grid_constant__ CUtensorMap tmYg,
-                      const __grid_constant__ CUtensorMap tmXg, const __grid_constant__ CUtensorMap tmDX,
-                      const __grid_constant__ CUtensorMap tmDY, const BwdP P) {
+bwd_dataflow_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+                    const __grid_constant__ CUtensorMap tmGst, const __grid_constant__ CUtensorMap tmGk,
+                    const __grid_constant__ CUtensorMap tmGmn, const __grid_constant__ CUtensorMap tmYg,
+                    const __grid_constant__ CUtensorMap tmXg, const __grid_constant__ CUtensorMap tmDX,
+                    const __grid_constant__ CUtensorMap tmDY, const BwdP P) {
     constexpr int STAGES = stages_of(MODE_GRAD);
     static_assert(stages_of(MODE_GRAD) == stages_of(MODE_OUT), "GRAD and OUT share one shared-memory layout");
     const Cta c = cta_setup<STAGES, true>();
     const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     const int n_panels = P.n_rp * P.n_cp;
+    constexpr unsigned int kTileDone = 2 * NUM_EPI_WARPS;   // epilogue warps of both CTAs
     Pipe p;
     if (c.warp == 0 && c.lane == 0) {
         ptx::prefetch_tmap(&tmX); ptx::prefetch_tmap(&tmY); ptx::prefetch_tmap(&tmGk); ptx::prefetch_tmap(&tmGmn);
         ptx::prefetch_tmap(&tmYg); ptx::prefetch_tmap(&tmXg);
     }
     const bool active = (c.warp == 0 && c.lane == 0) || (c.warp == 1 && c.lane == 0 && c.leader) || c.warp >= 2;
+    // experiments (CLIPK_DBG & 1024): the MMA thread of every pair stamps globaltimer at [cluster][panel][0..3] =
+    // panel start, recompute tiles issued, job start, job issued
+    const bool gt = P.base.trace && (P.base.dbg & 1024) && c.warp == 1;
+    auto GT = [&](int q, int k) {
+        if (gt) {
+            long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            P.base.trace[((size_t)cluster * n_panels + q) * 4 + k] = t;
+        }
+    };
 
-    for (int ph = 0; ph <= n_panels; ++ph) {
-        if (active) {
-            // producer: loads of this phase may only start once every CTA finished the previous phase
-            if (c.warp == 0 && P.base.trace && blockIdx.x == 0 && ph < 20) P.base.trace[3 * ph] = clock64();
-            if (c.warp == 0 && ph > 0) grid_barrier_wait(P.barrier, gridDim.x * (unsigned int)ph);
-            if (c.warp == 0 && P.base.trace && blockIdx.x == 0 && ph < 20) P.base.trace[3 * ph + 1] = clock64();
-            // ---- gradient-GEMM tiles of panel ph-1 (long K: first, so that they start early)
-            if (ph >= 1 && !(P.base.dbg & 64)) {
-                const int q = ph - 1;
-                const Panel x = panel_of(P, q);
-                const int jobs0 = P.want_dx ? cdiv_d(x.nr, 2 * BM) * P.nt : 0;
-                const int jobs1 = P.want_dy ? cdiv_d(x.nc, 2 * BM) * P.nt : 0;
-                for (int j = cluster; j < jobs0 + jobs1; j += n_clusters) {
-                    const int which = j < jobs0 ? 0 : 1;
-                    const int k = which == 0 ? j : j - jobs0;
-                    KArgs a;
-                    make_out_args(P, q, which, a);
-                    const int m_blk = 2 * (k / P.nt) + int(c.cta_rank);
-                    const int t = k % P.nt;
-                    if (c.warp == 0) {
-                        produce_unit<STAGES>(c, p, which == 0 ? &tmGk : &tmGmn, which == 0 ? &tmYg : &tmXg, a, m_blk, t, t + 1);
-                    } else if (c.warp == 1) {
-                        mma_unit<STAGES>(c, p, a, 1);
-                    } else {
-                        epilogue_unit<MODE_OUT>(c, p, which == 0 ? &tmDX : &tmDY, a, m_blk, t, t, t + 1);
-                    }
-                }
-            }
-            // ---- recompute tiles of panel ph: the flat list (row pair, column tile) is cut evenly over the clusters
-            if (ph < n_panels && !(P.base.dbg & 128)) {
-                const int q = ph;
-                const Panel x = panel_of(P, q);
-                const int m_pairs = cdiv_d(x.nr, 2 * BM), n_tiles = cdiv_d(x.nc, BN);
-                const long long total = (long long)m_pairs * n_tiles;
-                int f0 = int(total * cluster / n_clusters), f1 = int(total * (cluster + 1) / n_clusters);
+    if (active) {
+        for (int q = 0; q < n_panels; ++q) {
+            GT(q, 0);
+            const Panel x = panel_of(P, q);
+            const int m_pairs = cdiv_d(x.nr, 2 * BM), n_tiles = cdiv_d(x.nc, BN);
+            const int v = (cluster + __ldg(P.plan_shift + q)) % n_clusters;
+            int f0 = __ldg(P.plan_start + ((size_t)q * n_clusters + cluster) * 2);
+            const int f1 = __ldg(P.plan_start + ((size_t)q * n_clusters + cluster) * 2 + 1);
+            unsigned int* flags_q = P.tile_flags + (size_t)q * P.max_tiles;
+            const unsigned char* pos_q = P.plan_pos + (size_t)q * P.max_tiles;
+
+            // ---- recompute tiles [f0, f1) of panel q (flat index = row pair * n_tiles + column tile)
+            if (f0 < f1 && !(P.base.dbg & 128)) {
                 KArgs a;
                 make_grad_args(P, q, a);
+                a.trace_on = (blockIdx.x == 0 && !(P.base.dbg & 1024)) ? 2 : 0;
+                if (c.warp >= 2 && q >= 2 && !(P.base.dbg & 64)) {
+                    // buffer q & 1 was last read by the jobs of panel q - 2
+                    if (c.lane == 0) flag_wait(P.out_done + (q - 2), (unsigned int)jobs_of(P, panel_of(P, q - 2)));
+                    __syncwarp();
+                }
                 while (f0 < f1) {
                     const int m_pair = f0 / n_tiles;
                     const int t0 = f0 - m_pair * n_tiles;
@@ -769,22 +982,43 @@ bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                     } else if (c.warp == 1) {
                         mma_unit<STAGES>(c, p, a, t1 - t0);
                     } else {
-                        epilogue_unit<MODE_GRAD>(c, p, &tmGst, a, m_blk, 1 + f0, t0, t1);
+                        if (a.g_planes == 2) grad_epilogue_unit<true>(c, p, &tmGst, a, m_blk, t0, t1, flags_q + m_pair * n_tiles);
+                        else grad_epilogue_unit<false>(c, p, &tmGst, a, m_blk, t0, t1, flags_q + m_pair * n_tiles);
                     }
                     f0 += t1 - t0;
                 }
+                if (c.warp >= 2) epilogue_flush_flag(c, p);
             }
-        }
-        // ---- end of phase: this CTA's stores are complete and visible, then it arrives at the grid barrier
-        if (c.warp >= 2 && ph < n_panels) {
-            epilogue_drain(c);
-            ptx::named_bar_sync(1, NUM_EPI_WARPS * 32);
-            if (c.warp == 2 && c.lane == 0) {
-                if (P.base.trace && blockIdx.x == 0 && ph < 20) P.base.trace[3 * ph + 2] = clock64();
-                // a CTA without work in this phase must not run ahead: its arrival for phase ph may only be counted
-                // once every CTA arrived for phase ph-1, or the counter would reach a target early
-                if (ph > 0) grid_barrier_wait(P.barrier, gridDim.x * (unsigned int)ph);
-                grid_barrier_arrive(P.barrier);
+            GT(q, 1);
+            // ---- gradient-GEMM jobs v, v + n, ... of panel q
+            if (!(P.base.dbg & 64)) {
+                const int jobs0 = P.want_dx ? m_pairs * P.nt : 0;
+                const int jobs1 = P.want_dy ? cdiv_d(x.nc, 2 * BM) * P.nt : 0;
+                for (int j = v; j < jobs0 + jobs1; j += n_clusters) {
+                    const int which = j < jobs0 ? 0 : 1;
+                    const int k = which == 0 ? j : j - jobs0;
+                    KArgs a;
+                    make_out_args(P, q, which, a);
+                    a.trace_on = (blockIdx.x == 0 && !(P.base.dbg & 1024)) ? 2 : 0;
+                    GT(q, 2);
+                    const int blk = k / P.nt;          // 256-row block of the panel (dX) or 256-column block (dY)
+                    const int m_blk = 2 * blk + int(c.cta_rank);
+                    const int t = k - blk * P.nt;
+                    if (c.warp == 0) {
+                        const unsigned int target = (P.base.dbg & 128) ? 0u : kTileDone;
+                        if (which == 0)
+                            produce_job<STAGES>(c, p, &tmGk, &tmYg, a, m_blk, t, n_tiles, flags_q + blk * n_tiles,
+                                                pos_q + blk * n_tiles, 1, target);
+                        else
+                            produce_job<STAGES>(c, p, &tmGmn, &tmXg, a, m_blk, t, m_pairs, flags_q + blk, pos_q + blk,
+                                                n_tiles, target);
+                    } else if (c.warp == 1) {
+                        mma_unit<STAGES>(c, p, a, 1);
+                    } else {
+                        epilogue_unit<MODE_OUT>(c, p, which == 0 ? &tmDX : &tmDY, a, m_blk, t, t, t + 1, P.out_done + q);
+                    }
+                    GT(q, 3);
+                }
             }
         }
     }

@@ -1,4 +1,4 @@
-"""Manual experiment: phase timeline of CTA 0 in the persistent backward kernel."""
+"""Manual experiment: per-role clock64 timeline of CTA 0 in the dataflow backward kernel."""
 import sys, os
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "megatron-clip_b200"))
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
@@ -18,15 +18,21 @@ Xg, Yg = be.prepare_grad(X), be.prepare_grad(Y)
 gs = torch.tensor([1.0 / (2 * b)], device="cuda")
 for _ in range(2): be.bwd(X, Y, Xg, Yg, sc, 0, lr, lcl, 1.0, 1.0, gs, True, True)
 torch.cuda.synchronize()
-tr = torch.zeros(3 * 3 * 64, dtype=torch.int64, device="cuda")
+TN = 512
+tr = torch.zeros(3 * TN, dtype=torch.int64, device="cuda")
 lib.clipk_debug_set_trace(tr.data_ptr())
 be.bwd(X, Y, Xg, Yg, sc, 0, lr, lcl, 1.0, 1.0, gs, True, True)
 torch.cuda.synchronize()
 lib.clipk_debug_set_trace(None)
-v = tr[:60].tolist()
-base = v[0]
-print("phase: [start, after-barrier-wait, arrive]  (cycles since start); wait = time producer waited for the grid barrier")
-prev_arr = 0
-for ph in range(12):
-    s0, s1, s2 = (v[3 * ph] - base, v[3 * ph + 1] - base, v[3 * ph + 2] - base)
-    print(f"ph {ph:2d}: start {s0:8d}  go {s1:8d} (wait {s1 - s0:6d})  arrive {s2:8d}  work {s2 - s1:6d}")
+v = tr.tolist()
+base = min(x for x in v if x > 0)
+names = ["producer (tile/job: start, issued)", "mma (per tile: start, acc free, first data, committed)",
+         "epilogue w2 (per tile: start, acc full, acc released, done)"]
+per = [2, 4, 4]
+nshow = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+for role in range(3):
+    print(names[role])
+    s = [x - base for x in v[role * TN:(role + 1) * TN] if x > 0]
+    for i in range(0, min(len(s), per[role] * nshow), per[role]):
+        row = s[i:i + per[role]]
+        print("  ", " ".join(f"{x:9d}" for x in row), "  d=", " ".join(f"{b - a:7d}" for a, b in zip(row, row[1:])))
