@@ -75,6 +75,18 @@ int clipk_fwd_stats(const void* X, const void* Y, int rows, int cols, int d, lon
                     long long diag_offset, float* row_max, float* row_sum, float* row_dot, float* pos_logit,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* clipk_fwd_both: the statistics of BOTH directions of the same block - what two clipk_fwd_stats calls (X against Y,
+ * then Y against X) return - as row_stats [3][rows] and col_stats [3][cols] (max, sum, dot planes, natural-log units).
+ * For bf16 operands with d <= 512 whose logits are provably bounded (logit_scale * max|x_i| * max|y_j| <= ~34, checked
+ * on the device from the row norms) this is ONE sweep over the tiles: every tile feeds the row and the column sums, with
+ * the rows of X resident in shared memory.  Otherwise the library runs the exact two-sweep form by itself (same
+ * results, the cost of two clipk_fwd_stats calls).  pos_logit may be NULL. */
+size_t clipk_fwd_both_workspace_bytes(int rows, int cols, int d, int dtype);
+int clipk_fwd_both(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
+                   const float* x_inv_scale, const float* y_inv_scale, const float* logit_scale, long long diag_offset,
+                   float* row_stats, float* pos_logit, float* col_stats, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
 /* clipk_finalize merges statistics into log-sum-exps, the two cross-entropy sums (loss.py:135-138) and the two
  * sums that make up dloss/dlogit_scale:
  *   lse_row[i] = row_max[i] + log(row_sum[i])                                  i < rows
@@ -117,6 +129,11 @@ int clipk_cast(const float* src, void* dst, long long n, int dtype, void* stream
 /* Experiments only: a device buffer of 3 * 512 int64 that CTA 0 of every following launch fills with clock64
  * stamps of its producer / MMA / epilogue roles ([role][stamp]); NULL switches it off (the default). */
 int clipk_debug_set_trace(long long* device_buffer);
+
+/* Test hook: dumps the register <-> (lane, column) mapping of tcgen05.ld.16x256b, which the single-sweep forward relies
+ * on: out (8 * 32 * 16 ints) receives, for warp w, 16-lane half h, thread t, register k, the value lane * 1000 + column
+ * at index ((w * 2 + h) * 32 + t) * 16 + k. */
+int clipk_debug_tmem_layout(int* out, void* stream);
 
 /* ---- test hook for the tensor-core mainloop: D[M, N] (fp32, ldd) (+)= A * B^T with 16-bit operands
  *   (bf16 when f16 == 0, fp16 when f16 == 1; both operands share the format - the hardware rejects a mix).

@@ -3,8 +3,8 @@
 Data flow on rank r of W (b local rows, N = W*b), replacing open_CLIP/src/open_clip/loss.py:104-140:
 
   forward   T_all = all_gather(T_loc)                                  (NCCL, one contiguous [N, d] buffer)
-            row stats of  S = s * I_loc @ T_all^T   [b x N]            clipk_fwd_stats      (logits_per_image rows)
-            col stats of the same block              [N]               clipk_fwd_stats with operands swapped
+            row stats of  S = s * I_loc @ T_all^T   [b x N]            clipk_fwd_both: ONE sweep over the tiles feeds
+            col stats of the same block              [N]               both (two exact sweeps when logits are unbounded)
             all_gather of the (max, sum) column pairs                  (2*N floats per rank)
             lse_row[b], lse_col[N], cross-entropy sums                 clipk_finalize
   backward  G = s*g*(alpha*(P_row-Id) + beta*(P_col-Id)) tile by tile; dI_loc = G @ T_all;
@@ -29,7 +29,7 @@ _TEST_BACKEND = None
 
 
 def set_backend_for_testing(backend):
-    """Install an object exposing fwd_stats/finalize/bwd/cast/prepare (tests only; None restores CUDA)."""
+    """Install an object exposing fwd_stats/fwd_both/finalize/bwd/cast/prepare (tests only; None restores CUDA)."""
     global _TEST_BACKEND
     _TEST_BACKEND = backend
 
@@ -103,6 +103,24 @@ class CudaBackend:
                                             ws.data_ptr(), nbytes, self._stream()), "clipk_fwd_stats")
         self.launches += 2
         return out, pos
+
+    def fwd_both(self, X: Operand, Y: Operand, scale, diag_offset, col_out=None):
+        """(max, sum, dot) of every row AND every column of s * X @ Y^T in one call (one sweep over the tiles when the
+        logits are provably bounded, see clipk_fwd_both): row_stats [3, rows], pos [rows], col_stats [3, cols]."""
+        dev = X.data.device
+        rows, cols, d = X.rows, Y.rows, X.d
+        row_stats = torch.empty(3, rows, dtype=torch.float32, device=dev)
+        if col_out is None:
+            col_out = torch.empty(3, cols, dtype=torch.float32, device=dev)
+        pos = torch.zeros(rows, dtype=torch.float32, device=dev)
+        nbytes = self.lib.clipk_fwd_both_workspace_bytes(rows, cols, d, X.dtype)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.check(self.lib.clipk_fwd_both(X.data.data_ptr(), Y.data.data_ptr(), rows, cols, d, X.ld, Y.ld, X.dtype,
+                                           X.inv_ptr(), Y.inv_ptr(), scale.data_ptr(), diag_offset,
+                                           row_stats.data_ptr(), pos.data_ptr(), col_out.data_ptr(), ws.data_ptr(),
+                                           nbytes, self._stream()), "clipk_fwd_both")
+        self.launches += 4
+        return row_stats, pos, col_out
 
     def finalize(self, row_stats, pos, col_parts, diag_offset):
         """row_stats [3, rows]; col_parts [nparts, 3, cols] fp32 (max, sum, dot).
@@ -211,9 +229,8 @@ class FusedClipLoss(torch.autograd.Function):
         Y = be.prepare(t_all)
         off = rank * b if W > 1 else 0
 
-        row_stats, pos = be.fwd_stats(X, Y, scale, off, True)
         parts = torch.empty(1, 3, N, dtype=torch.float32, device=dev)        # (max, sum, dot) of every column
-        be.fwd_stats(Y, X, scale, 0, False, out=parts[0])
+        row_stats, pos, _ = be.fwd_both(X, Y, scale, off, col_out=parts[0])
         if W > 1:
             parts = _all_gather_rows(parts, W, group)                        # [W, 3, N]
         lse_row, lse_col, sums = be.finalize(row_stats, pos, parts, off)

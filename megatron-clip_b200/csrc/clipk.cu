@@ -351,6 +351,125 @@ __global__ void to_f16_kernel(const T* __restrict__ src, __half* __restrict__ ds
     if (planes == 2) *reinterpret_cast<uint4*>(o + dpad) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+// ---- forward sweep helpers
+// out[which] = max over rows of |row|^2 as float bits (non-negative floats order like unsigned ints); one warp per row,
+// 16-byte loads, d % 8 == 0.  Both operands in one launch: blocks [0, bx) take X, the rest take Y.
+__global__ void norm2_max_kernel(const __nv_bfloat16* __restrict__ X, long long rows_x, long long ldx,
+                                 const __nv_bfloat16* __restrict__ Y, long long rows_y, long long ldy, int d8, int bx,
+                                 unsigned int* __restrict__ out) {
+    const bool second = int(blockIdx.x) >= bx;
+    const __nv_bfloat16* src = second ? Y : X;
+    const long long rows = second ? rows_y : rows_x, ld = second ? ldy : ldx;
+    const int nb = second ? int(gridDim.x) - bx : bx, b = second ? int(blockIdx.x) - bx : int(blockIdx.x);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    float best = 0.f;
+    for (long long r = (long long)b * wpb + warp; r < rows; r += (long long)nb * wpb) {
+        float acc = 0.f;
+        for (int k = lane; k < d8; k += 32) {
+            float v[8];
+            load8(src + r * ld + (long long)k * 8, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc = fmaf(v[j], v[j], acc);
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        // NaN / Inf propagate into the bound, which then fails its test (exact mode)
+        best = (acc > best || !(acc == acc)) ? acc : best;
+    }
+    __shared__ float sh[32];
+    if (lane == 0) sh[warp] = best;
+    __syncthreads();
+    if (warp == 0) {
+        float v = lane < wpb ? sh[lane] : 0.f;
+        bool bad = !(v == v);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const float o = __shfl_xor_sync(0xffffffffu, v, off);
+            bad = bad || !(o == o);
+            v = fmaxf(v, o);
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        if (lane == 0) atomicMax(out + (second ? 1 : 0), bad ? 0x7f800000u : __float_as_uint(v));
+    }
+}
+
+// rows: merge the per-item parts (max, sum, dot; log2-scaled domain) into natural-log (max, sum, dot), as
+// merge_row_parts_kernel.  columns: in single-sweep mode sum the per-row-block partial (sum, dot) of the global
+// reference u; in exact mode merge the parts the swapped launch wrote.  The mode is recomputed from the same scalars.
+__global__ void fwd_merge_kernel(const FwdArgs a0, int parts0, const float* __restrict__ p1_max,
+                                 const float* __restrict__ p1_sum, const float* __restrict__ p1_dot, int parts1,
+                                 int m_blocks, float* __restrict__ row_out, float* __restrict__ col_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int rows = a0.M, cols = a0.N;
+    auto merge_parts = [](const float* pmx, const float* psm, const float* pdt, int nparts, int n, int idx, float* o, int on) {
+        float m = -CUDART_INF_F;
+        for (int p = 0; p < nparts; ++p) m = fmaxf(m, pmx[(size_t)p * n + idx]);
+        float l = 0.f, t = 0.f;
+        for (int p = 0; p < nparts; ++p) {
+            const float pm = pmx[(size_t)p * n + idx];
+            if (pm > -CUDART_INF_F) {
+                const float w = exp2f(pm - m);
+                l += psm[(size_t)p * n + idx] * w;
+                t += pdt[(size_t)p * n + idx] * w;
+            }
+        }
+        o[idx] = m * LN2;
+        o[on + idx] = l;
+        o[2 * on + idx] = t * LN2;
+    };
+    if (i < rows) merge_parts(a0.part_max, a0.part_sum, a0.part_dot, parts0, rows, i, row_out, rows);
+    if (i < cols) {
+        float u;
+        if (fwd_bound(a0, &u)) {
+            float L = 0.f, D = 0.f;
+            for (int b = 0; b < m_blocks; ++b) {
+                L += a0.colpart_sum[(size_t)b * a0.ldc + i];
+                D += a0.colpart_dot[(size_t)b * a0.ldc + i];
+            }
+            col_out[i] = u * LN2;
+            col_out[cols + i] = L;
+            col_out[2 * cols + i] = fmaf(u, L, D) * LN2;
+        } else {
+            merge_parts(p1_max, p1_sum, p1_dot, parts1, cols, i, col_out, cols);
+        }
+    }
+}
+
+// Test hook: where does tcgen05.ld.16x256b put the accumulator elements?  Four warps fill 128 lanes x 32 columns
+// with lane * 1000 + column through the 32x32b shape (thread == lane); every warp then reads the two 16-lane halves of
+// its lane quarter with the 16x256b shape and dumps its registers: out[(warp * 2 + h) * 32 * 16 + thread * 16 + k].
+__global__ void tmem_layout_kernel(int* out) {
+    __shared__ uint32_t tmem_ptr;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) {
+        ptx::tmem_alloc(ptx::smem_u32(&tmem_ptr), 32);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t base = tmem_ptr;
+    uint32_t v[32];
+    for (int k = 0; k < 32; ++k) v[k] = uint32_t((warp * 32 + lane) * 1000 + k);
+    ptx::tmem_st_32x32(base + (uint32_t(warp * 32) << 16), v);
+    ptx::tmem_st_wait();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    for (int h = 0; h < 2; ++h) {
+        uint32_t r[16];
+        ptx::tmem_ld_16x256b_x4(base + (uint32_t(warp * 32 + h * 16) << 16), r);
+        ptx::tmem_ld_wait();
+        for (int k = 0; k < 16; ++k) out[((warp * 2 + h) * 32 + lane) * 16 + k] = int(r[k]);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(base, 32);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ launch helpers
 static inline int cdiv(long long a, long long b) { return int((a + b - 1) / b); }
 static inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
@@ -465,22 +584,6 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     aa.trace_on = 1;
     aa.f16 = F16;
     return launch_clustered(kfn, dim3(2 * m_pairs, units), dim3(2, 1, 1), smem, st, ta, tb, tc, aa);
-}
-
-template <int F16>
-static int launch_ares(const CUtensorMap& ta, const CUtensorMap& tb, const KArgs& a, int units, int m_pairs, cudaStream_t st) {
-    auto kfn = stats_ares_kernel<F16>;
-    constexpr int smem = smem_bytes_ares();
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
-    if (attr_err != cudaSuccess) return fail(int(attr_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-    KArgs aa = a;
-    aa.dbg = dbg_flags();
-    aa.trace = g_trace;
-    aa.trace_on = 1;
-    aa.f16 = F16;
-    return launch_clustered(kfn, dim3(2 * m_pairs, units), dim3(2, 1, 1), smem, st, ta, tb, aa);
 }
 
 // jobs0 / jobs1 are counted in PAIRS (256 x 256 output tiles)
@@ -635,6 +738,49 @@ static int check_common(const void* X, const void* Y, int rows, int cols, int d,
     return CLIPK_OK;
 }
 
+// ---- host helpers of clipk_fwd_both
+constexpr int FWD_MAX_SPLIT = 16;
+// how many column runs per row pair: fill the clusters in as few equal rounds as possible
+int choose_item_split(int m_pairs, int n_tiles, int n_clusters) {
+    int best = 1;
+    double best_cost = 1e30;
+    const int lim = n_tiles < FWD_MAX_SPLIT ? n_tiles : FWD_MAX_SPLIT;
+    for (int s = 1; s <= lim; ++s) {
+        const int per = cdiv(n_tiles, s);
+        const int rounds = cdiv((long long)m_pairs * s, n_clusters);
+        const double cost = rounds * (per + 0.6);    // ~0.6 tile-times to swap the resident rows and write the item
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+    }
+    return best;
+}
+struct FwdCarve {
+    size_t norm2, parts0, parts1, colparts, total;
+    int ldc, m_blocks;
+};
+FwdCarve fwd_carve(int rows, int cols) {
+    FwdCarve c;
+    c.ldc = int(round_up(cols, BN));
+    c.m_blocks = 2 * cdiv(rows, 2 * BM);
+    size_t off = 0;
+    c.norm2 = off; off += 256;
+    c.parts0 = off; off += size_t(3) * FWD_MAX_SPLIT * PARTS_PER_UNIT * rows * sizeof(float);
+    c.parts1 = off; off += size_t(3) * FWD_MAX_SPLIT * PARTS_PER_UNIT * cols * sizeof(float);
+    off = size_t(round_up((long long)off, 256));
+    c.colparts = off; off += size_t(2) * c.m_blocks * c.ldc * sizeof(float);
+    c.total = off + 256;
+    return c;
+}
+template <int F16>
+int launch_fwd_sweep(const CUtensorMap& ta, const CUtensorMap& tb, const FwdArgs& a, int n_clusters, cudaStream_t st) {
+    auto kfn = fwd_sweep_kernel<F16>;
+    constexpr int smem = smem_bytes_fwd();
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
+    if (attr_err != cudaSuccess) return fail(int(attr_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+    return launch_clustered(kfn, dim3(2 * n_clusters), dim3(2, 1, 1), smem, st, ta, tb, a);
+}
+
 }  // namespace clipk
 
 using namespace clipk;
@@ -720,12 +866,7 @@ int clipk_fwd_stats(const void* X, const void* Y, int rows, int cols, int d, lon
     a.part_dot = a.part_sum + size_t(MAX_PARTS) * rows;
     a.pos = pos_logit;
     if (!pos_logit) a.diag_offset = -(1LL << 40);   // no row has a positive inside [0, cols)
-    const bool ares = a.nseg == 1 && a.num_kb <= ARES_KB && !(dbg_flags() & 512);
-    if (ares) {
-        // rows of X resident in shared memory, only Y streams (see stats_ares_kernel)
-        if ((rc = tmap_kmajor(&tb, Y, cols, kext, ldy, BN / 2))) return rc;
-        rc = is_f16(dtype) ? launch_ares<1>(ta, tb, a, units, m_pairs, st) : launch_ares<0>(ta, tb, a, units, m_pairs, st);
-    } else if (is_f16(dtype)) {
+    if (is_f16(dtype)) {
         rc = launch_gemm<MODE_STATS, 1>(ta, tb, ta, a, units, m_pairs, st);
     } else {
         rc = launch_gemm<MODE_STATS, 0>(ta, tb, ta, a, units, m_pairs, st);
@@ -733,6 +874,106 @@ int clipk_fwd_stats(const void* X, const void* Y, int rows, int cols, int d, lon
     if (rc) return rc;
     merge_row_parts_kernel<<<cdiv(rows, 256), 256, 0, st>>>(a.part_max, a.part_sum, a.part_dot, units * PARTS_PER_UNIT,
                                                             rows, row_max, row_sum, row_dot);
+    CK_CUDA(cudaGetLastError());
+    return CLIPK_OK;
+}
+
+// ---- both directions of the forward (see fwd_sweep_kernel)
+
+size_t clipk_fwd_both_workspace_bytes(int rows, int cols, int d, int dtype) {
+    if (rows <= 0 || cols <= 0) return 0;
+    const size_t two = clipk_fwd_workspace_bytes(rows, cols, d, dtype) + clipk_fwd_workspace_bytes(cols, rows, d, dtype);
+    const size_t one = fwd_carve(rows, cols).total;
+    return one > two ? one : two;
+}
+
+int clipk_fwd_both(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
+                   const float* x_inv_scale, const float* y_inv_scale, const float* logit_scale, long long diag_offset,
+                   float* row_stats, float* pos_logit, float* col_stats, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+    int rc = check_common(X, Y, rows, cols, d, ldx, ldy, dtype);
+    if (rc) return rc;
+    if (!logit_scale || !row_stats || !col_stats || !workspace) return fail(CLIPK_EINVAL, "null pointer argument");
+    if (workspace_bytes < clipk_fwd_both_workspace_bytes(rows, cols, d, dtype)) return fail(CLIPK_EWORKSPACE, "workspace too small");
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail(CLIPK_EINVAL, "workspace must be 256-byte aligned");
+    DevInfo di;
+    if ((rc = device_info(&di))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int planes = planes_of(dtype);
+    const long long dpad = round_up(d, BK);
+    const int num_kb = cdiv(d, BK);
+    if (planes != 1 || num_kb > ARES_KB || (dbg_flags() & 512)) {
+        // operands too wide for the resident-rows kernel (or split-precision): two streaming sweeps
+        char* ws = static_cast<char*>(workspace);
+        const size_t w0 = clipk_fwd_workspace_bytes(rows, cols, d, dtype);
+        rc = clipk_fwd_stats(X, Y, rows, cols, d, ldx, ldy, dtype, x_inv_scale, y_inv_scale, logit_scale, diag_offset,
+                             row_stats, row_stats + rows, row_stats + 2 * (size_t)rows, pos_logit, ws, w0, stream);
+        if (rc) return rc;
+        return clipk_fwd_stats(Y, X, cols, rows, d, ldy, ldx, dtype, y_inv_scale, x_inv_scale, logit_scale, -(1LL << 40),
+                               col_stats, col_stats + cols, col_stats + 2 * (size_t)cols, nullptr, ws + round_up((long long)w0, 256),
+                               workspace_bytes - size_t(round_up((long long)w0, 256)), stream);
+    }
+    const long long kext = (dtype == CLIPK_BF16) ? d : dpad;
+    const int n_clusters = di.sms / 2;
+    const FwdCarve cv = fwd_carve(rows, cols);
+    char* ws = static_cast<char*>(workspace);
+    unsigned int* norm2 = reinterpret_cast<unsigned int*>(ws + cv.norm2);
+    float* parts0 = reinterpret_cast<float*>(ws + cv.parts0);
+    float* parts1 = reinterpret_cast<float*>(ws + cv.parts1);
+    float* colparts = reinterpret_cast<float*>(ws + cv.colparts);
+    const bool bounded = (dtype == CLIPK_BF16) && !(dbg_flags() & 16384);
+    if (bounded) {
+        CK_CUDA(cudaMemsetAsync(norm2, 0, 2 * sizeof(unsigned int), st));
+        const int wpb = 8;
+        const int bx = std::max(1, std::min(cdiv(rows, wpb), 2 * di.sms)), by = std::max(1, std::min(cdiv(cols, wpb), 2 * di.sms));
+        norm2_max_kernel<<<bx + by, wpb * 32, 0, st>>>(static_cast<const __nv_bfloat16*>(X), rows, ldx,
+                                                        static_cast<const __nv_bfloat16*>(Y), cols, ldy, d / 8, bx, norm2);
+        CK_CUDA(cudaGetLastError());
+    }
+    CUtensorMap tx_a, ty_b, ty_a, tx_b;
+    if ((rc = tmap_kmajor(&tx_a, X, rows, kext, ldx, BM))) return rc;
+    if ((rc = tmap_kmajor(&ty_b, Y, cols, kext, ldy, BN / 2))) return rc;
+    if ((rc = tmap_kmajor(&ty_a, Y, cols, kext, ldy, BM))) return rc;
+    if ((rc = tmap_kmajor(&tx_b, X, rows, kext, ldx, BN / 2))) return rc;
+
+    FwdArgs a0{};
+    a0.M = rows; a0.N = cols; a0.num_kb = num_kb;
+    a0.n_tiles = cdiv(cols, BN); a0.m_pairs = cdiv(rows, 2 * BM);
+    a0.split = choose_item_split(a0.m_pairs, a0.n_tiles, n_clusters);
+    a0.tiles_per_item = cdiv(a0.n_tiles, a0.split);
+    a0.split = cdiv(a0.n_tiles, a0.tiles_per_item);
+    a0.pass = 0; a0.force_exact = bounded ? 0 : 1;
+    a0.scale = logit_scale; a0.xs = x_inv_scale; a0.ys = y_inv_scale; a0.norm2 = norm2;
+    a0.diag_offset = pos_logit ? diag_offset : -(1LL << 40);
+    const size_t pstride0 = size_t(FWD_MAX_SPLIT) * PARTS_PER_UNIT * rows;
+    a0.part_max = parts0; a0.part_sum = parts0 + pstride0; a0.part_dot = parts0 + 2 * pstride0;
+    a0.pos = pos_logit;
+    a0.colpart_sum = colparts; a0.colpart_dot = colparts + size_t(cv.m_blocks) * cv.ldc; a0.ldc = cv.ldc;
+    a0.trace = g_trace; a0.dbg = dbg_flags();
+
+    FwdArgs a1 = a0;
+    a1.M = cols; a1.N = rows;
+    a1.n_tiles = cdiv(rows, BN); a1.m_pairs = cdiv(cols, 2 * BM);
+    a1.split = choose_item_split(a1.m_pairs, a1.n_tiles, n_clusters);
+    a1.tiles_per_item = cdiv(a1.n_tiles, a1.split);
+    a1.split = cdiv(a1.n_tiles, a1.tiles_per_item);
+    a1.pass = 1; a1.xs = y_inv_scale; a1.ys = x_inv_scale;
+    a1.diag_offset = -(1LL << 40);
+    const size_t pstride1 = size_t(FWD_MAX_SPLIT) * PARTS_PER_UNIT * cols;
+    a1.part_max = parts1; a1.part_sum = parts1 + pstride1; a1.part_dot = parts1 + 2 * pstride1;
+    a1.pos = nullptr; a1.colpart_sum = nullptr; a1.colpart_dot = nullptr;
+
+    const int nc0 = std::min(n_clusters, a0.m_pairs * a0.split), nc1 = std::min(n_clusters, a1.m_pairs * a1.split);
+    if (is_f16(dtype)) {
+        if ((rc = launch_fwd_sweep<1>(tx_a, ty_b, a0, nc0, st))) return rc;
+        if ((rc = launch_fwd_sweep<1>(ty_a, tx_b, a1, nc1, st))) return rc;
+    } else {
+        if ((rc = launch_fwd_sweep<0>(tx_a, ty_b, a0, nc0, st))) return rc;
+        if ((rc = launch_fwd_sweep<0>(ty_a, tx_b, a1, nc1, st))) return rc;
+    }
+    const int n = rows > cols ? rows : cols;
+    fwd_merge_kernel<<<cdiv(n, 128), 128, 0, st>>>(a0, a0.split * PARTS_PER_UNIT, a1.part_max, a1.part_sum, a1.part_dot,
+                                                   a1.split * PARTS_PER_UNIT, cv.m_blocks, row_stats, col_stats);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
 }
@@ -987,6 +1228,16 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
 // Experiments only: device buffer of 3*64 int64 that CTA (0,0) of every following launch fills with clock64 stamps.
 int clipk_debug_set_trace(long long* device_buffer) {
     g_trace = device_buffer;
+    return CLIPK_OK;
+}
+
+int clipk_debug_tmem_layout(int* out, void* stream) {
+    if (!out) return fail(CLIPK_EINVAL, "null pointer");
+    DevInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    tmem_layout_kernel<<<1, 128, 0, static_cast<cudaStream_t>(stream)>>>(out);
+    CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
 }
 

@@ -229,7 +229,7 @@ __device__ __forceinline__ void grad16_store(const float (&g)[16], uint32_t stg,
 // stage, staging-buffer use) across calls, so the same code serves the one-unit-per-CTA kernels and the persistent
 // backward kernel that walks many units per CTA.
 struct Cta {
-    uint32_t sA, sB, sStg, bar_full, bar_empty, bar_tfull, bar_tempty, bar_afull, tmem_base;
+    uint32_t sA, sB, sStg, bar_full, bar_empty, bar_tfull, bar_tempty, bar_afull, bar_aempty, tmem_base;
     uint32_t cta_rank;
     bool leader;
     int warp, lane;
@@ -252,7 +252,7 @@ __device__ __forceinline__ void trace_stamp(const KArgs& args, Pipe& p, int role
 
 // Shared memory: A region (A_BYTES) | NB B stages | epilogue staging | barriers.  The streaming kernels use one A slot
 // per stage (A_BYTES = STAGES * A_STAGE_BYTES, NB = STAGES); the A-resident forward keeps all K blocks of its rows.
-template <int STAGES, bool HAS_STG, int A_BYTES = STAGES * A_STAGE_BYTES>
+template <int STAGES, int EXTRA_BYTES, int A_BYTES = STAGES * A_STAGE_BYTES>
 __device__ __forceinline__ Cta cta_setup() {
     Cta c;
     c.cta_rank = ptx::cluster_ctarank();   // 0 = leader (issues the pair's MMAs), 1 = peer
@@ -264,7 +264,7 @@ __device__ __forceinline__ Cta cta_setup() {
     const uint32_t base = (raw_u32 + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - raw_u32);
     // layout (1024-byte aligned up to the barriers): A stages | B stages | epilogue staging | barriers
-    constexpr uint32_t kStg = HAS_STG ? uint32_t(STG_TOTAL) : 0u;
+    constexpr uint32_t kStg = uint32_t(EXTRA_BYTES);   // epilogue staging (GRAD / OUT) or the column buffer (forward sweep)
     c.sA = base;
     c.sB = c.sA + A_BYTES;
     c.sStg = c.sB + STAGES * B_STAGE_BYTES;
@@ -274,9 +274,10 @@ __device__ __forceinline__ Cta cta_setup() {
     c.bar_tfull = sBar + 2 * STAGES * 8;
     c.bar_tempty = c.bar_tfull + 16;
     c.bar_afull = c.bar_tempty + 16;
-    const uint32_t sTmemPtr = c.bar_afull + 8;
+    c.bar_aempty = c.bar_afull + 8;
+    const uint32_t sTmemPtr = c.bar_aempty + 8;
     volatile uint32_t* tmem_ptr_gen =
-        reinterpret_cast<volatile uint32_t*>(base_ptr + A_BYTES + STAGES * B_STAGE_BYTES + kStg + (2 * STAGES + 5) * 8);
+        reinterpret_cast<volatile uint32_t*>(base_ptr + A_BYTES + STAGES * B_STAGE_BYTES + kStg + (2 * STAGES + 6) * 8);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -288,6 +289,7 @@ __device__ __forceinline__ Cta cta_setup() {
             ptx::mbar_init(c.bar_tempty + 8 * a, 2 * NUM_EPI_WARPS);   // epilogue warps of both CTAs (leader's copy is used)
         }
         ptx::mbar_init(c.bar_afull, 1);
+        ptx::mbar_init(c.bar_aempty, 1);
         ptx::fence_barrier_init();
     }
     if (c.warp == 1) {
@@ -693,7 +695,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const KArgs args) {
     constexpr int STAGES = stages_of(MODE);
-    const Cta c = cta_setup<STAGES, MODE != MODE_STATS>();
+    const Cta c = cta_setup<STAGES, MODE != MODE_STATS ? STG_TOTAL : 0>();
     const int m_blk = int(blockIdx.x);          // = 2 * m_pair + cta_rank
     const int unit = int(blockIdx.y);
     const int t0 = unit * args.tiles_per_unit;
@@ -719,78 +721,319 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     cta_teardown(c);
 }
 
-// ---------------------------------------------------------------------------------------------------- A-resident forward
-// The mainloop of the streaming kernels is bound by L2 -> SM bandwidth, not by the tensor pipe: 148 CTAs x 32 KB per K
-// block against ~6300 B/clk of L2 is ~770 clk for 512 clk of MMA.  A forward unit sweeps MANY column tiles with the same
-// 128 rows of A per CTA, so for K <= ARES_KB * 64 those rows are loaded ONCE and stay in shared memory (128 KB); only the
-// B half-tiles stream (16 KB per K block and CTA, 6 stages), which halves the L2 traffic and leaves the tensor pipe as
-// the limit.
+// ---------------------------------------------------------------------------------------------------- forward sweep
+// Persistent forward kernel: one CTA pair per SM pair walks work items (256 rows x a run of column tiles).
+//
+// A-resident.  The 128 rows of A a CTA needs stay in shared memory for the whole item (K <= 512: 128 KB) and only the
+// B half-tiles stream (16 KB per K block and CTA), which halves the L2 -> SM traffic of the mainloop.
+//
+// Single sweep.  The forward needs the log-sum-exp of every ROW and of every COLUMN of the block (loss.py:135-138 takes
+// the cross-entropy of logits_per_image and of logits_per_text).  Both come from ONE pass over the tiles when the
+// logits are bounded: with u >= |v| for every logit v (log2 units; u = s * max|x_i| * max|y_j| * log2(e) from the row
+// norms) and 2u + 26 <= 126, e = 2^(v - u) of every element stays a normal fp32 number down to 2^-24 of the smallest
+// possible row or column maximum, so ONE exponential per element with the global reference u serves both directions,
+// sums are plain additions (no running maximum, no rescaling) and partial sums can be merged in any order.
+// The accumulator is read in the 16x256b fragment layout (a thread holds 2 rows x 8 columns of a 16-lane half-chunk),
+// which makes the column sums cheap: 3 additions over the 4 rows a thread sees per chunk, then a 3-step butterfly over
+// the 8 threads that share the columns; the 4 lane-quarter warps are merged through shared memory and every CTA
+// writes one partial (sum, dot) per column and 128-row block, summed later by fwd_merge_kernel.
+// When the bound does not hold (logit_scale * norms > ~35) the same launch runs the exact online-max row sweep
+// instead and a second launch with the operands swapped produces the column statistics; when it holds the second
+// launch exits at once.  The decision is taken on the device from device scalars: no host synchronisation.
 constexpr int ARES_KB = 8;                       // resident K blocks (K <= 512)
-constexpr int ARES_STAGES = 6;
-__host__ __device__ constexpr int smem_bytes_ares() {
-    return 1024 + ARES_KB * A_STAGE_BYTES + ARES_STAGES * B_STAGE_BYTES + 256 + MISC_BYTES;
+constexpr int FWD_STAGES = 5;
+constexpr int COLBUF_BYTES = 2 * 2 * 4 * 128 * 2 * 4;   // [tile parity][half][lane quarter][128 columns][sum, dot]
+__host__ __device__ constexpr int smem_bytes_fwd() {
+    return 1024 + ARES_KB * A_STAGE_BYTES + FWD_STAGES * B_STAGE_BYTES + COLBUF_BYTES + 256 + MISC_BYTES;
+}
+constexpr float FWD_SAFE_U = 50.f;               // 2u + 26 <= 126
+
+struct FwdArgs {
+    int M, N;                  // rows of A (X), rows of B (Y)
+    int num_kb;                // K blocks, <= ARES_KB
+    int n_tiles, m_pairs;
+    int split, tiles_per_item; // item = m_pair * split + part; tiles [part * tiles_per_item, ...)
+    int pass;                  // 0: X rows against Y columns; 1: the swapped launch (exact mode only)
+    int force_exact;           // operands are not plain bf16: no norm bound
+    const float* scale;
+    const float* xs;           // dequant scalars of the operands (null = 1)
+    const float* ys;
+    const unsigned int* norm2; // [2] max |x_i|^2, max |y_j|^2 as float bits (only read when !force_exact)
+    long long diag_offset;
+    float* part_max;           // [split * 2][M]
+    float* part_sum;
+    float* part_dot;
+    float* pos;                // [M] or null
+    float* colpart_sum;        // [2 * m_pairs][ldc]   (pass 0, single sweep)
+    float* colpart_dot;
+    int ldc;
+    long long* trace;
+    int dbg;
+};
+
+// u (log2 units) and whether the single sweep is allowed; identical in every thread of every CTA of both launches
+__device__ __forceinline__ bool fwd_bound(const FwdArgs& a, float* u_out) {
+    if (a.force_exact) { *u_out = 0.f; return false; }
+    const float nx2 = __uint_as_float(a.norm2[0]), ny2 = __uint_as_float(a.norm2[1]);
+    const float u = fabsf(__ldg(a.scale)) * sqrtf(nx2) * sqrtf(ny2) * (LOG2E * 1.001f);
+    *u_out = u;
+    return u <= FWD_SAFE_U;     // false for NaN / Inf
+}
+
+// one 16-lane half-chunk (2 rows x 8 columns per thread) of the single sweep
+template <bool EDGE>
+__device__ __forceinline__ void rowcol_half(const uint32_t (&r)[16], float sc, float u, float& l0, float& t0, float& l1,
+                                            float& t1, float (&cs)[8], float (&cd)[8], bool first, int col0, int ncols,
+                                            bool ok0, bool ok1, long long dcol0, long long dcol1, float s_nat, float* pos,
+                                            int row0, int row1) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float xa = fmaf(__uint_as_float(r[4 * k + j]), sc, -u);
+            const float xb = fmaf(__uint_as_float(r[4 * k + 2 + j]), sc, -u);
+            float ea = ptx::ex2(xa), eb = ptx::ex2(xb);
+            if (EDGE) {
+                const int col = col0 + 8 * k + j;
+                const bool cok = col < ncols;
+                if (!(cok && ok0)) ea = 0.f;
+                if (!(cok && ok1)) eb = 0.f;
+                if (pos && cok && ok0 && col == dcol0) pos[row0] = __uint_as_float(r[4 * k + j]) * s_nat;
+                if (pos && cok && ok1 && col == dcol1) pos[row1] = __uint_as_float(r[4 * k + 2 + j]) * s_nat;
+            }
+            l0 += ea; t0 = fmaf(ea, xa, t0);
+            l1 += eb; t1 = fmaf(eb, xb, t1);
+            const int cc = 2 * k + j;
+            if (first) { cs[cc] = ea + eb; cd[cc] = fmaf(ea, xa, eb * xb); }
+            else { cs[cc] += ea + eb; cd[cc] = fmaf(ea, xa, fmaf(eb, xb, cd[cc])); }
+        }
+    }
 }
 
 template <int F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-stats_ares_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KArgs args) {
-    constexpr int STAGES = ARES_STAGES;
-    const Cta c = cta_setup<STAGES, false, ARES_KB * A_STAGE_BYTES>();
-    const int m_blk = int(blockIdx.x);          // = 2 * m_pair + cta_rank
-    const int unit = int(blockIdx.y);
-    const int t0 = unit * args.tiles_per_unit;
-    const int t1 = min(args.n_tiles, t0 + args.tiles_per_unit);
-    const int num_kb = args.num_kb;             // <= ARES_KB, one segment, both operands K-major
+fwd_sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FwdArgs args) {
+    constexpr int STAGES = FWD_STAGES;
+    const Cta c = cta_setup<STAGES, COLBUF_BYTES, ARES_KB * A_STAGE_BYTES>();
+    const uint32_t colbuf = c.sStg;
+    float u = 0.f;
+    const bool safe = fwd_bound(args, &u);
+    const bool single = safe && args.pass == 0;
+    const bool skip = safe && args.pass == 1;
+    const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int n_items = args.m_pairs * args.split;
+    const int num_kb = args.num_kb;
     Pipe p;
-    if (c.warp == 0) {
-        if (c.lane == 0) {
-            ptx::prefetch_tmap(&tmA);
-            ptx::prefetch_tmap(&tmB);
-            // the rows of A, all K blocks, once: both CTAs' loads complete on the leader's barrier
-            if (c.leader) ptx::mbar_arrive_expect_tx(c.bar_afull, 2 * num_kb * A_STAGE_BYTES);
-            for (int kb = 0; kb < num_kb; ++kb)
-                ptx::tma_load_2d_pair(c.sA + kb * A_STAGE_BYTES, &tmA, kb * BK, args.a_outer_off + m_blk * BM, c.bar_afull);
-            for (int t = t0; t < t1; ++t) {
-                const int bn0 = t * BN + int(c.cta_rank) * (BN / 2);
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    ptx::mbar_wait(c.bar_empty + 8 * p.s, p.ph ^ 1);
-                    const uint32_t full = c.bar_full + 8 * p.s;
-                    if (c.leader) ptx::mbar_arrive_expect_tx(full, 2 * B_STAGE_BYTES);
-                    ptx::tma_load_2d_pair(c.sB + p.s * B_STAGE_BYTES, &tmB, kb * BK, args.b_outer_off + bn0, full);
-                    if (++p.s == STAGES) { p.s = 0; p.ph ^= 1; }
-                }
-            }
-        }
-    } else if (c.warp == 1) {
-        if (c.lane == 0 && c.leader) {
-            const uint32_t idesc = ptx::make_idesc_16bit(2 * BM, BN, 0, 0, !F16, !F16);
-            const uint64_t desc_hi = ptx::make_smem_desc_sw128(16, 1024);
-            ptx::mbar_wait(c.bar_afull, 0);
-            ptx::tc_fence_after();
-            for (int t = t0; t < t1; ++t, ++p.it) {
-                const int a = p.it & 1;
-                const uint32_t aph = (p.it >> 1) & 1;
-                ptx::mbar_wait(c.bar_tempty + 8 * a, aph ^ 1);
-                ptx::tc_fence_after();
-                const uint32_t d_tmem = c.tmem_base + a * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    ptx::mbar_wait(c.bar_full + 8 * p.s, p.ph);
-                    ptx::tc_fence_after();
-                    const uint32_t a_src = c.sA + kb * A_STAGE_BYTES;
-                    const uint32_t b_src = c.sB + p.s * B_STAGE_BYTES;
-#pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        ptx::mma_f16_ss_pair(d_tmem, ptx::desc_with_addr(desc_hi, a_src + k * 32),
-                                             ptx::desc_with_addr(desc_hi, b_src + k * 32), idesc, (kb | k) != 0);
+
+    if (!skip) {
+        if (c.warp == 0) {
+            if (c.lane == 0) {
+                ptx::prefetch_tmap(&tmA);
+                ptx::prefetch_tmap(&tmB);
+                uint32_t it_n = 0;
+                for (int item = cluster; item < n_items; item += n_clusters, ++it_n) {
+                    const int m_pair = item / args.split, part = item - m_pair * args.split;
+                    const int m_blk = 2 * m_pair + int(c.cta_rank);
+                    const int t0 = part * args.tiles_per_item, t1 = min(args.n_tiles, t0 + args.tiles_per_item);
+                    // the resident rows of A may be replaced once every MMA of the previous item has completed
+                    if (it_n > 0) ptx::mbar_wait(c.bar_aempty, (it_n - 1) & 1);
+                    if (c.leader) ptx::mbar_arrive_expect_tx(c.bar_afull, 2 * num_kb * A_STAGE_BYTES);
+                    for (int kb = 0; kb < num_kb; ++kb)
+                        ptx::tma_load_2d_pair(c.sA + kb * A_STAGE_BYTES, &tmA, kb * BK, m_blk * BM, c.bar_afull);
+                    for (int t = t0; t < t1; ++t) {
+                        const int bn0 = t * BN + int(c.cta_rank) * (BN / 2);
+                        for (int kb = 0; kb < num_kb; ++kb) {
+                            ptx::mbar_wait(c.bar_empty + 8 * p.s, p.ph ^ 1);
+                            const uint32_t full = c.bar_full + 8 * p.s;
+                            if (c.leader) ptx::mbar_arrive_expect_tx(full, 2 * B_STAGE_BYTES);
+                            ptx::tma_load_2d_pair(c.sB + p.s * B_STAGE_BYTES, &tmB, kb * BK, bn0, full);
+                            if (++p.s == STAGES) { p.s = 0; p.ph ^= 1; }
+                        }
                     }
-                    ptx::mma_commit_pair(c.bar_empty + 8 * p.s);
-                    if (++p.s == STAGES) { p.s = 0; p.ph ^= 1; }
                 }
-                ptx::mma_commit_pair(c.bar_tfull + 8 * a);
+            }
+        } else if (c.warp == 1) {
+            if (c.lane == 0 && c.leader) {
+                const uint32_t idesc = ptx::make_idesc_16bit(2 * BM, BN, 0, 0, !F16, !F16);
+                const uint64_t desc_hi = ptx::make_smem_desc_sw128(16, 1024);
+                uint32_t it_n = 0;
+                for (int item = cluster; item < n_items; item += n_clusters, ++it_n) {
+                    const int part = item % args.split;
+                    const int t0 = part * args.tiles_per_item, t1 = min(args.n_tiles, t0 + args.tiles_per_item);
+                    ptx::mbar_wait(c.bar_afull, it_n & 1);
+                    ptx::tc_fence_after();
+                    for (int t = t0; t < t1; ++t, ++p.it) {
+                        const int a = p.it & 1;
+                        const uint32_t aph = (p.it >> 1) & 1;
+                        ptx::mbar_wait(c.bar_tempty + 8 * a, aph ^ 1);
+                        ptx::tc_fence_after();
+                        const uint32_t d_tmem = c.tmem_base + a * BN;
+                        for (int kb = 0; kb < num_kb; ++kb) {
+                            ptx::mbar_wait(c.bar_full + 8 * p.s, p.ph);
+                            ptx::tc_fence_after();
+                            const uint32_t a_src = c.sA + kb * A_STAGE_BYTES;
+                            const uint32_t b_src = c.sB + p.s * B_STAGE_BYTES;
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k) {
+                                ptx::mma_f16_ss_pair(d_tmem, ptx::desc_with_addr(desc_hi, a_src + k * 32),
+                                                     ptx::desc_with_addr(desc_hi, b_src + k * 32), idesc, (kb | k) != 0);
+                            }
+                            ptx::mma_commit_pair(c.bar_empty + 8 * p.s);
+                            if (++p.s == STAGES) { p.s = 0; p.ph ^= 1; }
+                        }
+                        ptx::mma_commit_pair(c.bar_tfull + 8 * a);
+                    }
+                    ptx::mma_commit_pair(c.bar_aempty);   // both CTAs' producers wait on their own copy
+                }
+            }
+        } else if (!single) {
+            // ---- exact mode: online-max row statistics, one row per thread (same code as the streaming STATS kernel)
+            KArgs ka{};
+            ka.M = args.M; ka.N = args.N; ka.scale = args.scale; ka.xs = args.xs; ka.ys = args.ys;
+            ka.diag_offset = args.diag_offset; ka.part_max = args.part_max; ka.part_sum = args.part_sum;
+            ka.part_dot = args.part_dot; ka.pos = args.pos; ka.dbg = args.dbg; ka.trace = args.trace;
+            ka.trace_on = (blockIdx.x == 0) ? 2 : 0;
+            for (int item = cluster; item < n_items; item += n_clusters) {
+                const int m_pair = item / args.split, part = item - m_pair * args.split;
+                const int m_blk = 2 * m_pair + int(c.cta_rank);
+                const int t0 = part * args.tiles_per_item, t1 = min(args.n_tiles, t0 + args.tiles_per_item);
+                epilogue_unit<MODE_STATS>(c, p, &tmA, ka, m_blk, part, t0, t1);
+            }
+        } else {
+            // ---- single sweep: row and column statistics of every tile
+            const int warp = c.warp, lane = c.lane;
+            const int q = warp & 3, half = (warp - 2) >> 2;
+            const int g = lane >> 2, cq = 2 * (lane & 3);
+            float dequant = 1.f;
+            if (args.xs) dequant *= __ldg(args.xs);
+            if (args.ys) dequant *= __ldg(args.ys);
+            const float s_nat = __ldg(args.scale) * dequant;
+            const float sc = s_nat * LOG2E;
+            const int ncols = args.N, M = args.M;
+            float* const pos = args.pos;
+            KArgs ktr{};
+            ktr.trace = args.trace; ktr.trace_on = (blockIdx.x == 0) ? 2 : 0;
+            auto TR = [&]() {
+                if (warp == 2 && lane == 0) trace_stamp(ktr, p, 2);
+            };
+            // column of the chunk this lane owns after the butterfly, and its slot in the column buffer
+            const int own_col = 8 * (g >> 1) + cq + (g & 1);
+            for (int item = cluster; item < n_items; item += n_clusters) {
+                const int m_pair = item / args.split, part = item - m_pair * args.split;
+                const int m_blk = 2 * m_pair + int(c.cta_rank);
+                const int t0 = part * args.tiles_per_item, t1 = min(args.n_tiles, t0 + args.tiles_per_item);
+                const int rbase = m_blk * BM + q * 32;             // rows rbase + {g, 8 + g, 16 + g, 24 + g}
+                float l[4] = {0.f, 0.f, 0.f, 0.f}, tt[4] = {0.f, 0.f, 0.f, 0.f};
+                const bool row_edge = (m_blk + 1) * BM > M;
+                const long long d_lo = args.diag_offset + (long long)m_blk * BM;
+                for (int t = t0; t < t1; ++t, ++p.it) {
+                    const int a = p.it & 1;
+                    const uint32_t aph = (p.it >> 1) & 1;
+                    const int n0 = t * BN;
+                    const int colh = n0 + half * (BN / 2);
+                    TR();
+                    ptx::mbar_wait(c.bar_tfull + 8 * a, aph);
+                    ptx::tc_fence_after();
+                    TR();
+                    const uint32_t taddr = c.tmem_base + a * BN + half * (BN / 2) + (uint32_t(q * 32) << 16);
+                    const bool edge = row_edge || (n0 + BN > ncols) ||
+                                      (pos && (d_lo + BM - 1 >= n0) && (d_lo < (long long)n0 + BN));
+                    const uint32_t cbuf = colbuf + uint32_t(((((t & 1) * 2 + half) * 4 + q) * 128) * 8);
+                    float cs[8], cd[8];
+                    auto half_chunk = [&](const uint32_t (&r)[16], int hc) {
+                        if (args.dbg & 1) return;
+                        const int h = hc & 1, chunk = hc >> 1;
+                        const int col0 = colh + chunk * 32 + cq;
+                        const int r0 = rbase + 16 * h + g, r1 = r0 + 8;
+                        if (edge)
+                            rowcol_half<true>(r, sc, u, l[2 * h], tt[2 * h], l[2 * h + 1], tt[2 * h + 1], cs, cd, h == 0, col0,
+                                              ncols, r0 < M, r1 < M, args.diag_offset + r0, args.diag_offset + r1, s_nat, pos,
+                                              r0, r1);
+                        else
+                            rowcol_half<false>(r, sc, u, l[2 * h], tt[2 * h], l[2 * h + 1], tt[2 * h + 1], cs, cd, h == 0, col0,
+                                               ncols, true, true, 0, 0, s_nat, nullptr, 0, 0);
+                        if (h == 1) {
+                            // butterfly over the 8 lanes that hold the same columns (lane bits 4, 3, 2): after the
+                            // three steps this lane owns column `own_col` of the chunk
+#pragma unroll
+                            for (int step = 0; step < 3; ++step) {
+                                const int n = 4 >> step;                  // values kept per quantity
+                                const int mask = 16 >> step;
+                                const bool up = (lane & mask) != 0;
+#pragma unroll
+                                for (int i = 0; i < n; ++i) {
+                                    const float ks = up ? cs[i + n] : cs[i], ss = up ? cs[i] : cs[i + n];
+                                    const float kd = up ? cd[i + n] : cd[i], sd = up ? cd[i] : cd[i + n];
+                                    cs[i] = ks + __shfl_xor_sync(0xffffffffu, ss, mask);
+                                    cd[i] = kd + __shfl_xor_sync(0xffffffffu, sd, mask);
+                                }
+                            }
+                            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(cbuf + uint32_t((chunk * 32 + own_col) * 8)),
+                                         "f"(cs[0]), "f"(cd[0]) : "memory");
+                        }
+                    };
+                    // TMEM loads are double buffered; half-chunk hc = 2 * chunk + h covers lanes 16h.. of the quarter
+                    uint32_t ra[16], rb[16];
+                    ptx::tmem_ld_16x256b_x4(taddr, ra);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int hc = 0; hc < 8; hc += 2) {
+                        ptx::tmem_ld_16x256b_x4(taddr + (hc >> 1) * 32 + (16u << 16), rb);
+                        half_chunk(ra, hc);
+                        ptx::tmem_ld_wait();
+                        if (hc + 2 < 8) {
+                            ptx::tmem_ld_16x256b_x4(taddr + ((hc + 2) >> 1) * 32, ra);
+                        } else {
+                            ptx::tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) ptx::mbar_arrive_leader(c.bar_tempty + 8 * a);
+                            TR();
+                        }
+                        half_chunk(rb, hc + 1);
+                        if (hc + 2 < 8) ptx::tmem_ld_wait();
+                    }
+                    // merge the four lane quarters of this half: thread (q, lane) sums column q * 32 + lane
+                    ptx::named_bar_sync(1 + half, 128);
+                    {
+                        const int idx = q * 32 + lane;
+                        const uint32_t src = colbuf + uint32_t((((t & 1) * 2 + half) * 4 * 128 + idx) * 8);
+                        float S = 0.f, D = 0.f;
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) {
+                            float x, y;
+                            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "r"(src + qq * 128 * 8));
+                            S += x; D += y;
+                        }
+                        if (!(args.dbg & 1)) {
+                            const size_t o = (size_t)m_blk * args.ldc + colh + idx;
+                            args.colpart_sum[o] = S;
+                            args.colpart_dot[o] = D;
+                        }
+                    }
+                    TR();
+                }
+                // row statistics of the item: merge the 4 lanes that share the rows, lane (lane & 3) == 0 writes
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    l[i] += __shfl_xor_sync(0xffffffffu, l[i], 1);
+                    tt[i] += __shfl_xor_sync(0xffffffffu, tt[i], 1);
+                    l[i] += __shfl_xor_sync(0xffffffffu, l[i], 2);
+                    tt[i] += __shfl_xor_sync(0xffffffffu, tt[i], 2);
+                }
+                if ((lane & 3) == 0) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = rbase + 8 * i + g;
+                        if (row < M) {
+                            const size_t slot = (size_t)(part * PARTS_PER_UNIT + half) * M + row;
+                            args.part_max[slot] = u;
+                            args.part_sum[slot] = l[i];
+                            args.part_dot[slot] = fmaf(u, l[i], tt[i]);   // sum e * v with v = x + u
+                        }
+                    }
+                }
             }
         }
-    } else {
-        epilogue_unit<MODE_STATS>(c, p, &tmA, args, m_blk, unit, t0, t1);
     }
     cta_teardown(c);
 }
@@ -804,7 +1047,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                  const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                  const __grid_constant__ CUtensorMap tmC1, const KArgs args1, const int jobs0) {
     constexpr int STAGES = stages_of(MODE_OUT);
-    const Cta c = cta_setup<STAGES, true>();
+    const Cta c = cta_setup<STAGES, STG_TOTAL>();
     const int j = blockIdx.x >> 1;   // cluster (2, 1, 1): one job per CTA pair = a 256 x 256 output tile
     const bool first = j < jobs0;
     const KArgs& args = first ? args0 : args1;
@@ -930,7 +1173,7 @@ bwd_dataflow_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     const __grid_constant__ CUtensorMap tmDY, const BwdP P) {
     constexpr int STAGES = stages_of(MODE_GRAD);
     static_assert(stages_of(MODE_GRAD) == stages_of(MODE_OUT), "GRAD and OUT share one shared-memory layout");
-    const Cta c = cta_setup<STAGES, true>();
+    const Cta c = cta_setup<STAGES, STG_TOTAL>();
     const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     const int n_panels = P.n_rp * P.n_cp;
     constexpr unsigned int kTileDone = 2 * NUM_EPI_WARPS;   // epilogue warps of both CTAs

@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     header = open(os.path.join(ROOT, "include", "clipk.h")).read()
     declared = set(re.findall(r"\b(clipk_[a-z0-9_]+)\s*\(", header))
-    assert {"clipk_fwd_stats", "clipk_finalize", "clipk_bwd", "clipk_to_f16", "clipk_cast", "clipk_gemm16"} <= declared
+    assert {"clipk_fwd_stats", "clipk_fwd_both", "clipk_finalize", "clipk_bwd", "clipk_to_f16", "clipk_cast", "clipk_gemm16"} <= declared
     for name in declared:
         assert hasattr(lib, name), name                 # dlsym resolves it
     assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
