@@ -45,6 +45,8 @@ extern "C" {
                          product to ~2^-22 on the 16-bit tensor pipe. */
 
 int clipk_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+long long clipk_launch_count(void);
 const char* clipk_last_error(void);
 
 /* 0 when the current CUDA device can run the kernels (CC 10.x), CLIPK_EARCH otherwise. */

@@ -24,6 +24,7 @@ _ERRNAMES = {-1: "CLIPK_EINVAL", -2: "CLIPK_EUNSUPPORTED", -3: "CLIPK_EARCH", -4
 _vp, _i, _ll, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_size_t
 PROTOTYPES = {
     "clipk_version": (_i, []),
+    "clipk_launch_count": (_ll, []),
     "clipk_last_error": (ctypes.c_char_p, []),
     "clipk_check_device": (_i, []),
     "clipk_to_f16": (_i, [_vp, _i, _ll, _ll, _ll, _vp, _i, _ll, _vp, _vp]),

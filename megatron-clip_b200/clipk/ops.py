@@ -55,7 +55,6 @@ class CudaBackend:
 
     def __init__(self):
         self.lib = _lib.load()
-        self.launches = 0   # kernels launched by this library (counted for bench.py's gpu_launches)
 
     @staticmethod
     def _stream():
@@ -69,7 +68,6 @@ class CudaBackend:
         src_dt = _lib.BF16 if x.dtype == torch.bfloat16 else _lib.F32
         _lib.check(self.lib.clipk_to_f16(x.data_ptr(), src_dt, rows, d, x.stride(0), out.data_ptr(), planes,
                                          planes * dpad, scale_io.data_ptr(), self._stream()), "clipk_to_f16")
-        self.launches += 2
         return Operand(out, _lib.F16 if planes == 1 else _lib.F16X2, planes * dpad, scale_io[1:2], rows, d, scale_io)
 
     def prepare(self, x: torch.Tensor) -> Operand:
@@ -101,7 +99,6 @@ class CudaBackend:
                                             X.inv_ptr(), Y.inv_ptr(), scale.data_ptr(), diag_offset,
                                             out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), _ptr(pos),
                                             ws.data_ptr(), nbytes, self._stream()), "clipk_fwd_stats")
-        self.launches += 2
         return out, pos
 
     def fwd_both(self, X: Operand, Y: Operand, scale, diag_offset, col_out=None):
@@ -119,7 +116,6 @@ class CudaBackend:
                                            X.inv_ptr(), Y.inv_ptr(), scale.data_ptr(), diag_offset,
                                            row_stats.data_ptr(), pos.data_ptr(), col_out.data_ptr(), ws.data_ptr(),
                                            nbytes, self._stream()), "clipk_fwd_both")
-        self.launches += 4
         return row_stats, pos, col_out
 
     def finalize(self, row_stats, pos, col_parts, diag_offset):
@@ -136,7 +132,6 @@ class CudaBackend:
                                            pos.data_ptr(), rows, cbase, cbase + cols * 4, cbase + 2 * cols * 4, nparts,
                                            3 * cols, cols, diag_offset, lse_row.data_ptr(), lse_col.data_ptr(),
                                            sums.data_ptr(), self._stream()), "clipk_finalize")
-        self.launches += 1
         return lse_row, lse_col, sums
 
     def bwd(self, X: Operand, Y: Operand, Xg: Operand, Yg: Operand, scale, diag_offset, lse_row, lse_col, alpha,
@@ -153,7 +148,6 @@ class CudaBackend:
                                       lse_row.data_ptr(), lse_col.data_ptr(), float(alpha), float(beta),
                                       gscale.data_ptr(), _ptr(dX), _ptr(dY), ws.data_ptr(), nbytes, self._stream()),
                    "clipk_bwd")
-        self.launches += 2 * ((rows + 4735) // 4736) * ((cols + 4863) // 4864)   # approximate: 2 launches per panel
         return dX, dY
 
     def cast(self, src: torch.Tensor, dtype: torch.dtype):
@@ -162,7 +156,6 @@ class CudaBackend:
         out = torch.empty(src.shape, dtype=dtype, device=src.device)
         _lib.check(self.lib.clipk_cast(src.data_ptr(), out.data_ptr(), src.numel(), _lib.BF16, self._stream()),
                    "clipk_cast")
-        self.launches += 1
         return out
 
 
@@ -180,7 +173,7 @@ def _backend():
 
 def gpu_launches() -> int:
     """Number of clipk kernels launched so far in this process."""
-    return 0 if _CUDA_BACKEND is None else _CUDA_BACKEND.launches
+    return 0 if _CUDA_BACKEND is None else int(_CUDA_BACKEND.lib.clipk_launch_count())
 
 
 # ----------------------------------------------------------------------------------------------------- collectives

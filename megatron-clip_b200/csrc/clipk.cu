@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -14,6 +15,7 @@ namespace clipk {
 
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};   // kernels launched by this library (clipk_launch_count)
 
 static int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -476,8 +478,11 @@ static inline long long round_up(long long a, long long b) { return (a + b - 1) 
 
 constexpr int MAX_SPLIT = 32;
 constexpr int MAX_PARTS = MAX_SPLIT * PARTS_PER_UNIT;
-// Budget of the fp16 G panel.  48 MB keeps it L2 resident (126 MB L2) next to the operands; CLIPK_PANEL_MB overrides
-// it for experiments (a larger panel spills to HBM but amortises the per-launch fill/drain over longer kernels).
+// Budget of the fp16 G panel (CLIPK_PANEL_MB overrides it).  It is a constant, independent of the problem size: the
+// softmax gradient only ever exists as one panel.  Measured at N = 32768, d = 512 (B200, bwd only): 48 MB (18 x 19
+// blocks of 256, fully L2 resident, 56 panels) 3.13 ms; 134-179 MB (32 x 32 blocks, 16 panels, two tiles per CTA pair in
+// the gradient-GEMM launch) 2.82 ms - the panel no longer fits the 126 MB L2 entirely and part of it streams through
+// HBM, but the per-launch fill / drain is paid 16 instead of 56 times, which is worth more.
 static int use_persistent() {
     static int v = [] { const char* e = getenv("CLIPK_PERSISTENT"); return e ? atoi(e) : 0; }();
     return v;
@@ -487,10 +492,21 @@ static int dbg_flags() {
     return v;
 }
 static long long* g_trace = nullptr;   // set by clipk_debug_set_trace (experiments only)
+// the dataflow backward keeps THREE panels alive (written / waiting / read): 3 x 32 MB still fits the 126 MB L2
+static long long df_panel_bytes() {
+    static long long v = [] {
+        const char* e = getenv("CLIPK_DF_PANEL_MB");
+        long long mb = e ? atoll(e) : 32;
+        if (mb < 4) mb = 4;
+        if (mb > 1024) mb = 1024;
+        return mb << 20;
+    }();
+    return v;
+}
 static long long panel_bytes() {
     static long long v = [] {
         const char* e = getenv("CLIPK_PANEL_MB");
-        long long mb = e ? atoll(e) : 48;
+        long long mb = e ? atoll(e) : 192;
         if (mb < 8) mb = 8;
         if (mb > 1024) mb = 1024;
         return mb << 20;
@@ -516,7 +532,7 @@ static int choose_split(int m_pairs, int n_tiles, int sms) {
 // Panel of the backward: G[rp x cp] is produced once and consumed by the dX tiles (rp/128 * nt CTAs, K = cp) and the
 // dY tiles (cp/128 * nt CTAs, K = rp) of ONE launch; pick rp, cp so that launch is close to a whole number of waves
 // with long K, and the panel fits the L2 budget.  Then even the panels out over the problem.
-static void choose_panel(int rows, int cols, int d, int gplanes, int sms, long long* rp_out, long long* cp_out) {
+static void choose_panel(int rows, int cols, int d, int gplanes, int sms, long long budget, long long* rp_out, long long* cp_out) {
     const int nt = cdiv(d, BN);
     const int R = cdiv(rows, 2 * BM), C = cdiv(cols, BN);       // available 256-row / 256-col blocks
     const int pairs = sms / 2;
@@ -529,7 +545,7 @@ static void choose_panel(int rows, int cols, int d, int gplanes, int sms, long l
         int cb = total - rb;
         if (cb > C) { cb = C; rb = total - cb < R ? total - cb : R; }
         if (cb < 1) cb = 1;
-        while ((long long)rb * cb * 4 * BM * BM * 2 * gplanes > panel_bytes() && (rb > 1 || cb > 1)) {
+        while ((long long)rb * cb * 4 * BM * BM * 2 * gplanes > budget && (rb > 1 || cb > 1)) {
             if (rb >= cb && rb > 1) --rb; else --cb;
         }
         const int jobs = (rb + cb) * nt;
@@ -539,6 +555,9 @@ static void choose_panel(int rows, int cols, int d, int gplanes, int sms, long l
         const double per_area = t / ((double)rb * cb);
         if (per_area < best) { best = per_area; best_rb = rb; best_cb = cb; }
     }
+    // experiments: CLIPK_PANEL_RB / CLIPK_PANEL_CB force the panel extents (in 256-blocks)
+    if (const char* e = getenv("CLIPK_PANEL_RB")) best_rb = std::max(1, std::min(R, atoi(e)));
+    if (const char* e = getenv("CLIPK_PANEL_CB")) best_cb = std::max(1, std::min(C, atoi(e)));
     const int nrp = cdiv(R, best_rb), ncp = cdiv(C, best_cb);
     *rp_out = (long long)cdiv(R, nrp) * 2 * BM;
     *cp_out = (long long)cdiv(C, ncp) * BN;
@@ -564,6 +583,7 @@ static int launch_clustered(void (*kfn)(Args...), dim3 grid, dim3 cluster, int s
     cfg.attrs = attr;
     cfg.numAttrs = (dbg_flags() & 32) ? 1 : 2;
     CK_CUDA(cudaLaunchKernelEx(&cfg, kfn, args...));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return CLIPK_OK;
 }
 
@@ -635,7 +655,7 @@ static void set_segments(KArgs& a, int planes, int k_extent, long long a_plane, 
 struct BwdPlanDev {
     int* shift;
     int* start;
-    unsigned char* pos;
+    unsigned char* owner;
 };
 struct BwdPlanKey {
     int dev, rows, cols, d, rp, cp, nt, want_dx, want_dy, s_kb, g_nseg, n_clusters, tile_extra;
@@ -677,9 +697,9 @@ static int get_bwd_plan(const BwdP& P, int n_clusters, const BwdPlanDev** out) {
     std::vector<unsigned char> host(bytes, 0);
     int* shift = reinterpret_cast<int*>(host.data());
     int* start = shift + n_panels;            // [q][cluster] = {first tile, end tile}
-    unsigned char* pos = host.data() + n_int * 4;
-    // A cluster's sequence is G(0) O(0) G(1) O(1) ...: the tiles of panel q are needed by every job right after they
-    // are produced, so what has to take equally long on every cluster is O(q - 1) followed by G(q).
+    unsigned char* owner = host.data() + n_int * 4;
+    // A cluster's sequence is G(0) G(1) O(0) G(2) O(1) ...: what has to take equally long on every cluster is the
+    // phase G(q) followed by O(q - 1).
     std::vector<double> prev_work(n, 0.0), work(n);
     for (int q = 0; q < n_panels; ++q) {
         const int ri = q / P.n_cp, ci = q - ri * P.n_cp;
@@ -704,7 +724,7 @@ static int get_bwd_plan(const BwdP& P, int n_clusters, const BwdPlanDev** out) {
             if (i == n - 1) f1 = tiles;
             if (f1 < f) f1 = f;
             st[2 * c] = f; st[2 * c + 1] = f1;
-            for (int t = f; t < f1; ++t) pos[size_t(q) * max_tiles + t] = (unsigned char)std::min(t - f, 255);
+            for (int t = f; t < f1; ++t) owner[size_t(q) * max_tiles + t] = (unsigned char)c;
             f = f1;
         }
         for (int c = 0; c < n; ++c) {
@@ -722,7 +742,7 @@ static int get_bwd_plan(const BwdP& P, int n_clusters, const BwdPlanDev** out) {
     en.key = key; en.block = block;
     en.dev.shift = static_cast<int*>(block);
     en.dev.start = en.dev.shift + n_panels;
-    en.dev.pos = static_cast<unsigned char*>(block) + n_int * 4;
+    en.dev.owner = static_cast<unsigned char*>(block) + n_int * 4;
     *out = &en.dev;
     return CLIPK_OK;
 }
@@ -789,6 +809,7 @@ using namespace clipk;
 extern "C" {
 
 int clipk_version(void) { return CLIPK_VERSION; }
+long long clipk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 const char* clipk_last_error(void) { return g_err; }
 
 int clipk_check_device(void) {
@@ -819,11 +840,15 @@ int clipk_to_f16(const void* src, int src_dtype, long long rows, long long d, lo
     if (src_dtype == CLIPK_BF16) {
         const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(src);
         amax_kernel<<<rblocks, 256, 0, st>>>(p, rows, d / 8, ld_src, bits);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
         to_f16_kernel<<<cdiv(n, 256), 256, 0, st>>>(p, out, rows, d, ld_src, dpad, planes, scale_io);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
     } else {
         const float* p = static_cast<const float*>(src);
         amax_kernel<<<rblocks, 256, 0, st>>>(p, rows, d / 8, ld_src, bits);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
         to_f16_kernel<<<cdiv(n, 256), 256, 0, st>>>(p, out, rows, d, ld_src, dpad, planes, scale_io);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
     }
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
@@ -874,6 +899,7 @@ int clipk_fwd_stats(const void* X, const void* Y, int rows, int cols, int d, lon
     if (rc) return rc;
     merge_row_parts_kernel<<<cdiv(rows, 256), 256, 0, st>>>(a.part_max, a.part_sum, a.part_dot, units * PARTS_PER_UNIT,
                                                             rows, row_max, row_sum, row_dot);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
 }
@@ -928,6 +954,7 @@ int clipk_fwd_both(const void* X, const void* Y, int rows, int cols, int d, long
         const int bx = std::max(1, std::min(cdiv(rows, wpb), 2 * di.sms)), by = std::max(1, std::min(cdiv(cols, wpb), 2 * di.sms));
         norm2_max_kernel<<<bx + by, wpb * 32, 0, st>>>(static_cast<const __nv_bfloat16*>(X), rows, ldx,
                                                         static_cast<const __nv_bfloat16*>(Y), cols, ldy, d / 8, bx, norm2);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
         CK_CUDA(cudaGetLastError());
     }
     CUtensorMap tx_a, ty_b, ty_a, tx_b;
@@ -974,6 +1001,7 @@ int clipk_fwd_both(const void* X, const void* Y, int rows, int cols, int d, long
     const int n = rows > cols ? rows : cols;
     fwd_merge_kernel<<<cdiv(n, 128), 128, 0, st>>>(a0, a0.split * PARTS_PER_UNIT, a1.part_max, a1.part_sum, a1.part_dot,
                                                    a1.split * PARTS_PER_UNIT, cv.m_blocks, row_stats, col_stats);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
 }
@@ -996,19 +1024,17 @@ int clipk_finalize(const float* row_max, const float* row_sum, const float* row_
     finalize_kernel<<<cdiv(n, 256), 256, 0, st>>>(row_max, row_sum, row_dot, pos_logit, rows, col_max_parts, col_sum_parts,
                                                   col_dot_parts, nparts, part_stride, cols, diag_offset, lse_row, lse_col,
                                                   sums);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
 }
 
 size_t clipk_bwd_workspace_bytes(int rows, int cols, int d, int g_dtype) {
     if (rows <= 0 || cols <= 0 || d <= 0) return 0;
-    long long rp, cp;
-    choose_panel(rows, cols, d, planes_of(g_dtype), 148, &rp, &cp);
-    // the SM count only nudges the split; size for the L2 budget so any device fits
-    (void)rp; (void)cp;
-    // two G panels, slack for their padding, the reference vectors, and the per-tile / per-panel counters of the dataflow schedule
+    // G panels (one of panel_bytes() for the per-panel path, three of df_panel_bytes() for the dataflow path), slack for their padding, the reference vectors, and the per-tile / per-panel counters of the dataflow schedule
     const size_t counters = (size_t(cdiv(rows, 2 * BM)) + 64) * (size_t(cdiv(cols, BN)) + 64) * 2 * sizeof(int);
-    return size_t(2) * size_t(panel_bytes()) + size_t(4) * 1024 * 1024 + (size_t(rows) + size_t(cols)) * sizeof(float) + counters + 4096;
+    const size_t panels = std::max(size_t(2) * size_t(panel_bytes()), size_t(3) * size_t(df_panel_bytes()));
+    return panels + size_t(4) * 1024 * 1024 + (size_t(rows) + size_t(cols)) * sizeof(float) + counters + 4096;
 }
 
 int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
@@ -1035,7 +1061,7 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
     const long long kext = (dtype == CLIPK_BF16) ? d : planes * dpad;   // inner extent of X / Y rows
     const long long gext = gplanes * dpad;                              // inner extent of Xg / Yg rows
     long long rp_max, cp_max;
-    choose_panel(rows, cols, d, gplanes, di.sms, &rp_max, &cp_max);
+    choose_panel(rows, cols, d, gplanes, di.sms, use_persistent() ? df_panel_bytes() : panel_bytes(), &rp_max, &cp_max);
     const int ncp = int(cp_max);                        // panel width (multiple of BN) = G plane stride
     const int ldg = gplanes * ncp;
     if ((unsigned long long)round_up(rp_max, 2 * BM) * ldg * 2 > workspace_bytes) return fail(CLIPK_EWORKSPACE, "panel does not fit the workspace");
@@ -1060,7 +1086,7 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
         });
         if (attr_err != cudaSuccess) return fail(int(attr_err), "dataflow backward setup: %s", cudaGetErrorString(attr_err));
         const int n_clusters = max_clusters < di.sms / 2 ? max_clusters : di.sms / 2;
-        if (n_clusters < 1) return fail(CLIPK_EUNSUPPORTED, "no CTA pair of the dataflow backward fits this device");
+        if (n_clusters < 1 || n_clusters > 255) return fail(CLIPK_EUNSUPPORTED, "the dataflow backward needs 1..255 co-resident CTA pairs");
 
         BwdP P{};
         P.rows = rows; P.cols = cols; P.d = d; P.diag_offset = diag_offset;
@@ -1082,22 +1108,22 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
         P.max_tiles = cdiv(P.rp, 2 * BM) * cdiv(P.cp, BN);
         const BwdPlanDev* plan = nullptr;
         if ((rc = get_bwd_plan(P, n_clusters, &plan))) return rc;
-        P.plan_shift = plan->shift; P.plan_start = plan->start; P.plan_pos = plan->pos;
+        P.plan_shift = plan->shift; P.plan_start = plan->start; P.plan_owner = plan->owner;
 
-        // workspace: two G buffers | avec | bvec | gref[4] | minmax[2] | out_done[n_panels] | tile_flags[n_panels][max_tiles]
+        // workspace: three G buffers | avec | bvec | gref[4] | minmax[2] | out_done[n_panels] | done[n_clusters]
         const int gbuf_rows = int(round_up(rp_max, 2 * BM));
         P.gbuf_rows = gbuf_rows;
-        const size_t g2_bytes = size_t(round_up((long long)2 * gbuf_rows * ldg * 2, 256));
+        const size_t g2_bytes = size_t(round_up((long long)3 * gbuf_rows * ldg * 2, 256));
         float* avec2 = reinterpret_cast<float*>(static_cast<char*>(workspace) + g2_bytes);
         float* bvec2 = avec2 + round_up(rows, 64);
         float* gref2 = bvec2 + round_up(cols, 64);
         int* mm2 = reinterpret_cast<int*>(gref2 + 4);
         unsigned int* out_done = reinterpret_cast<unsigned int*>(mm2 + 4);
-        unsigned int* tile_flags = out_done + round_up(n_panels, 4);
-        const size_t ctl_words = size_t(round_up(n_panels, 4)) + size_t(n_panels) * P.max_tiles;
+        unsigned int* done = out_done + round_up(n_panels, 4);
+        const size_t ctl_words = size_t(round_up(n_panels, 4)) + size_t(round_up(n_clusters, 4));
         const size_t need = g2_bytes + (round_up(rows, 64) + round_up(cols, 64) + 8) * sizeof(float) + ctl_words * 4;
-        if (need > workspace_bytes) return fail(CLIPK_EWORKSPACE, "workspace too small for two G panels, the reference vectors and the flags (%zu > %zu)", need, workspace_bytes);
-        P.out_done = out_done; P.tile_flags = tile_flags;
+        if (need > workspace_bytes) return fail(CLIPK_EWORKSPACE, "workspace too small for three G panels, the reference vectors and the flags (%zu > %zu)", need, workspace_bytes);
+        P.out_done = out_done; P.done = done;
         CK_CUDA(cudaMemsetAsync(mm2, 0x7f, sizeof(int), st));
         CK_CUDA(cudaMemsetAsync(mm2 + 1, 0x80, sizeof(int), st));
         CK_CUDA(cudaMemsetAsync(out_done, 0, ctl_words * 4, st));
@@ -1108,16 +1134,18 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
             int blocks = cdiv(n, 256);
             if (blocks > 4 * di.sms) blocks = 4 * di.sms;
             lse_minmax_kernel<<<blocks, 256, 0, st>>>(lse_row, rows, lse_col, cols, mm2);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
             const int m = rows > cols ? rows : cols;
             grad_prep_kernel<<<cdiv(m, 256), 256, 0, st>>>(lse_row, rows, lse_col, cols, mm2, avec2, bvec2, gref2);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
             CK_CUDA(cudaGetLastError());
         }
         CUtensorMap tmX, tmY, tmGst, tmGk, tmGmn, tmYg, tmXg, tmDX, tmDY;
         if ((rc = tmap_kmajor(&tmX, X, rows, kext, ldx, BM))) return rc;
         if ((rc = tmap_kmajor(&tmY, Y, cols, kext, ldy, BN / 2))) return rc;
-        if ((rc = tmap_g_store(&tmGst, G, 2 * gbuf_rows, ldg, ldg))) return rc;
-        if ((rc = tmap_kmajor(&tmGk, G, 2 * gbuf_rows, ldg, ldg, BM))) return rc;
-        if ((rc = tmap_mnmajor(&tmGmn, G, ldg, 2 * gbuf_rows, ldg))) return rc;
+        if ((rc = tmap_g_store(&tmGst, G, 3 * gbuf_rows, ldg, ldg))) return rc;
+        if ((rc = tmap_kmajor(&tmGk, G, 3 * gbuf_rows, ldg, ldg, BM))) return rc;
+        if ((rc = tmap_mnmajor(&tmGmn, G, ldg, 3 * gbuf_rows, ldg))) return rc;
         if ((rc = tmap_mnmajor(&tmYg, Yg, gext, cols, ldyg))) return rc;
         if ((rc = tmap_mnmajor(&tmXg, Xg, gext, rows, ldxg))) return rc;
         // a skipped gradient still needs a valid descriptor: point it at the other output
@@ -1153,8 +1181,10 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
         int blocks = cdiv(n, 256);
         if (blocks > 4 * di.sms) blocks = 4 * di.sms;
         lse_minmax_kernel<<<blocks, 256, 0, st>>>(lse_row, rows, lse_col, cols, mm);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
         const int m = rows > cols ? rows : cols;
         grad_prep_kernel<<<cdiv(m, 256), 256, 0, st>>>(lse_row, rows, lse_col, cols, mm, avec, bvec, gref);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
         CK_CUDA(cudaGetLastError());
     }
     const size_t esz = 2;
@@ -1237,6 +1267,7 @@ int clipk_debug_tmem_layout(int* out, void* stream) {
     int rc = device_info(&di);
     if (rc) return rc;
     tmem_layout_kernel<<<1, 128, 0, static_cast<cudaStream_t>(stream)>>>(out);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
 }
@@ -1246,6 +1277,7 @@ int clipk_cast(const float* src, void* dst, long long n, int dtype, void* stream
     if (dtype != CLIPK_BF16 && dtype != CLIPK_F32) return fail(CLIPK_EUNSUPPORTED, "dtype %d", dtype);
     if (n == 0) return CLIPK_OK;
     cast_kernel<<<cdiv(cdiv(n, 4), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, n, dtype);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
 }

@@ -240,7 +240,6 @@ struct Pipe {
     int it = 0;         // tiles processed so far (MMA / epilogue): accumulator stage = it & 1
     int stg_use = 0;    // TMA stores issued so far by this epilogue warp
     int tr = 0;         // clock64 stamps recorded so far by this role (experiments)
-    unsigned int* pend = nullptr;   // dataflow backward: completion counter of the G tile whose stores may still be in flight
 };
 
 // experiments: stamp number p.tr of `role` (0 producer, 1 MMA, 2 first epilogue warp)
@@ -378,24 +377,26 @@ __device__ __forceinline__ void flag_signal(unsigned int* flag) {
 }
 
 // Gradient-GEMM job of the dataflow backward: the K extent is made of `nkt` 256-wide pieces, piece i being one G tile
-// whose completion counter is flags[i * fstride].  Pieces are loaded in the order they were produced (`pos` = rank
-// of the tile in its producer's list), so the job starts on the oldest tiles while the newest are still being written.
+// written by cluster owner[i * fstride].  Before the first load that touches a tile its owner must have published the
+// panel (done[owner] >= target); `seen` remembers the owners already checked for this panel.
 template <int STAGES>
 __device__ __forceinline__ void produce_job(const Cta& c, Pipe& p, const CUtensorMap* tmA, const CUtensorMap* tmB,
-                                            const KArgs& args, int m_blk, int t, int nkt, const unsigned int* flags,
-                                            const unsigned char* pos, int fstride, unsigned int target) {
+                                            const KArgs& args, int m_blk, int t, int nkt, const unsigned int* done,
+                                            const unsigned char* owner, int fstride, unsigned int target,
+                                            unsigned long long (&seen)[4]) {
     constexpr int KB_PER_TILE = BN / BK;
     trace_stamp(args, p, 0);
     for (int seg = 0; seg < args.nseg; ++seg) {
-        int done = 0;
-        for (int pass = 0; done < nkt; ++pass) {
-            for (int i = 0; i < nkt; ++i) {
-                if (int(pos[i * fstride]) != pass) continue;
-                if (seg == 0) flag_wait(flags + i * fstride, target);
-                const int kb1 = min(args.kb_per_seg, (i + 1) * KB_PER_TILE);
-                for (int kb = i * KB_PER_TILE; kb < kb1; ++kb) load_kblock<STAGES>(c, p, tmA, tmB, args, m_blk, t, seg, kb);
-                ++done;
+        for (int i = 0; i < nkt; ++i) {
+            if (seg == 0 && target) {
+                const int o = owner[i * fstride];
+                if (!((seen[o >> 6] >> (o & 63)) & 1ull)) {
+                    flag_wait(done + o, target);
+                    seen[o >> 6] |= 1ull << (o & 63);
+                }
             }
+            const int kb1 = min(args.kb_per_seg, (i + 1) * KB_PER_TILE);
+            for (int kb = i * KB_PER_TILE; kb < kb1; ++kb) load_kblock<STAGES>(c, p, tmA, tmB, args, m_blk, t, seg, kb);
         }
     }
     trace_stamp(args, p, 0);
@@ -559,7 +560,7 @@ __device__ __forceinline__ void epilogue_unit(const Cta& c, Pipe& p, const CUten
 // 168 a 10-warp CTA allows; four pieces (64 columns = 128 B of fp16 per row) fill one staging buffer = one TMA store.
 template <bool TWO_PLANES>
 __device__ __forceinline__ void grad_epilogue_unit(const Cta& c, Pipe& p, const CUtensorMap* tmC, const KArgs& args,
-                                                   int m_blk, int t0, int t1, unsigned int* tile_flags = nullptr) {
+                                                   int m_blk, int t0, int t1) {
     const int warp = c.warp, lane = c.lane;
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
@@ -660,16 +661,6 @@ __device__ __forceinline__ void grad_epilogue_unit(const Cta& c, Pipe& p, const 
             if (pi + 2 < 8) ptx::tmem_ld_wait();
         }
         TR();
-        if (tile_flags && lane == 0) {
-            // the stores of the PREVIOUS tile were committed a whole tile ago: wait for them (the two groups of this
-            // tile may stay in flight) and publish that tile
-            if (p.pend) {
-                if (dbg & 8192) atomicAdd(p.pend, 1u);
-                else { ptx::tma_store_wait<2>(); flag_signal(p.pend); }
-            }
-            p.pend = tile_flags + t;
-        }
-        if (dbg & 2048) TR();
     }
 }
 
@@ -678,16 +669,6 @@ __device__ __forceinline__ void epilogue_drain(const Cta& c) {
     if (c.lane == 0) ptx::tma_store_wait<0>();
     __syncwarp();
 }
-// dataflow backward: publish the last G tile this warp wrote
-__device__ __forceinline__ void epilogue_flush_flag(const Cta& c, Pipe& p) {
-    if (c.lane == 0 && p.pend) {
-        ptx::tma_store_wait<0>();
-        flag_signal(p.pend);
-        p.pend = nullptr;
-    }
-    __syncwarp();
-}
-
 // ---------------------------------------------------------------------------------------------------- kernels
 // One unit per CTA pair: grid = (2 * m_pairs, units), cluster (2, 1, 1).
 template <int MODE, int F16>
@@ -1075,18 +1056,20 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
 // ---------------------------------------------------------------------------------------------------- dataflow backward
 // ONE launch for the whole backward, one CTA pair per SM pair, no grid-wide barrier.  The [rows x cols] block is cut
-// into panels (rp x cp, both multiples of 256); the fp16 G of panel q lives in L2-sized buffer q & 1.  Every pair
-// walks the panels in order and runs, per panel, its share of the recompute (GRAD) tiles and then its gradient-GEMM
-// job(s) on the SAME panel, back to back through one set of smem / TMEM pipelines - so the epilogue of one item
-// overlaps the MMAs of the next across item types.  Dependencies are tracked per G tile:
-//   * an epilogue warp counts a tile as done (tile_flags[q][tile] += 1; 16 per tile) once its bulk stores of the
-//     tile have completed; the TMA producer of a gradient-GEMM job waits for the flag of the tile behind each
-//     256-wide piece of its K extent, visiting the pieces in the order they were produced;
-//   * a job counts itself done (out_done[q] += 1) once its last MMA has completed; the first G store of panel q + 2
-//     (same buffer) waits until all jobs of panel q are done.
-// Every pair executes GRAD(0) < OUT(0) < GRAD(1) < ... in this order and every dependency points backwards in it,
-// so with all pairs co-resident the schedule cannot deadlock.  The share of GRAD tiles of a pair is weighted by the
-// length of its job (plan computed on the host, see build_bwd_plan), which evens out the work per panel.
+// into panels (rp x cp, both multiples of 256); the fp16 G of panel q lives in L2-sized buffer q % 3.  Every pair
+// walks the sequence  G(0) G(1) O(0) G(2) O(1) G(3) O(2) ...  where G(q) is its share of the recompute tiles of panel
+// q and O(q) its gradient-GEMM job(s) on panel q, back to back through one set of smem / TMEM pipelines - so the
+// epilogue of one item overlaps the MMAs of the next across item types.  Dependencies:
+//   * after G(q) the epilogue warps of a CTA wait for their bulk stores, meet at a named barrier, and ONE thread
+//     publishes with a gpu-scope fence: done[cluster] += 1 (2 per panel and pair).  This costs several microseconds
+//     (store completion + fence) but runs while the MMA thread is already inside O(q - 1), whose epilogue is far away;
+//   * the TMA producer of O(q) checks done[owner] >= 2 (q + 1) for the owners of the G tiles behind its K extent.
+//     They were produced a whole G stretch earlier, so the check normally passes at once;
+//   * a job counts itself done (out_done[q] += 1) once its last MMA has completed; the first G store of panel q + 3
+//     (same buffer) waits until all jobs of panel q are done - two phases of slack.
+// Every pair executes the items in the same global order and every dependency points backwards in it, so with all pairs
+// co-resident the schedule cannot deadlock.  The share of recompute tiles of a pair is weighted by the length of the
+// job it runs in the same phase (plan computed on the host, see get_bwd_plan), which evens out the phases.
 struct BwdP {
     int rows, cols, d;
     long long diag_offset;
@@ -1098,12 +1081,12 @@ struct BwdP {
     int s_nseg, s_kb_per_seg, s_a_off[3], s_b_off[3];       // K segments of the recompute GEMM
     int g_nseg, g_a_off[3], g_b_off[3];                     // plane pairs of the gradient GEMMs (K extent varies per panel)
     // plan (read only): shift[q] (cluster c runs jobs v, v + n, ... with v = (c + shift[q]) % n); start[q][c] = {first,
-    // end} recompute tile of cluster c; pos[q][tile] = rank of the tile in its producer's list
+    // end} recompute tile of cluster c; owner[q][tile] = cluster that recomputes the tile
     const int* plan_shift;
     const int* plan_start;
-    const unsigned char* plan_pos;
+    const unsigned char* plan_owner;
     int max_tiles;               // stride of the per-panel tile arrays
-    unsigned int* tile_flags;    // [n_panels][max_tiles], zero at launch
+    unsigned int* done;          // [n_clusters] panels published per cluster (x 2 CTAs), zero at launch
     unsigned int* out_done;      // [n_panels], zero at launch
     const float* xg_inv;         // dequant scalars of the fp16 feature copies used by the gradient GEMMs (null = 1)
     const float* yg_inv;
@@ -1141,7 +1124,7 @@ __device__ __forceinline__ void make_grad_args(const BwdP& P, int q, KArgs& a) {
     a.diag_offset = P.diag_offset + x.r0 - x.c0;
     a.lse_row = P.base.lse_row + x.r0; a.lse_col = P.base.lse_col + x.c0;
     a.avec = P.base.avec + x.r0; a.bvec = P.base.bvec + x.c0;
-    a.c_col_off = 0; a.c_row_off = (q & 1) * P.gbuf_rows;
+    a.c_col_off = 0; a.c_row_off = (q % 3) * P.gbuf_rows;
 }
 // gradient-GEMM job of panel q: which = 0: dX[r0.., :] (+)= G * Yg[c0.., :]; which = 1: dY[c0.., :] (+)= G^T * Xg[r0.., :]
 __device__ __forceinline__ void make_out_args(const BwdP& P, int q, int which, KArgs& a) {
@@ -1155,7 +1138,7 @@ __device__ __forceinline__ void make_out_args(const BwdP& P, int q, int which, K
     for (int i = 0; i < 3; ++i) { a.a_off[i] = P.g_a_off[i]; a.b_off[i] = P.g_b_off[i]; }
     a.a_mn = which; a.b_mn = 1; a.f16 = 1;
     // A = G: K-major rows of the buffer (job 0) or its transpose, K = buffer rows (job 1); B = features, K = their rows
-    a.a_outer_off = (q & 1) * P.gbuf_rows;
+    a.a_outer_off = (q % 3) * P.gbuf_rows;
     a.b_outer_off = which == 0 ? x.c0 : x.r0;
     a.n_tiles = P.nt;
     a.c_col_off = 0; a.c_row_off = which == 0 ? x.r0 : x.c0;
@@ -1195,72 +1178,81 @@ bwd_dataflow_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     };
 
     if (active) {
-        for (int q = 0; q < n_panels; ++q) {
-            GT(q, 0);
-            const Panel x = panel_of(P, q);
-            const int m_pairs = cdiv_d(x.nr, 2 * BM), n_tiles = cdiv_d(x.nc, BN);
-            const int v = (cluster + __ldg(P.plan_shift + q)) % n_clusters;
-            int f0 = __ldg(P.plan_start + ((size_t)q * n_clusters + cluster) * 2);
-            const int f1 = __ldg(P.plan_start + ((size_t)q * n_clusters + cluster) * 2 + 1);
-            unsigned int* flags_q = P.tile_flags + (size_t)q * P.max_tiles;
-            const unsigned char* pos_q = P.plan_pos + (size_t)q * P.max_tiles;
-
-            // ---- recompute tiles [f0, f1) of panel q (flat index = row pair * n_tiles + column tile)
-            if (f0 < f1 && !(P.base.dbg & 128)) {
-                KArgs a;
-                make_grad_args(P, q, a);
-                a.trace_on = (blockIdx.x == 0 && !(P.base.dbg & 1024)) ? 2 : 0;
-                if (c.warp >= 2 && q >= 2 && !(P.base.dbg & 64)) {
-                    // buffer q & 1 was last read by the jobs of panel q - 2
-                    if (c.lane == 0) flag_wait(P.out_done + (q - 2), (unsigned int)jobs_of(P, panel_of(P, q - 2)));
-                    __syncwarp();
-                }
-                while (f0 < f1) {
-                    const int m_pair = f0 / n_tiles;
-                    const int t0 = f0 - m_pair * n_tiles;
-                    const int t1 = min(n_tiles, t0 + (f1 - f0));
-                    const int m_blk = 2 * m_pair + int(c.cta_rank);
-                    if (c.warp == 0) {
-                        produce_unit<STAGES>(c, p, &tmX, &tmY, a, m_blk, t0, t1);
-                    } else if (c.warp == 1) {
-                        mma_unit<STAGES>(c, p, a, t1 - t0);
-                    } else {
-                        if (a.g_planes == 2) grad_epilogue_unit<true>(c, p, &tmGst, a, m_blk, t0, t1, flags_q + m_pair * n_tiles);
-                        else grad_epilogue_unit<false>(c, p, &tmGst, a, m_blk, t0, t1, flags_q + m_pair * n_tiles);
+        for (int q = 0; q <= n_panels; ++q) {
+            if (q < n_panels) GT(q, 0);
+            // ---- G(q): recompute tiles [f0, f1) of panel q (flat index = row pair * n_tiles + column tile)
+            if (q < n_panels) {
+                const Panel x = panel_of(P, q);
+                const int n_tiles = cdiv_d(x.nc, BN);
+                int f0 = __ldg(P.plan_start + ((size_t)q * n_clusters + cluster) * 2);
+                const int f1 = __ldg(P.plan_start + ((size_t)q * n_clusters + cluster) * 2 + 1);
+                if (f0 < f1 && !(P.base.dbg & 128)) {
+                    KArgs a;
+                    make_grad_args(P, q, a);
+                    a.trace_on = (blockIdx.x == 0 && !(P.base.dbg & 1024)) ? 2 : 0;
+                    if (c.warp >= 2 && q >= 3 && !(P.base.dbg & 64)) {
+                        // buffer q % 3 was last read by the jobs of panel q - 3
+                        if (c.lane == 0) flag_wait(P.out_done + (q - 3), (unsigned int)jobs_of(P, panel_of(P, q - 3)));
+                        __syncwarp();
                     }
-                    f0 += t1 - t0;
+                    while (f0 < f1) {
+                        const int m_pair = f0 / n_tiles;
+                        const int t0 = f0 - m_pair * n_tiles;
+                        const int t1 = min(n_tiles, t0 + (f1 - f0));
+                        const int m_blk = 2 * m_pair + int(c.cta_rank);
+                        if (c.warp == 0) {
+                            produce_unit<STAGES>(c, p, &tmX, &tmY, a, m_blk, t0, t1);
+                        } else if (c.warp == 1) {
+                            mma_unit<STAGES>(c, p, a, t1 - t0);
+                        } else {
+                            if (a.g_planes == 2) grad_epilogue_unit<true>(c, p, &tmGst, a, m_blk, t0, t1);
+                            else grad_epilogue_unit<false>(c, p, &tmGst, a, m_blk, t0, t1);
+                        }
+                        f0 += t1 - t0;
+                    }
                 }
-                if (c.warp >= 2) epilogue_flush_flag(c, p);
+                if (c.warp >= 2) {
+                    // publish panel q of this CTA (also when it had no tiles: the counters advance in lockstep)
+                    epilogue_drain(c);
+                    ptx::named_bar_sync(3, NUM_EPI_WARPS * 32);
+                    if (c.warp == 2 && c.lane == 0) flag_signal(P.done + cluster);
+                }
+                GT(q, 1);
             }
-            GT(q, 1);
-            // ---- gradient-GEMM jobs v, v + n, ... of panel q
-            if (!(P.base.dbg & 64)) {
+            // ---- O(q - 1): gradient-GEMM jobs v, v + n, ... of the previous panel
+            if (q >= 1 && !(P.base.dbg & 64)) {
+                const int qo = q - 1;
+                const Panel x = panel_of(P, qo);
+                const int m_pairs = cdiv_d(x.nr, 2 * BM), n_tiles = cdiv_d(x.nc, BN);
+                const int v = (cluster + __ldg(P.plan_shift + qo)) % n_clusters;
+                const unsigned char* own_q = P.plan_owner + (size_t)qo * P.max_tiles;
                 const int jobs0 = P.want_dx ? m_pairs * P.nt : 0;
                 const int jobs1 = P.want_dy ? cdiv_d(x.nc, 2 * BM) * P.nt : 0;
+                unsigned long long seen[4] = {0ull, 0ull, 0ull, 0ull};
                 for (int j = v; j < jobs0 + jobs1; j += n_clusters) {
                     const int which = j < jobs0 ? 0 : 1;
                     const int k = which == 0 ? j : j - jobs0;
                     KArgs a;
-                    make_out_args(P, q, which, a);
+                    make_out_args(P, qo, which, a);
                     a.trace_on = (blockIdx.x == 0 && !(P.base.dbg & 1024)) ? 2 : 0;
-                    GT(q, 2);
+                    GT(qo, 2);
                     const int blk = k / P.nt;          // 256-row block of the panel (dX) or 256-column block (dY)
                     const int m_blk = 2 * blk + int(c.cta_rank);
                     const int t = k - blk * P.nt;
                     if (c.warp == 0) {
-                        const unsigned int target = (P.base.dbg & 128) ? 0u : kTileDone;
+                        const unsigned int target = (P.base.dbg & 128) ? 0u : 2u * (unsigned int)(qo + 1);
                         if (which == 0)
-                            produce_job<STAGES>(c, p, &tmGk, &tmYg, a, m_blk, t, n_tiles, flags_q + blk * n_tiles,
-                                                pos_q + blk * n_tiles, 1, target);
+                            produce_job<STAGES>(c, p, &tmGk, &tmYg, a, m_blk, t, n_tiles, P.done, own_q + blk * n_tiles, 1,
+                                                target, seen);
                         else
-                            produce_job<STAGES>(c, p, &tmGmn, &tmXg, a, m_blk, t, m_pairs, flags_q + blk, pos_q + blk,
-                                                n_tiles, target);
+                            produce_job<STAGES>(c, p, &tmGmn, &tmXg, a, m_blk, t, m_pairs, P.done, own_q + blk, n_tiles,
+                                                target, seen);
                     } else if (c.warp == 1) {
                         mma_unit<STAGES>(c, p, a, 1);
                     } else {
-                        epilogue_unit<MODE_OUT>(c, p, which == 0 ? &tmDX : &tmDY, a, m_blk, t, t, t + 1, P.out_done + q);
+                        epilogue_unit<MODE_OUT>(c, p, which == 0 ? &tmDX : &tmDY, a, m_blk, t, t, t + 1, P.out_done + qo);
                     }
-                    GT(q, 3);
+                    GT(qo, 3);
                 }
             }
         }

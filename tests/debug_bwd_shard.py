@@ -13,8 +13,8 @@ sc = torch.tensor([1 / 0.07], device="cuda")
 gs = torch.tensor([1.0 / (2 * rows)], device="cuda")
 def step():
     X, Y = be.prepare(I), be.prepare(T)
-    rs, pos = be.fwd_stats(X, Y, sc, 0, True)
-    parts = torch.empty(1, 3, N, device="cuda"); be.fwd_stats(Y, X, sc, 0, False, out=parts[0])
+    parts = torch.empty(1, 3, N, device="cuda")
+    rs, pos, _ = be.fwd_both(X, Y, sc, 0, col_out=parts[0])
     lr, lcl, sums = be.finalize(rs, pos, parts, 0)
     Xg, Yg = be.prepare_grad(X), be.prepare_grad(Y)
     return be.bwd(X, Y, Xg, Yg, sc, 0, lr, lcl, 1.0, 1.0, gs, True, True)
