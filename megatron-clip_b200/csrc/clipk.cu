@@ -398,9 +398,8 @@ __global__ void norm2_max_kernel(const __nv_bfloat16* __restrict__ X, long long 
 // rows: merge the per-item parts (max, sum, dot; log2-scaled domain) into natural-log (max, sum, dot), as
 // merge_row_parts_kernel.  columns: in single-sweep mode sum the per-row-block partial (sum, dot) of the global
 // reference u; in exact mode merge the parts the swapped launch wrote.  The mode is recomputed from the same scalars.
-__global__ void fwd_merge_kernel(const FwdArgs a0, int parts0, const float* __restrict__ p1_max,
-                                 const float* __restrict__ p1_sum, const float* __restrict__ p1_dot, int parts1,
-                                 int m_blocks, float* __restrict__ row_out, float* __restrict__ col_out) {
+__global__ void fwd_merge_kernel(const FwdArgs a0, const FwdArgs a1, int m_blocks, float* __restrict__ row_out,
+                                 float* __restrict__ col_out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int rows = a0.M, cols = a0.N;
     auto merge_parts = [](const float* pmx, const float* psm, const float* pdt, int nparts, int n, int idx, float* o, int on) {
@@ -419,7 +418,12 @@ __global__ void fwd_merge_kernel(const FwdArgs a0, int parts0, const float* __re
         o[on + idx] = l;
         o[2 * on + idx] = t * LN2;
     };
-    if (i < rows) merge_parts(a0.part_max, a0.part_sum, a0.part_dot, parts0, rows, i, row_out, rows);
+    // parts of a row = (clusters whose tile range touches its row pair) x 2 column halves
+    auto nparts_of = [](const FwdArgs& a, int row) {
+        const long long total = (long long)a.m_pairs * a.n_tiles, f = (long long)(row / (2 * BM)) * a.n_tiles;
+        return PARTS_PER_UNIT * (sweep_cluster_of(total, f + a.n_tiles - 1, a.n_clusters) - sweep_cluster_of(total, f, a.n_clusters) + 1);
+    };
+    if (i < rows) merge_parts(a0.part_max, a0.part_sum, a0.part_dot, nparts_of(a0, i), rows, i, row_out, rows);
     if (i < cols) {
         float u;
         if (fwd_bound(a0, &u)) {
@@ -432,7 +436,7 @@ __global__ void fwd_merge_kernel(const FwdArgs a0, int parts0, const float* __re
             col_out[cols + i] = L;
             col_out[2 * cols + i] = fmaf(u, L, D) * LN2;
         } else {
-            merge_parts(p1_max, p1_sum, p1_dot, parts1, cols, i, col_out, cols);
+            merge_parts(a1.part_max, a1.part_sum, a1.part_dot, nparts_of(a1, i), cols, i, col_out, cols);
         }
     }
 }
@@ -758,20 +762,28 @@ static int check_common(const void* X, const void* Y, int rows, int cols, int d,
     return CLIPK_OK;
 }
 
+template <int F16>
+static int launch_grad_sweep(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const KArgs& a,
+                             const SweepGeom& g, int n_clusters, cudaStream_t st) {
+    auto kfn = grad_sweep_kernel<F16>;
+    constexpr int smem = smem_bytes_grad_sweep();
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
+    if (attr_err != cudaSuccess) return fail(int(attr_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+    KArgs aa = a;
+    aa.dbg = dbg_flags();
+    aa.trace = g_trace;
+    aa.trace_on = 1;
+    aa.f16 = F16;
+    return launch_clustered(kfn, dim3(2 * n_clusters), dim3(2, 1, 1), smem, st, ta, tb, tc, aa, g);
+}
+
 // ---- host helpers of clipk_fwd_both
-constexpr int FWD_MAX_SPLIT = 16;
-// how many column runs per row pair: fill the clusters in as few equal rounds as possible
-int choose_item_split(int m_pairs, int n_tiles, int n_clusters) {
-    int best = 1;
-    double best_cost = 1e30;
-    const int lim = n_tiles < FWD_MAX_SPLIT ? n_tiles : FWD_MAX_SPLIT;
-    for (int s = 1; s <= lim; ++s) {
-        const int per = cdiv(n_tiles, s);
-        const int rounds = cdiv((long long)m_pairs * s, n_clusters);
-        const double cost = rounds * (per + 0.6);    // ~0.6 tile-times to swap the resident rows and write the item
-        if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
-    }
-    return best;
+// upper bound of the parts (clusters) that share one row pair of a sweep, for any device with <= 256 SMs
+static int sweep_parts_bound(int rows) {
+    const int m_pairs = cdiv(rows, 2 * BM);
+    return std::min(128, cdiv(128, m_pairs) + 1);
 }
 struct FwdCarve {
     size_t norm2, parts0, parts1, colparts, total;
@@ -783,8 +795,8 @@ FwdCarve fwd_carve(int rows, int cols) {
     c.m_blocks = 2 * cdiv(rows, 2 * BM);
     size_t off = 0;
     c.norm2 = off; off += 256;
-    c.parts0 = off; off += size_t(3) * FWD_MAX_SPLIT * PARTS_PER_UNIT * rows * sizeof(float);
-    c.parts1 = off; off += size_t(3) * FWD_MAX_SPLIT * PARTS_PER_UNIT * cols * sizeof(float);
+    c.parts0 = off; off += size_t(3) * sweep_parts_bound(rows) * PARTS_PER_UNIT * rows * sizeof(float);
+    c.parts1 = off; off += size_t(3) * sweep_parts_bound(cols) * PARTS_PER_UNIT * cols * sizeof(float);
     off = size_t(round_up((long long)off, 256));
     c.colparts = off; off += size_t(2) * c.m_blocks * c.ldc * sizeof(float);
     c.total = off + 256;
@@ -966,13 +978,11 @@ int clipk_fwd_both(const void* X, const void* Y, int rows, int cols, int d, long
     FwdArgs a0{};
     a0.M = rows; a0.N = cols; a0.num_kb = num_kb;
     a0.n_tiles = cdiv(cols, BN); a0.m_pairs = cdiv(rows, 2 * BM);
-    a0.split = choose_item_split(a0.m_pairs, a0.n_tiles, n_clusters);
-    a0.tiles_per_item = cdiv(a0.n_tiles, a0.split);
-    a0.split = cdiv(a0.n_tiles, a0.tiles_per_item);
+    a0.n_clusters = int(std::min<long long>(n_clusters, (long long)a0.m_pairs * a0.n_tiles));
     a0.pass = 0; a0.force_exact = bounded ? 0 : 1;
     a0.scale = logit_scale; a0.xs = x_inv_scale; a0.ys = y_inv_scale; a0.norm2 = norm2;
     a0.diag_offset = pos_logit ? diag_offset : -(1LL << 40);
-    const size_t pstride0 = size_t(FWD_MAX_SPLIT) * PARTS_PER_UNIT * rows;
+    const size_t pstride0 = size_t(sweep_parts_bound(rows)) * PARTS_PER_UNIT * rows;
     a0.part_max = parts0; a0.part_sum = parts0 + pstride0; a0.part_dot = parts0 + 2 * pstride0;
     a0.pos = pos_logit;
     a0.colpart_sum = colparts; a0.colpart_dot = colparts + size_t(cv.m_blocks) * cv.ldc; a0.ldc = cv.ldc;
@@ -981,16 +991,14 @@ int clipk_fwd_both(const void* X, const void* Y, int rows, int cols, int d, long
     FwdArgs a1 = a0;
     a1.M = cols; a1.N = rows;
     a1.n_tiles = cdiv(rows, BN); a1.m_pairs = cdiv(cols, 2 * BM);
-    a1.split = choose_item_split(a1.m_pairs, a1.n_tiles, n_clusters);
-    a1.tiles_per_item = cdiv(a1.n_tiles, a1.split);
-    a1.split = cdiv(a1.n_tiles, a1.tiles_per_item);
+    a1.n_clusters = int(std::min<long long>(n_clusters, (long long)a1.m_pairs * a1.n_tiles));
     a1.pass = 1; a1.xs = y_inv_scale; a1.ys = x_inv_scale;
     a1.diag_offset = -(1LL << 40);
-    const size_t pstride1 = size_t(FWD_MAX_SPLIT) * PARTS_PER_UNIT * cols;
+    const size_t pstride1 = size_t(sweep_parts_bound(cols)) * PARTS_PER_UNIT * cols;
     a1.part_max = parts1; a1.part_sum = parts1 + pstride1; a1.part_dot = parts1 + 2 * pstride1;
     a1.pos = nullptr; a1.colpart_sum = nullptr; a1.colpart_dot = nullptr;
 
-    const int nc0 = std::min(n_clusters, a0.m_pairs * a0.split), nc1 = std::min(n_clusters, a1.m_pairs * a1.split);
+    const int nc0 = a0.n_clusters, nc1 = a1.n_clusters;
     if (is_f16(dtype)) {
         if ((rc = launch_fwd_sweep<1>(tx_a, ty_b, a0, nc0, st))) return rc;
         if ((rc = launch_fwd_sweep<1>(ty_a, tx_b, a1, nc1, st))) return rc;
@@ -999,8 +1007,7 @@ int clipk_fwd_both(const void* X, const void* Y, int rows, int cols, int d, long
         if ((rc = launch_fwd_sweep<0>(ty_a, tx_b, a1, nc1, st))) return rc;
     }
     const int n = rows > cols ? rows : cols;
-    fwd_merge_kernel<<<cdiv(n, 128), 128, 0, st>>>(a0, a0.split * PARTS_PER_UNIT, a1.part_max, a1.part_sum, a1.part_dot,
-                                                   a1.split * PARTS_PER_UNIT, cv.m_blocks, row_stats, col_stats);
+    fwd_merge_kernel<<<cdiv(n, 128), 128, 0, st>>>(a0, a1, cv.m_blocks, row_stats, col_stats);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
@@ -1217,8 +1224,17 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
                 a.alpha = alpha; a.beta = beta;
                 a.avec = avec + r0; a.bvec = bvec + c0; a.gref = gref;
                 a.G = G; a.ldg = ldg; a.g_planes = gplanes; a.g_plane_stride = ncp;
-                if (is_f16(dtype)) rc = launch_gemm<MODE_GRAD, 1>(ta, tb, tc, a, units, m_pairs, st);
-                else rc = launch_gemm<MODE_GRAD, 0>(ta, tb, tc, a, units, m_pairs, st);
+                if (planes == 1 && gplanes == 1 && a.num_kb <= ARES_KB && !(dbg_flags() & 512)) {
+                    // rows of X resident in shared memory, persistent over the panel (see grad_sweep_kernel)
+                    SweepGeom g{};
+                    g.num_kb = a.num_kb; g.n_tiles = a.n_tiles; g.m_pairs = m_pairs;
+                    const int nc = int(std::min<long long>(di.sms / 2, (long long)m_pairs * a.n_tiles));
+                    rc = is_f16(dtype) ? launch_grad_sweep<1>(ta, tb, tc, a, g, nc, st) : launch_grad_sweep<0>(ta, tb, tc, a, g, nc, st);
+                } else if (is_f16(dtype)) {
+                    rc = launch_gemm<MODE_GRAD, 1>(ta, tb, tc, a, units, m_pairs, st);
+                } else {
+                    rc = launch_gemm<MODE_GRAD, 0>(ta, tb, tc, a, units, m_pairs, st);
+                }
                 if (rc) return rc;
             }
             // ---- job 0: dX[r0:r0+nr, :] (+)= G[nr, nc] * Yg[c0:c0+nc, :]      (A K-major, B MN-major, fp16 x fp16)
@@ -1246,6 +1262,9 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
                 a1.oscale0 = logit_scale; a1.oscale1 = gscale; a1.oscale2 = xg_inv_scale; a1.oconst = 1.f / 16384.f;
                 jobs1 = cdiv(nc, 2 * BM) * nt;
             }
+            // One job (256 x 256 output tile, full K of the panel) per CTA pair.  A stream-K split of the K blocks over
+            // all 74 pairs was measured SLOWER (2.94 vs 2.73 ms per backward at N = 32768): the step runs at the 1 kW
+            // power cap, so evening out the MMAs buys nothing and the extra partial-tile reduces cost energy.
             if (dX_acc && dY_acc) rc = launch_pair(ta0, tb0, tc0, a0, jobs0, ta1, tb1, tc1, a1, jobs1, st);
             else if (dX_acc) rc = launch_gemm<MODE_OUT, 1>(ta0, tb0, tc0, a0, nt, cdiv(nr, 2 * BM), st);
             else rc = launch_gemm<MODE_OUT, 1>(ta1, tb1, tc1, a1, nt, cdiv(nc, 2 * BM), st);

@@ -558,9 +558,12 @@ __device__ __forceinline__ void epilogue_unit(const Cta& c, Pipe& p, const CUten
 // Recompute tiles: S tile -> G tile (fp16, x 2^14) -> swizzled staging -> TMA store into the L2-resident panel.
 // The tile is drained in 16-column pieces (tcgen05.ld x16, double buffered) to keep the live registers well under the
 // 168 a 10-warp CTA allows; four pieces (64 columns = 128 B of fp16 per row) fill one staging buffer = one TMA store.
-template <bool TWO_PLANES>
+// NBUF = staging buffers per warp: 2 (one fills while the other leaves; both planes of a two-plane G) or 1 (the
+// A-resident recompute kernel, whose shared memory goes to the resident rows instead).
+template <bool TWO_PLANES, int NBUF = 2>
 __device__ __forceinline__ void grad_epilogue_unit(const Cta& c, Pipe& p, const CUtensorMap* tmC, const KArgs& args,
                                                    int m_blk, int t0, int t1) {
+    static_assert(NBUF == 2 || !TWO_PLANES, "a two-plane G needs both staging buffers");
     const int warp = c.warp, lane = c.lane;
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
@@ -583,7 +586,7 @@ __device__ __forceinline__ void grad_epilogue_unit(const Cta& c, Pipe& p, const 
     const int dbg = args.dbg, ncols = args.N, plane_stride = args.g_plane_stride;
     const int c_col_off = args.c_col_off, c_row_off = args.c_row_off + m_blk * BM + q * 32;
     const long long d_lo = args.diag_offset + (long long)m_blk * BM;
-    const uint32_t stg0 = c.sStg + (warp - 2) * 2 * STG_BYTES;   // this warp's two staging buffers
+    const uint32_t stg0 = c.sStg + (warp - 2) * NBUF * STG_BYTES;   // this warp's staging buffer(s)
     auto TR = [&]() {
         if (warp == 2 && lane == 0) trace_stamp(args, p, 2);
     };
@@ -617,11 +620,11 @@ __device__ __forceinline__ void grad_epilogue_unit(const Cta& c, Pipe& p, const 
                 // (re)use of a staging buffer: at most one older bulk store may still be reading shared memory; with
                 // two planes both buffers are written, so nothing of this warp may still be in flight
                 if (lane == 0) {
-                    if (TWO_PLANES) ptx::tma_store_wait_read<0>();
+                    if (TWO_PLANES || NBUF == 1) ptx::tma_store_wait_read<0>();
                     else ptx::tma_store_wait_read<1>();
                 }
                 __syncwarp();
-                stg = stg0 + (p.stg_use & 1) * STG_BYTES;
+                stg = NBUF == 1 ? stg0 : stg0 + (p.stg_use & 1) * STG_BYTES;
                 stg_lo = stg0 + ((p.stg_use + 1) & 1) * STG_BYTES;
             }
             float g[16];
@@ -732,8 +735,8 @@ constexpr float FWD_SAFE_U = 50.f;               // 2u + 26 <= 126
 struct FwdArgs {
     int M, N;                  // rows of A (X), rows of B (Y)
     int num_kb;                // K blocks, <= ARES_KB
-    int n_tiles, m_pairs;
-    int split, tiles_per_item; // item = m_pair * split + part; tiles [part * tiles_per_item, ...)
+ int n_tiles, m_pairs;
+    int n_clusters;            // clusters of the launch (the part index of a unit is derived from it)
     int pass;                  // 0: X rows against Y columns; 1: the swapped launch (exact mode only)
     int force_exact;           // operands are not plain bf16: no norm bound
     const float* scale;
@@ -741,7 +744,7 @@ struct FwdArgs {
     const float* ys;
     const unsigned int* norm2; // [2] max |x_i|^2, max |y_j|^2 as float bits (only read when !force_exact)
     long long diag_offset;
-    float* part_max;           // [split * 2][M]
+    float* part_max;           // [max parts * 2][M]; part = cluster - first cluster that touches the row pair
     float* part_sum;
     float* part_dot;
     float* pos;                // [M] or null
@@ -791,6 +794,100 @@ __device__ __forceinline__ void rowcol_half(const uint32_t (&r)[16], float sc, f
     }
 }
 
+// Work distribution of the A-resident sweeps: the tiles of the block, in row-pair-major order (flat index = m_pair *
+// n_tiles + column tile), are cut into n equal contiguous ranges, one per cluster; a range is walked as "units" =
+// runs of column tiles inside one row pair (the resident rows of A are swapped at a row-pair boundary).
+struct SweepGeom {
+    int num_kb, n_tiles, m_pairs;
+};
+__host__ __device__ __forceinline__ long long sweep_begin(long long total, int cluster, int n) { return total * cluster / n; }
+// cluster whose range contains flat tile f
+__host__ __device__ __forceinline__ int sweep_cluster_of(long long total, long long f, int n) {
+    return int(((f + 1) * n + total - 1) / total - 1);
+}
+struct SweepUnit { int m_pair, t0, t1; };
+struct SweepWalk {
+    long long f, f1;
+    int n_tiles;
+    __device__ __forceinline__ SweepWalk(const SweepGeom& g, int cluster, int n) {
+        const long long total = (long long)g.m_pairs * g.n_tiles;
+        f = sweep_begin(total, cluster, n);
+        f1 = sweep_begin(total, cluster + 1, n);
+        n_tiles = g.n_tiles;
+    }
+    __device__ __forceinline__ bool next(SweepUnit& u) {
+        if (f >= f1) return false;
+        u.m_pair = int(f / n_tiles);
+        u.t0 = int(f - (long long)u.m_pair * n_tiles);
+        u.t1 = int(min((long long)n_tiles, u.t0 + (f1 - f)));
+        f += u.t1 - u.t0;
+        return true;
+    }
+};
+
+// TMA producer of an A-resident sweep (one lane of warp 0, both CTAs)
+template <int STAGES>
+__device__ __forceinline__ void sweep_produce(const Cta& c, Pipe& p, const CUtensorMap* tmA, const CUtensorMap* tmB,
+                                              const SweepGeom& g, int cluster, int n_clusters) {
+    SweepWalk w(g, cluster, n_clusters);
+    SweepUnit u;
+    uint32_t it_n = 0;
+    for (; w.next(u); ++it_n) {
+        const int m_blk = 2 * u.m_pair + int(c.cta_rank);
+        // the resident rows of A may be replaced once every MMA of the previous unit has completed
+        if (it_n > 0) ptx::mbar_wait(c.bar_aempty, (it_n - 1) & 1);
+        if (c.leader) ptx::mbar_arrive_expect_tx(c.bar_afull, 2 * g.num_kb * A_STAGE_BYTES);
+        for (int kb = 0; kb < g.num_kb; ++kb)
+            ptx::tma_load_2d_pair(c.sA + kb * A_STAGE_BYTES, tmA, kb * BK, m_blk * BM, c.bar_afull);
+        for (int t = u.t0; t < u.t1; ++t) {
+            const int bn0 = t * BN + int(c.cta_rank) * (BN / 2);
+            for (int kb = 0; kb < g.num_kb; ++kb) {
+                ptx::mbar_wait(c.bar_empty + 8 * p.s, p.ph ^ 1);
+                const uint32_t full = c.bar_full + 8 * p.s;
+                if (c.leader) ptx::mbar_arrive_expect_tx(full, 2 * B_STAGE_BYTES);
+                ptx::tma_load_2d_pair(c.sB + p.s * B_STAGE_BYTES, tmB, kb * BK, bn0, full);
+                if (++p.s == STAGES) { p.s = 0; p.ph ^= 1; }
+            }
+        }
+    }
+}
+
+// MMA issuer of an A-resident sweep (one lane of warp 1, leader CTA)
+template <int STAGES, int F16>
+__device__ __forceinline__ void sweep_mma(const Cta& c, Pipe& p, const SweepGeom& g, int cluster, int n_clusters) {
+    const uint32_t idesc = ptx::make_idesc_16bit(2 * BM, BN, 0, 0, !F16, !F16);
+    const uint64_t desc_hi = ptx::make_smem_desc_sw128(16, 1024);
+    SweepWalk w(g, cluster, n_clusters);
+    SweepUnit u;
+    uint32_t it_n = 0;
+    for (; w.next(u); ++it_n) {
+        ptx::mbar_wait(c.bar_afull, it_n & 1);
+        ptx::tc_fence_after();
+        for (int t = u.t0; t < u.t1; ++t, ++p.it) {
+            const int a = p.it & 1;
+            const uint32_t aph = (p.it >> 1) & 1;
+            ptx::mbar_wait(c.bar_tempty + 8 * a, aph ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = c.tmem_base + a * BN;
+            for (int kb = 0; kb < g.num_kb; ++kb) {
+                ptx::mbar_wait(c.bar_full + 8 * p.s, p.ph);
+                ptx::tc_fence_after();
+                const uint32_t a_src = c.sA + kb * A_STAGE_BYTES;
+                const uint32_t b_src = c.sB + p.s * B_STAGE_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    ptx::mma_f16_ss_pair(d_tmem, ptx::desc_with_addr(desc_hi, a_src + k * 32),
+                                         ptx::desc_with_addr(desc_hi, b_src + k * 32), idesc, (kb | k) != 0);
+                }
+                ptx::mma_commit_pair(c.bar_empty + 8 * p.s);
+                if (++p.s == STAGES) { p.s = 0; p.ph ^= 1; }
+            }
+            ptx::mma_commit_pair(c.bar_tfull + 8 * a);
+        }
+        ptx::mma_commit_pair(c.bar_aempty);   // both CTAs' producers wait on their own copy
+    }
+}
+
 template <int F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fwd_sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FwdArgs args) {
@@ -802,71 +899,18 @@ fwd_sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool single = safe && args.pass == 0;
     const bool skip = safe && args.pass == 1;
     const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-    const int n_items = args.m_pairs * args.split;
-    const int num_kb = args.num_kb;
     Pipe p;
-
+    const SweepGeom geom{args.num_kb, args.n_tiles, args.m_pairs};
+    const long long total_tiles = (long long)args.m_pairs * args.n_tiles;
     if (!skip) {
         if (c.warp == 0) {
             if (c.lane == 0) {
                 ptx::prefetch_tmap(&tmA);
                 ptx::prefetch_tmap(&tmB);
-                uint32_t it_n = 0;
-                for (int item = cluster; item < n_items; item += n_clusters, ++it_n) {
-                    const int m_pair = item / args.split, part = item - m_pair * args.split;
-                    const int m_blk = 2 * m_pair + int(c.cta_rank);
-                    const int t0 = part * args.tiles_per_item, t1 = min(args.n_tiles, t0 + args.tiles_per_item);
-                    // the resident rows of A may be replaced once every MMA of the previous item has completed
-                    if (it_n > 0) ptx::mbar_wait(c.bar_aempty, (it_n - 1) & 1);
-                    if (c.leader) ptx::mbar_arrive_expect_tx(c.bar_afull, 2 * num_kb * A_STAGE_BYTES);
-                    for (int kb = 0; kb < num_kb; ++kb)
-                        ptx::tma_load_2d_pair(c.sA + kb * A_STAGE_BYTES, &tmA, kb * BK, m_blk * BM, c.bar_afull);
-                    for (int t = t0; t < t1; ++t) {
-                        const int bn0 = t * BN + int(c.cta_rank) * (BN / 2);
-                        for (int kb = 0; kb < num_kb; ++kb) {
-                            ptx::mbar_wait(c.bar_empty + 8 * p.s, p.ph ^ 1);
-                            const uint32_t full = c.bar_full + 8 * p.s;
-                            if (c.leader) ptx::mbar_arrive_expect_tx(full, 2 * B_STAGE_BYTES);
-                            ptx::tma_load_2d_pair(c.sB + p.s * B_STAGE_BYTES, &tmB, kb * BK, bn0, full);
-                            if (++p.s == STAGES) { p.s = 0; p.ph ^= 1; }
-                        }
-                    }
-                }
+                sweep_produce<STAGES>(c, p, &tmA, &tmB, geom, cluster, n_clusters);
             }
         } else if (c.warp == 1) {
-            if (c.lane == 0 && c.leader) {
-                const uint32_t idesc = ptx::make_idesc_16bit(2 * BM, BN, 0, 0, !F16, !F16);
-                const uint64_t desc_hi = ptx::make_smem_desc_sw128(16, 1024);
-                uint32_t it_n = 0;
-                for (int item = cluster; item < n_items; item += n_clusters, ++it_n) {
-                    const int part = item % args.split;
-                    const int t0 = part * args.tiles_per_item, t1 = min(args.n_tiles, t0 + args.tiles_per_item);
-                    ptx::mbar_wait(c.bar_afull, it_n & 1);
-                    ptx::tc_fence_after();
-                    for (int t = t0; t < t1; ++t, ++p.it) {
-                        const int a = p.it & 1;
-                        const uint32_t aph = (p.it >> 1) & 1;
-                        ptx::mbar_wait(c.bar_tempty + 8 * a, aph ^ 1);
-                        ptx::tc_fence_after();
-                        const uint32_t d_tmem = c.tmem_base + a * BN;
-                        for (int kb = 0; kb < num_kb; ++kb) {
-                            ptx::mbar_wait(c.bar_full + 8 * p.s, p.ph);
-                            ptx::tc_fence_after();
-                            const uint32_t a_src = c.sA + kb * A_STAGE_BYTES;
-                            const uint32_t b_src = c.sB + p.s * B_STAGE_BYTES;
-#pragma unroll
-                            for (int k = 0; k < BK / 16; ++k) {
-                                ptx::mma_f16_ss_pair(d_tmem, ptx::desc_with_addr(desc_hi, a_src + k * 32),
-                                                     ptx::desc_with_addr(desc_hi, b_src + k * 32), idesc, (kb | k) != 0);
-                            }
-                            ptx::mma_commit_pair(c.bar_empty + 8 * p.s);
-                            if (++p.s == STAGES) { p.s = 0; p.ph ^= 1; }
-                        }
-                        ptx::mma_commit_pair(c.bar_tfull + 8 * a);
-                    }
-                    ptx::mma_commit_pair(c.bar_aempty);   // both CTAs' producers wait on their own copy
-                }
-            }
+            if (c.lane == 0 && c.leader) sweep_mma<STAGES, F16>(c, p, geom, cluster, n_clusters);
         } else if (!single) {
             // ---- exact mode: online-max row statistics, one row per thread (same code as the streaming STATS kernel)
             KArgs ka{};
@@ -874,11 +918,12 @@ fwd_sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ka.diag_offset = args.diag_offset; ka.part_max = args.part_max; ka.part_sum = args.part_sum;
             ka.part_dot = args.part_dot; ka.pos = args.pos; ka.dbg = args.dbg; ka.trace = args.trace;
             ka.trace_on = (blockIdx.x == 0) ? 2 : 0;
-            for (int item = cluster; item < n_items; item += n_clusters) {
-                const int m_pair = item / args.split, part = item - m_pair * args.split;
-                const int m_blk = 2 * m_pair + int(c.cta_rank);
-                const int t0 = part * args.tiles_per_item, t1 = min(args.n_tiles, t0 + args.tiles_per_item);
-                epilogue_unit<MODE_STATS>(c, p, &tmA, ka, m_blk, part, t0, t1);
+            SweepWalk w(geom, cluster, n_clusters);
+            SweepUnit un;
+            while (w.next(un)) {
+                const int m_blk = 2 * un.m_pair + int(c.cta_rank);
+                const int part = cluster - sweep_cluster_of(total_tiles, (long long)un.m_pair * args.n_tiles, n_clusters);
+                epilogue_unit<MODE_STATS>(c, p, &tmA, ka, m_blk, part, un.t0, un.t1);
             }
         } else {
             // ---- single sweep: row and column statistics of every tile
@@ -899,10 +944,12 @@ fwd_sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             };
             // column of the chunk this lane owns after the butterfly, and its slot in the column buffer
             const int own_col = 8 * (g >> 1) + cq + (g & 1);
-            for (int item = cluster; item < n_items; item += n_clusters) {
-                const int m_pair = item / args.split, part = item - m_pair * args.split;
+            SweepWalk w(geom, cluster, n_clusters);
+            SweepUnit un;
+            while (w.next(un)) {
+                const int m_pair = un.m_pair, t0 = un.t0, t1 = un.t1;
                 const int m_blk = 2 * m_pair + int(c.cta_rank);
-                const int t0 = part * args.tiles_per_item, t1 = min(args.n_tiles, t0 + args.tiles_per_item);
+                const int part = cluster - sweep_cluster_of(total_tiles, (long long)m_pair * args.n_tiles, n_clusters);
                 const int rbase = m_blk * BM + q * 32;             // rows rbase + {g, 8 + g, 16 + g, 24 + g}
                 float l[4] = {0.f, 0.f, 0.f, 0.f}, tt[4] = {0.f, 0.f, 0.f, 0.f};
                 const bool row_edge = (m_blk + 1) * BM > M;
@@ -1015,6 +1062,40 @@ fwd_sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
             }
         }
+    }
+    cta_teardown(c);
+}
+
+// Recompute (GRAD) tiles of one panel as an A-resident persistent sweep: same mainloop as the forward sweep (rows of X
+// resident, 4 B stages, one staging buffer per epilogue warp), G tiles leave through TMA stores.  One-plane operands
+// and G only (bf16 / fp16 features with K <= 512); everything else takes the streaming gemm_kernel<MODE_GRAD>.
+constexpr int GRAD_SWEEP_STAGES = 4;
+constexpr int GRAD_SWEEP_STG = NUM_EPI_WARPS * STG_BYTES;   // 32 KB
+__host__ __device__ constexpr int smem_bytes_grad_sweep() {
+    return 1024 + ARES_KB * A_STAGE_BYTES + GRAD_SWEEP_STAGES * B_STAGE_BYTES + GRAD_SWEEP_STG + 256 + MISC_BYTES;
+}
+
+template <int F16>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+grad_sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmC, const KArgs args, const SweepGeom geom) {
+    constexpr int STAGES = GRAD_SWEEP_STAGES;
+    const Cta c = cta_setup<STAGES, GRAD_SWEEP_STG, ARES_KB * A_STAGE_BYTES>();
+    const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    Pipe p;
+    if (c.warp == 0) {
+        if (c.lane == 0) {
+            ptx::prefetch_tmap(&tmA);
+            ptx::prefetch_tmap(&tmB);
+            sweep_produce<STAGES>(c, p, &tmA, &tmB, geom, cluster, n_clusters);
+        }
+    } else if (c.warp == 1) {
+        if (c.lane == 0 && c.leader) sweep_mma<STAGES, F16>(c, p, geom, cluster, n_clusters);
+    } else {
+        SweepWalk w(geom, cluster, n_clusters);
+        SweepUnit un;
+        while (w.next(un)) grad_epilogue_unit<false, 1>(c, p, &tmC, args, 2 * un.m_pair + int(c.cta_rank), un.t0, un.t1);
+        epilogue_drain(c);
     }
     cta_teardown(c);
 }
