@@ -253,7 +253,13 @@ def run_clipk(args):
         lse_row, lse_col, sums = be.finalize(rstats, pos, gparts, off)
         breakdown["to_f16_ms"], (Xg, Yg) = ev(lambda: (be.prepare_grad(X), be.prepare_grad(Y)))
         gscale = torch.tensor([1.0 / (2 * b)], device=dev)
-        breakdown["bwd_ms"], _ = ev(lambda: be.bwd(X, Y, Xg, Yg, sc, off, lse_row, lse_col, 1.0, 1.0, gscale, True, True))
+        breakdown["bwd_ms"], (dXa, dYa) = ev(lambda: be.bwd(X, Y, Xg, Yg, sc, off, lse_row, lse_col, 1.0, 1.0, gscale, True, True))
+        if world > 1:
+            # the three collectives of a step, timed alone (they are issued on the same stream as the kernels)
+            tl = T.detach()
+            breakdown["all_gather_T_ms"], _ = ev(lambda: ops._all_gather_rows(tl, world))
+            breakdown["all_gather_colstats_ms"], _ = ev(lambda: ops._all_gather_rows(parts, world))
+            breakdown["reduce_scatter_dT_ms"], _ = ev(lambda: ops._reduce_scatter_rows(dYa, world))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -150,6 +150,28 @@ class CudaBackend:
                    "clipk_bwd")
         return dX, dY
 
+    def bwd_peer(self, X: Operand, Y: Operand, Xg: Operand, Yg: Operand, scale, diag_offset, lse_row, lse_col, alpha,
+                 beta, gscale, peer):
+        """clipk_bwd with the dY tiles added straight into the owners' accumulators (peer-mapped, over NVLink):
+        the reduce-scatter of the text gradient is fused into the gradient GEMM.  Returns dX only."""
+        dev = X.data.device
+        rows, cols, d = X.rows, Y.rows, X.d
+        dX = torch.empty(rows, d, dtype=torch.float32, device=dev)
+        nbytes = self.lib.clipk_bwd_workspace_bytes(rows, cols, d, Xg.dtype)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.check(self.lib.clipk_bwd_peer(X.data.data_ptr(), Y.data.data_ptr(), rows, cols, d, X.ld, Y.ld, X.dtype,
+                                           X.inv_ptr(), Y.inv_ptr(), Xg.data.data_ptr(), Yg.data.data_ptr(), Xg.ld,
+                                           Yg.ld, Xg.dtype, Xg.inv_ptr(), Yg.inv_ptr(), scale.data_ptr(), diag_offset,
+                                           lse_row.data_ptr(), lse_col.data_ptr(), float(alpha), float(beta),
+                                           gscale.data_ptr(), dX.data_ptr(), peer.acc_ptrs, peer.world,
+                                           peer.rows_per_rank, ws.data_ptr(), nbytes, self._stream()), "clipk_bwd_peer")
+        return dX
+
+    def peer_barrier(self, peer):
+        peer.epoch += 1
+        _lib.check(self.lib.clipk_peer_barrier(peer.flag_ptrs, peer.rank, peer.world, peer.epoch, self._stream()),
+                   "clipk_peer_barrier")
+
     def cast(self, src: torch.Tensor, dtype: torch.dtype):
         if dtype == torch.float32:
             return src
@@ -174,6 +196,56 @@ def _backend():
 def gpu_launches() -> int:
     """Number of clipk kernels launched so far in this process."""
     return 0 if _CUDA_BACKEND is None else int(_CUDA_BACKEND.lib.clipk_launch_count())
+
+
+# ----------------------------------------------------------------------------------------------------- peer memory
+class PeerState:
+    """Symmetric (peer-mapped) buffers of one (local batch, dim, group): the fp32 accumulator of this rank's text
+    gradient, into which every rank's gradient GEMM adds its tiles over NVLink, and the flag words of the barrier."""
+
+    def __init__(self, b, d, rank, world, group, dev):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        pg = group if group is not None else dist.group.WORLD
+        self.acc = symm.empty(b, d, dtype=torch.float32, device=dev)
+        self.acc.zero_()
+        h_acc = symm.rendezvous(self.acc, pg)
+        self.flags = symm.empty(8, dtype=torch.int32, device=dev)
+        self.flags.zero_()
+        h_flags = symm.rendezvous(self.flags, pg)
+        if h_acc.rank != rank or h_acc.world_size != world:
+            raise RuntimeError("rank / world_size of the loss do not match the process group")
+        self.rank, self.world, self.rows_per_rank, self.epoch = rank, world, b, 0
+        self.acc_ptrs = (ctypes.c_void_p * world)(*[int(p) for p in h_acc.buffer_ptrs])
+        self.flag_ptrs = (ctypes.c_void_p * world)(*[int(p) for p in h_flags.buffer_ptrs])
+        self._handles = (h_acc, h_flags)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=pg)          # every rank's buffers are zero before anyone adds or signals
+
+
+_PEER_STATES = {}
+_PEER_DISABLED = [False]
+
+
+def _peer_state(b, d, rank, world, group, dev):
+    """PeerState for this shape, or None when the fused path does not apply (then NCCL reduce_scatter is used)."""
+    import os
+    if _PEER_DISABLED[0] or os.environ.get("CLIPK_PEER", "1") == "0" or _TEST_BACKEND is not None:
+        return None
+    if dev.type != "cuda" or world < 2 or world > 8 or b % 128 != 0:
+        return None
+    key = (b, d, rank, world, id(group), dev.index)
+    st = _PEER_STATES.get(key)
+    if st is None:
+        try:
+            st = PeerState(b, d, rank, world, group, dev)
+        except Exception as e:   # no symmetric memory on this system: every rank takes the NCCL path
+            import warnings
+            warnings.warn(f"clipk: peer-memory reduce unavailable ({e!r}); using NCCL reduce_scatter")
+            _PEER_DISABLED[0] = True
+            return None
+        _PEER_STATES[key] = st
+    return st
 
 
 # ----------------------------------------------------------------------------------------------------- collectives
@@ -268,11 +340,23 @@ class FusedClipLoss(torch.autograd.Function):
                 # softmax and dT only the text->image one.
                 dX, _ = be.bwd(X, Y, Xg, Yg, scale, off, lse_row, lse_col, 1.0, 0.0, gscale, True, False)
                 _, dY = be.bwd(X, Y, Xg, Yg, scale, off, lse_row, lse_col, 0.0, 1.0, gscale, False, True)
+                dT = _reduce_scatter_rows(dY, W, group)
             else:
-                dX, dY = be.bwd(X, Y, Xg, Yg, scale, off, lse_row, lse_col, 1.0, 1.0, gscale, True, True)
-            dT = _reduce_scatter_rows(dY, W, group) if W > 1 else dY
+                peer = _peer_state(b, d, rank, W, group, scale.device) if W > 1 else None
+                if peer is not None:
+                    # gradient GEMM fused with the reduce-scatter: dY tiles are added into their owners' accumulators
+                    be.peer_barrier(peer)            # every owner has zeroed its accumulator
+                    dX = be.bwd_peer(X, Y, Xg, Yg, scale, off, lse_row, lse_col, 1.0, 1.0, gscale, peer)
+                    be.peer_barrier(peer)            # every rank's tiles have landed
+                    d_text = be.cast(peer.acc, in_dtype) if in_dtype != torch.float32 else peer.acc.clone()
+                    peer.acc.zero_()
+                    dT = None
+                else:
+                    dX, dY = be.bwd(X, Y, Xg, Yg, scale, off, lse_row, lse_col, 1.0, 1.0, gscale, True, True)
+                    dT = _reduce_scatter_rows(dY, W, group) if W > 1 else dY
             d_image = be.cast(dX, in_dtype)
-            d_text = be.cast(dT, in_dtype)
+            if dT is not None:
+                d_text = be.cast(dT, in_dtype)
 
         d_scale = None
         if ctx.scale_is_param and ctx.needs_input_grad[2]:

@@ -441,6 +441,24 @@ __global__ void fwd_merge_kernel(const FwdArgs a0, const FwdArgs a1, int m_block
     }
 }
 
+// Barrier between the ranks of one NVLink domain through peer-mapped flags: thread t publishes `epoch` in slot
+// [rank] of rank t's flag array (after everything this stream did before became visible system-wide), then waits
+// until rank t has published the same epoch here.  Epochs only grow, so the flags are never reset.
+struct PeerFlags {
+    unsigned int* flags[MAX_PEERS];   // flags[t] = rank t's array of MAX_PEERS words, peer-mapped
+};
+__global__ void peer_barrier_kernel(const PeerFlags pf, int rank, int world, unsigned int epoch) {
+    const int t = threadIdx.x;
+    if (t < world && t != rank) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pf.flags[t] + rank), "r"(epoch) : "memory");
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(pf.flags[rank] + t) : "memory");
+        } while (v < epoch);
+    }
+}
+
 // Test hook: where does tcgen05.ld.16x256b put the accumulator elements?  Four warps fill 128 lanes x 32 columns
 // with lane * 1000 + column through the 32x32b shape (thread == lane); every warp then reads the two 16-lane halves of
 // its lane quarter with the 16x256b shape and dumps its registers: out[(warp * 2 + h) * 32 * 16 + thread * 16 + k].
@@ -613,7 +631,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
 // jobs0 / jobs1 are counted in PAIRS (256 x 256 output tiles)
 static int launch_pair(const CUtensorMap& ta0, const CUtensorMap& tb0, const CUtensorMap& tc0, const KArgs& a0, int jobs0,
                        const CUtensorMap& ta1, const CUtensorMap& tb1, const CUtensorMap& tc1, const KArgs& a1, int jobs1,
-                       cudaStream_t st) {
+                       const PeerOut& peers, cudaStream_t st) {
     auto kfn = gemm_pair_kernel<1>;
     constexpr int smem = smem_bytes_of(MODE_OUT);
     static std::once_flag once;
@@ -626,7 +644,7 @@ static int launch_pair(const CUtensorMap& ta0, const CUtensorMap& tb0, const CUt
     b0.trace_on = 1;
     b0.f16 = b1.f16 = 1;
     return launch_clustered(kfn, dim3(2 * (jobs0 + jobs1)), dim3(2, 1, 1), smem, st, ta0, tb0, tc0, b0, ta1, tb1, tc1, b1,
-                            jobs0);
+                            jobs0, peers);
 }
 
 // plane pairs of the split-precision product, SMALLEST terms first: the tensor core truncates when it adds into the
@@ -1044,14 +1062,31 @@ size_t clipk_bwd_workspace_bytes(int rows, int cols, int d, int g_dtype) {
     return panels + size_t(4) * 1024 * 1024 + (size_t(rows) + size_t(cols)) * sizeof(float) + counters + 4096;
 }
 
-int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
-              const float* x_inv_scale, const float* y_inv_scale, const void* Xg, const void* Yg, long long ldxg,
-              long long ldyg, int g_dtype, const float* xg_inv_scale, const float* yg_inv_scale,
-              const float* logit_scale, long long diag_offset, const float* lse_row, const float* lse_col,
-              float alpha, float beta, const float* gscale, float* dX_acc, float* dY_acc, void* workspace,
-              size_t workspace_bytes, void* stream) {
+static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
+                    const float* x_inv_scale, const float* y_inv_scale, const void* Xg, const void* Yg, long long ldxg,
+                    long long ldyg, int g_dtype, const float* xg_inv_scale, const float* yg_inv_scale,
+                    const float* logit_scale, long long diag_offset, const float* lse_row, const float* lse_col,
+                    float alpha, float beta, const float* gscale, float* dX_acc, float* dY_acc, void* const* dY_peer_acc,
+                    int world, int rows_per_rank, void* workspace, size_t workspace_bytes, void* stream) {
     int rc = check_common(X, Y, rows, cols, d, ldx, ldy, dtype);
     if (rc) return rc;
+    PeerOut peers;
+    memset(&peers, 0, sizeof(peers));
+    if (dY_peer_acc) {
+        // fused reduce-scatter: dY tiles are added into the owners' accumulators (see gemm_pair_kernel)
+        if (world < 1 || world > MAX_PEERS) return fail(CLIPK_EUNSUPPORTED, "peer output supports 1..%d ranks (got %d)", MAX_PEERS, world);
+        if (rows_per_rank <= 0 || rows_per_rank % BM != 0 || (long long)rows_per_rank * world != cols)
+            return fail(CLIPK_EUNSUPPORTED, "peer output needs cols == world * rows_per_rank and rows_per_rank %% 128 == 0");
+        if (!dX_acc || dY_acc) return fail(CLIPK_EINVAL, "peer output: dX_acc is required and dY_acc must be NULL");
+        if (use_persistent()) return fail(CLIPK_EUNSUPPORTED, "peer output is not available in the dataflow backward");
+        for (int o = 0; o < world; ++o) {
+            if (!dY_peer_acc[o]) return fail(CLIPK_EINVAL, "null peer accumulator %d", o);
+            if ((rc = tmap_out_f32(&peers.map[o], static_cast<const float*>(dY_peer_acc[o]), rows_per_rank, d, d))) return rc;
+        }
+        peers.world = world;
+        peers.rows_per_rank = rows_per_rank;
+        dY_acc = static_cast<float*>(dY_peer_acc[0]);   // only marks "dY wanted" below; job 1 never writes through it
+    }
     if (g_dtype != CLIPK_F16 && g_dtype != CLIPK_F16X2) return fail(CLIPK_EUNSUPPORTED, "g_dtype must be CLIPK_F16 or CLIPK_F16X2");
     if ((rc = check_common(Xg, Yg, rows, cols, d, ldxg, ldyg, g_dtype))) return rc;
     if (!logit_scale || !lse_row || !lse_col || !gscale || !workspace) return fail(CLIPK_EINVAL, "null pointer argument");
@@ -1255,22 +1290,63 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
             if (dY_acc) {
                 if ((rc = tmap_mnmajor(&ta1, G, gplanes == 2 ? ldg : nc, nr, ldg))) return rc;
                 if ((rc = tmap_mnmajor(&tb1, Xgb + r0 * ldxg * esz, gext, nr, ldxg))) return rc;
-                if ((rc = tmap_out_f32(&tc1, dY_acc + c0 * d, nc, d, d))) return rc;
+                if ((rc = tmap_out_f32(&tc1, peers.world ? dY_acc : dY_acc + c0 * d, peers.world ? peers.rows_per_rank : nc, d, d))) return rc;
                 a1.M = nc; a1.N = d; a1.n_tiles = nt; a1.tiles_per_unit = 1; a1.a_mn = 1; a1.b_mn = 1;
                 set_segments(a1, gplanes, nr, ncp, dpad);
                 a1.out = dY_acc + c0 * d; a1.ldo = d; a1.accumulate = (r0 > 0);
+                if (peers.world) a1.c_row_off = int(c0);   // global dY row of the panel (owner = row / rows_per_rank)
                 a1.oscale0 = logit_scale; a1.oscale1 = gscale; a1.oscale2 = xg_inv_scale; a1.oconst = 1.f / 16384.f;
                 jobs1 = cdiv(nc, 2 * BM) * nt;
             }
             // One job (256 x 256 output tile, full K of the panel) per CTA pair.  A stream-K split of the K blocks over
             // all 74 pairs was measured SLOWER (2.94 vs 2.73 ms per backward at N = 32768): the step runs at the 1 kW
             // power cap, so evening out the MMAs buys nothing and the extra partial-tile reduces cost energy.
-            if (dX_acc && dY_acc) rc = launch_pair(ta0, tb0, tc0, a0, jobs0, ta1, tb1, tc1, a1, jobs1, st);
+            if (dX_acc && dY_acc) rc = launch_pair(ta0, tb0, tc0, a0, jobs0, ta1, tb1, tc1, a1, jobs1, peers, st);
             else if (dX_acc) rc = launch_gemm<MODE_OUT, 1>(ta0, tb0, tc0, a0, nt, cdiv(nr, 2 * BM), st);
             else rc = launch_gemm<MODE_OUT, 1>(ta1, tb1, tc1, a1, nt, cdiv(nc, 2 * BM), st);
             if (rc) return rc;
         }
     }
+    return CLIPK_OK;
+}
+
+int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
+              const float* x_inv_scale, const float* y_inv_scale, const void* Xg, const void* Yg, long long ldxg,
+              long long ldyg, int g_dtype, const float* xg_inv_scale, const float* yg_inv_scale,
+              const float* logit_scale, long long diag_offset, const float* lse_row, const float* lse_col,
+              float alpha, float beta, const float* gscale, float* dX_acc, float* dY_acc, void* workspace,
+              size_t workspace_bytes, void* stream) {
+    return bwd_impl(X, Y, rows, cols, d, ldx, ldy, dtype, x_inv_scale, y_inv_scale, Xg, Yg, ldxg, ldyg, g_dtype,
+                    xg_inv_scale, yg_inv_scale, logit_scale, diag_offset, lse_row, lse_col, alpha, beta, gscale, dX_acc,
+                    dY_acc, nullptr, 0, 0, workspace, workspace_bytes, stream);
+}
+
+int clipk_bwd_peer(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
+                   const float* x_inv_scale, const float* y_inv_scale, const void* Xg, const void* Yg, long long ldxg,
+                   long long ldyg, int g_dtype, const float* xg_inv_scale, const float* yg_inv_scale,
+                   const float* logit_scale, long long diag_offset, const float* lse_row, const float* lse_col,
+                   float alpha, float beta, const float* gscale, float* dX_acc, void* const* dY_peer_acc, int world,
+                   int rows_per_rank, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!dY_peer_acc) return fail(CLIPK_EINVAL, "null peer accumulator table");
+    return bwd_impl(X, Y, rows, cols, d, ldx, ldy, dtype, x_inv_scale, y_inv_scale, Xg, Yg, ldxg, ldyg, g_dtype,
+                    xg_inv_scale, yg_inv_scale, logit_scale, diag_offset, lse_row, lse_col, alpha, beta, gscale, dX_acc,
+                    nullptr, dY_peer_acc, world, rows_per_rank, workspace, workspace_bytes, stream);
+}
+
+int clipk_peer_barrier(void* const* peer_flags, int rank, int world, unsigned int epoch, void* stream) {
+    if (!peer_flags || world < 1 || world > MAX_PEERS || rank < 0 || rank >= world) return fail(CLIPK_EINVAL, "bad argument");
+    DevInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    PeerFlags pf;
+    memset(&pf, 0, sizeof(pf));
+    for (int t = 0; t < world; ++t) {
+        if (!peer_flags[t]) return fail(CLIPK_EINVAL, "null flag array %d", t);
+        pf.flags[t] = static_cast<unsigned int*>(peer_flags[t]);
+    }
+    peer_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pf, rank, world, epoch);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
 }
 

@@ -1102,23 +1102,43 @@ grad_sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 // The two gradient GEMMs of one panel in ONE launch, so that their tiles together fill the SMs:
 // pairs [0, jobs0) run job 0 (dX = G * Yg), the rest run job 1 (dY = G^T * Xg).  A pair is one 256 x 256 output tile.
+// Fused gradient GEMM + reduce-scatter (data-parallel ranks of one NVLink domain).  The rows of dY (the gradient on
+// the GATHERED text features) belong to their home ranks: rank o owns global rows [o * rows_per_rank, +rows_per_rank).
+// With peers.world > 0 every dY tile is ADDED (TMA reduce, fp32) straight into the owner's accumulator through its
+// peer-mapped address - over NVLink for remote owners - while the following tiles are still being multiplied, so
+// the separate reduce-scatter of loss.py's all_gather backward (and its 4 * N * d byte input buffer) disappears.
+constexpr int MAX_PEERS = 8;
+struct PeerOut {
+    CUtensorMap map[MAX_PEERS];   // fp32 [rows_per_rank, d] accumulator of every rank (zeroed by its owner)
+    int world;                    // 0 = job 1 writes through tmC1 (single GPU, or the NCCL reduce-scatter path)
+    int rows_per_rank;            // multiple of 128: a CTA's 128 output rows never straddle two owners
+};
+
 template <int F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                  const __grid_constant__ CUtensorMap tmC0, const KArgs args0,
                  const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
-                 const __grid_constant__ CUtensorMap tmC1, const KArgs args1, const int jobs0) {
+                 const __grid_constant__ CUtensorMap tmC1, const KArgs args1, const int jobs0,
+                 const __grid_constant__ PeerOut peers) {
     constexpr int STAGES = stages_of(MODE_OUT);
     const Cta c = cta_setup<STAGES, STG_TOTAL>();
     const int j = blockIdx.x >> 1;   // cluster (2, 1, 1): one job per CTA pair = a 256 x 256 output tile
     const bool first = j < jobs0;
-    const KArgs& args = first ? args0 : args1;
+    KArgs args = first ? args0 : args1;
     const CUtensorMap* tmA = first ? &tmA0 : &tmA1;
     const CUtensorMap* tmB = first ? &tmB0 : &tmB1;
     const CUtensorMap* tmC = first ? &tmC0 : &tmC1;
     const int k = first ? j : j - jobs0;
     const int m_blk = 2 * (k / args.n_tiles) + int(c.cta_rank);
     const int t0 = k % args.n_tiles;
+    if (!first && peers.world > 0) {
+        const int grow = args.c_row_off + m_blk * BM;           // first global dY row of this CTA
+        const int owner = min(grow / peers.rows_per_rank, peers.world - 1);
+        tmC = &peers.map[owner];
+        args.c_row_off -= owner * peers.rows_per_rank;
+        args.accumulate = 1;
+    }
     Pipe p;
     if (c.warp == 0) {
         if (c.lane == 0) {

@@ -84,3 +84,52 @@ def test_bf16_modes_against_oracle(world, ll, gwg):
         assert abs(float(o["loss"]) - g.loss) <= 2e-3 * abs(g.loss)
         assert rel(o["d_image"], g.d_image) <= 2e-3 and rel(o["d_text"], g.d_text) <= 2e-3
         assert abs(float(o["d_scale"]) - g.d_scale) <= 2e-3 * max(abs(g.d_scale), 0.07)
+
+
+def _steps_worker(rank, world, tmp, case):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "megatron-clip_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    from clipk import ClipLoss, ops
+    from oracle import cliploss_oracle as O
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"file://{tmp}/store", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    mod = ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True, rank=rank, world_size=world)
+    out = {}
+    for step in range(case["steps"]):
+        x, t = O.synthetic_features(case["b"], case["d"], seed=100 + step, rank=rank)
+        I = torch.from_numpy(x).cuda().bfloat16().requires_grad_(True)
+        T = torch.from_numpy(t).cuda().bfloat16().requires_grad_(True)
+        S = torch.tensor(1 / 0.07, device="cuda", requires_grad=True)
+        mod(I, T, S).backward()
+        out[f"d_image{step}"] = I.grad.float().cpu().numpy()
+        out[f"d_text{step}"] = T.grad.float().cpu().numpy()
+        out[f"image{step}"] = I.detach().float().cpu().numpy()
+        out[f"text{step}"] = T.detach().float().cpu().numpy()
+    torch.cuda.synchronize()
+    out["peer_used"] = np.array(len(ops._PEER_STATES))
+    np.savez(f"{tmp}/out{rank}.npz", **out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_peer_reduce_over_consecutive_steps():
+    """The fused gradient-GEMM + reduce-scatter path (dY tiles added into the owners' peer-mapped accumulators) over
+    several steps with different inputs: the accumulators are zeroed, filled and read in the right order."""
+    _need(2)
+    import torch.multiprocessing as mp
+    from oracle import cliploss_oracle as O
+    world, case = 2, {"b": 384, "d": 128, "steps": 3}
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(_steps_worker, args=(world, tmp, case), nprocs=world, join=True)
+        outs = [dict(np.load(f"{tmp}/out{r}.npz")) for r in range(world)]
+    assert all(int(o["peer_used"]) == 1 for o in outs), "peer-memory path was not taken"
+    for step in range(case["steps"]):
+        ref = O.clip_loss_world([o[f"image{step}"] for o in outs], [o[f"text{step}"] for o in outs], 1 / 0.07, True, True)
+        for r in range(world):
+            assert rel(outs[r][f"d_image{step}"], ref[r].d_image) <= 2e-3
+            assert rel(outs[r][f"d_text{step}"], ref[r].d_text) <= 2e-3
