@@ -306,6 +306,11 @@ def run_clipk(args):
 
 
 def main():
+    # exactly ONE JSON line may reach stdout: libraries (NCCL's version banner) write there too, so everything but the
+    # final line is sent to stderr at the file-descriptor level
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

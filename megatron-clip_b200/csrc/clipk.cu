@@ -441,6 +441,22 @@ __global__ void fwd_merge_kernel(const FwdArgs a0, const FwdArgs a1, int m_block
     }
 }
 
+// dst[i] = (dtype) sum_w src[w * n + i]: the owner's sum over the per-source slots of the fused reduce-scatter
+__global__ void reduce_slots_kernel(const float* __restrict__ src, long long n, int world, void* __restrict__ dst, int dtype) {
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;
+    float4 acc = *reinterpret_cast<const float4*>(src + i);
+    for (int w = 1; w < world; ++w) {
+        const float4 v = *reinterpret_cast<const float4*>(src + (size_t)w * n + i);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (dtype == CLIPK_BF16)
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(dst) + i) =
+            make_uint2(ptx::pack_bf16x2(acc.x, acc.y), ptx::pack_bf16x2(acc.z, acc.w));
+    else
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + i) = acc;
+}
+
 // Barrier between the ranks of one NVLink domain through peer-mapped flags: thread t publishes `epoch` in slot
 // [rank] of rank t's flag array (after everything this stream did before became visible system-wide), then waits
 // until rank t has published the same epoch here.  Epochs only grow, so the flags are never reset.
@@ -1073,7 +1089,7 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
     PeerOut peers;
     memset(&peers, 0, sizeof(peers));
     if (dY_peer_acc) {
-        // fused reduce-scatter: dY tiles are added into the owners' accumulators (see gemm_pair_kernel)
+        // fused reduce-scatter: dY tiles are written into this rank's slot at their owners (see gemm_pair_kernel)
         if (world < 1 || world > MAX_PEERS) return fail(CLIPK_EUNSUPPORTED, "peer output supports 1..%d ranks (got %d)", MAX_PEERS, world);
         if (rows_per_rank <= 0 || rows_per_rank % BM != 0 || (long long)rows_per_rank * world != cols)
             return fail(CLIPK_EUNSUPPORTED, "peer output needs cols == world * rows_per_rank and rows_per_rank %% 128 == 0");
@@ -1331,6 +1347,17 @@ int clipk_bwd_peer(const void* X, const void* Y, int rows, int cols, int d, long
     return bwd_impl(X, Y, rows, cols, d, ldx, ldy, dtype, x_inv_scale, y_inv_scale, Xg, Yg, ldxg, ldyg, g_dtype,
                     xg_inv_scale, yg_inv_scale, logit_scale, diag_offset, lse_row, lse_col, alpha, beta, gscale, dX_acc,
                     nullptr, dY_peer_acc, world, rows_per_rank, workspace, workspace_bytes, stream);
+}
+
+int clipk_reduce_slots(const float* src, long long n, int world, void* dst, int dtype, void* stream) {
+    if (!src || !dst || n <= 0 || world < 1) return fail(CLIPK_EINVAL, "bad argument");
+    if (n % 4 != 0 || (reinterpret_cast<uintptr_t>(src) & 15) != 0 || (reinterpret_cast<uintptr_t>(dst) & 15) != 0)
+        return fail(CLIPK_EUNSUPPORTED, "n must be a multiple of 4 and the pointers 16-byte aligned");
+    if (dtype != CLIPK_BF16 && dtype != CLIPK_F32) return fail(CLIPK_EUNSUPPORTED, "dtype %d", dtype);
+    reduce_slots_kernel<<<cdiv(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, n, world, dst, dtype);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CK_CUDA(cudaGetLastError());
+    return CLIPK_OK;
 }
 
 int clipk_peer_barrier(void* const* peer_flags, int rank, int world, unsigned int epoch, void* stream) {

@@ -667,8 +667,15 @@ __device__ __forceinline__ void grad_epilogue_unit(const Cta& c, Pipe& p, const 
     }
 }
 
-// all bulk stores of this epilogue warp complete (writes performed) - before the CTA exits
+// Before the CTA exits: the bulk stores of this epilogue warp have READ their shared-memory source.  Their global
+// writes may still be in flight - the grid does not complete before they have been performed, so the next kernel of
+// the stream sees them - which lets slow destinations (peer accumulators over NVLink) drain under the next kernel.
 __device__ __forceinline__ void epilogue_drain(const Cta& c) {
+    if (c.lane == 0) ptx::tma_store_wait_read<0>();
+    __syncwarp();
+}
+// all bulk stores of this epilogue warp complete (writes performed): before publishing them to other CTAs of the SAME grid
+__device__ __forceinline__ void epilogue_drain_complete(const Cta& c) {
     if (c.lane == 0) ptx::tma_store_wait<0>();
     __syncwarp();
 }
@@ -1104,12 +1111,14 @@ grad_sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // pairs [0, jobs0) run job 0 (dX = G * Yg), the rest run job 1 (dY = G^T * Xg).  A pair is one 256 x 256 output tile.
 // Fused gradient GEMM + reduce-scatter (data-parallel ranks of one NVLink domain).  The rows of dY (the gradient on
 // the GATHERED text features) belong to their home ranks: rank o owns global rows [o * rows_per_rank, +rows_per_rank).
-// With peers.world > 0 every dY tile is ADDED (TMA reduce, fp32) straight into the owner's accumulator through its
-// peer-mapped address - over NVLink for remote owners - while the following tiles are still being multiplied, so
-// the separate reduce-scatter of loss.py's all_gather backward (and its 4 * N * d byte input buffer) disappears.
+// With peers.world > 0 every dY tile is written straight into the owner's memory through its peer-mapped address -
+// over NVLink for remote owners - into the slot reserved for THIS source rank (plain TMA stores: reductions over
+// NVLink were measured ~3x slower), and the CTA does not wait for the remote writes: they drain while the next
+// panel is being recomputed.  The owner sums its `world` slots afterwards (clipk_reduce_slots).  The separate
+// reduce-scatter of loss.py's all_gather backward and its 4 * N * d byte input buffer disappear.
 constexpr int MAX_PEERS = 8;
 struct PeerOut {
-    CUtensorMap map[MAX_PEERS];   // fp32 [rows_per_rank, d] accumulator of every rank (zeroed by its owner)
+    CUtensorMap map[MAX_PEERS];   // fp32 [rows_per_rank, d] slot of this source rank in the memory of every owner
     int world;                    // 0 = job 1 writes through tmC1 (single GPU, or the NCCL reduce-scatter path)
     int rows_per_rank;            // multiple of 128: a CTA's 128 output rows never straddle two owners
 };
@@ -1136,8 +1145,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int grow = args.c_row_off + m_blk * BM;           // first global dY row of this CTA
         const int owner = min(grow / peers.rows_per_rank, peers.world - 1);
         tmC = &peers.map[owner];
-        args.c_row_off -= owner * peers.rows_per_rank;
-        args.accumulate = 1;
+        args.c_row_off -= owner * peers.rows_per_rank;   // args.accumulate stays: first row panel stores, later ones add
     }
     Pipe p;
     if (c.warp == 0) {
@@ -1314,7 +1322,7 @@ bwd_dataflow_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 }
                 if (c.warp >= 2) {
                     // publish panel q of this CTA (also when it had no tiles: the counters advance in lockstep)
-                    epilogue_drain(c);
+                    epilogue_drain_complete(c);
                     ptx::named_bar_sync(3, NUM_EPI_WARPS * 32);
                     if (c.warp == 2 && c.lane == 0) flag_signal(P.done + cluster);
                 }
