@@ -20,7 +20,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -46,46 +45,57 @@ def peaks():
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """nvidia-smi polling the clocks of one GPU during the timed region.  The samples go to a file that is read after
+    the run: a reader thread in this process would fight the launching thread for the interpreter lock."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.proc, self.path, self.fh = index, None, None, None
 
     def start(self):
+        import tempfile
         try:
+            self.fh = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.path = self.fh.name
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("CLIPK_BENCH_SMI_MS", "100")],
+                                         stdout=self.fh, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.3)         # let the first samples land before the timed region starts
         except OSError:
             self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.fh.close()
+        with open(self.path) as f:
+            rows = [[c.strip() for c in line.split(",")] for line in f if line.strip()]
+        os.unlink(self.path)
+        sm, mx, power, reasons = [], None, [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx = float(r[2])
+                power.append(float(r[3]))
                 for n, v in zip(names, r[4:8]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
             except (ValueError, IndexError):
                 pass
-        sm.sort()
-        # median over the busier half of the samples = clocks under load
-        load = sm[len(sm) // 2:] if sm else []
+        # clocks under load = the samples taken while the GPU drew the most power (busier half)
+        order = sorted(range(len(sm)), key=lambda i: power[i])
+        load = sorted(sm[i] for i in order[len(order) // 2:])
         med = load[len(load) // 2] if load else None
-        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power) if power else None}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
@@ -184,9 +194,10 @@ def run_clipk(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        total_ms = 0.0
-        l0 = ops.gpu_launches()
+        # every step has its own event pair; the L2 flush between steps is enqueued outside the pairs and the host
+        # does not synchronise inside the timed region, so launch latency hides behind the previous step's kernels
         launches = 0
+        pairs = []
         for _ in range(steps):
             flush.fill_(1)                          # L2 flush, outside the event pair
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -195,8 +206,9 @@ def run_clipk(args):
             fn()
             e1.record()
             launches += ops.gpu_launches() - la
-            torch.cuda.synchronize()
-            total_ms += e0.elapsed_time(e1)
+            pairs.append((e0, e1))
+        torch.cuda.synchronize()
+        total_ms = sum(e0.elapsed_time(e1) for e0, e1 in pairs)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()

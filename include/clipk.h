@@ -59,6 +59,9 @@ int clipk_check_device(void);
  * fp32 -> two planes replaces the fp32 matmul of loss.py:112-119 when autocast is off. */
 int clipk_to_f16(const void* src, int src_dtype, long long rows, long long d, long long ld_src, void* dst, int planes,
                  long long ld_dst, float* scale_io, void* stream);
+/* same with max |x| already known (a device float, finite and from the same data) */
+int clipk_to_f16_amax(const void* src, int src_dtype, long long rows, long long d, long long ld_src, void* dst, int planes,
+                      long long ld_dst, float* scale_io, const float* amax, void* stream);
 
 /* ---- forward ------------------------------------------------------------------------------------------
  * clipk_fwd_stats replaces, for one direction, the logits GEMM and the log-softmax reduction of
@@ -82,12 +85,14 @@ int clipk_fwd_stats(const void* X, const void* Y, int rows, int cols, int d, lon
  * For bf16 operands with d <= 512 whose logits are provably bounded (logit_scale * max|x_i| * max|y_j| <= ~34, checked
  * on the device from the row norms) this is ONE sweep over the tiles: every tile feeds the row and the column sums, with
  * the rows of X resident in shared memory.  Otherwise the library runs the exact two-sweep form by itself (same
- * results, the cost of two clipk_fwd_stats calls).  pos_logit may be NULL. */
+ * results, the cost of two clipk_fwd_stats calls).  pos_logit may be NULL.  amax_xy (may be NULL) receives max |x| of
+ * X and of Y when the single-sweep path computed them on its way (NaN otherwise): clipk_to_f16_amax takes them, so the
+ * backward need not read the features again just to find its fp16 scale. */
 size_t clipk_fwd_both_workspace_bytes(int rows, int cols, int d, int dtype);
 int clipk_fwd_both(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
                    const float* x_inv_scale, const float* y_inv_scale, const float* logit_scale, long long diag_offset,
-                   float* row_stats, float* pos_logit, float* col_stats, void* workspace, size_t workspace_bytes,
-                   void* stream);
+                   float* row_stats, float* pos_logit, float* col_stats, float* amax_xy, void* workspace,
+                   size_t workspace_bytes, void* stream);
 
 /* clipk_finalize merges statistics into log-sum-exps, the two cross-entropy sums (loss.py:135-138) and the two
  * sums that make up dloss/dlogit_scale:

@@ -20,6 +20,8 @@ product: without libclipk.so or without a compute-capability-10.x device the cal
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -40,11 +42,12 @@ def _ptr(t):
 
 class Operand:
     """A feature matrix in the layout the kernels consume (see include/clipk.h, CLIPK_BF16 / F16 / F16X2)."""
-    __slots__ = ("data", "dtype", "ld", "inv_scale", "rows", "d", "scale_io")
+    __slots__ = ("data", "dtype", "ld", "inv_scale", "rows", "d", "scale_io", "amax")
 
     def __init__(self, data, dtype, ld, inv_scale, rows, d, scale_io=None):
         self.data, self.dtype, self.ld, self.inv_scale, self.rows, self.d = data, dtype, ld, inv_scale, rows, d
         self.scale_io = scale_io     # keeps the device scalar behind inv_scale alive
+        self.amax = None             # device float: max |x|, when the forward sweep computed it on its way
 
     def inv_ptr(self):
         return None if self.inv_scale is None else self.inv_scale.data_ptr()
@@ -60,14 +63,19 @@ class CudaBackend:
     def _stream():
         return torch.cuda.current_stream().cuda_stream
 
-    def _to_f16(self, x: torch.Tensor, planes: int) -> Operand:
+    def _to_f16(self, x: torch.Tensor, planes: int, amax=None) -> Operand:
         rows, d = x.shape
         dpad = (d + 63) // 64 * 64
         out = torch.empty(rows, planes * dpad, dtype=torch.float16, device=x.device)
         scale_io = torch.empty(2, dtype=torch.float32, device=x.device)
         src_dt = _lib.BF16 if x.dtype == torch.bfloat16 else _lib.F32
-        _lib.check(self.lib.clipk_to_f16(x.data_ptr(), src_dt, rows, d, x.stride(0), out.data_ptr(), planes,
-                                         planes * dpad, scale_io.data_ptr(), self._stream()), "clipk_to_f16")
+        if amax is not None:
+            _lib.check(self.lib.clipk_to_f16_amax(x.data_ptr(), src_dt, rows, d, x.stride(0), out.data_ptr(), planes,
+                                                  planes * dpad, scale_io.data_ptr(), amax.data_ptr(), self._stream()),
+                       "clipk_to_f16_amax")
+        else:
+            _lib.check(self.lib.clipk_to_f16(x.data_ptr(), src_dt, rows, d, x.stride(0), out.data_ptr(), planes,
+                                             planes * dpad, scale_io.data_ptr(), self._stream()), "clipk_to_f16")
         return Operand(out, _lib.F16 if planes == 1 else _lib.F16X2, planes * dpad, scale_io[1:2], rows, d, scale_io)
 
     def prepare(self, x: torch.Tensor) -> Operand:
@@ -83,7 +91,7 @@ class CudaBackend:
         """Operand of the gradient GEMMs (fp16 x fp16): exact one-plane fp16 copy of bf16 features; the two-plane
         fp16 form of fp32 features is reused as is."""
         if op.dtype == _lib.BF16:
-            return self._to_f16(op.data, 1)
+            return self._to_f16(op.data, 1, amax=op.amax)
         return op
 
     def fwd_stats(self, X: Operand, Y: Operand, scale, diag_offset, want_pos, out=None):
@@ -110,12 +118,17 @@ class CudaBackend:
         if col_out is None:
             col_out = torch.empty(3, cols, dtype=torch.float32, device=dev)
         pos = torch.zeros(rows, dtype=torch.float32, device=dev)
+        # the single-sweep path leaves max |x| of both operands here (the backward's fp16 scale needs it)
+        want_amax = X.dtype == _lib.BF16 and d <= 512
+        amax = torch.empty(2, dtype=torch.float32, device=dev) if want_amax else None
         nbytes = self.lib.clipk_fwd_both_workspace_bytes(rows, cols, d, X.dtype)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         _lib.check(self.lib.clipk_fwd_both(X.data.data_ptr(), Y.data.data_ptr(), rows, cols, d, X.ld, Y.ld, X.dtype,
                                            X.inv_ptr(), Y.inv_ptr(), scale.data_ptr(), diag_offset,
-                                           row_stats.data_ptr(), pos.data_ptr(), col_out.data_ptr(), ws.data_ptr(),
-                                           nbytes, self._stream()), "clipk_fwd_both")
+                                           row_stats.data_ptr(), pos.data_ptr(), col_out.data_ptr(), _ptr(amax),
+                                           ws.data_ptr(), nbytes, self._stream()), "clipk_fwd_both")
+        if want_amax and not os.environ.get("CLIPK_DBG"):
+            X.amax, Y.amax = amax[0:1], amax[1:2]
         return row_stats, pos, col_out
 
     def finalize(self, row_stats, pos, col_parts, diag_offset):
@@ -317,7 +330,7 @@ class FusedClipLoss(torch.autograd.Function):
         # sums[0:2] -> loss, sums[2:4] -> s * dloss/ds; the global (local_loss=False) loss is the same N x N problem
         # on every rank, so both are all-reduced there.  dlogit_scale is never reduced by the loss in local mode
         # (DDP averages it later), exactly like the reference.
-        pair = torch.stack((sums[0] + sums[1], sums[2] + sums[3]))
+        pair = sums.view(2, 2).sum(dim=1)
         if W > 1 and not local_loss:
             dist.all_reduce(pair, op=dist.ReduceOp.SUM, group=group)
             pair = pair / (2.0 * N)

@@ -355,53 +355,69 @@ __global__ void to_f16_kernel(const T* __restrict__ src, __half* __restrict__ ds
 
 // ---- forward sweep helpers
 // out[which] = max over rows of |row|^2 as float bits (non-negative floats order like unsigned ints); one warp per row,
-// 16-byte loads, d % 8 == 0.  Both operands in one launch: blocks [0, bx) take X, the rest take Y.
+// 16-byte loads, d % 8 == 0.  Both operands in one launch: blocks [0, bx) take X, the rest take Y.  amax (optional,
+// two floats) receives max |element| of X and of Y - what clipk_to_f16 needs for its scale, so that the backward does
+// not have to read the features once more just for that.
 __global__ void norm2_max_kernel(const __nv_bfloat16* __restrict__ X, long long rows_x, long long ldx,
                                  const __nv_bfloat16* __restrict__ Y, long long rows_y, long long ldy, int d8, int bx,
-                                 unsigned int* __restrict__ out) {
+                                 unsigned int* __restrict__ out, unsigned int* __restrict__ amax) {
     const bool second = int(blockIdx.x) >= bx;
     const __nv_bfloat16* src = second ? Y : X;
     const long long rows = second ? rows_y : rows_x, ld = second ? ldy : ldx;
     const int nb = second ? int(gridDim.x) - bx : bx, b = second ? int(blockIdx.x) - bx : int(blockIdx.x);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-    float best = 0.f;
+    float best = 0.f, am = 0.f;
     for (long long r = (long long)b * wpb + warp; r < rows; r += (long long)nb * wpb) {
         float acc = 0.f;
         for (int k = lane; k < d8; k += 32) {
             float v[8];
             load8(src + r * ld + (long long)k * 8, v);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc = fmaf(v[j], v[j], acc);
+            for (int j = 0; j < 8; ++j) {
+                acc = fmaf(v[j], v[j], acc);
+                const float a = fabsf(v[j]);
+                if (a < CUDART_INF_F) am = fmaxf(am, a);     // as amax_kernel: Inf / NaN do not set the scale
+            }
         }
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
         // NaN / Inf propagate into the bound, which then fails its test (exact mode)
         best = (acc > best || !(acc == acc)) ? acc : best;
     }
-    __shared__ float sh[32];
-    if (lane == 0) sh[warp] = best;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, off));
+    __shared__ float sh[32], sha[32];
+    if (lane == 0) { sh[warp] = best; sha[warp] = am; }
     __syncthreads();
     if (warp == 0) {
         float v = lane < wpb ? sh[lane] : 0.f;
+        float a = lane < wpb ? sha[lane] : 0.f;
         bool bad = !(v == v);
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
             const float o = __shfl_xor_sync(0xffffffffu, v, off);
             bad = bad || !(o == o);
             v = fmaxf(v, o);
+            a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, off));
         }
         bad = __any_sync(0xffffffffu, bad);
-        if (lane == 0) atomicMax(out + (second ? 1 : 0), bad ? 0x7f800000u : __float_as_uint(v));
+        if (lane == 0) {
+            atomicMax(out + (second ? 1 : 0), bad ? 0x7f800000u : __float_as_uint(v));
+            if (amax && a > 0.f) atomicMax(amax + (second ? 1 : 0), __float_as_uint(a));
+        }
     }
 }
 
 // rows: merge the per-item parts (max, sum, dot; log2-scaled domain) into natural-log (max, sum, dot), as
 // merge_row_parts_kernel.  columns: in single-sweep mode sum the per-row-block partial (sum, dot) of the global
 // reference u; in exact mode merge the parts the swapped launch wrote.  The mode is recomputed from the same scalars.
+// Block = 32 indices x 8 slices: the (up to hundreds of) row-block partials of a column are summed by 8 threads.
 __global__ void fwd_merge_kernel(const FwdArgs a0, const FwdArgs a1, int m_blocks, float* __restrict__ row_out,
                                  float* __restrict__ col_out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;      // blockDim.x == 256
+    const int i = blockIdx.x * 32 + lane;
     const int rows = a0.M, cols = a0.N;
+    __shared__ float shL[8][32], shD[8][32];
     auto merge_parts = [](const float* pmx, const float* psm, const float* pdt, int nparts, int n, int idx, float* o, int on) {
         float m = -CUDART_INF_F;
         for (int p = 0; p < nparts; ++p) m = fmaxf(m, pmx[(size_t)p * n + idx]);
@@ -423,21 +439,27 @@ __global__ void fwd_merge_kernel(const FwdArgs a0, const FwdArgs a1, int m_block
         const long long total = (long long)a.m_pairs * a.n_tiles, f = (long long)(row / (2 * BM)) * a.n_tiles;
         return PARTS_PER_UNIT * (sweep_cluster_of(total, f + a.n_tiles - 1, a.n_clusters) - sweep_cluster_of(total, f, a.n_clusters) + 1);
     };
-    if (i < rows) merge_parts(a0.part_max, a0.part_sum, a0.part_dot, nparts_of(a0, i), rows, i, row_out, rows);
-    if (i < cols) {
-        float u;
-        if (fwd_bound(a0, &u)) {
-            float L = 0.f, D = 0.f;
-            for (int b = 0; b < m_blocks; ++b) {
+    if (sl == 0 && i < rows) merge_parts(a0.part_max, a0.part_sum, a0.part_dot, nparts_of(a0, i), rows, i, row_out, rows);
+    float u;
+    const bool single = fwd_bound(a0, &u);      // uniform over the grid
+    if (single) {
+        float L = 0.f, D = 0.f;
+        if (i < cols)
+            for (int b = sl; b < m_blocks; b += 8) {
                 L += a0.colpart_sum[(size_t)b * a0.ldc + i];
                 D += a0.colpart_dot[(size_t)b * a0.ldc + i];
             }
+        shL[sl][lane] = L; shD[sl][lane] = D;
+        __syncthreads();
+        if (sl == 0 && i < cols) {
+#pragma unroll
+            for (int k = 1; k < 8; ++k) { L += shL[k][lane]; D += shD[k][lane]; }
             col_out[i] = u * LN2;
             col_out[cols + i] = L;
             col_out[2 * cols + i] = fmaf(u, L, D) * LN2;
-        } else {
-            merge_parts(a1.part_max, a1.part_sum, a1.part_dot, nparts_of(a1, i), cols, i, col_out, cols);
         }
+    } else if (sl == 0 && i < cols) {
+        merge_parts(a1.part_max, a1.part_sum, a1.part_dot, nparts_of(a1, i), cols, i, col_out, cols);
     }
 }
 
@@ -863,8 +885,22 @@ int clipk_check_device(void) {
     return device_info(&di);
 }
 
+static int to_f16_impl(const void* src, int src_dtype, long long rows, long long d, long long ld_src, void* dst, int planes,
+                       long long ld_dst, float* scale_io, const float* amax, void* stream);
+
 int clipk_to_f16(const void* src, int src_dtype, long long rows, long long d, long long ld_src, void* dst, int planes,
                  long long ld_dst, float* scale_io, void* stream) {
+    return to_f16_impl(src, src_dtype, rows, d, ld_src, dst, planes, ld_dst, scale_io, nullptr, stream);
+}
+
+int clipk_to_f16_amax(const void* src, int src_dtype, long long rows, long long d, long long ld_src, void* dst, int planes,
+                      long long ld_dst, float* scale_io, const float* amax, void* stream) {
+    if (!amax) return fail(CLIPK_EINVAL, "null amax");
+    return to_f16_impl(src, src_dtype, rows, d, ld_src, dst, planes, ld_dst, scale_io, amax, stream);
+}
+
+static int to_f16_impl(const void* src, int src_dtype, long long rows, long long d, long long ld_src, void* dst, int planes,
+                       long long ld_dst, float* scale_io, const float* amax, void* stream) {
     if (!src || !dst || !scale_io || rows <= 0 || d <= 0) return fail(CLIPK_EINVAL, "bad argument");
     if (planes != 1 && planes != 2) return fail(CLIPK_EINVAL, "planes must be 1 or 2");
     if (src_dtype != CLIPK_BF16 && src_dtype != CLIPK_F32) return fail(CLIPK_EUNSUPPORTED, "source dtype %d", src_dtype);
@@ -874,7 +910,9 @@ int clipk_to_f16(const void* src, int src_dtype, long long rows, long long d, lo
     int rc = device_info(&di);
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    CK_CUDA(cudaMemsetAsync(scale_io, 0, 2 * sizeof(float), st));
+    // scale_io[0] = max |x| (bit pattern): computed here, or handed in by the caller (clipk_fwd_both's amax_xy)
+    if (amax) CK_CUDA(cudaMemcpyAsync(scale_io, amax, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    else CK_CUDA(cudaMemsetAsync(scale_io, 0, 2 * sizeof(float), st));
     if (d % 8 != 0) return fail(CLIPK_EUNSUPPORTED, "d = %lld is not a multiple of 8", d);
     if ((reinterpret_cast<uintptr_t>(src) & 15) != 0 || (ld_src * (src_dtype == CLIPK_BF16 ? 2 : 4)) % 16 != 0)
         return fail(CLIPK_EINVAL, "source rows must be 16-byte aligned");
@@ -885,14 +923,18 @@ int clipk_to_f16(const void* src, int src_dtype, long long rows, long long d, lo
     __half* out = static_cast<__half*>(dst);
     if (src_dtype == CLIPK_BF16) {
         const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(src);
-        amax_kernel<<<rblocks, 256, 0, st>>>(p, rows, d / 8, ld_src, bits);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (!amax) {
+            amax_kernel<<<rblocks, 256, 0, st>>>(p, rows, d / 8, ld_src, bits);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+        }
         to_f16_kernel<<<cdiv(n, 256), 256, 0, st>>>(p, out, rows, d, ld_src, dpad, planes, scale_io);
         g_launches.fetch_add(1, std::memory_order_relaxed);
     } else {
         const float* p = static_cast<const float*>(src);
-        amax_kernel<<<rblocks, 256, 0, st>>>(p, rows, d / 8, ld_src, bits);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (!amax) {
+            amax_kernel<<<rblocks, 256, 0, st>>>(p, rows, d / 8, ld_src, bits);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+        }
         to_f16_kernel<<<cdiv(n, 256), 256, 0, st>>>(p, out, rows, d, ld_src, dpad, planes, scale_io);
         g_launches.fetch_add(1, std::memory_order_relaxed);
     }
@@ -961,8 +1003,8 @@ size_t clipk_fwd_both_workspace_bytes(int rows, int cols, int d, int dtype) {
 
 int clipk_fwd_both(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
                    const float* x_inv_scale, const float* y_inv_scale, const float* logit_scale, long long diag_offset,
-                   float* row_stats, float* pos_logit, float* col_stats, void* workspace, size_t workspace_bytes,
-                   void* stream) {
+                   float* row_stats, float* pos_logit, float* col_stats, float* amax_xy, void* workspace,
+                   size_t workspace_bytes, void* stream) {
     int rc = check_common(X, Y, rows, cols, d, ldx, ldy, dtype);
     if (rc) return rc;
     if (!logit_scale || !row_stats || !col_stats || !workspace) return fail(CLIPK_EINVAL, "null pointer argument");
@@ -974,6 +1016,7 @@ int clipk_fwd_both(const void* X, const void* Y, int rows, int cols, int d, long
     const int planes = planes_of(dtype);
     const long long dpad = round_up(d, BK);
     const int num_kb = cdiv(d, BK);
+    if (amax_xy) CK_CUDA(cudaMemsetAsync(amax_xy, 0xff, 2 * sizeof(float), static_cast<cudaStream_t>(stream)));   // NaN = not computed
     if (planes != 1 || num_kb > ARES_KB || (dbg_flags() & 512)) {
         // operands too wide for the resident-rows kernel (or split-precision): two streaming sweeps
         char* ws = static_cast<char*>(workspace);
@@ -996,10 +1039,12 @@ int clipk_fwd_both(const void* X, const void* Y, int rows, int cols, int d, long
     const bool bounded = (dtype == CLIPK_BF16) && !(dbg_flags() & 16384);
     if (bounded) {
         CK_CUDA(cudaMemsetAsync(norm2, 0, 2 * sizeof(unsigned int), st));
+        if (amax_xy) CK_CUDA(cudaMemsetAsync(amax_xy, 0, 2 * sizeof(float), st));
         const int wpb = 8;
         const int bx = std::max(1, std::min(cdiv(rows, wpb), 2 * di.sms)), by = std::max(1, std::min(cdiv(cols, wpb), 2 * di.sms));
         norm2_max_kernel<<<bx + by, wpb * 32, 0, st>>>(static_cast<const __nv_bfloat16*>(X), rows, ldx,
-                                                        static_cast<const __nv_bfloat16*>(Y), cols, ldy, d / 8, bx, norm2);
+                                                        static_cast<const __nv_bfloat16*>(Y), cols, ldy, d / 8, bx, norm2,
+                                                        reinterpret_cast<unsigned int*>(amax_xy));
         g_launches.fetch_add(1, std::memory_order_relaxed);
         CK_CUDA(cudaGetLastError());
     }
@@ -1041,7 +1086,7 @@ int clipk_fwd_both(const void* X, const void* Y, int rows, int cols, int d, long
         if ((rc = launch_fwd_sweep<0>(ty_a, tx_b, a1, nc1, st))) return rc;
     }
     const int n = rows > cols ? rows : cols;
-    fwd_merge_kernel<<<cdiv(n, 128), 128, 0, st>>>(a0, a1, cv.m_blocks, row_stats, col_stats);
+    fwd_merge_kernel<<<cdiv(n, 32), 256, 0, st>>>(a0, a1, cv.m_blocks, row_stats, col_stats);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;

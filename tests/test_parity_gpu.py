@@ -187,3 +187,82 @@ def test_persistent_backward_path_matches():
     assert out.returncode == 0, out.stderr[-2000:]
     e = json.loads(out.stdout.strip().splitlines()[-1])
     assert e[0] <= 2e-3 and e[1] <= 2e-3, e
+
+
+@pytest.mark.parametrize("rows,cols,d,s,off", [
+    (256, 256, 512, 1 / 0.07, 0),          # one tile
+    (1000, 3000, 256, 1 / 0.07, 500),      # ragged rows and columns, positives off the main diagonal
+    (384, 4100, 64, 20.0, 128),            # one K block, columns just past a tile boundary
+    (2048, 2048, 512, 100.0, 0),           # logit_scale 100: the norm bound fails -> exact two-sweep mode on device
+    (520, 520, 768, 1 / 0.07, 0),          # d > 512: the resident-rows kernel does not apply -> streaming sweeps
+])
+def test_fwd_both_matches_direct_statistics(rows, cols, d, s, off):
+    """clipk_fwd_both (one sweep feeding row AND column statistics when the logits are bounded; exact fallback
+    otherwise) against fp64 statistics of the same bf16 values."""
+    from clipk import ops
+    from oracle import cliploss_oracle as O
+    n = max(rows, cols)
+    x, t = O.synthetic_features(n, d, seed=5)
+    I = torch.from_numpy(x[:rows]).cuda().bfloat16().contiguous()
+    T = torch.from_numpy(t[:cols]).cuda().bfloat16().contiguous()
+    be = ops._backend()
+    X, Y = be.prepare(I), be.prepare(T)
+    sc = torch.tensor([s], device="cuda")
+    rs, pos, cs = be.fwd_both(X, Y, sc, off)
+    torch.cuda.synchronize()
+    S = (I.double() @ T.double().T) * float(sc[0])
+    tol = 2e-5 * max(1.0, s / 14.0)
+    lse_r, lse_c = rs[0] + rs[1].log(), cs[0] + cs[1].log()
+    assert torch.allclose(lse_r.double(), torch.logsumexp(S, 1), rtol=0, atol=tol)
+    assert torch.allclose(lse_c.double(), torch.logsumexp(S, 0), rtol=0, atol=tol)
+    assert torch.allclose((rs[2] / rs[1]).double(), (torch.softmax(S, 1) * S).sum(1), rtol=0, atol=5 * tol)
+    assert torch.allclose((cs[2] / cs[1]).double(), (torch.softmax(S, 0) * S).sum(0), rtol=0, atol=5 * tol)
+    idx = torch.arange(rows, device="cuda")
+    ok = idx + off < cols
+    assert torch.allclose(pos[ok].double(), S[idx[ok], idx[ok] + off], rtol=0, atol=tol)
+    if X.amax is not None:
+        assert float(X.amax) == float(I.abs().max()) and float(Y.amax) == float(T.abs().max())
+
+
+def test_single_sweep_and_exact_mode_agree():
+    """Same inputs through the single sweep and through the exact two-sweep mode (forced with CLIPK_DBG=512 in a
+    subprocess): the statistics agree to fp32 rounding."""
+    import os, subprocess, sys, json
+    code = (
+        "import sys, json, torch\n"
+        "sys.path.insert(0, 'megatron-clip_b200'); sys.path.insert(0, '.')\n"
+        "from clipk import ops\n"
+        "from oracle import cliploss_oracle as O\n"
+        "x, t = O.synthetic_features(1500, 512, seed=9)\n"
+        "I = torch.from_numpy(x).cuda().bfloat16(); T = torch.from_numpy(t).cuda().bfloat16()\n"
+        "be = ops._backend(); X, Y = be.prepare(I), be.prepare(T)\n"
+        "rs, pos, cs = be.fwd_both(X, Y, torch.tensor([1 / 0.07], device='cuda'), 0)\n"
+        "torch.cuda.synchronize()\n"
+        "print(json.dumps([(rs[0] + rs[1].log()).tolist(), (cs[0] + cs[1].log()).tolist()]))\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for dbg in ("0", "512"):
+        env = dict(os.environ, CLIPK_DBG=dbg)
+        out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        outs.append(json.loads(out.stdout.strip().splitlines()[-1]))
+    a, b = np.array(outs[0]), np.array(outs[1])
+    assert np.abs(a - b).max() <= 1e-5
+
+
+def test_tmem_fragment_layout_hook():
+    """tcgen05.ld.16x256b puts (lane, column) where the single-sweep epilogue expects it."""
+    from clipk import _lib
+    lib = _lib.load()
+    out = torch.zeros(8 * 32 * 16, dtype=torch.int32, device="cuda")
+    _lib.check(lib.clipk_debug_tmem_layout(out.data_ptr(), torch.cuda.current_stream().cuda_stream), "layout")
+    torch.cuda.synchronize()
+    o = out.cpu().view(4, 2, 32, 16)
+    for w in range(4):
+        for h in range(2):
+            for t in range(32):
+                for k in range(16):
+                    g, c = t // 4, 2 * (t % 4)
+                    lane = w * 32 + h * 16 + g + (8 if (k % 4) >= 2 else 0)
+                    col = 8 * (k // 4) + c + (k % 2)
+                    assert int(o[w, h, t, k]) == lane * 1000 + col
