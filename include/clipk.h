@@ -87,11 +87,13 @@ int clipk_fwd_stats(const void* X, const void* Y, int rows, int cols, int d, lon
  * the rows of X resident in shared memory.  Otherwise the library runs the exact two-sweep form by itself (same
  * results, the cost of two clipk_fwd_stats calls).  pos_logit may be NULL.  amax_xy (may be NULL) receives max |x| of
  * X and of Y when the single-sweep path computed them on its way (NaN otherwise): clipk_to_f16_amax takes them, so the
- * backward need not read the features again just to find its fp16 scale. */
+ * backward need not read the features again just to find its fp16 scale.  exact != 0 forces the two-sweep form, whose
+ * `max` planes are the true row / column maxima (the single sweep reports its global reference there; max + log(sum)
+ * is the log-sum-exp either way) - callers that want top-1 accuracy (pos_logit >= max) ask for it. */
 size_t clipk_fwd_both_workspace_bytes(int rows, int cols, int d, int dtype);
 int clipk_fwd_both(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
                    const float* x_inv_scale, const float* y_inv_scale, const float* logit_scale, long long diag_offset,
-                   float* row_stats, float* pos_logit, float* col_stats, float* amax_xy, void* workspace,
+                   float* row_stats, float* pos_logit, float* col_stats, float* amax_xy, int exact, void* workspace,
                    size_t workspace_bytes, void* stream);
 
 /* clipk_finalize merges statistics into log-sum-exps, the two cross-entropy sums (loss.py:135-138) and the two

@@ -31,7 +31,7 @@ PROTOTYPES = {
     "clipk_fwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "clipk_fwd_stats": (_i, [_vp, _vp, _i, _i, _i, _ll, _ll, _i, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "clipk_fwd_both_workspace_bytes": (_sz, [_i, _i, _i, _i]),
-    "clipk_fwd_both": (_i, [_vp, _vp, _i, _i, _i, _ll, _ll, _i, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "clipk_fwd_both": (_i, [_vp, _vp, _i, _i, _i, _ll, _ll, _i, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "clipk_to_f16_amax": (_i, [_vp, _i, _ll, _ll, _ll, _vp, _i, _ll, _vp, _vp, _vp]),
     "clipk_finalize": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _ll, _i, _ll, _vp, _vp, _vp, _vp]),
     "clipk_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),

@@ -1,0 +1,69 @@
+"""`loss_func` for the Megatron entry point of the reference (pretrain_CLIP.py:115-136) on top of the fused loss.
+
+The reference's `loss_func(text_output, image_output)` is an inlined single-process copy of the contrastive loss: fp32
+features, no logit scale, labels = arange, the mean of the two cross-entropies, plus the text->image top-1 accuracy,
+and it returns `(total_loss, {"loss": ..., "accuracy": ...})` with both values averaged over the data-parallel group
+(`megatron/utils.py:96-105`).  It materialises two b x b logit matrices; this adapter keeps the same signature and
+return convention and runs the fused kernels instead:
+
+    from clipk.megatron_adapter import make_loss_func
+    loss_func = make_loss_func()                                   # drop-in for pretrain_CLIP.py:115-136
+    loss_func = make_loss_func(data_parallel=True, group=mpu.get_data_parallel_group())   # contrast against the DP-global batch
+
+With data_parallel=False (the reference's behaviour) every rank contrasts its own micro-batch only.  With
+data_parallel=True the features are gathered over `group` (ClipLoss(local_loss=True, gather_with_grad=True)), which is
+what open_clip's training loop does (training/train.py:148) and what SURVEY.md section 0 says the Megatron script lacks.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .loss import ClipLoss
+
+
+def _top1_text_accuracy(image_features, text_features, logit_scale):
+    """Fraction of texts whose best-matching image is their own (argmax of text_logits == label, pretrain_CLIP.py:127-129),
+    from the exact column maxima of the fused forward instead of an argmax over materialised logits."""
+    be = ops._backend()
+    with torch.no_grad():
+        X, Y = be.prepare(image_features.detach()), be.prepare(text_features.detach())
+        scale = logit_scale.detach().to(device=image_features.device, dtype=torch.float32).reshape(1).contiguous()
+        _, pos, col = be.fwd_both(X, Y, scale, 0, exact=True)
+        # the positive comes from the row sweep and the maximum from the column sweep: the same element, rounded in a
+        # different order (fp32 inputs: different plane pairs) - compare with a few ulps of slack
+        return (pos >= col[0] - 1e-5 * (1.0 + col[0].abs())).float().mean()
+
+
+def make_loss_func(logit_scale=1.0, data_parallel=False, group=None, with_accuracy=True, cast_to_float=True):
+    """Returns loss_func(text_output, image_output[, logit_scale]) -> (loss, {"loss": avg, "accuracy": avg})."""
+    state = {"mod": None}
+
+    def loss_func(text_output: torch.Tensor, image_output: torch.Tensor, scale=None):
+        text_features, image_features = text_output.contiguous(), image_output.contiguous()
+        if cast_to_float:                       # the reference casts both to fp32 first (pretrain_CLIP.py:122-123)
+            text_features, image_features = text_features.float(), image_features.float()
+        s = logit_scale if scale is None else scale
+        if not isinstance(s, torch.Tensor):
+            s = torch.tensor(float(s), dtype=torch.float32, device=image_features.device)
+        if state["mod"] is None:
+            if data_parallel and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+                state["mod"] = ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True,
+                                        rank=dist.get_rank(group), world_size=dist.get_world_size(group))
+            else:
+                state["mod"] = ClipLoss(cache_labels=True)
+        total_loss = state["mod"](image_features, text_features, s)
+        stats = [total_loss.detach().reshape(1)]
+        if with_accuracy:
+            stats.append(_top1_text_accuracy(image_features, text_features, s).reshape(1))
+        averaged = torch.cat(stats)
+        if dist.is_available() and dist.is_initialized():
+            dist.all_reduce(averaged, group=group)
+            averaged = averaged / dist.get_world_size(group)
+        out = {"loss": averaged[0]}
+        if with_accuracy:
+            out["accuracy"] = averaged[1]
+        return total_loss, out
+
+    return loss_func

@@ -109,7 +109,7 @@ class CudaBackend:
                                             ws.data_ptr(), nbytes, self._stream()), "clipk_fwd_stats")
         return out, pos
 
-    def fwd_both(self, X: Operand, Y: Operand, scale, diag_offset, col_out=None):
+    def fwd_both(self, X: Operand, Y: Operand, scale, diag_offset, col_out=None, exact=False):
         """(max, sum, dot) of every row AND every column of s * X @ Y^T in one call (one sweep over the tiles when the
         logits are provably bounded, see clipk_fwd_both): row_stats [3, rows], pos [rows], col_stats [3, cols]."""
         dev = X.data.device
@@ -126,7 +126,7 @@ class CudaBackend:
         _lib.check(self.lib.clipk_fwd_both(X.data.data_ptr(), Y.data.data_ptr(), rows, cols, d, X.ld, Y.ld, X.dtype,
                                            X.inv_ptr(), Y.inv_ptr(), scale.data_ptr(), diag_offset,
                                            row_stats.data_ptr(), pos.data_ptr(), col_out.data_ptr(), _ptr(amax),
-                                           ws.data_ptr(), nbytes, self._stream()), "clipk_fwd_both")
+                                           1 if exact else 0, ws.data_ptr(), nbytes, self._stream()), "clipk_fwd_both")
         if want_amax and not os.environ.get("CLIPK_DBG"):
             X.amax, Y.amax = amax[0:1], amax[1:2]
         return row_stats, pos, col_out

@@ -77,7 +77,7 @@ static EncodeTiledFn encode_fn() {
 
 // 2D tensor map, SWIZZLE_128B, zero fill out of bounds.  inner = contiguous extent (elements of esize bytes).
 static int make_tmap(CUtensorMap* m, const void* base, long long inner, long long outer, long long ld_elems,
-                     int box_inner, int box_outer, int esize) {
+                     int box_inner, int box_outer, int esize, bool swizzle = true) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(CLIPK_EDRIVER, "cuTensorMapEncodeTiled entry point not available");
     if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(CLIPK_EINVAL, "operand pointer not 16-byte aligned");
@@ -88,7 +88,8 @@ static int make_tmap(CUtensorMap* m, const void* base, long long inner, long lon
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(CLIPK_EDRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", int(r));
     return CLIPK_OK;
 }
@@ -102,6 +103,10 @@ static int tmap_out_f32(CUtensorMap* m, const float* base, long long rows, long 
 }
 static int tmap_g_store(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld) {
     return make_tmap(m, base, cols, rows, ld, 64, 32, 2);
+}
+// the A-resident recompute kernel stores 32 columns x 32 rows from dense (not swizzled) 64-byte rows
+static int tmap_g_store_dense32(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld) {
+    return make_tmap(m, base, cols, rows, ld, 32, 32, 2, false);
 }
 // operand [rows, K] row-major, consumed K-major: box = 64 (K) x box_rows
 static int tmap_kmajor(CUtensorMap* m, const void* base, long long rows, long long K, long long ld, int box_rows) {
@@ -1003,7 +1008,7 @@ size_t clipk_fwd_both_workspace_bytes(int rows, int cols, int d, int dtype) {
 
 int clipk_fwd_both(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
                    const float* x_inv_scale, const float* y_inv_scale, const float* logit_scale, long long diag_offset,
-                   float* row_stats, float* pos_logit, float* col_stats, float* amax_xy, void* workspace,
+                   float* row_stats, float* pos_logit, float* col_stats, float* amax_xy, int exact, void* workspace,
                    size_t workspace_bytes, void* stream) {
     int rc = check_common(X, Y, rows, cols, d, ldx, ldy, dtype);
     if (rc) return rc;
@@ -1058,7 +1063,7 @@ int clipk_fwd_both(const void* X, const void* Y, int rows, int cols, int d, long
     a0.M = rows; a0.N = cols; a0.num_kb = num_kb;
     a0.n_tiles = cdiv(cols, BN); a0.m_pairs = cdiv(rows, 2 * BM);
     a0.n_clusters = int(std::min<long long>(n_clusters, (long long)a0.m_pairs * a0.n_tiles));
-    a0.pass = 0; a0.force_exact = bounded ? 0 : 1;
+    a0.pass = 0; a0.force_exact = (bounded && !exact) ? 0 : 1;
     a0.scale = logit_scale; a0.xs = x_inv_scale; a0.ys = y_inv_scale; a0.norm2 = norm2;
     a0.diag_offset = pos_logit ? diag_offset : -(1LL << 40);
     const size_t pstride0 = size_t(sweep_parts_bound(rows)) * PARTS_PER_UNIT * rows;
@@ -1325,6 +1330,7 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
                     SweepGeom g{};
                     g.num_kb = a.num_kb; g.n_tiles = a.n_tiles; g.m_pairs = m_pairs;
                     const int nc = int(std::min<long long>(di.sms / 2, (long long)m_pairs * a.n_tiles));
+                    if ((rc = tmap_g_store_dense32(&tc, G, round_up(nr, 2 * BM), ldg, ldg))) return rc;
                     rc = is_f16(dtype) ? launch_grad_sweep<1>(ta, tb, tc, a, g, nc, st) : launch_grad_sweep<0>(ta, tb, tc, a, g, nc, st);
                 } else if (is_f16(dtype)) {
                     rc = launch_gemm<MODE_GRAD, 1>(ta, tb, tc, a, units, m_pairs, st);

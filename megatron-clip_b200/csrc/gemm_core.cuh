@@ -202,12 +202,19 @@ __device__ __forceinline__ void grad16_exact(const uint32_t (&r)[16], float sc, 
         g[k] = inside ? ga * pr + gb * pc : 0.f;
     }
 }
-// g[16] -> fp16, into 16-byte pieces [piece0, piece0 + 2) of this row's 128 B line of the staging buffer(s)
-template <bool TWO_PLANES>
+// g[16] -> fp16, into 16-byte pieces [piece0, piece0 + 2) of this row's line of the staging buffer(s): 128-byte rows
+// in SWIZZLE_128B order, or (DENSE64) plain 64-byte rows - the half-size buffers of the A-resident recompute kernel,
+// whose 16 stores per tile and warp do not care about the 4-way bank conflict of that layout
+template <bool TWO_PLANES, bool DENSE64 = false>
 __device__ __forceinline__ void grad16_store(const float (&g)[16], uint32_t stg, uint32_t stg_lo, int lane, int piece0) {
     uint32_t pk[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) pk[k] = ptx::pack_f16x2(g[2 * k], g[2 * k + 1]);
+    if (DENSE64) {
+        st_shared_v4(stg + lane * 64 + piece0 * 16, pk[0], pk[1], pk[2], pk[3]);
+        st_shared_v4(stg + lane * 64 + piece0 * 16 + 16, pk[4], pk[5], pk[6], pk[7]);
+        return;
+    }
     st_shared_v4(stg_addr(stg, lane, piece0), pk[0], pk[1], pk[2], pk[3]);
     st_shared_v4(stg_addr(stg, lane, piece0 + 1), pk[4], pk[5], pk[6], pk[7]);
     if (TWO_PLANES) {
@@ -558,8 +565,9 @@ __device__ __forceinline__ void epilogue_unit(const Cta& c, Pipe& p, const CUten
 // Recompute tiles: S tile -> G tile (fp16, x 2^14) -> swizzled staging -> TMA store into the L2-resident panel.
 // The tile is drained in 16-column pieces (tcgen05.ld x16, double buffered) to keep the live registers well under the
 // 168 a 10-warp CTA allows; four pieces (64 columns = 128 B of fp16 per row) fill one staging buffer = one TMA store.
-// NBUF = staging buffers per warp: 2 (one fills while the other leaves; both planes of a two-plane G) or 1 (the
-// A-resident recompute kernel, whose shared memory goes to the resident rows instead).
+// NBUF = 4 KB of staging per warp: 2 (two 64-column buffers, one fills while the other leaves; both planes of a
+// two-plane G) or 1 (the A-resident recompute kernel, whose shared memory goes to the resident rows: its 4 KB are two
+// dense 32-column half buffers, written and stored alternately through a non-swizzled tensor map).
 template <bool TWO_PLANES, int NBUF = 2>
 __device__ __forceinline__ void grad_epilogue_unit(const Cta& c, Pipe& p, const CUtensorMap* tmC, const KArgs& args,
                                                    int m_blk, int t0, int t1) {
@@ -616,15 +624,37 @@ __device__ __forceinline__ void grad_epilogue_unit(const Cta& c, Pipe& p, const 
         auto piece = [&](const uint32_t (&r)[16], int pi) {
             if (dbg & 1) return;
             const int col0 = colh + pi * 16;
+            if (NBUF == 1) {
+                // half buffers of 32 columns: two pieces each
+                if ((pi & 1) == 0) {
+                    if (lane == 0) ptx::tma_store_wait_read<1>();
+                    __syncwarp();
+                    stg = stg0 + (p.stg_use & 1) * (STG_BYTES / 2);
+                }
+                float g[16];
+                if (exact) grad16_exact(r, sc, Lr, ga, gb, lse_col + col0, col0, ncols, dcol, g);
+                else grad16_fast(r, sc, cref, Ai, gb, bvec + col0, g);
+                grad16_store<false, true>(g, stg, 0, lane, (pi & 1) * 2);
+                if (pi & 1) {
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0 && !(dbg & 2)) {
+                        ptx::tma_store_2d(tmC, stg, c_col_off + col0 - 16, c_row_off);
+                        ptx::tma_store_commit();
+                    }
+                    ++p.stg_use;
+                }
+                return;
+            }
             if ((pi & 3) == 0) {
                 // (re)use of a staging buffer: at most one older bulk store may still be reading shared memory; with
                 // two planes both buffers are written, so nothing of this warp may still be in flight
                 if (lane == 0) {
-                    if (TWO_PLANES || NBUF == 1) ptx::tma_store_wait_read<0>();
+                    if (TWO_PLANES) ptx::tma_store_wait_read<0>();
                     else ptx::tma_store_wait_read<1>();
                 }
                 __syncwarp();
-                stg = NBUF == 1 ? stg0 : stg0 + (p.stg_use & 1) * STG_BYTES;
+                stg = stg0 + (p.stg_use & 1) * STG_BYTES;
                 stg_lo = stg0 + ((p.stg_use + 1) & 1) * STG_BYTES;
             }
             float g[16];

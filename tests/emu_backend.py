@@ -35,7 +35,7 @@ class EmuBackend:
             pos = S[torch.arange(X.rows), idx].to(torch.float32)
         return stats, pos
 
-    def fwd_both(self, X, Y, scale, diag_offset, col_out=None):
+    def fwd_both(self, X, Y, scale, diag_offset, col_out=None, exact=False):
         row_stats, pos = self.fwd_stats(X, Y, scale, diag_offset, True)
         col_stats, _ = self.fwd_stats(Y, X, scale, 0, False, out=col_out)
         return row_stats, pos, col_stats

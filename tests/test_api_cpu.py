@@ -115,3 +115,32 @@ def test_single_process_host_logic_with_emulated_kernels():
         assert abs(l2.item() - ref.loss) < 1e-5 * ref.loss
     finally:
         ops.set_backend_for_testing(None)
+
+
+def test_megatron_loss_func_adapter_matches_reference_formula():
+    """clipk.megatron_adapter.make_loss_func keeps the signature and return convention of pretrain_CLIP.py:115-136;
+    on the CPU emulation backend (host logic only) its values equal the reference's inlined formula."""
+    import torch.nn.functional as F
+    from clipk import ops
+    from clipk.megatron_adapter import make_loss_func
+    from tests.emu_backend import EmuBackend
+    ops.set_backend_for_testing(EmuBackend())
+    try:
+        g = torch.Generator().manual_seed(3)
+        text = torch.randn(48, 32, generator=g, requires_grad=True)
+        image = (text.detach() * 0.7 + 0.5 * torch.randn(48, 32, generator=g)).requires_grad_(True)
+        loss, out = make_loss_func()(text, image)
+        loss.backward()
+        t2, i2 = text.detach().clone().requires_grad_(True), image.detach().clone().requires_grad_(True)
+        labels = torch.arange(48)
+        tl, il = t2.float() @ i2.float().T, i2.float() @ t2.float().T
+        ref = (F.cross_entropy(tl, labels) + F.cross_entropy(il, labels)) / 2
+        ref.backward()
+        acc = (tl.argmax(-1) == labels).float().mean()
+        assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
+        assert float(out["loss"]) == pytest.approx(float(ref), rel=1e-5)
+        assert float(out["accuracy"]) == pytest.approx(float(acc), abs=1e-6)
+        assert torch.allclose(text.grad, t2.grad, rtol=1e-4, atol=1e-6)
+        assert torch.allclose(image.grad, i2.grad, rtol=1e-4, atol=1e-6)
+    finally:
+        ops.set_backend_for_testing(None)

@@ -266,3 +266,26 @@ def test_tmem_fragment_layout_hook():
                     lane = w * 32 + h * 16 + g + (8 if (k % 4) >= 2 else 0)
                     col = 8 * (k // 4) + c + (k % 2)
                     assert int(o[w, h, t, k]) == lane * 1000 + col
+
+
+def test_megatron_loss_func_adapter_on_gpu():
+    """The pretrain_CLIP.py loss_func replacement on the real kernels: loss, gradients and the top-1 accuracy (from the
+    exact column maxima) against the reference's inlined formula (pretrain_CLIP.py:115-136)."""
+    import torch.nn.functional as F
+    from clipk.megatron_adapter import make_loss_func
+    g = torch.Generator().manual_seed(11)
+    text = torch.nn.functional.normalize(torch.randn(700, 256, generator=g), dim=-1)
+    image = torch.nn.functional.normalize(0.25 * text + torch.nn.functional.normalize(torch.randn(700, 256, generator=g), dim=-1), dim=-1)
+    text, image = (10 * text).cuda().requires_grad_(True), image.cuda().requires_grad_(True)   # un-normalised on one side
+    loss, out = make_loss_func()(text, image)
+    loss.backward()
+    t2, i2 = text.detach().clone().requires_grad_(True), image.detach().clone().requires_grad_(True)
+    labels = torch.arange(700, device="cuda")
+    tl, il = t2.double() @ i2.double().T, i2.double() @ t2.double().T
+    ref = (F.cross_entropy(tl, labels) + F.cross_entropy(il, labels)) / 2
+    ref.backward()
+    acc = (tl.argmax(-1) == labels).float().mean()
+    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
+    assert abs(float(out["accuracy"]) - float(acc)) <= 2.0 / 700
+    assert rel(text.grad.cpu().numpy(), t2.grad.float().cpu().numpy()) <= 1e-5
+    assert rel(image.grad.cpu().numpy(), i2.grad.float().cpu().numpy()) <= 1e-5
