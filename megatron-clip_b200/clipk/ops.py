@@ -119,7 +119,7 @@ class CudaBackend:
             col_out = torch.empty(3, cols, dtype=torch.float32, device=dev)
         pos = torch.zeros(rows, dtype=torch.float32, device=dev)
         # the single-sweep path leaves max |x| of both operands here (the backward's fp16 scale needs it)
-        want_amax = X.dtype == _lib.BF16 and d <= 512
+        want_amax = X.dtype == _lib.BF16
         amax = torch.empty(2, dtype=torch.float32, device=dev) if want_amax else None
         nbytes = self.lib.clipk_fwd_both_workspace_bytes(rows, cols, d, X.dtype)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)

@@ -863,10 +863,10 @@ FwdCarve fwd_carve(int rows, int cols) {
     c.total = off + 256;
     return c;
 }
-template <int F16>
+template <int F16, bool ARES>
 int launch_fwd_sweep(const CUtensorMap& ta, const CUtensorMap& tb, const FwdArgs& a, int n_clusters, cudaStream_t st) {
-    auto kfn = fwd_sweep_kernel<F16>;
-    constexpr int smem = smem_bytes_fwd();
+    auto kfn = fwd_sweep_kernel<F16, ARES>;
+    constexpr int smem = smem_bytes_fwd(ARES);
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
@@ -1022,8 +1022,8 @@ int clipk_fwd_both(const void* X, const void* Y, int rows, int cols, int d, long
     const long long dpad = round_up(d, BK);
     const int num_kb = cdiv(d, BK);
     if (amax_xy) CK_CUDA(cudaMemsetAsync(amax_xy, 0xff, 2 * sizeof(float), static_cast<cudaStream_t>(stream)));   // NaN = not computed
-    if (planes != 1 || num_kb > ARES_KB || (dbg_flags() & 512)) {
-        // operands too wide for the resident-rows kernel (or split-precision): two streaming sweeps
+    if (planes != 1 || (dbg_flags() & 512)) {
+        // split-precision operands (fp32 inputs): two streaming sweeps
         char* ws = static_cast<char*>(workspace);
         const size_t w0 = clipk_fwd_workspace_bytes(rows, cols, d, dtype);
         rc = clipk_fwd_stats(X, Y, rows, cols, d, ldx, ldy, dtype, x_inv_scale, y_inv_scale, logit_scale, diag_offset,
@@ -1083,12 +1083,13 @@ int clipk_fwd_both(const void* X, const void* Y, int rows, int cols, int d, long
     a1.pos = nullptr; a1.colpart_sum = nullptr; a1.colpart_dot = nullptr;
 
     const int nc0 = a0.n_clusters, nc1 = a1.n_clusters;
+    const bool ares = num_kb <= ARES_KB;       // rows of the left operand resident in shared memory (K <= 512)
     if (is_f16(dtype)) {
-        if ((rc = launch_fwd_sweep<1>(tx_a, ty_b, a0, nc0, st))) return rc;
-        if ((rc = launch_fwd_sweep<1>(ty_a, tx_b, a1, nc1, st))) return rc;
+        if ((rc = ares ? launch_fwd_sweep<1, true>(tx_a, ty_b, a0, nc0, st) : launch_fwd_sweep<1, false>(tx_a, ty_b, a0, nc0, st))) return rc;
+        if ((rc = ares ? launch_fwd_sweep<1, true>(ty_a, tx_b, a1, nc1, st) : launch_fwd_sweep<1, false>(ty_a, tx_b, a1, nc1, st))) return rc;
     } else {
-        if ((rc = launch_fwd_sweep<0>(tx_a, ty_b, a0, nc0, st))) return rc;
-        if ((rc = launch_fwd_sweep<0>(ty_a, tx_b, a1, nc1, st))) return rc;
+        if ((rc = ares ? launch_fwd_sweep<0, true>(tx_a, ty_b, a0, nc0, st) : launch_fwd_sweep<0, false>(tx_a, ty_b, a0, nc0, st))) return rc;
+        if ((rc = ares ? launch_fwd_sweep<0, true>(ty_a, tx_b, a1, nc1, st) : launch_fwd_sweep<0, false>(ty_a, tx_b, a1, nc1, st))) return rc;
     }
     const int n = rows > cols ? rows : cols;
     fwd_merge_kernel<<<cdiv(n, 32), 256, 0, st>>>(a0, a1, cv.m_blocks, row_stats, col_stats);

@@ -745,8 +745,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // ---------------------------------------------------------------------------------------------------- forward sweep
 // Persistent forward kernel: one CTA pair per SM pair walks work items (256 rows x a run of column tiles).
 //
-// A-resident.  The 128 rows of A a CTA needs stay in shared memory for the whole item (K <= 512: 128 KB) and only the
-// B half-tiles stream (16 KB per K block and CTA), which halves the L2 -> SM traffic of the mainloop.
+// A-resident (ARES, K <= 512).  The 128 rows of A a CTA needs stay in shared memory for a whole run of column tiles
+// (128 KB) and only the B half-tiles stream (16 KB per K block and CTA), which halves the L2 -> SM traffic of the
+// mainloop.  For longer K (d = 768, 1024) the same kernel streams A with B, one K block per stage.
 //
 // Single sweep.  The forward needs the log-sum-exp of every ROW and of every COLUMN of the block (loss.py:135-138 takes
 // the cross-entropy of logits_per_image and of logits_per_text).  Both come from ONE pass over the tiles when the
@@ -764,14 +765,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 constexpr int ARES_KB = 8;                       // resident K blocks (K <= 512)
 constexpr int FWD_STAGES = 5;
 constexpr int COLBUF_BYTES = 2 * 2 * 4 * 128 * 2 * 4;   // [tile parity][half][lane quarter][128 columns][sum, dot]
-__host__ __device__ constexpr int smem_bytes_fwd() {
-    return 1024 + ARES_KB * A_STAGE_BYTES + FWD_STAGES * B_STAGE_BYTES + COLBUF_BYTES + 256 + MISC_BYTES;
+__host__ __device__ constexpr int smem_bytes_fwd(bool ares = true) {
+    return 1024 + (ares ? ARES_KB : FWD_STAGES) * A_STAGE_BYTES + FWD_STAGES * B_STAGE_BYTES + COLBUF_BYTES + 256 + MISC_BYTES;
 }
 constexpr float FWD_SAFE_U = 50.f;               // 2u + 26 <= 126
 
 struct FwdArgs {
     int M, N;                  // rows of A (X), rows of B (Y)
-    int num_kb;                // K blocks, <= ARES_KB
+    int num_kb;                // K blocks (<= ARES_KB in the A-resident kernel)
  int n_tiles, m_pairs;
     int n_clusters;            // clusters of the launch (the part index of a unit is derived from it)
     int pass;                  // 0: X rows against Y columns; 1: the swapped launch (exact mode only)
@@ -862,8 +863,9 @@ struct SweepWalk {
     }
 };
 
-// TMA producer of an A-resident sweep (one lane of warp 0, both CTAs)
-template <int STAGES>
+// TMA producer of a sweep (one lane of warp 0, both CTAs).  ARES: the rows of A are loaded once per unit and stay in
+// shared memory; otherwise (K > 512) A streams with B, one K block per stage.
+template <int STAGES, bool ARES = true>
 __device__ __forceinline__ void sweep_produce(const Cta& c, Pipe& p, const CUtensorMap* tmA, const CUtensorMap* tmB,
                                               const SweepGeom& g, int cluster, int n_clusters) {
     SweepWalk w(g, cluster, n_clusters);
@@ -871,17 +873,20 @@ __device__ __forceinline__ void sweep_produce(const Cta& c, Pipe& p, const CUten
     uint32_t it_n = 0;
     for (; w.next(u); ++it_n) {
         const int m_blk = 2 * u.m_pair + int(c.cta_rank);
-        // the resident rows of A may be replaced once every MMA of the previous unit has completed
-        if (it_n > 0) ptx::mbar_wait(c.bar_aempty, (it_n - 1) & 1);
-        if (c.leader) ptx::mbar_arrive_expect_tx(c.bar_afull, 2 * g.num_kb * A_STAGE_BYTES);
-        for (int kb = 0; kb < g.num_kb; ++kb)
-            ptx::tma_load_2d_pair(c.sA + kb * A_STAGE_BYTES, tmA, kb * BK, m_blk * BM, c.bar_afull);
+        if (ARES) {
+            // the resident rows of A may be replaced once every MMA of the previous unit has completed
+            if (it_n > 0) ptx::mbar_wait(c.bar_aempty, (it_n - 1) & 1);
+            if (c.leader) ptx::mbar_arrive_expect_tx(c.bar_afull, 2 * g.num_kb * A_STAGE_BYTES);
+            for (int kb = 0; kb < g.num_kb; ++kb)
+                ptx::tma_load_2d_pair(c.sA + kb * A_STAGE_BYTES, tmA, kb * BK, m_blk * BM, c.bar_afull);
+        }
         for (int t = u.t0; t < u.t1; ++t) {
             const int bn0 = t * BN + int(c.cta_rank) * (BN / 2);
             for (int kb = 0; kb < g.num_kb; ++kb) {
                 ptx::mbar_wait(c.bar_empty + 8 * p.s, p.ph ^ 1);
                 const uint32_t full = c.bar_full + 8 * p.s;
-                if (c.leader) ptx::mbar_arrive_expect_tx(full, 2 * B_STAGE_BYTES);
+                if (c.leader) ptx::mbar_arrive_expect_tx(full, 2 * (ARES ? B_STAGE_BYTES : STAGE_BYTES));
+                if (!ARES) ptx::tma_load_2d_pair(c.sA + p.s * A_STAGE_BYTES, tmA, kb * BK, m_blk * BM, full);
                 ptx::tma_load_2d_pair(c.sB + p.s * B_STAGE_BYTES, tmB, kb * BK, bn0, full);
                 if (++p.s == STAGES) { p.s = 0; p.ph ^= 1; }
             }
@@ -889,8 +894,8 @@ __device__ __forceinline__ void sweep_produce(const Cta& c, Pipe& p, const CUten
     }
 }
 
-// MMA issuer of an A-resident sweep (one lane of warp 1, leader CTA)
-template <int STAGES, int F16>
+// MMA issuer of a sweep (one lane of warp 1, leader CTA)
+template <int STAGES, int F16, bool ARES = true>
 __device__ __forceinline__ void sweep_mma(const Cta& c, Pipe& p, const SweepGeom& g, int cluster, int n_clusters) {
     const uint32_t idesc = ptx::make_idesc_16bit(2 * BM, BN, 0, 0, !F16, !F16);
     const uint64_t desc_hi = ptx::make_smem_desc_sw128(16, 1024);
@@ -898,8 +903,10 @@ __device__ __forceinline__ void sweep_mma(const Cta& c, Pipe& p, const SweepGeom
     SweepUnit u;
     uint32_t it_n = 0;
     for (; w.next(u); ++it_n) {
-        ptx::mbar_wait(c.bar_afull, it_n & 1);
-        ptx::tc_fence_after();
+        if (ARES) {
+            ptx::mbar_wait(c.bar_afull, it_n & 1);
+            ptx::tc_fence_after();
+        }
         for (int t = u.t0; t < u.t1; ++t, ++p.it) {
             const int a = p.it & 1;
             const uint32_t aph = (p.it >> 1) & 1;
@@ -909,7 +916,7 @@ __device__ __forceinline__ void sweep_mma(const Cta& c, Pipe& p, const SweepGeom
             for (int kb = 0; kb < g.num_kb; ++kb) {
                 ptx::mbar_wait(c.bar_full + 8 * p.s, p.ph);
                 ptx::tc_fence_after();
-                const uint32_t a_src = c.sA + kb * A_STAGE_BYTES;
+                const uint32_t a_src = c.sA + (ARES ? kb : p.s) * A_STAGE_BYTES;
                 const uint32_t b_src = c.sB + p.s * B_STAGE_BYTES;
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
@@ -921,15 +928,15 @@ __device__ __forceinline__ void sweep_mma(const Cta& c, Pipe& p, const SweepGeom
             }
             ptx::mma_commit_pair(c.bar_tfull + 8 * a);
         }
-        ptx::mma_commit_pair(c.bar_aempty);   // both CTAs' producers wait on their own copy
+        if (ARES) ptx::mma_commit_pair(c.bar_aempty);   // both CTAs' producers wait on their own copy
     }
 }
 
-template <int F16>
+template <int F16, bool ARES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fwd_sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FwdArgs args) {
     constexpr int STAGES = FWD_STAGES;
-    const Cta c = cta_setup<STAGES, COLBUF_BYTES, ARES_KB * A_STAGE_BYTES>();
+    const Cta c = cta_setup<STAGES, COLBUF_BYTES, (ARES ? ARES_KB : STAGES) * A_STAGE_BYTES>();
     const uint32_t colbuf = c.sStg;
     float u = 0.f;
     const bool safe = fwd_bound(args, &u);
@@ -944,10 +951,10 @@ fwd_sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (c.lane == 0) {
                 ptx::prefetch_tmap(&tmA);
                 ptx::prefetch_tmap(&tmB);
-                sweep_produce<STAGES>(c, p, &tmA, &tmB, geom, cluster, n_clusters);
+                sweep_produce<STAGES, ARES>(c, p, &tmA, &tmB, geom, cluster, n_clusters);
             }
         } else if (c.warp == 1) {
-            if (c.lane == 0 && c.leader) sweep_mma<STAGES, F16>(c, p, geom, cluster, n_clusters);
+            if (c.lane == 0 && c.leader) sweep_mma<STAGES, F16, ARES>(c, p, geom, cluster, n_clusters);
         } else if (!single) {
             // ---- exact mode: online-max row statistics, one row per thread (same code as the streaming STATS kernel)
             KArgs ka{};

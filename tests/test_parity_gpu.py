@@ -289,3 +289,43 @@ def test_megatron_loss_func_adapter_on_gpu():
     assert abs(float(out["accuracy"]) - float(acc)) <= 2.0 / 700
     assert rel(text.grad.cpu().numpy(), t2.grad.float().cpu().numpy()) <= 1e-5
     assert rel(image.grad.cpu().numpy(), i2.grad.float().cpu().numpy()) <= 1e-5
+
+
+def test_full_size_step_against_torch_fp32_on_gpu():
+    """BASELINE.json's benchmark shape (N = 32768, d = 512, bf16): loss, dI, dT and dlogit_scale of the fused path
+    against the reference's op sequence (loss.py:112-119,135-138) evaluated in fp32 on the same GPU from the same bf16
+    values (TF32 off).  The fp32 logits of that evaluation take 4.3 GB; the fused path never forms them."""
+    from clipk import ClipLoss
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 << 30:
+        pytest.skip("needs ~40 GB of free device memory for the fp32 reference")
+    N, d, s = 32768, 512, 1 / 0.07
+    x, t = O.synthetic_features(N, d, seed=1234)
+    I = torch.from_numpy(x).cuda().bfloat16().requires_grad_(True)
+    T = torch.from_numpy(t).cuda().bfloat16().requires_grad_(True)
+    S = torch.tensor(s, device="cuda", requires_grad=True)
+    loss = ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True)(I, T, S)
+    loss.backward()
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        I2 = I.detach().float().requires_grad_(True)
+        T2 = T.detach().float().requires_grad_(True)
+        S2 = torch.tensor(s, device="cuda", requires_grad=True)
+        labels = torch.arange(N, device="cuda")
+        per_image = S2 * I2 @ T2.T
+        ref = (torch.nn.functional.cross_entropy(per_image, labels) + torch.nn.functional.cross_entropy(per_image.T, labels)) / 2
+        ref.backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    r = lambda a, b: float((a.float() - b).norm() / b.norm())
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert r(I.grad, I2.grad) <= 2e-3 and r(T.grad, T2.grad) <= 2e-3
+    assert abs(S.grad.item() - S2.grad.item()) <= 1e-4 * abs(S2.grad.item())
+    # size-independent properties of the gradient: the softmax gradient has zero row and column sums, so
+    # sum_i dI_i = (1^T G) T = 0 up to the positives' part ... checked through the identity sum(dI * I) == sum(dT * T)
+    # (both equal s * sum(G * C), C = I T^T), which holds for any inputs
+    lhs, rhs = (I.grad.float() * I.detach().float()).sum().item(), (T.grad.float() * T.detach().float()).sum().item()
+    assert abs(lhs - rhs) <= 2e-3 * max(abs(lhs), abs(rhs), 1e-6)
+    del per_image
+    torch.cuda.empty_cache()
