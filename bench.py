@@ -282,14 +282,34 @@ def run_clipk(args):
     f_exec = 8.0 * b * N * DIM                                 # issued: 1 fwd sweep (rows + columns) + recompute + 2 gradient GEMMs
     achieved = f_alg / (ms * 1e-3) / 1e12
     gemm_ms = breakdown["fwd_both_ms"] + breakdown["bwd_ms"]
+    # per-kernel view, timed live above with CUDA events around each C entry (the small kernels of an entry included)
+    unit = 2.0 * b * N * DIM                                   # one dense pass over the block
+    kernels = [
+        {"entry": "clipk_fwd_both (norm2_max + fwd_sweep_kernel x2 + fwd_merge)", "algorithmic_flops": unit,
+         "ms": breakdown["fwd_both_ms"], "tflops": unit / (breakdown["fwd_both_ms"] * 1e-3) / 1e12},
+        {"entry": "clipk_bwd (grad_sweep_kernel + gemm_pair_kernel per panel)", "algorithmic_flops": 2 * unit,
+         "executed_mma_flops": 3 * unit, "ms": breakdown["bwd_ms"],
+         "tflops": 2 * unit / (breakdown["bwd_ms"] * 1e-3) / 1e12,
+         "executed_tflops": 3 * unit / (breakdown["bwd_ms"] * 1e-3) / 1e12},
+    ]
+    for k in kernels:
+        k["frac_of_peak"] = k.get("executed_tflops", k["tflops"]) / pk["tflops_sustained"]
+    # DRAM traffic per step from the committed ncu --set full captures (profiles/README.md, N = 32768 on one GPU):
+    # forward sweep 86 + 47 MB; per panel, recompute 20 + 77 MB and gradient GEMMs 265 + 24 MB; 16 panels
+    traffic = (133e6 + 16 * (97e6 + 289e6)) if (world == 1) else None
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
-        "frac": achieved / pk["tflops_sustained"], "traffic": None,
-        "kernel": "clipk::fwd_sweep_kernel (single sweep: row + column statistics per tile, rows of X resident in smem) + gemm_kernel<GRAD> / gemm_pair_kernel per panel; tcgen05 cta_group::2 256x256x64 tiles",
+        "frac": achieved / pk["tflops_sustained"], "traffic": traffic,
+        "traffic_note": "DRAM bytes per step (read + write) summed over the tensor-core kernels, ncu --set full, "
+                        "profiles/r01k_* and r01f_*; algorithmic operand bytes are 64 MB - the rest is the fp16 "
+                        "softmax-gradient panel streaming through HBM (5.4 GB) and 47 MB of column partials",
+        "kernel": "whole step (SURVEY 8d: F_alg = 6 b N d over t_step); dominant kernels: clipk::gemm_pair_kernel "
+                  "(gradient GEMMs, 49 % of the step), grad_sweep_kernel (26 %), fwd_sweep_kernel (21 %); tcgen05 "
+                  "cta_group::2 256x256x64 tiles",
         "algorithmic_flops_per_step_per_gpu": f_alg, "executed_mma_flops_per_step_per_gpu": f_exec,
         "executed_tflops_in_gemm_kernels": f_exec / (gemm_ms * 1e-3) / 1e12,
-        "gemm_kernels_share_of_step": gemm_ms / ms, "breakdown_ms": breakdown, "peak_source": pk["source"],
-        "peak_burst": pk["tflops_burst"],
+        "gemm_kernels_share_of_step": gemm_ms / ms, "breakdown_ms": breakdown, "kernels": kernels,
+        "peak_source": pk["source"], "peak_burst": pk["tflops_burst"],
     }
 
     cb = None
