@@ -594,31 +594,68 @@ static int choose_split(int m_pairs, int n_tiles, int sms) {
     return best;
 }
 
-// Panel of the backward: G[rp x cp] is produced once and consumed by the dX tiles (rp/128 * nt CTAs, K = cp) and the
-// dY tiles (cp/128 * nt CTAs, K = rp) of ONE launch; pick rp, cp so that launch is close to a whole number of waves
-// with long K, and the panel fits the L2 budget.  Then even the panels out over the problem.
+// Panel of the backward: G[rp x cp] (rp, cp multiples of 256) is produced by one recompute launch and consumed by the
+// dX jobs (rp/256 * nt tiles, K = cp) and dY jobs (cp/256 * nt tiles, K = rp) of one gradient-GEMM launch.  All even
+// splits of the block whose panel fits the budget are scored with a small cost model (us; constants measured at
+// N = 32768, d = 512 on B200): per launch a fixed fill / drain, the recompute at ~2.7 us per tile and CTA pair, and
+// the gradient GEMMs at 0.45 us per K block with the jobs list-scheduled, in launch order, over the CTA pairs.
+// The choice depends only on the shape and is cached.
+struct PanelKey {
+    int rows, cols, d, gplanes, sms;
+    long long budget;
+    bool operator==(const PanelKey& o) const {
+        return rows == o.rows && cols == o.cols && d == o.d && gplanes == o.gplanes && sms == o.sms && budget == o.budget;
+    }
+};
+struct PanelChoice { PanelKey key; long long rp, cp; };
+static std::mutex g_panel_mu;
+static std::vector<PanelChoice> g_panel_cache;
+
+static double panel_cost_us(int rb, int cb, int nt, int s_kb, int g_nseg, int pairs) {
+    // recompute: tiles cut evenly over the pairs
+    const double grad = 14.0 + cdiv((long long)rb * cb, pairs) * (2.7 * s_kb / 8.0);
+    // gradient GEMMs: dX jobs (K = cb * 4 blocks) first, then dY jobs (K = rb * 4), each to the earliest free pair
+    std::vector<double> free_at(pairs, 0.0);
+    auto run = [&](int jobs, double len) {
+        for (int j = 0; j < jobs; ++j) {
+            auto it = std::min_element(free_at.begin(), free_at.end());
+            *it += len;
+        }
+    };
+    run(rb * nt, 0.45 * 4 * cb * g_nseg);
+    run(cb * nt, 0.45 * 4 * rb * g_nseg);
+    const double pair = 12.0 + *std::max_element(free_at.begin(), free_at.end());
+    return grad + pair;
+}
+
 static void choose_panel(int rows, int cols, int d, int gplanes, int sms, long long budget, long long* rp_out, long long* cp_out) {
+    const PanelKey key{rows, cols, d, gplanes, sms, budget};
+    {
+        std::lock_guard<std::mutex> lk(g_panel_mu);
+        for (const PanelChoice& c : g_panel_cache)
+            if (c.key == key) { *rp_out = c.rp; *cp_out = c.cp; return; }
+    }
     const int nt = cdiv(d, BN);
     const int R = cdiv(rows, 2 * BM), C = cdiv(cols, BN);       // available 256-row / 256-col blocks
-    const int pairs = sms / 2;
-    double best = 1e30;
+    const int pairs = std::max(1, sms / 2);
+    const int s_kb = cdiv(d, BK) * (gplanes == 2 ? 3 : 1);       // K blocks of a recompute tile (three plane pairs for fp32 inputs)
+    const int g_nseg = gplanes == 2 ? 3 : 1;
+    double best = 1e300;
     int best_rb = 1, best_cb = 1;
-    for (int waves = 1; waves <= 4; ++waves) {
-        const int total = pairs * waves / nt;                    // 256-blocks (rows + cols) per launch
-        if (total < 2) continue;
-        int rb = total / 2 < R ? total / 2 : R;
-        int cb = total - rb;
-        if (cb > C) { cb = C; rb = total - cb < R ? total - cb : R; }
-        if (cb < 1) cb = 1;
-        while ((long long)rb * cb * 4 * BM * BM * 2 * gplanes > budget && (rb > 1 || cb > 1)) {
-            if (rb >= cb && rb > 1) --rb; else --cb;
+    int last_rb = 0;
+    for (int nr = 1; nr <= R; ++nr) {
+        const int rb = cdiv(R, nr);
+        if (rb == last_rb) continue;
+        last_rb = rb;
+        int last_cb = 0;
+        for (int nc = 1; nc <= C; ++nc) {
+            const int cb = cdiv(C, nc);
+            if (cb == last_cb) continue;
+            last_cb = cb;
+            if ((long long)rb * cb * 4 * BM * BM * 2 * gplanes > budget && (rb > 1 || cb > 1)) continue;
+            const double cost = panel_cost_us(rb, cb, nt, s_kb, g_nseg, pairs) * cdiv(R, rb) * cdiv(C, cb);
+            if (cost < best) { best = cost; best_rb = rb; best_cb = cb; }
         }
-        const int jobs = (rb + cb) * nt;
-        const int w = cdiv(jobs, pairs);
-        const int kmax = (rb > cb ? rb : cb) * 2 * BM;
-        const double t = w * (8.0 + kmax * (6.0 / 1024.0));      // us: ~8 us per CTA lifetime + 6 us per 1024 of K
-        const double per_area = t / ((double)rb * cb);
-        if (per_area < best) { best = per_area; best_rb = rb; best_cb = cb; }
     }
     // experiments: CLIPK_PANEL_RB / CLIPK_PANEL_CB force the panel extents (in 256-blocks)
     if (const char* e = getenv("CLIPK_PANEL_RB")) best_rb = std::max(1, std::min(R, atoi(e)));
@@ -626,6 +663,9 @@ static void choose_panel(int rows, int cols, int d, int gplanes, int sms, long l
     const int nrp = cdiv(R, best_rb), ncp = cdiv(C, best_cb);
     *rp_out = (long long)cdiv(R, nrp) * 2 * BM;
     *cp_out = (long long)cdiv(C, ncp) * BN;
+    if (getenv("CLIPK_VERBOSE")) fprintf(stderr, "[clipk] panel %d x %d blocks of 256 for a %d x %d x %d block (%d x %d panels, model %.0f us)\n", best_rb, best_cb, rows, cols, d, nrp, ncp, best);
+    std::lock_guard<std::mutex> lk(g_panel_mu);
+    if (g_panel_cache.size() < 256) g_panel_cache.push_back(PanelChoice{key, *rp_out, *cp_out});
 }
 
 // Launch with a thread-block cluster of two CTAs (the tcgen05 cta_group::2 pair).
