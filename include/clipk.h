@@ -156,6 +156,18 @@ int clipk_bwd_peer(const void* X, const void* Y, int rows, int cols, int d, long
 int clipk_reduce_slots(const float* src, long long n, int world, void* dst, int dtype, void* stream);
 int clipk_peer_barrier(void* const* peer_flags, int rank, int world, unsigned int epoch, void* stream);
 
+/* ---- opt-in: the L2 normalisation in front of the loss ---------------------------------------
+ * The reference normalises in the model, not in the loss (F.normalize, open_clip/model.py:216,231,277,281); these two
+ * entries let a caller hand RAW embeddings to clipk.fused_normalize_clip_loss and get gradients with respect to them.
+ *   clipk_normalize_fwd: y[r, :] = x[r, :] / max(|x[r, :]|, eps),  inv_norm[r] = 1 / max(|x[r, :]|, eps)
+ *   clipk_normalize_bwd: dx = (g - y (y . g)) * inv_norm   (the Jacobian of the normalisation; a plain scaling where
+ *                        |x| < eps)
+ * dtype CLIPK_BF16 or CLIPK_F32 for x, y, g, dx alike; d % 8 == 0; eps as in F.normalize (1e-12). */
+int clipk_normalize_fwd(const void* x, int dtype, long long rows, long long d, long long ldx, void* y, long long ldy,
+                        float* inv_norm, float eps, void* stream);
+int clipk_normalize_bwd(const void* g, long long ldg, const void* y, long long ldy, const float* inv_norm, int dtype,
+                        long long rows, long long d, void* dx, long long ldd, float eps, void* stream);
+
 /* dst[i] = (dtype) src[i]; the fp32 gradient accumulators are returned in the dtype of the inputs. */
 int clipk_cast(const float* src, void* dst, long long n, int dtype, void* stream);
 

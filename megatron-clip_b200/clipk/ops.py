@@ -194,6 +194,29 @@ class CudaBackend:
         _lib.check(self.lib.clipk_peer_barrier(peer.flag_ptrs, peer.rank, peer.world, peer.epoch, self._stream()),
                    "clipk_peer_barrier")
 
+    def normalize_fwd(self, x: torch.Tensor, eps: float):
+        """y = x / max(|x|, eps) row-wise (same dtype), and the fp32 factors 1 / max(|x|, eps)."""
+        if x.dtype not in (torch.bfloat16, torch.float32):
+            raise TypeError(f"clipk: unsupported feature dtype {x.dtype} (bf16 and fp32 only)")
+        x = x.contiguous()
+        rows, d = x.shape
+        y = torch.empty_like(x)
+        inv = torch.empty(rows, dtype=torch.float32, device=x.device)
+        dt = _lib.BF16 if x.dtype == torch.bfloat16 else _lib.F32
+        _lib.check(self.lib.clipk_normalize_fwd(x.data_ptr(), dt, rows, d, x.stride(0), y.data_ptr(), y.stride(0),
+                                                inv.data_ptr(), float(eps), self._stream()), "clipk_normalize_fwd")
+        return y, inv
+
+    def normalize_bwd(self, g: torch.Tensor, y: torch.Tensor, inv: torch.Tensor, eps: float):
+        g = g.contiguous()
+        rows, d = y.shape
+        dx = torch.empty_like(y)
+        dt = _lib.BF16 if y.dtype == torch.bfloat16 else _lib.F32
+        _lib.check(self.lib.clipk_normalize_bwd(g.data_ptr(), g.stride(0), y.data_ptr(), y.stride(0), inv.data_ptr(), dt,
+                                                rows, d, dx.data_ptr(), dx.stride(0), float(eps), self._stream()),
+                   "clipk_normalize_bwd")
+        return dx
+
     def cast(self, src: torch.Tensor, dtype: torch.dtype):
         if dtype == torch.float32:
             return src
@@ -397,3 +420,32 @@ def fused_clip_loss(image_features, text_features, logit_scale, local_loss=False
         logit_scale = torch.tensor(float(logit_scale), dtype=torch.float32, device=image_features.device)
     return FusedClipLoss.apply(image_features, text_features, logit_scale, local_loss, gather_with_grad, rank,
                                world_size, group)
+
+
+# ----------------------------------------------------------------------------------------------------- opt-in: normalise + loss
+class _Normalize(torch.autograd.Function):
+    """F.normalize(x, dim=-1) (open_clip/model.py:216,231) with its Jacobian, on the clipk kernels."""
+
+    @staticmethod
+    def forward(ctx, x, eps):
+        y, inv = _backend().normalize_fwd(x.detach(), eps)
+        ctx.save_for_backward(y, inv)
+        ctx.eps = eps
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        y, inv = ctx.saved_tensors
+        return _backend().normalize_bwd(g.to(y.dtype), y, inv, ctx.eps), None
+
+
+def fused_normalize_clip_loss(raw_image_features, raw_text_features, logit_scale, local_loss=False,
+                              gather_with_grad=False, rank=0, world_size=1, group=None, eps=1e-12):
+    """ClipLoss of the L2-normalised embeddings, taking the RAW tower outputs: what `model.py:216,231` followed by
+    `loss.py:123-140` computes, with gradients with respect to the raw embeddings.  Opt-in - the drop-in ClipLoss does
+    not normalise, exactly like the reference's (point 2)."""
+    image_features = _Normalize.apply(raw_image_features, eps)
+    text_features = _Normalize.apply(raw_text_features, eps)
+    return fused_clip_loss(image_features, text_features, logit_scale, local_loss, gather_with_grad, rank, world_size,
+                           group)

@@ -358,6 +358,77 @@ __global__ void to_f16_kernel(const T* __restrict__ src, __half* __restrict__ ds
     if (planes == 2) *reinterpret_cast<uint4*>(o + dpad) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+// ---- L2 normalisation of the embeddings (the F.normalize calls that feed the loss: open_clip/model.py:216,231)
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float (&v)[8]);
+template <>
+__device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(ptx::pack_bf16x2(v[0], v[1]), ptx::pack_bf16x2(v[2], v[3]),
+                                              ptx::pack_bf16x2(v[4], v[5]), ptx::pack_bf16x2(v[6], v[7]));
+}
+template <>
+__device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// y = x / max(|x|, eps) per row, inv[row] = 1 / max(|x|, eps).  One warp per row, 8 elements per lane and step.
+template <typename T>
+__global__ void normalize_fwd_kernel(const T* __restrict__ x, long long rows, int d8, long long ldx, T* __restrict__ y,
+                                     long long ldy, float* __restrict__ inv, float eps) {
+    const int lane = threadIdx.x & 31;
+    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    float ss = 0.f;
+    for (int k = lane; k < d8; k += 32) {
+        float v[8];
+        load8(x + r * ldx + (long long)k * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss = fmaf(v[j], v[j], ss);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    const float scale = 1.f / fmaxf(sqrtf(ss), eps);
+    if (lane == 0) inv[r] = scale;
+    for (int k = lane; k < d8; k += 32) {
+        float v[8];
+        load8(x + r * ldx + (long long)k * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= scale;
+        store8(y + r * ldy + (long long)k * 8, v);
+    }
+}
+
+// dx = (g - y * (y . g)) * inv for rows with |x| >= eps (y = x * inv is then a unit vector), dx = g * inv otherwise
+template <typename T>
+__global__ void normalize_bwd_kernel(const T* __restrict__ g, long long ldg, const T* __restrict__ y, long long ldy,
+                                     const float* __restrict__ inv, long long rows, int d8, T* __restrict__ dx,
+                                     long long ldd, float eps) {
+    const int lane = threadIdx.x & 31;
+    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    float dot = 0.f;
+    for (int k = lane; k < d8; k += 32) {
+        float a[8], b[8];
+        load8(g + r * ldg + (long long)k * 8, a);
+        load8(y + r * ldy + (long long)k * 8, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dot = fmaf(a[j], b[j], dot);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+    const float scale = inv[r];
+    if (scale >= 1.f / eps * 0.999999f) dot = 0.f;      // |x| < eps: y = x / eps, a plain scaling
+    for (int k = lane; k < d8; k += 32) {
+        float a[8], b[8];
+        load8(g + r * ldg + (long long)k * 8, a);
+        load8(y + r * ldy + (long long)k * 8, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = (a[j] - b[j] * dot) * scale;
+        store8(dx + r * ldd + (long long)k * 8, a);
+    }
+}
+
 // ---- forward sweep helpers
 // out[which] = max over rows of |row|^2 as float bits (non-negative floats order like unsigned ints); one warp per row,
 // 16-byte loads, d % 8 == 0.  Both operands in one launch: blocks [0, bx) take X, the rest take Y.  amax (optional,
@@ -1439,6 +1510,59 @@ int clipk_bwd_peer(const void* X, const void* Y, int rows, int cols, int d, long
     return bwd_impl(X, Y, rows, cols, d, ldx, ldy, dtype, x_inv_scale, y_inv_scale, Xg, Yg, ldxg, ldyg, g_dtype,
                     xg_inv_scale, yg_inv_scale, logit_scale, diag_offset, lse_row, lse_col, alpha, beta, gscale, dX_acc,
                     nullptr, dY_peer_acc, world, rows_per_rank, workspace, workspace_bytes, stream);
+}
+
+static int normalize_check(const void* a, const void* b, int dtype, long long rows, long long d, long long lda, long long ldb) {
+    if (!a || !b || rows <= 0 || d <= 0) return fail(CLIPK_EINVAL, "bad argument");
+    if (dtype != CLIPK_BF16 && dtype != CLIPK_F32) return fail(CLIPK_EUNSUPPORTED, "dtype %d", dtype);
+    if (d % 8 != 0) return fail(CLIPK_EUNSUPPORTED, "d = %lld is not a multiple of 8", d);
+    const int es = dtype == CLIPK_BF16 ? 2 : 4;
+    if (lda < d || ldb < d || (lda * es) % 16 != 0 || (ldb * es) % 16 != 0 || (reinterpret_cast<uintptr_t>(a) & 15) != 0 ||
+        (reinterpret_cast<uintptr_t>(b) & 15) != 0)
+        return fail(CLIPK_EINVAL, "rows must be 16-byte aligned and at least d wide");
+    return CLIPK_OK;
+}
+
+int clipk_normalize_fwd(const void* x, int dtype, long long rows, long long d, long long ldx, void* y, long long ldy,
+                        float* inv_norm, float eps, void* stream) {
+    int rc = normalize_check(x, y, dtype, rows, d, ldx, ldy);
+    if (rc) return rc;
+    if (!inv_norm) return fail(CLIPK_EINVAL, "null inv_norm");
+    DevInfo di;
+    if ((rc = device_info(&di))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int wpb = 8;
+    if (dtype == CLIPK_BF16)
+        normalize_fwd_kernel<<<cdiv(rows, wpb), wpb * 32, 0, st>>>(static_cast<const __nv_bfloat16*>(x), rows, int(d / 8), ldx,
+                                                                    static_cast<__nv_bfloat16*>(y), ldy, inv_norm, eps);
+    else
+        normalize_fwd_kernel<<<cdiv(rows, wpb), wpb * 32, 0, st>>>(static_cast<const float*>(x), rows, int(d / 8), ldx,
+                                                                    static_cast<float*>(y), ldy, inv_norm, eps);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CK_CUDA(cudaGetLastError());
+    return CLIPK_OK;
+}
+
+int clipk_normalize_bwd(const void* g, long long ldg, const void* y, long long ldy, const float* inv_norm, int dtype,
+                        long long rows, long long d, void* dx, long long ldd, float eps, void* stream) {
+    int rc = normalize_check(g, y, dtype, rows, d, ldg, ldy);
+    if (rc) return rc;
+    if ((rc = normalize_check(dx, y, dtype, rows, d, ldd, ldy))) return rc;
+    if (!inv_norm) return fail(CLIPK_EINVAL, "null inv_norm");
+    DevInfo di;
+    if ((rc = device_info(&di))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int wpb = 8;
+    if (dtype == CLIPK_BF16)
+        normalize_bwd_kernel<<<cdiv(rows, wpb), wpb * 32, 0, st>>>(static_cast<const __nv_bfloat16*>(g), ldg,
+                                                                    static_cast<const __nv_bfloat16*>(y), ldy, inv_norm, rows,
+                                                                    int(d / 8), static_cast<__nv_bfloat16*>(dx), ldd, eps);
+    else
+        normalize_bwd_kernel<<<cdiv(rows, wpb), wpb * 32, 0, st>>>(static_cast<const float*>(g), ldg, static_cast<const float*>(y),
+                                                                    ldy, inv_norm, rows, int(d / 8), static_cast<float*>(dx), ldd, eps);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CK_CUDA(cudaGetLastError());
+    return CLIPK_OK;
 }
 
 int clipk_reduce_slots(const float* src, long long n, int world, void* dst, int dtype, void* stream) {

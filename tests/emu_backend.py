@@ -69,5 +69,14 @@ class EmuBackend:
         dY = (G.T @ X.data).float() if want_dy else None
         return dX, dY
 
+    def normalize_fwd(self, x, eps):
+        n = x.double().norm(dim=-1, keepdim=True).clamp_min(eps)
+        return (x.double() / n).to(x.dtype), (1.0 / n.squeeze(-1)).float()
+
+    def normalize_bwd(self, g, y, inv, eps):
+        g64, y64 = g.double(), y.double()
+        dot = (g64 * y64).sum(-1, keepdim=True)
+        return ((g64 - y64 * dot) * inv.double()[:, None]).to(y.dtype)
+
     def cast(self, src, dtype):
         return src.to(dtype)

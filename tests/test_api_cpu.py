@@ -144,3 +144,28 @@ def test_megatron_loss_func_adapter_matches_reference_formula():
         assert torch.allclose(image.grad, i2.grad, rtol=1e-4, atol=1e-6)
     finally:
         ops.set_backend_for_testing(None)
+
+
+def test_fused_normalize_entry_host_logic():
+    """fused_normalize_clip_loss on the CPU emulation backend: normalise + loss + Jacobian against torch autograd."""
+    import torch.nn.functional as F
+    from clipk import ops, fused_normalize_clip_loss
+    from tests.emu_backend import EmuBackend
+    ops.set_backend_for_testing(EmuBackend())
+    try:
+        g = torch.Generator().manual_seed(5)
+        I = (torch.randn(40, 24, generator=g) * 2).requires_grad_(True)
+        T = (torch.randn(40, 24, generator=g) * 3).requires_grad_(True)
+        s = torch.tensor(8.0, requires_grad=True)
+        loss = fused_normalize_clip_loss(I, T, s)
+        loss.backward()
+        I2, T2, s2 = I.detach().clone().requires_grad_(True), T.detach().clone().requires_grad_(True), torch.tensor(8.0, requires_grad=True)
+        logits = s2 * F.normalize(I2, dim=-1) @ F.normalize(T2, dim=-1).T
+        labels = torch.arange(40)
+        ref = (F.cross_entropy(logits, labels) + F.cross_entropy(logits.T, labels)) / 2
+        ref.backward()
+        assert float(loss) == pytest.approx(float(ref), rel=1e-5)
+        assert torch.allclose(I.grad, I2.grad, rtol=1e-4, atol=1e-6) and torch.allclose(T.grad, T2.grad, rtol=1e-4, atol=1e-6)
+        assert float(s.grad) == pytest.approx(float(s2.grad), rel=1e-4)
+    finally:
+        ops.set_backend_for_testing(None)

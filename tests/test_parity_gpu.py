@@ -329,3 +329,36 @@ def test_full_size_step_against_torch_fp32_on_gpu():
     assert abs(lhs - rhs) <= 2e-3 * max(abs(lhs), abs(rhs), 1e-6)
     del per_image
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 4e-3)])
+def test_fused_normalize_clip_loss(dtype, tol):
+    """Opt-in entry: raw embeddings in, F.normalize (model.py:216,231) + ClipLoss (loss.py:123-140) out,
+    gradients with respect to the RAW embeddings (normalisation Jacobian included), against torch in fp64.  In bf16 the
+    normalised features are rounded to bf16 before the loss, like the reference's autocast tower outputs, so the
+    yardstick rounds them too and the tolerance covers two bf16 roundings (features in, gradients out)."""
+    from clipk import fused_normalize_clip_loss
+    g = torch.Generator().manual_seed(17)
+    b, d, s = 900, 256, 1 / 0.07
+    raw_t = torch.randn(b, d, generator=g) * 3.0
+    raw_i = 0.4 * raw_t + torch.randn(b, d, generator=g) * 2.0
+    I = raw_i.cuda().to(dtype).requires_grad_(True)
+    T = raw_t.cuda().to(dtype).requires_grad_(True)
+    S = torch.tensor(s, device="cuda", requires_grad=True)
+    loss = fused_normalize_clip_loss(I, T, S)
+    loss.backward()
+    I2 = I.detach().double().requires_grad_(True)
+    T2 = T.detach().double().requires_grad_(True)
+    S2 = torch.tensor(s, device="cuda", dtype=torch.float64, requires_grad=True)
+    ni, nt = torch.nn.functional.normalize(I2, dim=-1), torch.nn.functional.normalize(T2, dim=-1)
+    if dtype == torch.bfloat16:     # straight-through rounding of the normalised features, as the kernels see them
+        ni = ni + (ni.detach().bfloat16().double() - ni.detach())
+        nt = nt + (nt.detach().bfloat16().double() - nt.detach())
+    labels = torch.arange(b, device="cuda")
+    logits = S2 * ni @ nt.T
+    ref = (torch.nn.functional.cross_entropy(logits, labels) + torch.nn.functional.cross_entropy(logits.T, labels)) / 2
+    ref.backward()
+    r = lambda a, c: float((a.double() - c).norm() / c.norm())
+    assert abs(loss.item() - ref.item()) <= max(tol, 1e-5) * abs(ref.item())
+    assert r(I.grad, I2.grad) <= tol and r(T.grad, T2.grad) <= tol
+    assert abs(S.grad.item() - S2.grad.item()) <= max(tol, 1e-4) * abs(S2.grad.item())
