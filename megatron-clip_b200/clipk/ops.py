@@ -182,9 +182,13 @@ class CudaBackend:
 
     def reduce_slots(self, peer, dtype):
         """Sum of the `world` slots of this rank's text gradient, in the dtype of the inputs."""
-        b, d = peer.slots.shape[1], peer.slots.shape[2]
-        out = torch.empty(b, d, dtype=dtype, device=peer.slots.device)
-        _lib.check(self.lib.clipk_reduce_slots(peer.slots.data_ptr(), b * d, peer.world, out.data_ptr(),
+        return self.sum_slots(peer.slots, dtype)
+
+    def sum_slots(self, slots: torch.Tensor, dtype):
+        """slots [world, b, d] fp32 -> their sum over the first axis, cast to `dtype` (bf16 or fp32), in one pass."""
+        world, b, d = slots.shape
+        out = torch.empty(b, d, dtype=dtype, device=slots.device)
+        _lib.check(self.lib.clipk_reduce_slots(slots.data_ptr(), b * d, world, out.data_ptr(),
                                                _lib.BF16 if dtype == torch.bfloat16 else _lib.F32, self._stream()),
                    "clipk_reduce_slots")
         return out
@@ -276,22 +280,31 @@ _PEER_DISABLED = [False]
 def _peer_state(b, d, rank, world, group, dev):
     """PeerState for this shape, or None when the fused path does not apply (then NCCL reduce_scatter is used)."""
     import os
-    # Opt-in (CLIPK_PEER=1).  Measured on 8 x B200, N = 32768, d = 512 (backward of one rank, ms): gradient GEMMs alone
-    # 0.43; + NCCL reduce_scatter 0.59; fused, TMA reduce-adds into the owners 0.72; fused, TMA stores into per-source
-    # slots 0.71.  The 4 KB (32 x 128 B) TMA boxes of the epilogue reach only ~200 GB/s over NVLink and all tiles of a
-    # panel finish together, so the transfer is neither fast nor hidden; NCCL's reduce_scatter stays the default.
-    if _PEER_DISABLED[0] or os.environ.get("CLIPK_PEER", "0") != "1" or _TEST_BACKEND is not None:
+    # CLIPK_PEER: "1" always, "0" never, unset = where it was measured faster than NCCL's reduce_scatter.  Backward of
+    # one rank at N = 32768, d = 512 (ms), gradient GEMMs alone / + NCCL reduce_scatter / fused peer stores:
+    #   8 GPUs, 2 panels of 4096 x 16384 (current panel model): 0.406 / 0.549 / 0.525  -> fused on
+    #   8 GPUs, 7 panels of 4096 x 4864 (earlier):              0.43  / 0.59  / 0.71
+    #   2 GPUs (b = 16384, second row panel adds over NVLink):  1.54  / 1.58  / 1.59   -> NCCL
+    # (an all-to-all of the row chunks + one local sum instead of the reduce_scatter: 0.576 at 8 GPUs.)
+    mode = os.environ.get("CLIPK_PEER", "auto")
+    if _PEER_DISABLED[0] or mode == "0" or _TEST_BACKEND is not None or (mode != "1" and world < 8):
         return None
     if dev.type != "cuda" or world < 2 or world > 8 or b % 128 != 0:
         return None
     key = (b, d, rank, world, id(group), dev.index)
     st = _PEER_STATES.get(key)
     if st is None:
+        err = None
         try:
             st = PeerState(b, d, rank, world, group, dev)
-        except Exception as e:   # no symmetric memory on this system: every rank takes the NCCL path
+        except Exception as e:   # no symmetric memory on this system
+            st, err = None, e
+        # all ranks take the same path: one failure sends everyone to NCCL (first use of a shape only)
+        ok = torch.tensor([0 if st is None else 1], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
             import warnings
-            warnings.warn(f"clipk: peer-memory reduce unavailable ({e!r}); using NCCL reduce_scatter")
+            warnings.warn(f"clipk: peer-memory reduce unavailable ({err!r}); using NCCL reduce_scatter")
             _PEER_DISABLED[0] = True
             return None
         _PEER_STATES[key] = st
@@ -312,6 +325,16 @@ def _reduce_scatter_rows(x: torch.Tensor, world_size: int, group=None) -> torch.
     out = torch.empty((n,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
     dist.reduce_scatter_tensor(out, x.contiguous(), op=dist.ReduceOp.SUM, group=group)
     return out
+
+
+def _reduce_scatter_rows_a2a(be, x: torch.Tensor, world_size: int, out_dtype, group=None) -> torch.Tensor:
+    """Same result as _reduce_scatter_rows followed by a cast, as an all-to-all of the W row chunks (every rank sends
+    chunk o straight to rank o: full NVSwitch bisection, no ring) and ONE local pass that sums the W received slots and
+    casts them (clipk_reduce_slots).  Measured at 8 x B200 on the [32768, 512] fp32 gradient: see profiles/README.md."""
+    n = x.shape[0] // world_size
+    recv = torch.empty((world_size, n) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_to_all_single(recv, x.contiguous(), group=group)
+    return be.sum_slots(recv, out_dtype)
 
 
 # ----------------------------------------------------------------------------------------------------- autograd
