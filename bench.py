@@ -295,14 +295,14 @@ def run_clipk(args):
     for k in kernels:
         k["frac_of_peak"] = k.get("executed_tflops", k["tflops"]) / pk["tflops_sustained"]
     # DRAM traffic per step from the committed ncu --set full captures (profiles/README.md, N = 32768 on one GPU):
-    # forward sweep 86 + 47 MB; per panel, recompute 20 + 77 MB and gradient GEMMs 265 + 24 MB; 16 panels
-    traffic = (133e6 + 16 * (97e6 + 289e6)) if (world == 1) else None
+    # forward sweep 85 + 46 MB; per panel (5632 x 16384), recompute 29 + 135 MB and gradient GEMMs 339 + 63 MB; 12 panels
+    traffic = (131e6 + 12 * (164e6 + 402e6)) if (world == 1) else None
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
         "frac": achieved / pk["tflops_sustained"], "traffic": traffic,
         "traffic_note": "DRAM bytes per step (read + write) summed over the tensor-core kernels, ncu --set full, "
-                        "profiles/r01k_* and r01f_*; algorithmic operand bytes are 64 MB - the rest is the fp16 "
-                        "softmax-gradient panel streaming through HBM (5.4 GB) and 47 MB of column partials",
+                        "profiles/r01m_*; algorithmic operand bytes are 64 MB - the rest is the fp16 "
+                        "softmax-gradient panel streaming through HBM (6.7 GB) and 46 MB of column partials",
         "kernel": "whole step (SURVEY 8d: F_alg = 6 b N d over t_step); dominant kernels: clipk::gemm_pair_kernel "
                   "(gradient GEMMs, 49 % of the step), grad_sweep_kernel (26 %), fwd_sweep_kernel (21 %); tcgen05 "
                   "cta_group::2 256x256x64 tiles",

@@ -451,7 +451,8 @@ __device__ __forceinline__ void mma_unit(const Cta& c, Pipe& p, const KArgs& arg
 // STATS and OUT tiles (the recompute tiles have their own epilogue below)
 template <int MODE>
 __device__ __forceinline__ void epilogue_unit(const Cta& c, Pipe& p, const CUtensorMap* tmC, const KArgs& args, int m_blk,
-                                              int unit, int t0, int t1, unsigned int* done_ctr = nullptr) {
+                                              int unit, int t0, int t1, unsigned int* done_ctr = nullptr,
+                                              int row_shift = 0) {
     static_assert(MODE == MODE_STATS || MODE == MODE_OUT, "GRAD tiles go through grad_epilogue_unit");
     const int warp = c.warp, lane = c.lane;
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
@@ -480,7 +481,7 @@ __device__ __forceinline__ void epilogue_unit(const Cta& c, Pipe& p, const CUten
     };
     const uint32_t stg0 = c.sStg + (warp - 2) * 2 * STG_BYTES;   // this warp's two staging buffers
     const int dbg = args.dbg, accumulate = args.accumulate, ncols = args.N;
-    const int c_col_off = args.c_col_off, c_row_off = args.c_row_off;
+    const int c_col_off = args.c_col_off, c_row_off = args.c_row_off + row_shift;   // row_shift: output row of a peer slot
 
     for (int t = t0; t < t1; ++t, ++p.it) {
         const int a = p.it & 1;
@@ -1171,18 +1172,19 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const Cta c = cta_setup<STAGES, STG_TOTAL>();
     const int j = blockIdx.x >> 1;   // cluster (2, 1, 1): one job per CTA pair = a 256 x 256 output tile
     const bool first = j < jobs0;
-    KArgs args = first ? args0 : args1;
+    const KArgs& args = first ? args0 : args1;
     const CUtensorMap* tmA = first ? &tmA0 : &tmA1;
     const CUtensorMap* tmB = first ? &tmB0 : &tmB1;
     const CUtensorMap* tmC = first ? &tmC0 : &tmC1;
     const int k = first ? j : j - jobs0;
     const int m_blk = 2 * (k / args.n_tiles) + int(c.cta_rank);
     const int t0 = k % args.n_tiles;
+    int row_shift = 0;
     if (!first && peers.world > 0) {
         const int grow = args.c_row_off + m_blk * BM;           // first global dY row of this CTA
         const int owner = min(grow / peers.rows_per_rank, peers.world - 1);
         tmC = &peers.map[owner];
-        args.c_row_off -= owner * peers.rows_per_rank;   // args.accumulate stays: first row panel stores, later ones add
+        row_shift = -owner * peers.rows_per_rank;   // args.accumulate stays: first row panel stores, later ones add
     }
     Pipe p;
     if (c.warp == 0) {
@@ -1194,7 +1196,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     } else if (c.warp == 1) {
         if (c.lane == 0 && c.leader) mma_unit<STAGES>(c, p, args, 1);
     } else {
-        epilogue_unit<MODE_OUT>(c, p, tmC, args, m_blk, t0, t0, t0 + 1);
+        epilogue_unit<MODE_OUT>(c, p, tmC, args, m_blk, t0, t0, t0 + 1, nullptr, row_shift);
         epilogue_drain(c);
     }
     cta_teardown(c);
