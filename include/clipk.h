@@ -82,7 +82,7 @@ int clipk_fwd_stats(const void* X, const void* Y, int rows, int cols, int d, lon
 
 /* clipk_fwd_both: the statistics of BOTH directions of the same block - what two clipk_fwd_stats calls (X against Y,
  * then Y against X) return - as row_stats [3][rows] and col_stats [3][cols] (max, sum, dot planes, natural-log units).
- * For bf16 operands whose logits are provably bounded (logit_scale * max|x_i| * max|y_j| <= ~34, checked on the device
+ * For bf16 operands whose logits are provably bounded (logit_scale * max|x_i| * max|y_j| <= ~66, checked on the device
  * from the row norms) this is ONE sweep over the tiles: every tile feeds the row and the column sums (for d <= 512 with
  * the rows of X resident in shared memory).  Otherwise the library runs the exact two-sweep form by itself (same
  * results, the cost of two clipk_fwd_stats calls).  pos_logit may be NULL.  amax_xy (may be NULL) receives max |x| of

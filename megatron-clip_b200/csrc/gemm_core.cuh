@@ -753,14 +753,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // Single sweep.  The forward needs the log-sum-exp of every ROW and of every COLUMN of the block (loss.py:135-138 takes
 // the cross-entropy of logits_per_image and of logits_per_text).  Both come from ONE pass over the tiles when the
 // logits are bounded: with u >= |v| for every logit v (log2 units; u = s * max|x_i| * max|y_j| * log2(e) from the row
-// norms) and 2u + 26 <= 126, e = 2^(v - u) of every element stays a normal fp32 number down to 2^-24 of the smallest
-// possible row or column maximum, so ONE exponential per element with the global reference u serves both directions,
-// sums are plain additions (no running maximum, no rescaling) and partial sums can be merged in any order.
+// norms) ONE exponential per element, e = 2^(v - c) with the global reference c = u - 90, serves both directions: it
+// never overflows (e <= 2^90, sums of 2^20 terms and their products with |v - c| < 2^8 stay below 2^127), and every
+// element within 2^-24 of ANY possible row or column maximum (>= -u) is a normal fp32 number as long as
+// -2u - 24 + 90 >= -126, i.e. u <= 96 (logit_scale * norms <= 66).  Sums are then plain additions (no running
+// maximum, no rescaling) and partial sums can be merged in any order.
 // The accumulator is read in the 16x256b fragment layout (a thread holds 2 rows x 8 columns of a 16-lane half-chunk),
 // which makes the column sums cheap: 3 additions over the 4 rows a thread sees per chunk, then a 3-step butterfly over
 // the 8 threads that share the columns; the 4 lane-quarter warps are merged through shared memory and every CTA
 // writes one partial (sum, dot) per column and 128-row block, summed later by fwd_merge_kernel.
-// When the bound does not hold (logit_scale * norms > ~35) the same launch runs the exact online-max row sweep
+// When the bound does not hold (logit_scale * norms > ~66) the same launch runs the exact online-max row sweep
 // instead and a second launch with the operands swapped produces the column statistics; when it holds the second
 // launch exits at once.  The decision is taken on the device from device scalars: no host synchronisation.
 constexpr int ARES_KB = 8;                       // resident K blocks (K <= 512)
@@ -769,7 +771,8 @@ constexpr int COLBUF_BYTES = 2 * 2 * 4 * 128 * 2 * 4;   // [tile parity][half][l
 __host__ __device__ constexpr int smem_bytes_fwd(bool ares = true) {
     return 1024 + (ares ? ARES_KB : FWD_STAGES) * A_STAGE_BYTES + FWD_STAGES * B_STAGE_BYTES + COLBUF_BYTES + 256 + MISC_BYTES;
 }
-constexpr float FWD_SAFE_U = 50.f;               // 2u + 26 <= 126
+constexpr float FWD_SAFE_U = 96.f;               // -2u - 24 + FWD_REF_SHIFT >= -126
+constexpr float FWD_REF_SHIFT = 90.f;            // reference c = u - 90: uses the overflow headroom of fp32 as well
 
 struct FwdArgs {
     int M, N;                  // rows of A (X), rows of B (Y)
@@ -794,12 +797,13 @@ struct FwdArgs {
     int dbg;
 };
 
-// u (log2 units) and whether the single sweep is allowed; identical in every thread of every CTA of both launches
-__device__ __forceinline__ bool fwd_bound(const FwdArgs& a, float* u_out) {
-    if (a.force_exact) { *u_out = 0.f; return false; }
+// the reference c of the single sweep (log2 units) and whether the single sweep is allowed; identical in every
+// thread of every CTA of both launches and of the merge kernel
+__device__ __forceinline__ bool fwd_bound(const FwdArgs& a, float* c_out) {
+    if (a.force_exact) { *c_out = 0.f; return false; }
     const float nx2 = __uint_as_float(a.norm2[0]), ny2 = __uint_as_float(a.norm2[1]);
     const float u = fabsf(__ldg(a.scale)) * sqrtf(nx2) * sqrtf(ny2) * (LOG2E * 1.001f);
-    *u_out = u;
+    *c_out = u - FWD_REF_SHIFT;
     return u <= FWD_SAFE_U;     // false for NaN / Inf
 }
 

@@ -169,3 +169,20 @@ def test_fused_normalize_entry_host_logic():
         assert float(s.grad) == pytest.approx(float(s2.grad), rel=1e-4)
     finally:
         ops.set_backend_for_testing(None)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the GPU arm): exactly one JSON line on stdout
+    with the contract's keys; here with a tiny sample so that it takes seconds."""
+    import json, subprocess, sys
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    code = ("import sys; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0'];"
+            "import runpy, bench; bench.CPU_SAMPLE_BATCH = 512; bench.main()")
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["unit"] == "samples/s" and j["higher_is_better"] is True
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
+    assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0 and j["value"] > 0

@@ -193,6 +193,7 @@ def test_persistent_backward_path_matches():
     (256, 256, 512, 1 / 0.07, 0),          # one tile
     (1000, 3000, 256, 1 / 0.07, 500),      # ragged rows and columns, positives off the main diagonal
     (384, 4100, 64, 20.0, 128),            # one K block, columns just past a tile boundary
+    (1536, 1800, 512, 60.0, 0),            # logit_scale 60: still one sweep (reference u - 90 uses both ends of the fp32 range)
     (2048, 2048, 512, 100.0, 0),           # logit_scale 100: the norm bound fails -> exact two-sweep mode on device
     (520, 520, 768, 1 / 0.07, 0),          # d > 512: the resident-rows kernel does not apply -> streaming sweeps
 ])
