@@ -44,8 +44,11 @@ class _GatherRowsWithGrad(torch.autograd.Function):
 
 
 def gather_features(image_features, text_features, local_loss=False, gather_with_grad=False, rank=0, world_size=1,
-                    use_horovod=False):
+                    use_horovod=False, group=None):
     """Rank-major [world*b, d] copies of both feature matrices (reference loss.py:20-64).
+
+    `group` (not in the reference, optional, last): the process group to gather over when it is not WORLD, e.g.
+    Megatron's data-parallel group; `rank` / `world_size` are then the values inside that group.
 
     gather_with_grad=True : gradients flow back through the gather (reduce-scatter SUM).
     gather_with_grad=False: gathered rows carry no gradient, except that with local_loss=False this rank's own
@@ -56,11 +59,11 @@ def gather_features(image_features, text_features, local_loss=False, gather_with
     if not (dist.is_available() and dist.is_initialized()):
         raise RuntimeError("gather_features needs an initialised torch.distributed process group")
     if gather_with_grad:
-        return (_GatherRowsWithGrad.apply(image_features, world_size, None),
-                _GatherRowsWithGrad.apply(text_features, world_size, None))
+        return (_GatherRowsWithGrad.apply(image_features, world_size, group),
+                _GatherRowsWithGrad.apply(text_features, world_size, group))
     with torch.no_grad():
-        all_i = _all_gather_rows(image_features, world_size)
-        all_t = _all_gather_rows(text_features, world_size)
+        all_i = _all_gather_rows(image_features, world_size, group)
+        all_t = _all_gather_rows(text_features, world_size, group)
     if not local_loss:
         b = image_features.shape[0]
         lo, hi = rank * b, (rank + 1) * b
@@ -84,6 +87,18 @@ class ClipLoss(nn.Module):
         # label cache, same observable state as the reference (loss.py:87-89)
         self.prev_num_logits = 0
         self.labels = {}
+        # collectives run on WORLD like the reference's; set_process_group() narrows them (Megatron DP group)
+        self.group = None
+
+    def set_process_group(self, group, rank=None, world_size=None):
+        """Run the gather / statistics exchange / reduce-scatter over `group` instead of WORLD.  rank and world_size
+        default to this process's values inside the group.  Not in the reference (its ClipLoss always uses WORLD,
+        loss.py:50-56); needed when the data-parallel group is a subset of the job (megatron/core/parallel_state.py)."""
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world_size = dist.get_world_size(group) if world_size is None else world_size
+        self.labels, self.prev_num_logits = {}, 0
+        return self
 
     def get_ground_truth(self, device, num_logits) -> torch.Tensor:
         """int64 arange labels, offset by num_logits*rank in local-loss mode; cached per device when enabled."""
@@ -102,7 +117,7 @@ class ClipLoss(nn.Module):
         """Materialised (logits_per_image, logits_per_text); only DistillClipLoss needs them."""
         if self.world_size > 1:
             all_i, all_t = gather_features(image_features, text_features, self.local_loss, self.gather_with_grad,
-                                           self.rank, self.world_size, self.use_horovod)
+                                           self.rank, self.world_size, self.use_horovod, self.group)
             if self.local_loss:
                 per_image = logit_scale * image_features @ all_t.T
                 per_text = logit_scale * text_features @ all_i.T
@@ -116,7 +131,7 @@ class ClipLoss(nn.Module):
 
     def forward(self, image_features, text_features, logit_scale, output_dict=False):
         loss = fused_clip_loss(image_features, text_features, logit_scale, self.local_loss, self.gather_with_grad,
-                               self.rank, self.world_size)
+                               self.rank, self.world_size, self.group)
         return {"contrastive_loss": loss} if output_dict else loss
 
 
@@ -138,16 +153,22 @@ class CoCaLoss(ClipLoss):
 
 
 class DistillClipLoss(ClipLoss):
+    """Contrastive loss of the student plus the cross-entropy of the student's softmax against a teacher's
+    (reference loss.py:186-221).  Needs both models' logits on the same tile, so it stays on the materialising
+    get_logits path; a fused two-model sweep is listed in DESIGN.md section 9."""
+
     def dist_loss(self, teacher_logits, student_logits):
-        return -(teacher_logits.softmax(dim=1) * student_logits.log_softmax(dim=1)).sum(dim=1).mean(dim=0)
+        # -sum_j p_t(j) * log_softmax(student)(j) = lse(student) - sum_j p_t(j) * student(j), since sum_j p_t(j) = 1
+        expected = (teacher_logits.softmax(dim=1) * student_logits).sum(dim=1)
+        return (torch.logsumexp(student_logits, dim=1) - expected).mean()
 
     def forward(self, image_features, text_features, logit_scale, dist_image_features, dist_text_features,
                 dist_logit_scale, output_dict=False):
-        per_image, per_text = self.get_logits(image_features, text_features, logit_scale)
-        t_per_image, t_per_text = self.get_logits(dist_image_features, dist_text_features, dist_logit_scale)
-        labels = self.get_ground_truth(image_features.device, per_image.shape[0])
-        contrastive_loss = (F.cross_entropy(per_image, labels) + F.cross_entropy(per_text, labels)) / 2
-        distill_loss = (self.dist_loss(t_per_image, per_image) + self.dist_loss(t_per_text, per_text)) / 2
+        student = self.get_logits(image_features, text_features, logit_scale)
+        teacher = self.get_logits(dist_image_features, dist_text_features, dist_logit_scale)
+        labels = self.get_ground_truth(image_features.device, student[0].shape[0])
+        contrastive_loss = sum(F.cross_entropy(lg, labels) for lg in student) / 2
+        distill_loss = sum(self.dist_loss(t, lg) for t, lg in zip(teacher, student)) / 2
         if output_dict:
             return {"contrastive_loss": contrastive_loss, "distill_loss": distill_loss}
         return contrastive_loss, distill_loss

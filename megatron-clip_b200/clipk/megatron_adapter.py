@@ -49,8 +49,8 @@ def make_loss_func(logit_scale=1.0, data_parallel=False, group=None, with_accura
             s = torch.tensor(float(s), dtype=torch.float32, device=image_features.device)
         if state["mod"] is None:
             if data_parallel and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-                state["mod"] = ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True,
-                                        rank=dist.get_rank(group), world_size=dist.get_world_size(group))
+                state["mod"] = ClipLoss(local_loss=True, gather_with_grad=True,
+                                        cache_labels=True).set_process_group(group)
             else:
                 state["mod"] = ClipLoss(cache_labels=True)
         total_loss = state["mod"](image_features, text_features, s)

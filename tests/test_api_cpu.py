@@ -59,7 +59,9 @@ def test_module_surface_matches_reference():
     assert list(sig.parameters)[1:] == ["local_loss", "gather_with_grad", "cache_labels", "rank", "world_size", "use_horovod"]
     assert [p.default for p in list(sig.parameters.values())[1:]] == [False, False, False, 0, 1, False]
     assert list(inspect.signature(L.ClipLoss.forward).parameters)[1:] == ["image_features", "text_features", "logit_scale", "output_dict"]
-    assert list(inspect.signature(L.gather_features).parameters) == ["image_features", "text_features", "local_loss", "gather_with_grad", "rank", "world_size", "use_horovod"]
+    # the reference's parameters in the reference's order; `group` is an optional extension after them
+    assert list(inspect.signature(L.gather_features).parameters) == ["image_features", "text_features", "local_loss", "gather_with_grad", "rank", "world_size", "use_horovod", "group"]
+    assert inspect.signature(L.gather_features).parameters["group"].default is None
     with pytest.raises(NotImplementedError):
         L.ClipLoss(use_horovod=True)
 

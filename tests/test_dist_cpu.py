@@ -65,3 +65,63 @@ def test_world_matches_reference(path):
             assert np.linalg.norm(o[k] - ref) <= tol * np.linalg.norm(ref), (k, r)
         ds_ref = float(g["d_scale"])
         assert abs(float(o["d_scale"]) - ds_ref) <= tol * max(abs(ds_ref), float(z["grad_output"]) / float(z["scale"]))
+
+
+def _subgroup_worker(rank, world, path, tmp):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "megatron-clip_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from clipk import ClipLoss, ops
+    from clipk.megatron_adapter import make_loss_func
+    from tests.emu_backend import EmuBackend
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", init_method=f"file://{tmp}/store", rank=rank, world_size=world)
+    ops.set_backend_for_testing(EmuBackend())
+    # two data-parallel groups of two ranks inside a world of four, interleaved like Megatron's DP groups at TP=2
+    groups = [dist.new_group([0, 2]), dist.new_group([1, 3])]
+    group, grank = groups[rank % 2], rank // 2
+    z, W, ranks = load_golden(path)
+    g = ranks[grank]
+    I = torch.from_numpy(g["image"].astype(np.float32)).requires_grad_(True)
+    T = torch.from_numpy(g["text"].astype(np.float32)).requires_grad_(True)
+    s = torch.tensor(float(z["scale"]), requires_grad=True)
+    mod = ClipLoss(local_loss=bool(z["local_loss"]), gather_with_grad=bool(z["gather_with_grad"]),
+                   cache_labels=True).set_process_group(group)
+    assert (mod.rank, mod.world_size) == (grank, 2)
+    loss = mod(I, T, s)
+    (loss * float(z["grad_output"])).backward()
+    # the Megatron adapter over the same group: local + gather_with_grad, averaged over the group only
+    I2, T2 = I.detach().clone().requires_grad_(True), T.detach().clone().requires_grad_(True)
+    l2, avg = make_loss_func(logit_scale=float(z["scale"]), data_parallel=True, group=group)(T2, I2)
+    np.savez(f"{tmp}/out{rank}.npz", loss=loss.detach().numpy(), d_image=I.grad.numpy(), d_text=T.grad.numpy(),
+             d_scale=s.grad.numpy(), adapter_loss=l2.detach().numpy(), adapter_avg=avg["loss"].numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["w2_b12_d64_raw_float32_s100_ll1_gwg1.npz", "w2_b8_d32_unit_float64_s14_ll0_gwg0.npz",
+                                  "w2_b33_d128_unit_float32_s14_ll1_gwg1.npz"])
+def test_data_parallel_subgroups_of_a_larger_world(name):
+    """ClipLoss.set_process_group: two independent 2-rank data-parallel groups inside a 4-rank job (the layout Megatron
+    produces with tensor parallelism 2, megatron/core/parallel_state.py) each reproduce the reference's 2-rank golden;
+    nothing leaks between the groups."""
+    z, W, ranks = load_golden(name)
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(_subgroup_worker, args=(4, os.path.join(os.path.dirname(__file__), "golden", name), tmp), nprocs=4,
+                 join=True)
+        outs = [dict(np.load(f"{tmp}/out{r}.npz")) for r in range(4)]
+    tol = 2e-5 if float(z["scale"]) < 50 else 3e-4
+    for r in range(4):
+        g, o = ranks[r // 2], outs[r]
+        assert abs(float(o["loss"]) - float(g["loss"])) <= tol * abs(float(g["loss"]))
+        for k in ("d_image", "d_text"):
+            ref = g[k].astype(np.float64)
+            assert np.linalg.norm(o[k] - ref) <= tol * np.linalg.norm(ref), (k, r)
+        ds_ref = float(g["d_scale"])
+        assert abs(float(o["d_scale"]) - ds_ref) <= tol * max(abs(ds_ref), float(z["grad_output"]) / float(z["scale"]))
+        if bool(z["local_loss"]) and bool(z["gather_with_grad"]):
+            assert abs(float(o["adapter_loss"]) - float(g["loss"])) <= tol * abs(float(g["loss"]))
+            mean = 0.5 * (float(ranks[0]["loss"]) + float(ranks[1]["loss"]))
+            assert abs(float(o["adapter_avg"]) - mean) <= tol * abs(mean)
