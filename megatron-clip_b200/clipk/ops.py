@@ -28,6 +28,12 @@ import torch.distributed as dist
 from . import _lib
 
 _TEST_BACKEND = None
+_FEATURE_DTYPES = (torch.bfloat16, torch.float16, torch.float32)
+_K_BLOCK = 64           # K extent of one TMA box / MMA stage (BK in csrc/gemm_core.cuh)
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
 
 
 def set_backend_for_testing(backend):
@@ -349,11 +355,13 @@ class FusedClipLoss(torch.autograd.Function):
             raise ValueError("image_features and text_features must both be [batch, dim]")
         if image_features.dtype != text_features.dtype:
             raise TypeError("image_features and text_features must have the same dtype")
-        b, d = image_features.shape
+        b, d_in = image_features.shape
         W = int(world_size)
         N = W * b
         dev = image_features.device
         in_dtype = image_features.dtype
+        if in_dtype not in _FEATURE_DTYPES:
+            raise TypeError(f"clipk: unsupported feature dtype {in_dtype} (bf16, fp16 and fp32 only)")
         scale = logit_scale.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
 
         # under torch.autocast the reference's matmuls run in the autocast dtype
@@ -361,6 +369,16 @@ class FusedClipLoss(torch.autograd.Function):
         if in_dtype == torch.float32 and dev.type == "cuda" and torch.is_autocast_enabled("cuda") and \
                 torch.get_autocast_dtype("cuda") == torch.bfloat16:
             feats_i, feats_t = feats_i.to(torch.bfloat16), feats_t.to(torch.bfloat16)
+        if in_dtype == torch.float16:
+            # fp16 features (open_clip --precision fp16 / amp): every fp16 value is an fp32 value, so they take the
+            # split-precision fp32 path unchanged; gradients are rounded back to fp16 at the end
+            feats_i, feats_t = feats_i.float(), feats_t.float()
+        # the kernels stream K in 64-element blocks from 16-byte aligned rows: other widths are zero-padded to the
+        # next multiple of 64 (zero columns change no logit; their gradient columns are dropped in the backward)
+        d = _round_up(d_in, _K_BLOCK)
+        if d != d_in:
+            feats_i = torch.nn.functional.pad(feats_i, (0, d - d_in))
+            feats_t = torch.nn.functional.pad(feats_t, (0, d - d_in))
 
         t_all = _all_gather_rows(feats_t, W, group) if W > 1 else feats_t
         X = be.prepare(feats_i)
@@ -386,7 +404,7 @@ class FusedClipLoss(torch.autograd.Function):
 
         ctx.save_for_backward(scale, lse_row, lse_col, pair)
         ctx.operands = (X, Y)
-        ctx.cfg = (b, d, W, rank, off, bool(local_loss), bool(gather_with_grad), group, in_dtype)
+        ctx.cfg = (b, d, W, rank, off, bool(local_loss), bool(gather_with_grad), group, in_dtype, d_in)
         ctx.scale_is_param = isinstance(logit_scale, torch.Tensor)
         ctx.scale_dtype = logit_scale.dtype
         ctx.scale_shape = logit_scale.shape
@@ -398,7 +416,9 @@ class FusedClipLoss(torch.autograd.Function):
         be = _backend()
         scale, lse_row, lse_col, pair = ctx.saved_tensors
         X, Y = ctx.operands
-        b, d, W, rank, off, local_loss, gwg, group, in_dtype = ctx.cfg
+        b, d, W, rank, off, local_loss, gwg, group, in_dtype, d_in = ctx.cfg
+        # dtype the kernels produce directly (clipk_cast / clipk_reduce_slots write bf16 or fp32)
+        k_dtype = torch.bfloat16 if in_dtype == torch.bfloat16 else torch.float32
         N = W * b
         go = grad_out.detach().to(torch.float32).reshape(1)
         d_image = d_text = None
@@ -421,14 +441,20 @@ class FusedClipLoss(torch.autograd.Function):
                     be.peer_barrier(peer)            # every owner is done reading the previous contents of its slots
                     dX = be.bwd_peer(X, Y, Xg, Yg, scale, off, lse_row, lse_col, 1.0, 1.0, gscale, peer)
                     be.peer_barrier(peer)            # every rank's tiles have landed
-                    d_text = be.reduce_slots(peer, in_dtype)
+                    d_text = be.reduce_slots(peer, k_dtype)
                     dT = None
                 else:
                     dX, dY = be.bwd(X, Y, Xg, Yg, scale, off, lse_row, lse_col, 1.0, 1.0, gscale, True, True)
                     dT = _reduce_scatter_rows(dY, W, group) if W > 1 else dY
-            d_image = be.cast(dX, in_dtype)
+            if d != d_in:                         # drop the gradient columns of the zero padding
+                dX = dX[:, :d_in].contiguous()
+                dT = dT if dT is None else dT[:, :d_in].contiguous()
+                d_text = d_text if d_text is None else d_text[:, :d_in].contiguous()
+            d_image = be.cast(dX, k_dtype)
             if dT is not None:
-                d_text = be.cast(dT, in_dtype)
+                d_text = be.cast(dT, k_dtype)
+            if k_dtype != in_dtype:               # fp16 features
+                d_image, d_text = d_image.to(in_dtype), d_text.to(in_dtype)
 
         d_scale = None
         if ctx.scale_is_param and ctx.needs_input_grad[2]:
@@ -441,6 +467,10 @@ def fused_clip_loss(image_features, text_features, logit_scale, local_loss=False
                     world_size=1, group=None):
     if not isinstance(logit_scale, torch.Tensor):
         logit_scale = torch.tensor(float(logit_scale), dtype=torch.float32, device=image_features.device)
+    if image_features.dim() == 2 and image_features.shape[0] == 0 and image_features.shape == text_features.shape:
+        # empty batch: the reference's cross-entropy means over zero rows, i.e. NaN with empty gradients
+        # (loss.py:135-138); nothing to launch
+        return (image_features.sum() + text_features.sum()).float() * logit_scale.float() * float("nan")
     return FusedClipLoss.apply(image_features, text_features, logit_scale, local_loss, gather_with_grad, rank,
                                world_size, group)
 

@@ -119,6 +119,59 @@ def test_single_process_host_logic_with_emulated_kernels():
         ops.set_backend_for_testing(None)
 
 
+@pytest.mark.parametrize("d,dtype,tol", [(100, torch.float32, 1e-5), (36, torch.float32, 1e-5), (72, torch.float16, 2e-3),
+                                         (64, torch.float16, 2e-3), (200, torch.bfloat16, 8e-3)])
+def test_odd_widths_and_fp16_features_host_logic(d, dtype, tol):
+    """Widths that are not a multiple of the 64-element K block are zero-padded on the host and the padding's gradient
+    columns dropped; fp16 features go through the fp32 path and come back as fp16.  Kernel calls emulated on CPU."""
+    from clipk import ClipLoss, ops
+    from oracle import cliploss_oracle as O
+    from tests.emu_backend import EmuBackend
+    seen = []
+
+    class Spy(EmuBackend):
+        def prepare(self, x):
+            seen.append((tuple(x.shape), x.dtype))
+            return super().prepare(x)
+
+    ops.set_backend_for_testing(Spy())
+    try:
+        x, t = O.synthetic_features(20, d, seed=d)
+        I = torch.from_numpy(x).to(dtype).requires_grad_(True)
+        T = torch.from_numpy(t).to(dtype).requires_grad_(True)
+        s = torch.tensor(9.0, requires_grad=True)
+        loss = ClipLoss()(I, T, s)
+        loss.backward()
+        assert all(shape[1] % 64 == 0 for shape, _ in seen), seen           # the kernels only ever see whole K blocks
+        assert all(dt == (torch.bfloat16 if dtype == torch.bfloat16 else torch.float32) for _, dt in seen), seen
+        assert I.grad.shape == I.shape and I.grad.dtype == dtype and T.grad.dtype == dtype and loss.dtype == torch.float32
+        ref = O.clip_loss_single(I.detach().float().numpy(), T.detach().float().numpy(), 9.0)
+        assert abs(loss.item() - ref.loss) <= 1e-5 * ref.loss
+        assert np.linalg.norm(I.grad.float().numpy() - ref.d_image) <= tol * np.linalg.norm(ref.d_image)
+        assert np.linalg.norm(T.grad.float().numpy() - ref.d_text) <= tol * np.linalg.norm(ref.d_text)
+        assert abs(s.grad.item() - ref.d_scale) <= 1e-5 * max(abs(ref.d_scale), 1 / 9.0)
+        with pytest.raises(TypeError):
+            ClipLoss()(I.detach().double(), T.detach().double(), s)
+    finally:
+        ops.set_backend_for_testing(None)
+
+
+def test_empty_batch_is_nan_like_the_reference():
+    """Zero rows: the reference's F.cross_entropy means over nothing -> NaN loss, empty gradients (loss.py:135-138).
+    Handled on the host, before any kernel: works without a GPU."""
+    from clipk import ClipLoss
+    I = torch.zeros(0, 64, requires_grad=True)
+    T = torch.zeros(0, 64, requires_grad=True)
+    s = torch.tensor(10.0, requires_grad=True)
+    loss = ClipLoss()(I, T, s)
+    assert loss.dim() == 0 and torch.isnan(loss)
+    loss.backward()
+    assert I.grad.shape == (0, 64) and T.grad.shape == (0, 64)
+    ref = (torch.nn.functional.cross_entropy(s * I.detach() @ T.detach().T, torch.arange(0)) +
+           torch.nn.functional.cross_entropy(s * T.detach() @ I.detach().T, torch.arange(0))) / 2
+    assert torch.isnan(ref)
+
+
 def test_megatron_loss_func_adapter_matches_reference_formula():
     """clipk.megatron_adapter.make_loss_func keeps the signature and return convention of pretrain_CLIP.py:115-136;
     on the CPU emulation backend (host logic only) its values equal the reference's inlined formula."""

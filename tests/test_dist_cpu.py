@@ -17,7 +17,7 @@ import torch.multiprocessing as mp
 from tests.util import golden_files, load_golden
 
 
-def _worker(rank, world, path, tmp):
+def _worker(rank, world, paths, tmp):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for p in (root, os.path.join(root, "megatron-clip_b200")):
@@ -28,19 +28,20 @@ def _worker(rank, world, path, tmp):
     torch.set_num_threads(1)
     dist.init_process_group("gloo", init_method=f"file://{tmp}/store", rank=rank, world_size=world)
     ops.set_backend_for_testing(EmuBackend())
-    z, W, ranks = load_golden(path)
-    g = ranks[rank]
-    I = torch.from_numpy(g["image"].astype(np.float32)).requires_grad_(True)
-    T = torch.from_numpy(g["text"].astype(np.float32)).requires_grad_(True)
-    s = torch.tensor(float(z["scale"]), requires_grad=True)
-    mod = ClipLoss(local_loss=bool(z["local_loss"]), gather_with_grad=bool(z["gather_with_grad"]), cache_labels=True,
-                   rank=rank, world_size=world)
-    loss = mod(I, T, s)
-    (loss * float(z["grad_output"])).backward()
-    n_logits = I.shape[0] if bool(z["local_loss"]) else I.shape[0] * world
-    labels = mod.get_ground_truth(I.device, n_logits)
-    np.savez(f"{tmp}/out{rank}.npz", loss=loss.detach().numpy(), d_image=I.grad.numpy(), d_text=T.grad.numpy(),
-             d_scale=s.grad.numpy(), labels=labels.numpy())
+    for i, path in enumerate(paths):
+        z, W, ranks = load_golden(path)
+        g = ranks[rank]
+        I = torch.from_numpy(g["image"].astype(np.float32)).requires_grad_(True)
+        T = torch.from_numpy(g["text"].astype(np.float32)).requires_grad_(True)
+        s = torch.tensor(float(z["scale"]), requires_grad=True)
+        mod = ClipLoss(local_loss=bool(z["local_loss"]), gather_with_grad=bool(z["gather_with_grad"]),
+                       cache_labels=True, rank=rank, world_size=world)
+        loss = mod(I, T, s)
+        (loss * float(z["grad_output"])).backward()
+        n_logits = I.shape[0] if bool(z["local_loss"]) else I.shape[0] * world
+        labels = mod.get_ground_truth(I.device, n_logits)
+        np.savez(f"{tmp}/out{i}_{rank}.npz", loss=loss.detach().numpy(), d_image=I.grad.numpy(),
+                 d_text=T.grad.numpy(), d_scale=s.grad.numpy(), labels=labels.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -49,12 +50,23 @@ def _multi_rank_goldens():
     return [p for p in golden_files() if not os.path.basename(p).startswith("w1_")]
 
 
+@pytest.fixture(scope="module")
+def world_outputs():
+    """Every golden of one world size in ONE set of gloo processes (a spawn per case costs ~5 s of imports each)."""
+    outs = {}
+    for W in (2, 4):
+        paths = golden_files(world=W)
+        with tempfile.TemporaryDirectory() as tmp:
+            mp.spawn(_worker, args=(W, paths, tmp), nprocs=W, join=True)
+            for i, p in enumerate(paths):
+                outs[p] = [dict(np.load(f"{tmp}/out{i}_{r}.npz")) for r in range(W)]
+    return outs
+
+
 @pytest.mark.parametrize("path", _multi_rank_goldens(), ids=lambda p: os.path.basename(p)[:-4])
-def test_world_matches_reference(path):
+def test_world_matches_reference(path, world_outputs):
     z, W, ranks = load_golden(path)
-    with tempfile.TemporaryDirectory() as tmp:
-        mp.spawn(_worker, args=(W, path, tmp), nprocs=W, join=True)
-        outs = [dict(np.load(f"{tmp}/out{r}.npz")) for r in range(W)]
+    outs = world_outputs[path]
     tol = 2e-5 if float(z["scale"]) < 50 else 3e-4      # the goldens are fp32 (or fp64) runs of the reference
     for r in range(W):
         g, o = ranks[r], outs[r]

@@ -69,6 +69,16 @@ def test_scale_one_bf16():
     check(x, t, 1.0, torch.bfloat16)
 
 
+@pytest.mark.parametrize("b,d,dtype,tol", [(300, 100, torch.bfloat16, 2e-3), (257, 36, torch.float32, 1e-5),
+                                           (200, 72, torch.float16, 1e-3), (384, 512, torch.float16, 1e-3)])
+def test_odd_widths_and_fp16_features(b, d, dtype, tol):
+    """Embedding widths that are not a multiple of the 64-element K block (zero-padded on the host) and fp16 features
+    (open_clip --precision fp16; carried exactly by the fp32 split-precision path, gradients rounded back to fp16:
+    2^-11 relative per element, hence 1e-3)."""
+    x, t = make_inputs(b, d, seed=b + d)
+    check(x, t, 1 / 0.07, dtype, tol=tol)
+
+
 def test_multi_panel_rows_and_cols():
     """More than one 4096 x 4096 G panel in both directions (accumulating gradient GEMMs)."""
     x, t = make_inputs(4300, 64, seed=12)
@@ -363,3 +373,72 @@ def test_fused_normalize_clip_loss(dtype, tol):
     assert abs(loss.item() - ref.item()) <= max(tol, 1e-5) * abs(ref.item())
     assert r(I.grad, I2.grad) <= tol and r(T.grad, T2.grad) <= tol
     assert abs(S.grad.item() - S2.grad.item()) <= max(tol, 1e-4) * abs(S2.grad.item())
+
+
+@pytest.mark.parametrize("name,b,N,d,rank", [
+    ("C2 shard, 8 ranks", 4096, 32768, 512, 7),
+    ("C3 shard, 8 ranks", 8192, 65536, 768, 3),
+    ("C3 one rank", 65536, 65536, 768, 0),
+    ("C4 shard, 8 ranks", 20480, 163840, 1024, 5),
+])
+def test_rank_block_at_baseline_sizes(name, b, N, d, rank):
+    """One rank's b x N block at the sizes of BASELINE.json configs[1..3] (C2, C3, C4), through the same
+    backend calls the autograd function makes (forward statistics, finalize, backward), bf16.  No O(b*N) oracle:
+    sampled rows and columns are recomputed directly in fp32 on the GPU from the same bf16 values, and the
+    size-independent identity <X, dX> = <Y, dY> (both equal s * sum(G * X Y^T)) covers the whole block."""
+    from clipk import ops
+    need = (N * d * 10 + b * d * 10 + 2 * (b // 128 + 1) * N * 4 + (1 << 30))
+    free, _ = torch.cuda.mem_get_info()
+    if free < need:
+        pytest.skip(f"needs {need >> 20} MiB of free device memory")
+    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    off, s = rank * b, 1 / 0.07
+    Yf = torch.nn.functional.normalize(torch.randn(N, d, device="cuda", generator=g), dim=-1)
+    Z = torch.nn.functional.normalize(torch.randn(b, d, device="cuda", generator=g), dim=-1)
+    X = torch.nn.functional.normalize(0.3 * Yf[off:off + b] + 0.954 * Z, dim=-1).bfloat16()   # positives: cos ~ 0.3
+    Y = Yf.bfloat16()
+    del Yf, Z
+    be = ops._backend()
+    sc = torch.tensor([s], device="cuda")
+    Xo, Yo = be.prepare(X), be.prepare(Y)
+    parts = torch.empty(1, 3, N, dtype=torch.float32, device="cuda")
+    row_stats, pos, _ = be.fwd_both(Xo, Yo, sc, off, col_out=parts[0])
+    lse_row, lse_col, sums = be.finalize(row_stats, pos, parts, off)
+    gscale = torch.tensor([1.0 / (2 * b)], device="cuda")
+    dX, dY = be.bwd(Xo, Yo, be.prepare_grad(Xo), be.prepare_grad(Yo), sc, off, lse_row, lse_col, 1.0, 1.0, gscale,
+                    True, True)
+    torch.cuda.synchronize()
+    assert dX.shape == (b, d) and dY.shape == (N, d)
+    assert bool(torch.isfinite(dX).all()) and bool(torch.isfinite(dY).all()) and bool(torch.isfinite(sums).all())
+
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        Xf, Yf = X.float(), Y.float()
+        ri = torch.randperm(b, device="cuda", generator=g)[:96].sort().values
+        ri[0], ri[-1] = 0, b - 1                                   # first and last row of the block
+        cj = torch.randperm(N, device="cuda", generator=g)[:96].sort().values
+        cj[0], cj[1], cj[-1] = 0, off, N - 1                        # first, a positive's and the last column
+        S_r = s * Xf[ri] @ Yf.T                                     # [96, N]
+        S_c = s * Xf @ Yf[cj].T                                     # [b, 96]
+        assert torch.allclose(lse_row[ri], torch.logsumexp(S_r, 1), rtol=0, atol=2e-4)
+        assert torch.allclose(lse_col[cj], torch.logsumexp(S_c, 0), rtol=0, atol=2e-4)
+        assert torch.allclose(pos[ri], S_r[torch.arange(96, device="cuda"), ri + off], rtol=0, atol=2e-4)
+        # cross-entropy sums of the block against the kernel's own statistics
+        assert abs(sums[0].item() - (lse_row - pos).double().sum().item()) <= 1e-4 * abs(sums[0].item())
+        # sampled gradient rows / columns; the other direction's LSEs come from the kernel (checked just above)
+        gs = s * gscale.item()
+        G_r = torch.exp(S_r - lse_row[ri, None]) + torch.exp(S_r - lse_col[None, :])
+        G_r[torch.arange(96, device="cuda"), ri + off] -= 2.0
+        ref_dX = gs * G_r @ Yf
+        G_c = torch.exp(S_c - lse_row[:, None]) + torch.exp(S_c - lse_col[None, cj])
+        inside = (cj >= off) & (cj < off + b)
+        G_c[(cj - off)[inside], torch.arange(96, device="cuda")[inside]] -= 2.0
+        ref_dY = gs * G_c.T @ Xf
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    r = lambda a, c: float((a.double() - c.double()).norm() / c.double().norm())
+    assert r(dX[ri], ref_dX) <= 2e-3, ("dX", r(dX[ri], ref_dX))
+    assert r(dY[cj], ref_dY) <= 2e-3, ("dY", r(dY[cj], ref_dY))
+    lhs, rhs = (Xf * dX).double().sum().item(), (Yf * dY).double().sum().item()
+    assert abs(lhs - rhs) <= 2e-3 * max(abs(lhs), abs(rhs)), (lhs, rhs)
