@@ -180,13 +180,28 @@ int clipk_debug_set_trace(long long* device_buffer);
  * at index ((w * 2 + h) * 32 + t) * 16 + k. */
 int clipk_debug_tmem_layout(int* out, void* stream);
 
-/* ---- test hook for the tensor-core mainloop: D[M, N] (fp32, ldd) (+)= A * B^T with 16-bit operands
+/* ---- dense logits tiles (evaluation side; also the test hook of the tensor-core mainloop) -----------------------------
+ * clipk_gemm16: D[M, N] (fp32, ldd) (+)= A * B^T with 16-bit operands on the same tcgen05/TMA mainloop as the loss
  *   (bf16 when f16 == 0, fp16 when f16 == 1; both operands share the format - the hardware rejects a mix).
  *   a_mn = 0: A is [M, K] row-major (K contiguous);  a_mn = 1: A is stored [K, M] row-major (M contiguous).
- *   b_mn likewise for B ([N, K] or [K, N]).
+ *   b_mn likewise for B ([N, K] or [K, N]).  N % 4 == 0, ldd % 4 == 0; rows of B past its extent read as zero.
+ * It materialises a panel of logits for the callers that rank instead of reduce: get_clip_metrics
+ * (training/train.py:631-648: logit_scale * image_features @ text_features.t(), argsort) and the zero-shot classifier
+ * (training/zero_shot.py:54-57: 100 * image_features @ classifier, topk).
  */
 int clipk_gemm16(const void* A, const void* B, float* D, int M, int N, int K, long long lda, long long ldb,
                  long long ldd, int a_mn, int b_mn, int f16, int accumulate, void* stream);
+
+/* clipk_rank_count: position of the target column in each row of such a panel, without sorting it.  S holds `rows` rows
+ * of `cols` logits (fp32, ld % 4 == 0, 16-byte aligned); the panel's first row is global row row0.  The target of global
+ * row g is target[g] (device int64, indexed by GLOBAL row) or, with target == NULL, column diag_offset + g.
+ *   greater[g]     = #{ j : S[g, j] >  S[g, t] }              (-1 when t is not a column of the panel)
+ *   ties_before[g] = #{ j < t : S[g, j] == S[g, t] }          (may be NULL)
+ * greater + ties_before is the index of the target in a stable descending sort of the row: what
+ * torch.where(torch.argsort(logits, descending=True) == ground_truth) yields (train.py:640-641), and `rank < k` is the
+ * top-k test of zero_shot.py:36-39.  Both outputs are indexed by global row. */
+int clipk_rank_count(const float* S, int rows, int cols, long long ld, const long long* target, long long diag_offset,
+                     long long row0, int* greater, int* ties_before, void* stream);
 
 #ifdef __cplusplus
 }

@@ -59,6 +59,14 @@ class Operand:
         return None if self.inv_scale is None else self.inv_scale.data_ptr()
 
 
+class DenseOperand:
+    """A matrix as clipk_gemm16 consumes it: one bf16 plane, or the [hi, lo] fp16 planes of an fp32 matrix."""
+    __slots__ = ("planes", "ld", "k", "f16", "rows", "keep")
+
+    def __init__(self, planes, ld, k, f16, rows, keep=None):
+        self.planes, self.ld, self.k, self.f16, self.rows, self.keep = planes, ld, k, f16, rows, keep
+
+
 class CudaBackend:
     """Calls libclipk.so on the current CUDA stream."""
 
@@ -226,6 +234,39 @@ class CudaBackend:
                                                 rows, d, dx.data_ptr(), dx.stride(0), float(eps), self._stream()),
                    "clipk_normalize_bwd")
         return dx
+
+    # ---- evaluation side: dense logits panels and target ranks (clipk/metrics.py)
+    def dense_operand(self, x: torch.Tensor) -> "DenseOperand":
+        """Operand of clipk_gemm16: bf16 as is (K zero-padded to whole 64-element blocks); fp32 / fp16 as two scaled
+        fp16 planes [hi | lo] (clipk_to_f16), contracted pair by pair like the loss's fp32 path."""
+        if x.dim() != 2 or x.shape[0] == 0 or x.shape[1] == 0:
+            raise ValueError("clipk: expected a non-empty [rows, dim] matrix")
+        if x.dtype == torch.bfloat16:
+            k = _round_up(x.shape[1], _K_BLOCK)
+            x = torch.nn.functional.pad(x, (0, k - x.shape[1])) if k != x.shape[1] else x.contiguous()
+            return DenseOperand([x], x.stride(0), k, 0, x.shape[0])
+        if x.dtype not in (torch.float32, torch.float16):
+            raise TypeError(f"clipk: unsupported feature dtype {x.dtype} (bf16, fp16 and fp32 only)")
+        op = self._to_f16(x.float().contiguous(), 2)
+        k = op.ld // 2
+        return DenseOperand([op.data[:, :k], op.data[:, k:]], op.ld, k, 1, x.shape[0], keep=op)
+
+    def logits_panel(self, Q: "DenseOperand", K: "DenseOperand", r0: int, nrows: int, out: torch.Tensor):
+        """out[:nrows, :] = Q[r0:r0+nrows] @ K^T (fp32; up to the operands' positive power-of-two scales).  out is
+        [>= nrows, round_up(K.rows, 4)] fp32, contiguous."""
+        if Q.f16 != K.f16 or Q.k != K.k:
+            raise TypeError("clipk: both operands of a logits panel must have the same dtype and width")
+        n4 = out.shape[1]
+        pairs = [(0, 0)] if Q.f16 == 0 else [(1, 0), (0, 1), (0, 0)]      # small products first: lo.hi, hi.lo, hi.hi
+        for i, (pq, pk) in enumerate(pairs):
+            a = Q.planes[pq][r0:r0 + nrows]
+            _lib.check(self.lib.clipk_gemm16(a.data_ptr(), K.planes[pk].data_ptr(), out.data_ptr(), nrows, n4, Q.k, Q.ld,
+                                             K.ld, out.stride(0), 0, 0, Q.f16, 1 if i else 0, self._stream()),
+                       "clipk_gemm16")
+
+    def rank_count(self, S: torch.Tensor, nrows: int, cols: int, target, diag_offset: int, row0: int, greater, ties):
+        _lib.check(self.lib.clipk_rank_count(S.data_ptr(), nrows, cols, S.stride(0), _ptr(target), diag_offset, row0,
+                                             greater.data_ptr(), ties.data_ptr(), self._stream()), "clipk_rank_count")
 
     def cast(self, src: torch.Tensor, dtype: torch.dtype):
         if dtype == torch.float32:

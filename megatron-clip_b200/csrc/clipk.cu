@@ -555,6 +555,58 @@ __global__ void reduce_slots_kernel(const float* __restrict__ src, long long n, 
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + i) = acc;
 }
 
+// Rank of the target column in every row of a materialised fp32 logits panel (evaluation side: retrieval ranks of
+// training/train.py:631-648, top-k accuracy of training/zero_shot.py:36-39) without sorting the row:
+//   greater[r]     = #{ j : S[r, j] >  S[r, t_r] }
+//   ties_before[r] = #{ j < t_r : S[r, j] == S[r, t_r] }       (greater + ties_before = position in a stable descending sort)
+// One block per row, float4 loads; HBM-bound (4 bytes per logit, read once).
+__global__ void rank_count_kernel(const float* __restrict__ S, long long ld, int cols, const long long* __restrict__ target,
+                                  long long diag_offset, long long row0, int* __restrict__ greater,
+                                  int* __restrict__ ties_before) {
+    const long long gr = row0 + blockIdx.x;
+    const long long tj = target ? target[gr] : diag_offset + gr;
+    const bool valid = tj >= 0 && tj < cols;
+    const float* row = S + (size_t)blockIdx.x * ld;
+    int g = 0, t = 0;
+    if (valid) {
+        const float thr = row[tj];
+        const int n4 = cols >> 2;
+        const float4* row4 = reinterpret_cast<const float4*>(row);
+        for (int q = threadIdx.x; q < n4; q += blockDim.x) {
+            const float4 v = row4[q];
+            const long long j = (long long)q << 2;
+            g += int(v.x > thr) + int(v.y > thr) + int(v.z > thr) + int(v.w > thr);
+            t += int(v.x == thr && j < tj) + int(v.y == thr && j + 1 < tj) + int(v.z == thr && j + 2 < tj) +
+                 int(v.w == thr && j + 3 < tj);
+        }
+        for (int j = (n4 << 2) + threadIdx.x; j < cols; j += blockDim.x) {
+            const float v = row[j];
+            g += int(v > thr);
+            t += int(v == thr && j < tj);
+        }
+    }
+    __shared__ int sg[32], st[32];
+    for (int o = 16; o > 0; o >>= 1) {
+        g += __shfl_xor_sync(0xffffffffu, g, o);
+        t += __shfl_xor_sync(0xffffffffu, t, o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    if (lane == 0) { sg[warp] = g; st[warp] = t; }
+    __syncthreads();
+    if (warp == 0) {
+        g = lane < nwarps ? sg[lane] : 0;
+        t = lane < nwarps ? st[lane] : 0;
+        for (int o = 16; o > 0; o >>= 1) {
+            g += __shfl_xor_sync(0xffffffffu, g, o);
+            t += __shfl_xor_sync(0xffffffffu, t, o);
+        }
+        if (lane == 0) {
+            greater[gr] = valid ? g : -1;       // -1: the target column does not exist in this row
+            if (ties_before) ties_before[gr] = valid ? t : 0;
+        }
+    }
+}
+
 // Barrier between the ranks of one NVLink domain through peer-mapped flags: thread t publishes `epoch` in slot
 // [rank] of rank t's flag array (after everything this stream did before became visible system-wide), then waits
 // until rank t has published the same epoch here.  Epochs only grow, so the flags are never reset.
@@ -1571,6 +1623,22 @@ int clipk_reduce_slots(const float* src, long long n, int world, void* dst, int 
         return fail(CLIPK_EUNSUPPORTED, "n must be a multiple of 4 and the pointers 16-byte aligned");
     if (dtype != CLIPK_BF16 && dtype != CLIPK_F32) return fail(CLIPK_EUNSUPPORTED, "dtype %d", dtype);
     reduce_slots_kernel<<<cdiv(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, n, world, dst, dtype);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CK_CUDA(cudaGetLastError());
+    return CLIPK_OK;
+}
+
+int clipk_rank_count(const float* S, int rows, int cols, long long ld, const long long* target, long long diag_offset,
+                     long long row0, int* greater, int* ties_before, void* stream) {
+    if (!S || !greater || rows < 0 || cols <= 0 || row0 < 0) return fail(CLIPK_EINVAL, "bad argument");
+    if (ld < cols || ld % 4 != 0 || (reinterpret_cast<uintptr_t>(S) & 15) != 0)
+        return fail(CLIPK_EINVAL, "ld must be >= cols and a multiple of 4, and S 16-byte aligned");
+    DevInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    if (rows == 0) return CLIPK_OK;
+    rank_count_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(S, ld, cols, target, diag_offset, row0, greater,
+                                                                           ties_before);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;

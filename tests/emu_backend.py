@@ -80,3 +80,27 @@ class EmuBackend:
 
     def cast(self, src, dtype):
         return src.to(dtype)
+
+    # evaluation side
+    def dense_operand(self, x):
+        op = EmuOperand(x)
+        op.f16, op.k = 0, x.shape[1]
+        return op
+
+    def logits_panel(self, Q, K, r0, nrows, out):
+        out.zero_()
+        assert K.rows == out.shape[1], "keys must be padded to the panel width"
+        out[:nrows] = (Q.data[r0:r0 + nrows] @ K.data.T).float()
+
+    def rank_count(self, S, nrows, cols, target, diag_offset, row0, greater, ties):
+        rows = torch.arange(row0, row0 + nrows)
+        t = target[rows] if target is not None else rows + diag_offset
+        ok = (t >= 0) & (t < cols)
+        tc = t.clamp(0, cols - 1)
+        logits = S[:nrows, :cols]
+        thr = logits[torch.arange(nrows), tc][:, None]
+        g = (logits > thr).sum(1)
+        before = torch.arange(cols)[None, :] < tc[:, None]
+        tb = ((logits == thr) & before).sum(1)
+        greater[rows] = torch.where(ok, g, torch.full_like(g, -1)).to(torch.int32)
+        ties[rows] = torch.where(ok, tb, torch.zeros_like(tb)).to(torch.int32)
