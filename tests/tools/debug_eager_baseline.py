@@ -2,7 +2,7 @@
 left operand, two mean cross-entropies, autograd) on the GPU through PyTorch eager - the "existing Blackwell kernels"
 (cuBLAS + ATen) that the fused path replaces.  Same synthetic inputs as bench.py."""
 import sys, os, json
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 import torch
 from oracle import cliploss_oracle as O
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 32768

@@ -1,7 +1,7 @@
 """Manual check: clipk_fwd_both against two clipk_fwd_stats calls and against torch, plus timing."""
 import sys, os
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "megatron-clip_b200"))
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "..", "megatron-clip_b200"))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 import torch
 from clipk import ops
 from oracle import cliploss_oracle as O

@@ -1,7 +1,7 @@
 """Manual diagnostic (not collected by pytest): print kernel-vs-oracle errors for a few shapes."""
 import sys, os
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "megatron-clip_b200"))
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "..", "megatron-clip_b200"))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 import numpy as np, torch
 from oracle import cliploss_oracle as O
 from tests.util import make_inputs, rel

@@ -1,7 +1,7 @@
 """Manual experiment (torchrun, >= 2 GPUs): backward with NCCL reduce-scatter vs fused peer reduce, and the peer barrier."""
 import os, sys
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "megatron-clip_b200"))
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "..", "megatron-clip_b200"))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 import torch, torch.distributed as dist
 from clipk import ops
 from oracle import cliploss_oracle as O

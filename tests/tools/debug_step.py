@@ -1,7 +1,7 @@
 """Manual profiling target (not collected by pytest): a few ClipLoss fwd+bwd steps at the bench shape."""
 import sys, os
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "megatron-clip_b200"))
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "..", "megatron-clip_b200"))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 import torch
 from clipk import ClipLoss
 from oracle import cliploss_oracle as O

@@ -1,7 +1,7 @@
 """Manual timing (not collected by pytest): ClipLoss fwd / bwd ms at a given shape, CUDA events, L2 flushed."""
 import sys, os
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "megatron-clip_b200"))
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "..", "megatron-clip_b200"))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 import torch
 from clipk import ClipLoss
 from oracle import cliploss_oracle as O

@@ -1,7 +1,7 @@
 """Manual experiment: per-role clock64 timeline of CTA 0 in the dataflow backward kernel."""
 import sys, os
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "megatron-clip_b200"))
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "..", "megatron-clip_b200"))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 import torch
 from clipk import ops, _lib
 from oracle import cliploss_oracle as O

@@ -2,8 +2,8 @@
 import sys, os
 os.environ["CLIPK_DBG"] = str(int(os.environ.get("CLIPK_DBG", "0")) | 1024)
 os.environ["CLIPK_PERSISTENT"] = "1"
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "megatron-clip_b200"))
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "..", "megatron-clip_b200"))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 import torch, numpy as np
 from clipk import ops, _lib
 from oracle import cliploss_oracle as O

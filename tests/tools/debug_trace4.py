@@ -1,8 +1,8 @@
 """Manual experiment: chunk-level clock64 stamps of epilogue warp 2 of CTA 0 (CLIPK_DBG bit 2048), forward or backward."""
 import sys, os
 os.environ["CLIPK_DBG"] = str(int(os.environ.get("CLIPK_DBG", "0")) | 2048)
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "megatron-clip_b200"))
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "..", "megatron-clip_b200"))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 import torch
 from clipk import ops, _lib
 from oracle import cliploss_oracle as O
