@@ -61,7 +61,7 @@ class ClockSampler:
             self.fh = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.path = self.fh.name
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("CLIPK_BENCH_SMI_MS", "100")],
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("CLIPK_BENCH_SMI_MS", "50")],
                                          stdout=self.fh, stderr=subprocess.DEVNULL, text=True)
             time.sleep(0.3)         # let the first samples land before the timed region starts
         except OSError:
@@ -275,7 +275,6 @@ def run_clipk(args):
     if sampler:
         sampler.start()
     ms, launches = timed(step_resident, args.steps, args.warmup)
-    clocks = sampler.stop() if sampler else None
     loss_resident = float(step_resident().detach())
     e2e_steps = max(3, args.steps // 2)
     ms_e2e_serial, _ = timed(step_e2e, e2e_steps, 3)
@@ -342,6 +341,23 @@ def run_clipk(args):
             breakdown["all_gather_T_ms"], _ = ev(lambda: ops._all_gather_rows(tl, world))
             breakdown["all_gather_colstats_ms"], _ = ev(lambda: ops._all_gather_rows(parts, world))
             breakdown["reduce_scatter_dT_ms"], _ = ev(lambda: ops._reduce_scatter_rows(dYa, world))
+    # nvidia-smi cannot sample faster than every ~50 ms and the timed region lasts ~0.1 s, so the sampler stays on from
+    # before the timed region until the end of a short untimed continuation of the same step (all ranks take part: the
+    # step holds collectives); `clocks` is the busier half of those samples.
+    probe_s = float(os.environ.get("CLIPK_BENCH_CLOCK_PROBE_S", "0.8"))
+    probe_steps = 0
+    try:
+        n_probe = int(min(400, probe_s / max(ms * 1e-3, 1e-4)))
+        for _ in range(n_probe):
+            step_resident()
+            probe_steps += 1
+        torch.cuda.synchronize()
+    except Exception as e:      # the probe must never cost the run its result line
+        print(f"clock probe stopped: {e!r}", file=sys.stderr)
+    clocks = sampler.stop() if sampler else None
+    if clocks is not None:
+        clocks["window"] = (f"timed region, e2e legs and per-kernel breakdown, then {probe_steps} more untimed steps "
+                            f"(~{probe_s} s) of the same workload")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
