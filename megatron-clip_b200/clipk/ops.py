@@ -20,7 +20,9 @@ product: without libclipk.so or without a compute-capability-10.x device the cal
 """
 from __future__ import annotations
 
+import ctypes
 import os
+import warnings
 
 import torch
 import torch.distributed as dist
@@ -300,8 +302,7 @@ class PeerState:
     gradient - slot w is written over NVLink by the gradient GEMM of rank w - and the flag words of the barrier."""
 
     def __init__(self, b, d, rank, world, group, dev):
-        import ctypes
-        import torch.distributed._symmetric_memory as symm
+        import torch.distributed._symmetric_memory as symm     # not importable on builds without CUDA support
         pg = group if group is not None else dist.group.WORLD
         self.slots = symm.empty(world, b, d, dtype=torch.float32, device=dev)
         self.slots.zero_()
@@ -326,7 +327,6 @@ _PEER_DISABLED = [False]
 
 def _peer_state(b, d, rank, world, group, dev):
     """PeerState for this shape, or None when the fused path does not apply (then NCCL reduce_scatter is used)."""
-    import os
     # CLIPK_PEER: "1" always, "0" never, unset = where it was measured faster than NCCL's reduce_scatter.  Backward of
     # one rank at N = 32768, d = 512 (ms), gradient GEMMs alone / + NCCL reduce_scatter / fused peer stores:
     #   8 GPUs, 2 panels of 4096 x 16384 (current panel model): 0.406 / 0.549 / 0.525  -> fused on
@@ -350,7 +350,6 @@ def _peer_state(b, d, rank, world, group, dev):
         ok = torch.tensor([0 if st is None else 1], dtype=torch.int32, device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
         if int(ok.item()) == 0:
-            import warnings
             warnings.warn(f"clipk: peer-memory reduce unavailable ({err!r}); using NCCL reduce_scatter")
             _PEER_DISABLED[0] = True
             return None
