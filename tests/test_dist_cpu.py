@@ -137,3 +137,50 @@ def test_data_parallel_subgroups_of_a_larger_world(name):
             assert abs(float(o["adapter_loss"]) - float(g["loss"])) <= tol * abs(float(g["loss"]))
             mean = 0.5 * (float(ranks[0]["loss"]) + float(ranks[1]["loss"]))
             assert abs(float(o["adapter_avg"]) - mean) <= tol * abs(mean)
+
+
+def _odd_worker(rank, world, tmp, cases):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "megatron-clip_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from clipk import ClipLoss, ops
+    from oracle import cliploss_oracle as O
+    from tests.emu_backend import EmuBackend
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", init_method=f"file://{tmp}/store", rank=rank, world_size=world)
+    ops.set_backend_for_testing(EmuBackend())
+    for i, (b, d, dtype, ll, gwg) in enumerate(cases):
+        x, t = O.synthetic_features(b, d, seed=40 + i, rank=rank)
+        I = torch.from_numpy(x).to(getattr(torch, dtype)).requires_grad_(True)
+        T = torch.from_numpy(t).to(getattr(torch, dtype)).requires_grad_(True)
+        s = torch.tensor(11.0, requires_grad=True)
+        loss = ClipLoss(local_loss=ll, gather_with_grad=gwg, rank=rank, world_size=world)(I, T, s)
+        loss.backward()
+        assert I.grad.shape == (b, d) and I.grad.dtype == I.dtype and T.grad.dtype == T.dtype
+        np.savez(f"{tmp}/odd{i}_{rank}.npz", loss=loss.detach().numpy(), d_image=I.grad.float().numpy(),
+                 d_text=T.grad.float().numpy(), d_scale=s.grad.numpy(), image=I.detach().float().numpy(),
+                 text=T.detach().float().numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_odd_widths_and_fp16_across_ranks():
+    """Widths that are not whole K blocks (host zero-padding, gradient columns dropped after the reduce-scatter) and fp16
+    features, two ranks, against the float64 oracle on the values the ranks held."""
+    from oracle import cliploss_oracle as O
+    cases = [(10, 100, "float32", True, True), (9, 72, "float16", False, True), (8, 40, "float32", True, False),
+             (6, 200, "bfloat16", False, False)]
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(_odd_worker, args=(2, tmp, cases), nprocs=2, join=True)
+        for i, (b, d, dtype, ll, gwg) in enumerate(cases):
+            outs = [dict(np.load(f"{tmp}/odd{i}_{r}.npz")) for r in range(2)]
+            ref = O.clip_loss_world([o["image"] for o in outs], [o["text"] for o in outs], 11.0, ll, gwg)
+            tol = {"float32": 1e-5, "float16": 2e-3, "bfloat16": 8e-3}[dtype]       # rounding of the returned gradients
+            for r in range(2):
+                o, g = outs[r], ref[r]
+                assert abs(float(o["loss"]) - g.loss) <= 1e-5 * abs(g.loss)
+                for k, want in (("d_image", g.d_image), ("d_text", g.d_text)):
+                    assert np.linalg.norm(o[k] - want) <= tol * np.linalg.norm(want), (i, r, k)
+                assert abs(float(o["d_scale"]) - g.d_scale) <= 1e-5 * max(abs(g.d_scale), 1 / 11.0)
