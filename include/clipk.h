@@ -203,6 +203,28 @@ int clipk_gemm16(const void* A, const void* B, float* D, int M, int N, int K, lo
 int clipk_rank_count(const float* S, int rows, int cols, long long ld, const long long* target, long long diag_offset,
                      long long row0, int* greater, int* ties_before, void* stream);
 
+/* ---- distillation term of DistillClipLoss (loss.py:187-216) on logits panels ----------------------------------------
+ * dist_loss(teacher, student) = mean_i [ lse(S_i) - sum_j softmax(T_i)(j) * S_ij ] per direction.  The LSEs of both
+ * models come from clipk_fwd_both + clipk_finalize; the cross term needs student and teacher logits of the same
+ * element, so it is taken from a pair of panels made by clipk_gemm16 (S = student, T = teacher raw products of the same
+ * [rows, cols] block, fp32, leading dimension ld; logits = S * (*s_mul), T * (*t_mul), device scalars that carry
+ * logit_scale and the operands' power-of-two scales).  The panel holds ALL columns of its rows; its first row is global
+ * row row0, and vectors indexed by row are indexed by GLOBAL row.
+ *   clipk_distill_cross: row_cross[g] = sum_j exp(T_gj - t_lse_row[g]) * S_gj                (complete per call)
+ *                        col_part[j]  = sum_{rows of the panel} exp(T_gj - t_lse_col[j]) * S_gj   (the caller adds panels)
+ *   clipk_distill_grad : G[r, j] = fp16( 2^14 * ( exp(S - s_lse_row[g]) - exp(T - t_lse_row[g])
+ *                                               + exp(S - s_lse_col[j]) - exp(T - t_lse_col[j]) ) ),  G is [rows, ldg]:
+ *                        the derivative of both directions' terms with respect to the student's logits times 2 n,
+ *                        in the operand format of the gradient GEMMs (clipk_gemm16 with f16 = 1).
+ * rows <= 65535 per call.  STATUS: built and covered on the CPU emulation; GPU validation pending (opt-in,
+ * CLIPK_FUSED_DISTILL=1). */
+int clipk_distill_cross(const float* S, const float* T, int rows, int cols, long long ld, const float* s_mul,
+                        const float* t_mul, const float* t_lse_row, const float* t_lse_col, long long row0,
+                        float* row_cross, float* col_part, void* stream);
+int clipk_distill_grad(const float* S, const float* T, int rows, int cols, long long ld, const float* s_mul,
+                       const float* t_mul, const float* s_lse_row, const float* t_lse_row, const float* s_lse_col,
+                       const float* t_lse_col, long long row0, void* G, long long ldg, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,8 @@ PROTOTYPES = {
     "clipk_debug_set_trace": (_i, [_vp]),
     "clipk_debug_tmem_layout": (_i, [_vp, _vp]),
     "clipk_rank_count": (_i, [_vp, _i, _i, _ll, _vp, _ll, _ll, _vp, _vp, _vp]),
+    "clipk_distill_cross": (_i, [_vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp]),
+    "clipk_distill_grad": (_i, [_vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _ll, _vp]),
     "clipk_gemm16": (_i, [_vp, _vp, _vp, _i, _i, _i, _ll, _ll, _ll, _i, _i, _i, _i, _vp]),
 }
 

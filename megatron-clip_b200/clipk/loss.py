@@ -22,11 +22,14 @@ libclipk.so).  Deviations from the reference, all deliberate:
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import distill
 from .ops import fused_clip_loss, _all_gather_rows, _reduce_scatter_rows
 
 
@@ -154,8 +157,9 @@ class CoCaLoss(ClipLoss):
 
 class DistillClipLoss(ClipLoss):
     """Contrastive loss of the student plus the cross-entropy of the student's softmax against a teacher's
-    (reference loss.py:186-221).  Needs both models' logits on the same tile, so it stays on the materialising
-    get_logits path; a fused two-model sweep is listed in DESIGN.md section 9."""
+    (reference loss.py:186-221).  Default: the reference's formula on materialised logits (get_logits), parity-pinned
+    by tests/golden/shells.  With CLIPK_FUSED_DISTILL=1, single-process bf16 calls take the fused contrastive loss and
+    the panel-based distillation term of clipk/distill.py instead (no N x N matrices; GPU validation pending)."""
 
     def dist_loss(self, teacher_logits, student_logits):
         # -sum_j p_t(j) * log_softmax(student)(j) = lse(student) - sum_j p_t(j) * student(j), since sum_j p_t(j) = 1
@@ -164,11 +168,17 @@ class DistillClipLoss(ClipLoss):
 
     def forward(self, image_features, text_features, logit_scale, dist_image_features, dist_text_features,
                 dist_logit_scale, output_dict=False):
-        student = self.get_logits(image_features, text_features, logit_scale)
-        teacher = self.get_logits(dist_image_features, dist_text_features, dist_logit_scale)
-        labels = self.get_ground_truth(image_features.device, student[0].shape[0])
-        contrastive_loss = sum(F.cross_entropy(lg, labels) for lg in student) / 2
-        distill_loss = sum(self.dist_loss(t, lg) for t, lg in zip(teacher, student)) / 2
+        if os.environ.get("CLIPK_FUSED_DISTILL") == "1" and distill.applicable(
+                image_features, text_features, dist_image_features, dist_text_features, self.world_size):
+            contrastive_loss = fused_clip_loss(image_features, text_features, logit_scale)
+            distill_loss = distill.fused_distill_term(image_features, text_features, logit_scale,
+                                                      dist_image_features, dist_text_features, dist_logit_scale)
+        else:
+            student = self.get_logits(image_features, text_features, logit_scale)
+            teacher = self.get_logits(dist_image_features, dist_text_features, dist_logit_scale)
+            labels = self.get_ground_truth(image_features.device, student[0].shape[0])
+            contrastive_loss = sum(F.cross_entropy(lg, labels) for lg in student) / 2
+            distill_loss = sum(self.dist_loss(t, lg) for t, lg in zip(teacher, student)) / 2
         if output_dict:
             return {"contrastive_loss": contrastive_loss, "distill_loss": distill_loss}
         return contrastive_loss, distill_loss

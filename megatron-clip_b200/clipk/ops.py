@@ -270,6 +270,34 @@ class CudaBackend:
         _lib.check(self.lib.clipk_rank_count(S.data_ptr(), nrows, cols, S.stride(0), _ptr(target), diag_offset, row0,
                                              greater.data_ptr(), ties.data_ptr(), self._stream()), "clipk_rank_count")
 
+    # ---- distillation term on logits panels (clipk/distill.py)
+    def gemm(self, A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, a_mn: bool, b_mn: bool, f16: bool,
+             accumulate: bool):
+        """out[M, N] (fp32) (+)= A * B^T on the tensor cores.  A is [M, K] (a_mn False) or stored [K, M] (True); B is
+        [N, K] or stored [K, N]; 16-bit operands of one format (fp16 when f16).  Rows may be strided views."""
+        M, N = out.shape
+        K = A.shape[0] if a_mn else A.shape[1]
+        _lib.check(self.lib.clipk_gemm16(A.data_ptr(), B.data_ptr(), out.data_ptr(), M, N, K, A.stride(0), B.stride(0),
+                                         out.stride(0), 1 if a_mn else 0, 1 if b_mn else 0, 1 if f16 else 0,
+                                         1 if accumulate else 0, self._stream()), "clipk_gemm16")
+
+    def distill_cross(self, S, T, nrows, cols, s_mul, t_mul, t_lse_row, t_lse_col, row0, row_cross, col_part):
+        _lib.check(self.lib.clipk_distill_cross(S.data_ptr(), T.data_ptr(), nrows, cols, S.stride(0), s_mul.data_ptr(),
+                                                t_mul.data_ptr(), t_lse_row.data_ptr(), t_lse_col.data_ptr(), row0,
+                                                row_cross.data_ptr(), col_part.data_ptr(), self._stream()),
+                   "clipk_distill_cross")
+
+    def distill_grad(self, S, T, nrows, cols, s_mul, t_mul, s_lse_row, t_lse_row, s_lse_col, t_lse_col, row0, G):
+        _lib.check(self.lib.clipk_distill_grad(S.data_ptr(), T.data_ptr(), nrows, cols, S.stride(0), s_mul.data_ptr(),
+                                               t_mul.data_ptr(), s_lse_row.data_ptr(), t_lse_row.data_ptr(),
+                                               s_lse_col.data_ptr(), t_lse_col.data_ptr(), row0, G.data_ptr(),
+                                               G.stride(0), self._stream()), "clipk_distill_grad")
+
+    def grad_operand(self, x: torch.Tensor):
+        """(fp16 copy [rows, round_up(d, 64)], inv_scale device scalar) of a bf16 matrix: exact, for the gradient GEMMs."""
+        op = self._to_f16(x.contiguous(), 1)
+        return op.data, op.inv_scale
+
     def cast(self, src: torch.Tensor, dtype: torch.dtype):
         if dtype == torch.float32:
             return src

@@ -607,6 +607,75 @@ __global__ void rank_count_kernel(const float* __restrict__ S, long long ld, int
     }
 }
 
+// ---- distillation term of DistillClipLoss (loss.py:187-216) over a pair of materialised fp32 logits panels ----------
+// S = student, T = teacher raw dot products of the same [rows, cols] block; logits are S * (*s_mul) and T * (*t_mul).
+//   -sum_j softmax(T_i)(j) * log_softmax(S_i)(j) = lse(S_i) - sum_j exp(T_ij - lse(T_i)) * S_ij: the LSEs come from the
+// fused forward of each model; the cross term needs both logits of an element at once, which is what these passes read.
+// HBM-bound: 8 bytes per logit and pass.
+__global__ void distill_row_cross_kernel(const float* __restrict__ S, const float* __restrict__ T, long long ld, int cols,
+                                         const float* __restrict__ s_mul, const float* __restrict__ t_mul,
+                                         const float* __restrict__ t_lse_row, long long row0,
+                                         float* __restrict__ row_cross) {
+    const long long g = row0 + blockIdx.x;
+    const float sm = __ldg(s_mul), tm = __ldg(t_mul) * LOG2E, L = __ldg(t_lse_row + g) * LOG2E;
+    const float* srow = S + (size_t)blockIdx.x * ld;
+    const float* trow = T + (size_t)blockIdx.x * ld;
+    float acc = 0.f;
+    for (int j = threadIdx.x; j < cols; j += blockDim.x) acc = fmaf(ptx::ex2(fmaf(trow[j], tm, -L)), srow[j] * sm, acc);
+    __shared__ float red[32];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        acc = lane < nwarps ? red[lane] : 0.f;
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) row_cross[g] = acc;
+    }
+}
+// col_part[j] = sum over the panel's rows of exp(T_ij - lse_col(T)(j)) * S_ij.  Block = 32 columns x 8 row lanes: a warp
+// reads 32 consecutive floats of one row.
+__global__ void distill_col_cross_kernel(const float* __restrict__ S, const float* __restrict__ T, int rows, int cols,
+                                         long long ld, const float* __restrict__ s_mul, const float* __restrict__ t_mul,
+                                         const float* __restrict__ t_lse_col, float* __restrict__ col_part) {
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + cx;
+    const float sm = __ldg(s_mul), tm = __ldg(t_mul) * LOG2E;
+    float acc = 0.f;
+    if (j < cols) {
+        const float L = __ldg(t_lse_col + j) * LOG2E;
+        for (int r = ry; r < rows; r += 8) {
+            const size_t o = (size_t)r * ld + j;
+            acc = fmaf(ptx::ex2(fmaf(T[o], tm, -L)), S[o] * sm, acc);
+        }
+    }
+    __shared__ float red[8][33];
+    red[ry][cx] = acc;
+    __syncthreads();
+    if (ry == 0 && j < cols) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][cx];
+        col_part[j] = t;
+    }
+}
+// G = 2^14 * (P_row(S) - P_row(T) + P_col(S) - P_col(T)) as fp16: the derivative of both directions' distillation terms
+// with respect to the student's logits (up to the 1 / (2 n) the caller applies), in the format the gradient GEMMs take.
+__global__ void distill_grad_kernel(const float* __restrict__ S, const float* __restrict__ T, int cols, long long ld,
+                                    const float* __restrict__ s_mul, const float* __restrict__ t_mul,
+                                    const float* __restrict__ s_lse_row, const float* __restrict__ t_lse_row, long long row0,
+                                    const float* __restrict__ s_lse_col, const float* __restrict__ t_lse_col,
+                                    __half* __restrict__ G, long long ldg) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cols) return;
+    const long long g = row0 + blockIdx.y;
+    const size_t o = (size_t)blockIdx.y * ld + j;
+    const float s = S[o] * (__ldg(s_mul) * LOG2E), t = T[o] * (__ldg(t_mul) * LOG2E);
+    const float v = ptx::ex2(s - __ldg(s_lse_row + g) * LOG2E) - ptx::ex2(t - __ldg(t_lse_row + g) * LOG2E) +
+                    ptx::ex2(s - __ldg(s_lse_col + j) * LOG2E) - ptx::ex2(t - __ldg(t_lse_col + j) * LOG2E);
+    G[(size_t)blockIdx.y * ldg + j] = __float2half_rn(16384.f * v);
+}
+
 // Barrier between the ranks of one NVLink domain through peer-mapped flags: thread t publishes `epoch` in slot
 // [rank] of rank t's flag array (after everything this stream did before became visible system-wide), then waits
 // until rank t has published the same epoch here.  Epochs only grow, so the flags are never reset.
@@ -1639,6 +1708,43 @@ int clipk_rank_count(const float* S, int rows, int cols, long long ld, const lon
     if (rows == 0) return CLIPK_OK;
     rank_count_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(S, ld, cols, target, diag_offset, row0, greater,
                                                                            ties_before);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CK_CUDA(cudaGetLastError());
+    return CLIPK_OK;
+}
+
+int clipk_distill_cross(const float* S, const float* T, int rows, int cols, long long ld, const float* s_mul,
+                        const float* t_mul, const float* t_lse_row, const float* t_lse_col, long long row0,
+                        float* row_cross, float* col_part, void* stream) {
+    if (!S || !T || !s_mul || !t_mul || !t_lse_row || !t_lse_col || !row_cross || !col_part)
+        return fail(CLIPK_EINVAL, "null pointer argument");
+    if (rows < 0 || rows > 65535 || cols <= 0 || ld < cols || row0 < 0) return fail(CLIPK_EINVAL, "bad extent");
+    DevInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    if (rows == 0) return CLIPK_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    distill_row_cross_kernel<<<rows, 256, 0, st>>>(S, T, ld, cols, s_mul, t_mul, t_lse_row, row0, row_cross);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CK_CUDA(cudaGetLastError());
+    distill_col_cross_kernel<<<cdiv(cols, 32), 256, 0, st>>>(S, T, rows, cols, ld, s_mul, t_mul, t_lse_col, col_part);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CK_CUDA(cudaGetLastError());
+    return CLIPK_OK;
+}
+
+int clipk_distill_grad(const float* S, const float* T, int rows, int cols, long long ld, const float* s_mul,
+                       const float* t_mul, const float* s_lse_row, const float* t_lse_row, const float* s_lse_col,
+                       const float* t_lse_col, long long row0, void* G, long long ldg, void* stream) {
+    if (!S || !T || !s_mul || !t_mul || !s_lse_row || !t_lse_row || !s_lse_col || !t_lse_col || !G)
+        return fail(CLIPK_EINVAL, "null pointer argument");
+    if (rows < 0 || rows > 65535 || cols <= 0 || ld < cols || ldg < cols || row0 < 0) return fail(CLIPK_EINVAL, "bad extent");
+    DevInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    if (rows == 0) return CLIPK_OK;
+    distill_grad_kernel<<<dim3(cdiv(cols, 256), rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        S, T, cols, ld, s_mul, t_mul, s_lse_row, t_lse_row, row0, s_lse_col, t_lse_col, static_cast<__half*>(G), ldg);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;

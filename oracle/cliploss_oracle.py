@@ -222,3 +222,29 @@ def synthetic_features(b: int, d: int, seed: int, rank: int = 0):
     t = 0.3 * x + 0.954 * z
     t /= np.linalg.norm(t, axis=1, keepdims=True)
     return x.astype(np.float32), t.astype(np.float32)
+
+
+def distill_loss_single(image, text, logit_scale, t_image, t_text, t_logit_scale, grad_output=1.0):
+    """float64 distillation term of DistillClipLoss.forward, single process (reference loss.py:187-189, 200-216):
+        dist_loss(t, s) = -(softmax(t, 1) * log_softmax(s, 1)).sum(1).mean(0),
+        distill_loss = (dist_loss(teacher per-image, student per-image) + dist_loss(teacher per-text, student per-text)) / 2
+    Returns (loss, d_image, d_text, d_scale) with respect to the STUDENT (the teacher carries no gradient)."""
+    I, T = np.asarray(image, dtype=np.float64), np.asarray(text, dtype=np.float64)
+    tI, tT = np.asarray(t_image, dtype=np.float64), np.asarray(t_text, dtype=np.float64)
+    s, ts, go = float(logit_scale), float(t_logit_scale), float(grad_output)
+    n = I.shape[0]
+    C = I @ T.T
+    S = s * C                                  # student logits_per_image (loss.py:118); per_text is its transpose
+    Tl = ts * tI @ tT.T
+
+    def softmax(x, axis):
+        e = np.exp(x - x.max(axis=axis, keepdims=True))
+        return e / e.sum(axis=axis, keepdims=True)
+
+    def lse(x, axis):
+        m = x.max(axis=axis)
+        return m + np.log(np.exp(x - np.expand_dims(m, axis)).sum(axis=axis))
+
+    loss = ((lse(S, 1) - (softmax(Tl, 1) * S).sum(1)).mean() + (lse(S, 0) - (softmax(Tl, 0) * S).sum(0)).mean()) / 2
+    G = (softmax(S, 1) - softmax(Tl, 1) + softmax(S, 0) - softmax(Tl, 0)) * (go / (2 * n))     # dloss / dS
+    return loss, s * G @ T, s * G.T @ I, float((G * C).sum())

@@ -84,8 +84,35 @@ class EmuBackend:
     # evaluation side
     def dense_operand(self, x):
         op = EmuOperand(x)
-        op.f16, op.k = 0, x.shape[1]
+        op.f16, op.k, op.planes = 0, x.shape[1], [x]
         return op
+
+    # distillation term
+    def gemm(self, A, B, out, a_mn, b_mn, f16, accumulate):
+        a = A.double().T if a_mn else A.double()
+        b = B.double() if b_mn else B.double().T
+        prod = (a @ b).float()
+        if accumulate:
+            out += prod
+        else:
+            out.copy_(prod)
+
+    def grad_operand(self, x):
+        return x.double(), torch.ones(1)
+
+    def distill_cross(self, S, T, nrows, cols, s_mul, t_mul, t_lse_row, t_lse_col, row0, row_cross, col_part):
+        s = S[:nrows, :cols].double() * float(s_mul[0])
+        t = T[:nrows, :cols].double() * float(t_mul[0])
+        row_cross[row0:row0 + nrows] = (torch.exp(t - t_lse_row[row0:row0 + nrows].double()[:, None]) * s).sum(1).float()
+        col_part.copy_((torch.exp(t - t_lse_col.double()[None, :cols]) * s).sum(0).float())
+
+    def distill_grad(self, S, T, nrows, cols, s_mul, t_mul, s_lse_row, t_lse_row, s_lse_col, t_lse_col, row0, G):
+        s = S[:nrows, :cols].double() * float(s_mul[0])
+        t = T[:nrows, :cols].double() * float(t_mul[0])
+        rows = slice(row0, row0 + nrows)
+        v = (torch.exp(s - s_lse_row[rows].double()[:, None]) - torch.exp(t - t_lse_row[rows].double()[:, None]) +
+             torch.exp(s - s_lse_col.double()[None, :cols]) - torch.exp(t - t_lse_col.double()[None, :cols]))
+        G[:nrows, :cols] = (16384.0 * v).to(G.dtype)
 
     def logits_panel(self, Q, K, r0, nrows, out):
         out.zero_()
