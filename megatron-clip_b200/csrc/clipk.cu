@@ -744,6 +744,39 @@ static int use_persistent() {
     static int v = [] { const char* e = getenv("CLIPK_PERSISTENT"); return e ? atoi(e) : 0; }();
     return v;
 }
+// Experiment (CLIPK_BWD_STREAMS=2, default 1): the recompute sweep of panel p+1 runs on a library-owned side stream
+// against the gradient GEMMs of panel p on the caller's stream, with two G buffers, so that the tail of one launch is
+// filled by the head of the other.  The side stream is forked from and joined to the caller's stream with events (legal
+// under stream capture).  One caller per device at a time in this mode: the events are per device.
+static int bwd_streams() {
+    static int v = [] { const char* e = getenv("CLIPK_BWD_STREAMS"); return e ? atoi(e) : 1; }();
+    return v;
+}
+struct SideStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t start = nullptr, ready[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
+    int ok = 0;
+};
+static SideStream g_side[64];
+static std::mutex g_side_mu;
+static int side_stream(SideStream** out) {
+    int dev = 0;
+    CK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(CLIPK_EINVAL, "device index %d out of range", dev);
+    std::lock_guard<std::mutex> lk(g_side_mu);
+    SideStream& ss = g_side[dev];
+    if (!ss.ok) {
+        CK_CUDA(cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking));
+        CK_CUDA(cudaEventCreateWithFlags(&ss.start, cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) {
+            CK_CUDA(cudaEventCreateWithFlags(&ss.ready[i], cudaEventDisableTiming));
+            CK_CUDA(cudaEventCreateWithFlags(&ss.freed[i], cudaEventDisableTiming));
+        }
+        ss.ok = 1;
+    }
+    *out = &ss;
+    return CLIPK_OK;
+}
 static int dbg_flags() {
     static int v = [] { const char* e = getenv("CLIPK_DBG"); return e ? atoi(e) : 0; }();
     return v;
@@ -1507,14 +1540,18 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
         return launch_clustered(kfn, dim3(2 * n_clusters), dim3(2, 1, 1), smem, st, tmX, tmY, tmGst, tmGk, tmGmn, tmYg,
                                 tmXg, tmDX, tmDY, P);
     }
-    // after the panel: avec[rows], bvec[cols], gref[2], minmax[2]
+    // after the panel(s): avec[rows], bvec[cols], gref[2], minmax[2]
     const size_t g_bytes = size_t(round_up(round_up(rp_max, 2 * BM) * ldg * 2, 256));
-    float* avec = reinterpret_cast<float*>(static_cast<char*>(workspace) + g_bytes);
+    const bool two_streams = bwd_streams() == 2;
+    const int n_gbuf = two_streams ? 2 : 1;
+    float* avec = reinterpret_cast<float*>(static_cast<char*>(workspace) + n_gbuf * g_bytes);
     float* bvec = avec + round_up(rows, 64);
     float* gref = bvec + round_up(cols, 64);
     int* mm = reinterpret_cast<int*>(gref + 4);
-    if (g_bytes + (round_up(rows, 64) + round_up(cols, 64) + 8) * sizeof(float) > workspace_bytes)
+    if (n_gbuf * g_bytes + (round_up(rows, 64) + round_up(cols, 64) + 8) * sizeof(float) > workspace_bytes)
         return fail(CLIPK_EWORKSPACE, "workspace too small for the panel and the reference vectors");
+    SideStream* side = nullptr;
+    if (two_streams && (rc = side_stream(&side))) return rc;
     CK_CUDA(cudaMemsetAsync(mm, 0x7f, sizeof(int), st));
     CK_CUDA(cudaMemsetAsync(mm + 1, 0x80, sizeof(int), st));
     {
@@ -1535,16 +1572,27 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
     const char* Ygb = static_cast<const char*>(Yg);
     const int nt = cdiv(d, BN);
 
+    if (two_streams) {
+        // fork: the side stream starts after everything enqueued so far (grad_prep's vectors, the caller's inputs)
+        CK_CUDA(cudaEventRecord(side->start, st));
+        CK_CUDA(cudaStreamWaitEvent(side->s, side->start, 0));
+    }
+    int panel = 0;
     for (long long r0 = 0; r0 < rows; r0 += rp_max) {
         const int nr = int(rows - r0 < rp_max ? rows - r0 : rp_max);
-        for (long long c0 = 0; c0 < cols; c0 += cp_max) {
+        for (long long c0 = 0; c0 < cols; c0 += cp_max, ++panel) {
             const int nc = int(cols - c0 < cp_max ? cols - c0 : cp_max);
+            const int gb = two_streams ? (panel & 1) : 0;
+            __half* const Gp = reinterpret_cast<__half*>(static_cast<char*>(workspace) + gb * g_bytes);
+            const cudaStream_t sg = two_streams ? side->s : st;      // stream of the recompute sweep
+            // buffer gb was last read by the gradient GEMMs of panel - 2
+            if (two_streams && panel >= 2) CK_CUDA(cudaStreamWaitEvent(side->s, side->freed[gb], 0));
             // ---- recompute S on the panel, write G (fp16, x 2^14)
             {
                 CUtensorMap ta, tb, tc;
                 if ((rc = tmap_kmajor(&ta, Xb + r0 * ldx * esz, nr, kext, ldx, BM))) return rc;
                 if ((rc = tmap_kmajor(&tb, Yb + c0 * ldy * esz, nc, kext, ldy, BN / 2))) return rc;
-                if ((rc = tmap_g_store(&tc, G, round_up(nr, 2 * BM), ldg, ldg))) return rc;
+                if ((rc = tmap_g_store(&tc, Gp, round_up(nr, 2 * BM), ldg, ldg))) return rc;
                 KArgs a{};
                 a.M = nr; a.N = nc; a.n_tiles = cdiv(nc, BN);
                 set_segments(a, planes, d, dpad, dpad);
@@ -1557,20 +1605,24 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
                 a.lse_row = lse_row + r0; a.lse_col = lse_col + c0;
                 a.alpha = alpha; a.beta = beta;
                 a.avec = avec + r0; a.bvec = bvec + c0; a.gref = gref;
-                a.G = G; a.ldg = ldg; a.g_planes = gplanes; a.g_plane_stride = ncp;
+                a.G = Gp; a.ldg = ldg; a.g_planes = gplanes; a.g_plane_stride = ncp;
                 if (planes == 1 && gplanes == 1 && a.num_kb <= ARES_KB && !(dbg_flags() & 512)) {
                     // rows of X resident in shared memory, persistent over the panel (see grad_sweep_kernel)
                     SweepGeom g{};
                     g.num_kb = a.num_kb; g.n_tiles = a.n_tiles; g.m_pairs = m_pairs;
                     const int nc = int(std::min<long long>(di.sms / 2, (long long)m_pairs * a.n_tiles));
-                    if ((rc = tmap_g_store_dense32(&tc, G, round_up(nr, 2 * BM), ldg, ldg))) return rc;
-                    rc = is_f16(dtype) ? launch_grad_sweep<1>(ta, tb, tc, a, g, nc, st) : launch_grad_sweep<0>(ta, tb, tc, a, g, nc, st);
+                    if ((rc = tmap_g_store_dense32(&tc, Gp, round_up(nr, 2 * BM), ldg, ldg))) return rc;
+                    rc = is_f16(dtype) ? launch_grad_sweep<1>(ta, tb, tc, a, g, nc, sg) : launch_grad_sweep<0>(ta, tb, tc, a, g, nc, sg);
                 } else if (is_f16(dtype)) {
-                    rc = launch_gemm<MODE_GRAD, 1>(ta, tb, tc, a, units, m_pairs, st);
+                    rc = launch_gemm<MODE_GRAD, 1>(ta, tb, tc, a, units, m_pairs, sg);
                 } else {
-                    rc = launch_gemm<MODE_GRAD, 0>(ta, tb, tc, a, units, m_pairs, st);
+                    rc = launch_gemm<MODE_GRAD, 0>(ta, tb, tc, a, units, m_pairs, sg);
                 }
                 if (rc) return rc;
+            }
+            if (two_streams) {
+                CK_CUDA(cudaEventRecord(side->ready[gb], side->s));
+                CK_CUDA(cudaStreamWaitEvent(st, side->ready[gb], 0));
             }
             // ---- job 0: dX[r0:r0+nr, :] (+)= G[nr, nc] * Yg[c0:c0+nc, :]      (A K-major, B MN-major, fp16 x fp16)
             // ---- job 1: dY[c0:c0+nc, :] (+)= G^T[nc, nr] * Xg[r0:r0+nr, :]    (A MN-major, B MN-major, fp16 x fp16)
@@ -1578,7 +1630,7 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
             KArgs a0{}, a1{};
             int jobs0 = 0, jobs1 = 0;
             if (dX_acc) {
-                if ((rc = tmap_kmajor(&ta0, G, nr, gplanes == 2 ? ldg : nc, ldg, BM))) return rc;
+                if ((rc = tmap_kmajor(&ta0, Gp, nr, gplanes == 2 ? ldg : nc, ldg, BM))) return rc;
                 if ((rc = tmap_mnmajor(&tb0, Ygb + c0 * ldyg * esz, gext, nc, ldyg))) return rc;
                 if ((rc = tmap_out_f32(&tc0, dX_acc + r0 * d, nr, d, d))) return rc;
                 a0.M = nr; a0.N = d; a0.n_tiles = nt; a0.tiles_per_unit = 1; a0.a_mn = 0; a0.b_mn = 1;
@@ -1588,7 +1640,7 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
                 jobs0 = cdiv(nr, 2 * BM) * nt;
             }
             if (dY_acc) {
-                if ((rc = tmap_mnmajor(&ta1, G, gplanes == 2 ? ldg : nc, nr, ldg))) return rc;
+                if ((rc = tmap_mnmajor(&ta1, Gp, gplanes == 2 ? ldg : nc, nr, ldg))) return rc;
                 if ((rc = tmap_mnmajor(&tb1, Xgb + r0 * ldxg * esz, gext, nr, ldxg))) return rc;
                 if ((rc = tmap_out_f32(&tc1, peers.world ? dY_acc : dY_acc + c0 * d, peers.world ? peers.rows_per_rank : nc, d, d))) return rc;
                 a1.M = nc; a1.N = d; a1.n_tiles = nt; a1.tiles_per_unit = 1; a1.a_mn = 1; a1.b_mn = 1;
@@ -1605,6 +1657,7 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
             else if (dX_acc) rc = launch_gemm<MODE_OUT, 1>(ta0, tb0, tc0, a0, nt, cdiv(nr, 2 * BM), st);
             else rc = launch_gemm<MODE_OUT, 1>(ta1, tb1, tc1, a1, nt, cdiv(nc, 2 * BM), st);
             if (rc) return rc;
+            if (two_streams) CK_CUDA(cudaEventRecord(side->freed[gb], st));
         }
     }
     return CLIPK_OK;
