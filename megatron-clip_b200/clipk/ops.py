@@ -455,8 +455,18 @@ class FusedClipLoss(torch.autograd.Function):
 
         parts = torch.empty(1, 3, N, dtype=torch.float32, device=dev)        # (max, sum, dot) of every column
         row_stats, pos, _ = be.fwd_both(X, Y, scale, off, col_out=parts[0])
+        grad_operands = None
         if W > 1:
-            parts = _all_gather_rows(parts, W, group)                        # [W, 3, N]
+            if os.environ.get("CLIPK_OVERLAP") == "1" and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
+                # experiment: the backward's fp16 copies of the features are made now, on the compute stream, while
+                # NCCL gathers the column statistics on its own stream
+                gathered = torch.empty((W,) + tuple(parts.shape[1:]), dtype=parts.dtype, device=dev)
+                work = dist.all_gather_into_tensor(gathered, parts, group=group, async_op=True)
+                grad_operands = (be.prepare_grad(X), be.prepare_grad(Y))
+                work.wait()
+                parts = gathered
+            else:
+                parts = _all_gather_rows(parts, W, group)                    # [W, 3, N]
         lse_row, lse_col, sums = be.finalize(row_stats, pos, parts, off)
 
         # sums[0:2] -> loss, sums[2:4] -> s * dloss/ds; the global (local_loss=False) loss is the same N x N problem
@@ -472,6 +482,7 @@ class FusedClipLoss(torch.autograd.Function):
 
         ctx.save_for_backward(scale, lse_row, lse_col, pair)
         ctx.operands = (X, Y)
+        ctx.grad_operands = grad_operands
         ctx.cfg = (b, d, W, rank, off, bool(local_loss), bool(gather_with_grad), group, in_dtype, d_in)
         ctx.scale_is_param = isinstance(logit_scale, torch.Tensor)
         ctx.scale_dtype = logit_scale.dtype
@@ -491,7 +502,7 @@ class FusedClipLoss(torch.autograd.Function):
         go = grad_out.detach().to(torch.float32).reshape(1)
         d_image = d_text = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
-            Xg, Yg = be.prepare_grad(X), be.prepare_grad(Y)
+            Xg, Yg = ctx.grad_operands or (be.prepare_grad(X), be.prepare_grad(Y))
             local = (W == 1) or local_loss
             # c of SURVEY App. A: 1/(2b) for W=1, both local modes and global+gather_with_grad; 1/(2N) otherwise
             c_feat = 1.0 / (2.0 * b) if (local or gwg) else 1.0 / (2.0 * N)

@@ -184,3 +184,20 @@ def test_odd_widths_and_fp16_across_ranks():
                 for k, want in (("d_image", g.d_image), ("d_text", g.d_text)):
                     assert np.linalg.norm(o[k] - want) <= tol * np.linalg.norm(want), (i, r, k)
                 assert abs(float(o["d_scale"]) - g.d_scale) <= 1e-5 * max(abs(g.d_scale), 1 / 11.0)
+
+
+def test_overlap_switch_gives_the_same_results(monkeypatch):
+    """CLIPK_OVERLAP=1 (fp16 copies for the backward made under the asynchronous gather of the column statistics) is a
+    reordering only: same losses and gradients as the default path on two ranks."""
+    from oracle import cliploss_oracle as O
+    cases = [(10, 64, "float32", True, True), (8, 64, "bfloat16", False, True)]
+    outs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("CLIPK_OVERLAP", flag)            # inherited by the spawned ranks
+        with tempfile.TemporaryDirectory() as tmp:
+            mp.spawn(_odd_worker, args=(2, tmp, cases), nprocs=2, join=True)
+            outs[flag] = [[dict(np.load(f"{tmp}/odd{i}_{r}.npz")) for r in range(2)] for i in range(len(cases))]
+    for i in range(len(cases)):
+        for r in range(2):
+            for k in ("loss", "d_image", "d_text", "d_scale"):
+                assert np.array_equal(outs["0"][i][r][k], outs["1"][i][r][k]), (i, r, k)
