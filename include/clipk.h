@@ -155,6 +155,12 @@ int clipk_bwd_peer(const void* X, const void* Y, int rows, int cols, int d, long
                    int rows_per_rank, void* workspace, size_t workspace_bytes, void* stream);
 int clipk_reduce_slots(const float* src, long long n, int world, void* dst, int dtype, void* stream);
 int clipk_peer_barrier(void* const* peer_flags, int rank, int world, unsigned int epoch, void* stream);
+/* clipk_peer_gather (experiment, CLIPK_PEER_GATHER=1; not yet run on a GPU): the all-gather of loss.py:50-56 by pulling -
+ * dst[o * bytes_per_rank ...] <- peer_src[o] for every rank o in one launch (peer_src: HOST array of `world` device
+ * pointers to the ranks' source buffers, peer-mapped for the remote ones; 16-byte aligned, bytes_per_rank % 16 == 0).
+ * Protocol (caller): copy the local rows into the own source buffer; clipk_peer_barrier; clipk_peer_gather.  With two
+ * source buffers used alternately the barrier of the next call also guarantees that every peer has finished reading. */
+int clipk_peer_gather(void* const* peer_src, void* dst, long long bytes_per_rank, int world, void* stream);
 
 /* ---- opt-in: the L2 normalisation in front of the loss ---------------------------------------
  * The reference normalises in the model, not in the loss (F.normalize, open_clip/model.py:216,231,277,281); these two

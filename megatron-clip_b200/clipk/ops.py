@@ -349,6 +349,58 @@ class PeerState:
         dist.barrier(group=pg)          # every rank's buffers are zero before anyone adds or signals
 
 
+class PeerGather:
+    """Experiment (CLIPK_PEER_GATHER=1): the all-gather of the text features by pulling from symmetric memory.  Every rank
+    copies its rows into one of two symmetric source buffers (used alternately), a flag barrier makes them visible, and ONE
+    kernel reads all ranks' rows over NVLink (clipk_peer_gather).  The barrier of call k+1 also tells that every peer has
+    finished reading the buffer of call k, so it may be overwritten in call k+2."""
+
+    def __init__(self, nbytes, rank, world, group, dev):
+        import torch.distributed._symmetric_memory as symm
+        pg = group if group is not None else dist.group.WORLD
+        self.src = symm.empty(2, nbytes, dtype=torch.uint8, device=dev)
+        h_src = symm.rendezvous(self.src, pg)
+        self.flags = symm.empty(8, dtype=torch.int32, device=dev)
+        self.flags.zero_()
+        h_flags = symm.rendezvous(self.flags, pg)
+        if h_src.rank != rank or h_src.world_size != world:
+            raise RuntimeError("rank / world_size of the loss do not match the process group")
+        self.rank, self.world, self.nbytes, self.epoch, self.calls = rank, world, nbytes, 0, 0
+        self.src_ptrs = [(ctypes.c_void_p * world)(*[int(p) + half * nbytes for p in h_src.buffer_ptrs]) for half in (0, 1)]
+        self.flag_ptrs = (ctypes.c_void_p * world)(*[int(p) for p in h_flags.buffer_ptrs])
+        self._handles = (h_src, h_flags)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=pg)
+
+    def gather(self, be, x: torch.Tensor) -> torch.Tensor:
+        half = self.calls & 1
+        self.calls += 1
+        self.src[half].view(x.dtype).view(x.shape).copy_(x)
+        be.peer_barrier(self)
+        out = torch.empty((self.world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        _lib.check(be.lib.clipk_peer_gather(self.src_ptrs[half], out.data_ptr(), self.nbytes, self.world, be._stream()),
+                   "clipk_peer_gather")
+        return out
+
+
+_PEER_GATHERS = {}
+
+
+def _gather_text(be, x: torch.Tensor, rank, world, group):
+    """[b, d] per rank -> [world * b, d]: NCCL all_gather_into_tensor, or (CLIPK_PEER_GATHER=1, CUDA, <= 8 ranks of one
+    NVLink domain) the pull-based gather over peer memory."""
+    x = x.contiguous()
+    nbytes = x.numel() * x.element_size()
+    if os.environ.get("CLIPK_PEER_GATHER") != "1" or _TEST_BACKEND is not None or x.device.type != "cuda" or world > 8 \
+            or nbytes % 16 != 0:
+        return _all_gather_rows(x, world, group)
+    key = (nbytes, rank, world, id(group), x.device.index)
+    pgather = _PEER_GATHERS.get(key)
+    if pgather is None:
+        pgather = _PEER_GATHERS[key] = PeerGather(nbytes, rank, world, group, x.device)
+    return pgather.gather(be, x)
+
+
 _PEER_STATES = {}
 _PEER_DISABLED = [False]
 
@@ -448,7 +500,7 @@ class FusedClipLoss(torch.autograd.Function):
             feats_i = torch.nn.functional.pad(feats_i, (0, d - d_in))
             feats_t = torch.nn.functional.pad(feats_t, (0, d - d_in))
 
-        t_all = _all_gather_rows(feats_t, W, group) if W > 1 else feats_t
+        t_all = _gather_text(be, feats_t, rank, W, group) if W > 1 else feats_t
         X = be.prepare(feats_i)
         Y = be.prepare(t_all)
         off = rank * b if W > 1 else 0

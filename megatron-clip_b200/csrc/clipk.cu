@@ -676,6 +676,19 @@ __global__ void distill_grad_kernel(const float* __restrict__ S, const float* __
     G[(size_t)blockIdx.y * ldg + j] = __float2half_rn(16384.f * v);
 }
 
+// All-gather by pulling: chunk o of dst <- rank o's (peer-mapped) source buffer, all ranks' chunks in one launch so that
+// the loads from the `world` peers are in flight together (NVSwitch gives every pair its full link).  16-byte units.
+struct PeerSrc {
+    const uint4* p[MAX_PEERS];
+};
+__global__ void peer_gather_kernel(const __grid_constant__ PeerSrc src, uint4* __restrict__ dst, long long n16) {
+    // blockIdx.y = source rank; the pointer table stays in parameter space (__grid_constant__), no local copy
+    const uint4* __restrict__ from = src.p[blockIdx.y];
+    uint4* __restrict__ to = dst + (long long)blockIdx.y * n16;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) to[i] = from[i];
+}
+
 // Barrier between the ranks of one NVLink domain through peer-mapped flags: thread t publishes `epoch` in slot
 // [rank] of rank t's flag array (after everything this stream did before became visible system-wide), then waits
 // until rank t has published the same epoch here.  Epochs only grow, so the flags are never reset.
@@ -1798,6 +1811,30 @@ int clipk_distill_grad(const float* S, const float* T, int rows, int cols, long 
     if (rows == 0) return CLIPK_OK;
     distill_grad_kernel<<<dim3(cdiv(cols, 256), rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         S, T, cols, ld, s_mul, t_mul, s_lse_row, t_lse_row, row0, s_lse_col, t_lse_col, static_cast<__half*>(G), ldg);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CK_CUDA(cudaGetLastError());
+    return CLIPK_OK;
+}
+
+int clipk_peer_gather(void* const* peer_src, void* dst, long long bytes_per_rank, int world, void* stream) {
+    if (!peer_src || !dst || bytes_per_rank <= 0 || world < 1 || world > MAX_PEERS) return fail(CLIPK_EINVAL, "bad argument");
+    if (bytes_per_rank % 16 != 0 || (reinterpret_cast<uintptr_t>(dst) & 15) != 0)
+        return fail(CLIPK_EINVAL, "bytes_per_rank must be a multiple of 16 and dst 16-byte aligned");
+    DevInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    PeerSrc ps;
+    memset(&ps, 0, sizeof(ps));
+    for (int o = 0; o < world; ++o) {
+        if (!peer_src[o] || (reinterpret_cast<uintptr_t>(peer_src[o]) & 15) != 0) return fail(CLIPK_EINVAL, "source %d null or misaligned", o);
+        ps.p[o] = static_cast<const uint4*>(peer_src[o]);
+    }
+    const long long n16 = bytes_per_rank / 16;
+    long long blocks = cdiv(n16, 256);
+    const long long cap = cdiv(8LL * di.sms, world);     // ~8 blocks per SM over all sources
+    if (blocks > cap) blocks = cap;
+    peer_gather_kernel<<<dim3(unsigned(blocks), unsigned(world)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        ps, static_cast<uint4*>(dst), n16);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
