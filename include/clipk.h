@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CLIPK_VERSION 1
+#define CLIPK_VERSION 2
 
 #define CLIPK_OK 0
 #define CLIPK_EINVAL (-1)       /* bad argument (null pointer, non-positive size, misaligned pointer or ld) */
@@ -145,7 +145,9 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
  * clipk_bwd_peer on every rank; clipk_peer_barrier; clipk_reduce_slots on every owner.
  * clipk_peer_barrier: barrier between the ranks through peer-mapped flag words (peer_flags[t] = device pointer to
  * rank t's array of 8 uint32, zero at start; HOST array of `world` pointers).  `epoch` must grow by one per call and be
- * the same on all ranks.  Everything the stream did before the barrier is visible to the peers after it.
+ * the same on all ranks.  Everything the stream did before the barrier is visible to the peers after it.  A wait that
+ * lasts longer than ~20 s (a peer died or skipped the call) gives up and stores 2 into *err (a word of pinned host
+ * memory, may be NULL) instead of hanging the device.
  * clipk_reduce_slots: dst[i] = (dtype) sum over w < world of src[w * n + i]   (dtype CLIPK_BF16 or CLIPK_F32). */
 int clipk_bwd_peer(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
                    const float* x_inv_scale, const float* y_inv_scale, const void* Xg, const void* Yg, long long ldxg,
@@ -154,13 +156,74 @@ int clipk_bwd_peer(const void* X, const void* Y, int rows, int cols, int d, long
                    float alpha, float beta, const float* gscale, float* dX_acc, void* const* dY_peer_slot, int world,
                    int rows_per_rank, void* workspace, size_t workspace_bytes, void* stream);
 int clipk_reduce_slots(const float* src, long long n, int world, void* dst, int dtype, void* stream);
-int clipk_peer_barrier(void* const* peer_flags, int rank, int world, unsigned int epoch, void* stream);
-/* clipk_peer_gather (experiment, CLIPK_PEER_GATHER=1; not yet run on a GPU): the all-gather of loss.py:50-56 by pulling -
- * dst[o * bytes_per_rank ...] <- peer_src[o] for every rank o in one launch (peer_src: HOST array of `world` device
- * pointers to the ranks' source buffers, peer-mapped for the remote ones; 16-byte aligned, bytes_per_rank % 16 == 0).
- * Protocol (caller): copy the local rows into the own source buffer; clipk_peer_barrier; clipk_peer_gather.  With two
- * source buffers used alternately the barrier of the next call also guarantees that every peer has finished reading. */
-int clipk_peer_gather(void* const* peer_src, void* dst, long long bytes_per_rank, int world, void* stream);
+int clipk_peer_barrier(void* const* peer_flags, int rank, int world, unsigned int epoch, int* err, void* stream);
+
+/* ---- the whole loss step in two calls ---------------------------------------------------------------------------------
+ * clipk_step_forward / clipk_step_backward run everything ClipLoss.forward (loss.py:123-140) and its autograd do on one
+ * rank - including, between the ranks of one NVLink domain, gather_features (loss.py:20-64) and the backward of its
+ * all-gather - as ONE enqueue each: no host work, allocation or synchronisation between the kernels.
+ *
+ *   forward   prep (one pass over the local rows: optional L2 normalisation + cast to the bf16 operands, operand
+ *             statistics; the text rows land in the buffer the peers pull from)
+ *             -> all-gather of the text rows and the statistics by pulling from peer memory (world > 1)
+ *             -> single-sweep tcgen05 forward (row AND column statistics of the [rows, cols] block), merge
+ *             -> all-gather of the [3, cols] column statistics (world > 1) -> finalize: lse_row, lse_col, loss.
+ *   backward  fp16 copies of both operands -> per panel: recompute G, gradient GEMMs (the text-gradient tiles go
+ *             straight into their owners' memory over NVLink when world > 1) -> barrier -> finish: sum of the slots,
+ *             Jacobian of the normalisation, cast, dlogit_scale.
+ *
+ * Operands are bf16 (src_dtype CLIPK_BF16, or CLIPK_F32 inputs cast on the way - what autocast does to the reference's
+ * matmul); d % 64 == 0; world == 1 or 2..8 ranks with rows % 128 == 0.  Everything else takes the individual entries
+ * above.  All pointers are device pointers except `peer` (host struct) and peer->err (pinned host memory).
+ */
+#define CLIPK_MAX_PEERS 8
+#define CLIPK_STAT_WORDS 8
+typedef struct clipk_peer {
+    int world, rank;
+    /* index = rank that OWNS the memory; entries of other ranks are their peer-mapped addresses */
+    void* text_src[CLIPK_MAX_PEERS];    /* [rows, d] bf16: the rank's text operand rows for this call                  */
+    void* stats_src[CLIPK_MAX_PEERS];   /* CLIPK_STAT_WORDS floats: the rank's operand statistics                      */
+    void* col_src[CLIPK_MAX_PEERS];     /* [3, cols] fp32: column statistics of the rank's block                       */
+    void* grad_slot[CLIPK_MAX_PEERS];   /* [rows, d] fp32: THIS rank's slot of the text gradient in the owner's memory */
+    void* flags_gather[CLIPK_MAX_PEERS];/* unsigned[CLIPK_MAX_PEERS] per purpose, zero at start                        */
+    void* flags_stats[CLIPK_MAX_PEERS];
+    void* flags_grad[CLIPK_MAX_PEERS];
+    unsigned int epoch_gather, epoch_stats, epoch_grad;   /* grow by one per call, same on all ranks                  */
+    const float* my_slots;              /* [world][rows, d] fp32: the slots this rank owns (slot w written by rank w)  */
+    int* err;                           /* pinned host word: non-zero after a peer wait timed out                      */
+} clipk_peer;
+
+typedef struct clipk_step {
+    int rows, cols, d;                  /* local rows b, global columns N = world * b, embedding width                 */
+    int src_dtype;                      /* CLIPK_BF16 or CLIPK_F32: dtype of image / text                              */
+    int normalize;                      /* 1: rows are L2-normalised first (F.normalize, open_clip/model.py:216,231)   */
+    float eps;
+    const void* image; const void* text;            /* this rank's [rows, d] inputs                                   */
+    long long ld_image, ld_text;
+    const float* logit_scale;           /* device scalar                                                               */
+    float loss_div;                     /* loss = (CE sums) / loss_div: 2b (single, local) or 2N (global, then summed  */
+                                        /* over the ranks by the caller)                                               */
+    float grad_coef;                    /* feature gradients = grad_out * grad_coef * d(CE sums): 1/2b or 1/2N         */
+    /* buffers that live from the forward to the backward (caller-allocated, one set per call) */
+    void* x_op;                         /* [rows, d] bf16 image operand; == image when nothing has to be produced      */
+    void* y_all;                        /* [cols, d] bf16 gathered text operand; == text under the same condition      */
+    float* inv_x; float* inv_y;         /* [rows] 1 / max(|row|, eps)  (normalize only)                                */
+    float* stats;                       /* [world][CLIPK_STAT_WORDS]                                                   */
+    float* lse_row; float* lse_col;     /* [rows], [cols]                                                              */
+    float* scal;                        /* 16 floats: [0..3] CE / dscale sums, [4] loss, [5] s * dloss/ds, [8..9] LSE   */
+                                        /* min / max (ints)                                                            */
+    /* backward only */
+    const float* grad_out;              /* device scalar                                                               */
+    void* d_image; void* d_text;        /* [rows, d] in out_dtype (NULL = not wanted)                                  */
+    float* d_scale;                     /* device scalar (NULL = not wanted)                                           */
+    int out_dtype;                      /* CLIPK_BF16 or CLIPK_F32                                                     */
+    const clipk_peer* peer;             /* NULL when world == 1                                                        */
+    void* workspace; size_t workspace_bytes;        /* scratch, may be shared by all calls of one shape               */
+    void* stream;
+} clipk_step;
+size_t clipk_step_workspace_bytes(const clipk_step* step);
+int clipk_step_forward(const clipk_step* step);
+int clipk_step_backward(const clipk_step* step);
 
 /* ---- opt-in: the L2 normalisation in front of the loss ---------------------------------------
  * The reference normalises in the model, not in the loss (F.normalize, open_clip/model.py:216,231,277,281); these two
@@ -177,9 +240,14 @@ int clipk_normalize_bwd(const void* g, long long ldg, const void* y, long long l
 /* dst[i] = (dtype) src[i]; the fp32 gradient accumulators are returned in the dtype of the inputs. */
 int clipk_cast(const float* src, void* dst, long long n, int dtype, void* stream);
 
-/* Experiments only: a device buffer of 3 * 512 int64 that CTA 0 of every following launch fills with clock64
- * stamps of its producer / MMA / epilogue roles ([role][stamp]); NULL switches it off (the default). */
-int clipk_debug_set_trace(long long* device_buffer);
+/* Measurement hooks (bench.py).  clipk_bwd_panel: extents of the softmax-gradient panel clipk_bwd uses for this block
+ * (one recompute launch + one gradient-GEMM launch per panel).  clipk_profile_begin / _end: while a profile runs every
+ * kernel launch of this library is followed by an event on its stream; _end synchronises and writes
+ * "kernel:launches:milliseconds;" per kernel name into `out` (time between consecutive events = the kernel launched in
+ * between, on one stream).  Not thread-safe; leave it off in production. */
+int clipk_bwd_panel(int rows, int cols, int d, long long* panel_rows, long long* panel_cols);
+int clipk_profile_begin(void* stream);
+int clipk_profile_end(char* out, size_t out_bytes);
 
 /* Test hook: dumps the register <-> (lane, column) mapping of tcgen05.ld.16x256b, which the single-sweep forward relies
  * on: out (8 * 32 * 16 ints) receives, for warp w, 16-lane half h, thread t, register k, the value lane * 1000 + column

@@ -40,18 +40,51 @@ PROTOTYPES = {
     "clipk_bwd_peer": (_i, [_vp, _vp, _i, _i, _i, _ll, _ll, _i, _vp, _vp, _vp, _vp, _ll, _ll, _i, _vp, _vp,
                             _vp, _ll, _vp, _vp, _f, _f, _vp, _vp, ctypes.POINTER(ctypes.c_void_p), _i, _i, _vp, _sz, _vp]),
     "clipk_reduce_slots": (_i, [_vp, _ll, _i, _vp, _i, _vp]),
-    "clipk_peer_gather": (_i, [ctypes.POINTER(ctypes.c_void_p), _vp, _ll, _i, _vp]),
-    "clipk_peer_barrier": (_i, [ctypes.POINTER(ctypes.c_void_p), _i, _i, ctypes.c_uint, _vp]),
+    "clipk_peer_barrier": (_i, [ctypes.POINTER(ctypes.c_void_p), _i, _i, ctypes.c_uint, _vp, _vp]),
     "clipk_normalize_fwd": (_i, [_vp, _i, _ll, _ll, _ll, _vp, _ll, _vp, _f, _vp]),
     "clipk_normalize_bwd": (_i, [_vp, _ll, _vp, _ll, _vp, _i, _ll, _ll, _vp, _ll, _f, _vp]),
     "clipk_cast": (_i, [_vp, _vp, _ll, _i, _vp]),
-    "clipk_debug_set_trace": (_i, [_vp]),
     "clipk_debug_tmem_layout": (_i, [_vp, _vp]),
     "clipk_rank_count": (_i, [_vp, _i, _i, _ll, _vp, _ll, _ll, _vp, _vp, _vp]),
     "clipk_distill_cross": (_i, [_vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp]),
     "clipk_distill_grad": (_i, [_vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _ll, _vp]),
     "clipk_gemm16": (_i, [_vp, _vp, _vp, _i, _i, _i, _ll, _ll, _ll, _i, _i, _i, _i, _vp]),
 }
+
+
+MAX_PEERS = 8
+STAT_WORDS = 8
+
+
+class Peer(ctypes.Structure):
+    """struct clipk_peer (include/clipk.h)."""
+    _fields_ = [("world", _i), ("rank", _i),
+                ("text_src", _vp * MAX_PEERS), ("stats_src", _vp * MAX_PEERS), ("col_src", _vp * MAX_PEERS),
+                ("grad_slot", _vp * MAX_PEERS), ("flags_gather", _vp * MAX_PEERS), ("flags_stats", _vp * MAX_PEERS),
+                ("flags_grad", _vp * MAX_PEERS),
+                ("epoch_gather", ctypes.c_uint), ("epoch_stats", ctypes.c_uint), ("epoch_grad", ctypes.c_uint),
+                ("my_slots", _vp), ("err", _vp)]
+
+
+class Step(ctypes.Structure):
+    """struct clipk_step (include/clipk.h)."""
+    _fields_ = [("rows", _i), ("cols", _i), ("d", _i), ("src_dtype", _i), ("normalize", _i), ("eps", _f),
+                ("image", _vp), ("text", _vp), ("ld_image", _ll), ("ld_text", _ll), ("logit_scale", _vp),
+                ("loss_div", _f), ("grad_coef", _f),
+                ("x_op", _vp), ("y_all", _vp), ("inv_x", _vp), ("inv_y", _vp), ("stats", _vp), ("lse_row", _vp),
+                ("lse_col", _vp), ("scal", _vp),
+                ("grad_out", _vp), ("d_image", _vp), ("d_text", _vp), ("d_scale", _vp), ("out_dtype", _i),
+                ("peer", ctypes.POINTER(Peer)), ("workspace", _vp), ("workspace_bytes", _sz), ("stream", _vp)]
+
+
+PROTOTYPES.update({
+    "clipk_bwd_panel": (_i, [_i, _i, _i, ctypes.POINTER(_ll), ctypes.POINTER(_ll)]),
+    "clipk_profile_begin": (_i, [_vp]),
+    "clipk_profile_end": (_i, [ctypes.c_char_p, _sz]),
+    "clipk_step_workspace_bytes": (_sz, [ctypes.POINTER(Step)]),
+    "clipk_step_forward": (_i, [ctypes.POINTER(Step)]),
+    "clipk_step_backward": (_i, [ctypes.POINTER(Step)]),
+})
 
 
 class ClipkError(RuntimeError):

@@ -133,6 +133,11 @@ class ClipLoss(nn.Module):
         return per_image, per_text
 
     def forward(self, image_features, text_features, logit_scale, output_dict=False):
+        if self.cache_labels:
+            # the fused kernels index the positives themselves; the label cache is kept in the state the reference's
+            # forward leaves it in (loss.py:131 calls get_ground_truth on every step)
+            n = image_features.shape[0]
+            self.get_ground_truth(image_features.device, n if (self.local_loss or self.world_size == 1) else n * self.world_size)
         loss = fused_clip_loss(image_features, text_features, logit_scale, self.local_loss, self.gather_with_grad,
                                self.rank, self.world_size, self.group)
         return {"contrastive_loss": loss} if output_dict else loss
@@ -157,9 +162,10 @@ class CoCaLoss(ClipLoss):
 
 class DistillClipLoss(ClipLoss):
     """Contrastive loss of the student plus the cross-entropy of the student's softmax against a teacher's
-    (reference loss.py:186-221).  Default: the reference's formula on materialised logits (get_logits), parity-pinned
-    by tests/golden/shells.  With CLIPK_FUSED_DISTILL=1, single-process bf16 calls take the fused contrastive loss and
-    the panel-based distillation term of clipk/distill.py instead (no N x N matrices; GPU validation pending)."""
+    (reference loss.py:186-221).  Single-process calls with bf16 operands (bf16 features, or fp32 under bf16 autocast)
+    take the fused contrastive loss and the panel-based distillation term of clipk/distill.py: no N x N matrix is ever
+    held (tests/test_distill_gpu.py; CLIPK_FUSED_DISTILL=0 switches it off).  Everything else evaluates the reference's
+    formula on materialised logits (get_logits), parity-pinned by tests/golden/shells."""
 
     def dist_loss(self, teacher_logits, student_logits):
         # -sum_j p_t(j) * log_softmax(student)(j) = lse(student) - sum_j p_t(j) * student(j), since sum_j p_t(j) = 1
@@ -168,7 +174,7 @@ class DistillClipLoss(ClipLoss):
 
     def forward(self, image_features, text_features, logit_scale, dist_image_features, dist_text_features,
                 dist_logit_scale, output_dict=False):
-        if os.environ.get("CLIPK_FUSED_DISTILL") == "1" and distill.applicable(
+        if os.environ.get("CLIPK_FUSED_DISTILL", "1") != "0" and distill.applicable(
                 image_features, text_features, dist_image_features, dist_text_features, self.world_size):
             contrastive_loss = fused_clip_loss(image_features, text_features, logit_scale)
             distill_loss = distill.fused_distill_term(image_features, text_features, logit_scale,

@@ -36,9 +36,33 @@ def _top1_text_accuracy(image_features, text_features, logit_scale):
         return (pos >= col[0] - 1e-5 * (1.0 + col[0].abs())).float().mean()
 
 
+def _megatron_data_parallel_group():
+    """Megatron's data-parallel group when Megatron is importable and initialised (megatron/utils.py:96-105 averages over
+    exactly this group), else None."""
+    for modname in ("megatron.core.mpu", "megatron.core.parallel_state", "megatron.mpu"):
+        try:
+            mod = __import__(modname, fromlist=["get_data_parallel_group"])
+            return mod.get_data_parallel_group()
+        except Exception:       # not installed, or model parallelism not initialised
+            continue
+    return None
+
+
 def make_loss_func(logit_scale=1.0, data_parallel=False, group=None, with_accuracy=True, cast_to_float=True):
-    """Returns loss_func(text_output, image_output[, logit_scale]) -> (loss, {"loss": avg, "accuracy": avg})."""
-    state = {"mod": None}
+    """Returns loss_func(text_output, image_output[, logit_scale]) -> (loss, {"loss": avg, "accuracy": avg}).
+
+    `group` is the data-parallel group the loss / accuracy are averaged over (and, with data_parallel=True, the features
+    gathered over).  When it is None the adapter asks Megatron for `mpu.get_data_parallel_group()` - what the reference
+    averages over - and only falls back to WORLD when Megatron is not there (open_clip-style pure data parallelism).
+    Ranks outside the group (other pipeline stages) simply never call loss_func: no collective here spans WORLD unless
+    WORLD is the data-parallel group."""
+    state = {"mod": None, "group": group, "resolved": group is not None}
+
+    def dp_group():
+        if not state["resolved"]:
+            state["group"] = _megatron_data_parallel_group()     # None = WORLD
+            state["resolved"] = True
+        return state["group"]
 
     def loss_func(text_output: torch.Tensor, image_output: torch.Tensor, scale=None):
         text_features, image_features = text_output.contiguous(), image_output.contiguous()
@@ -47,10 +71,12 @@ def make_loss_func(logit_scale=1.0, data_parallel=False, group=None, with_accura
         s = logit_scale if scale is None else scale
         if not isinstance(s, torch.Tensor):
             s = torch.tensor(float(s), dtype=torch.float32, device=image_features.device)
+        distributed = dist.is_available() and dist.is_initialized()
+        grp = dp_group() if distributed else None
         if state["mod"] is None:
-            if data_parallel and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            if data_parallel and distributed and dist.get_world_size(grp) > 1:
                 state["mod"] = ClipLoss(local_loss=True, gather_with_grad=True,
-                                        cache_labels=True).set_process_group(group)
+                                        cache_labels=True).set_process_group(grp)
             else:
                 state["mod"] = ClipLoss(cache_labels=True)
         total_loss = state["mod"](image_features, text_features, s)
@@ -58,9 +84,9 @@ def make_loss_func(logit_scale=1.0, data_parallel=False, group=None, with_accura
         if with_accuracy:
             stats.append(_top1_text_accuracy(image_features, text_features, s).reshape(1))
         averaged = torch.cat(stats)
-        if dist.is_available() and dist.is_initialized():
-            dist.all_reduce(averaged, group=group)
-            averaged = averaged / dist.get_world_size(group)
+        if distributed:
+            dist.all_reduce(averaged, group=grp)
+            averaged = averaged / dist.get_world_size(grp)
         out = {"loss": averaged[0]}
         if with_accuracy:
             out["accuracy"] = averaged[1]

@@ -143,7 +143,7 @@ class CudaBackend:
                                            X.inv_ptr(), Y.inv_ptr(), scale.data_ptr(), diag_offset,
                                            row_stats.data_ptr(), pos.data_ptr(), col_out.data_ptr(), _ptr(amax),
                                            1 if exact else 0, ws.data_ptr(), nbytes, self._stream()), "clipk_fwd_both")
-        if want_amax and not os.environ.get("CLIPK_DBG"):
+        if want_amax:
             X.amax, Y.amax = amax[0:1], amax[1:2]
         return row_stats, pos, col_out
 
@@ -179,40 +179,51 @@ class CudaBackend:
                    "clipk_bwd")
         return dX, dY
 
-    def bwd_peer(self, X: Operand, Y: Operand, Xg: Operand, Yg: Operand, scale, diag_offset, lse_row, lse_col, alpha,
-                 beta, gscale, peer):
-        """clipk_bwd with the dY tiles written straight into this rank's slot at their owners (peer-mapped memory,
-        over NVLink): the reduce-scatter of the text gradient is fused into the gradient GEMM.  Returns dX only."""
-        dev = X.data.device
-        rows, cols, d = X.rows, Y.rows, X.d
-        dX = torch.empty(rows, d, dtype=torch.float32, device=dev)
-        nbytes = self.lib.clipk_bwd_workspace_bytes(rows, cols, d, Xg.dtype)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        _lib.check(self.lib.clipk_bwd_peer(X.data.data_ptr(), Y.data.data_ptr(), rows, cols, d, X.ld, Y.ld, X.dtype,
-                                           X.inv_ptr(), Y.inv_ptr(), Xg.data.data_ptr(), Yg.data.data_ptr(), Xg.ld,
-                                           Yg.ld, Xg.dtype, Xg.inv_ptr(), Yg.inv_ptr(), scale.data_ptr(), diag_offset,
-                                           lse_row.data_ptr(), lse_col.data_ptr(), float(alpha), float(beta),
-                                           gscale.data_ptr(), dX.data_ptr(), peer.slot_ptrs, peer.world,
-                                           peer.rows_per_rank, ws.data_ptr(), nbytes, self._stream()), "clipk_bwd_peer")
-        return dX
+    # ---- the whole step in two enqueues (clipk_step_forward / clipk_step_backward)
+    def _c_step(self, st: "StepDesc"):
+        c = st.cstruct
+        if c is None:
+            c = st.cstruct = _lib.Step()
+            c.rows, c.cols, c.d = st.rows, st.cols, st.d
+            c.src_dtype = _lib.BF16 if st.image.dtype == torch.bfloat16 else _lib.F32
+            c.normalize, c.eps = int(st.normalize), float(st.eps)
+            c.image, c.text = st.image.data_ptr(), st.text.data_ptr()
+            c.ld_image, c.ld_text = st.image.stride(0), st.text.stride(0)
+            c.logit_scale = st.scale.data_ptr()
+            c.loss_div, c.grad_coef = float(st.loss_div), float(st.grad_coef)
+            c.x_op, c.y_all = st.x_op.data_ptr(), st.y_all.data_ptr()
+            c.inv_x, c.inv_y = _ptr(st.inv_x), _ptr(st.inv_y)
+            c.stats, c.lse_row, c.lse_col, c.scal = (st.stats.data_ptr(), st.lse_row.data_ptr(), st.lse_col.data_ptr(),
+                                                     st.scal.data_ptr())
+            c.workspace, c.workspace_bytes = st.ws.data_ptr(), st.ws.numel()
+        c.stream = self._stream()
+        return c
 
-    def reduce_slots(self, peer, dtype):
-        """Sum of the `world` slots of this rank's text gradient, in the dtype of the inputs."""
-        return self.sum_slots(peer.slots, dtype)
+    def step_workspace_bytes(self, rows, cols, d, world):
+        c = _lib.Step()
+        c.rows, c.cols, c.d = rows, cols, d
+        peer = _lib.Peer()
+        peer.world = world
+        if world > 1:
+            c.peer = ctypes.pointer(peer)
+        return int(self.lib.clipk_step_workspace_bytes(ctypes.byref(c)))
 
-    def sum_slots(self, slots: torch.Tensor, dtype):
-        """slots [world, b, d] fp32 -> their sum over the first axis, cast to `dtype` (bf16 or fp32), in one pass."""
-        world, b, d = slots.shape
-        out = torch.empty(b, d, dtype=dtype, device=slots.device)
-        _lib.check(self.lib.clipk_reduce_slots(slots.data_ptr(), b * d, world, out.data_ptr(),
-                                               _lib.BF16 if dtype == torch.bfloat16 else _lib.F32, self._stream()),
-                   "clipk_reduce_slots")
-        return out
+    def step_forward(self, st: "StepDesc"):
+        c = self._c_step(st)
+        if st.peer is not None:
+            st.cpeer = st.peer.begin_forward()
+            c.peer = ctypes.pointer(st.cpeer)
+        _lib.check(self.lib.clipk_step_forward(ctypes.byref(c)), "clipk_step_forward")
 
-    def peer_barrier(self, peer):
-        peer.epoch += 1
-        _lib.check(self.lib.clipk_peer_barrier(peer.flag_ptrs, peer.rank, peer.world, peer.epoch, self._stream()),
-                   "clipk_peer_barrier")
+    def step_backward(self, st: "StepDesc"):
+        c = self._c_step(st)
+        c.grad_out = st.grad_out.data_ptr()
+        c.d_image, c.d_text, c.d_scale = _ptr(st.d_image), _ptr(st.d_text), _ptr(st.d_scale)
+        c.out_dtype = _lib.BF16 if st.out_dtype == torch.bfloat16 else _lib.F32
+        if st.peer is not None:
+            st.cpeer = st.peer.begin_backward()
+            c.peer = ctypes.pointer(st.cpeer)
+        _lib.check(self.lib.clipk_step_backward(ctypes.byref(c)), "clipk_step_backward")
 
     def normalize_fwd(self, x: torch.Tensor, eps: float):
         """y = x / max(|x|, eps) row-wise (same dtype), and the fp32 factors 1 / max(|x|, eps)."""
@@ -324,117 +335,162 @@ def gpu_launches() -> int:
     return 0 if _CUDA_BACKEND is None else int(_CUDA_BACKEND.lib.clipk_launch_count())
 
 
-# ----------------------------------------------------------------------------------------------------- peer memory
-class PeerState:
-    """Symmetric (peer-mapped) buffers of one (local batch, dim, group): `world` fp32 slots [b, d] for this rank's text
-    gradient - slot w is written over NVLink by the gradient GEMM of rank w - and the flag words of the barrier."""
+# ----------------------------------------------------------------------------------------------------- the fused step
+class StepDesc:
+    """Everything one loss evaluation holds between its forward and its backward (mirrors struct clipk_step)."""
+    __slots__ = ("rows", "cols", "d", "world", "rank", "normalize", "eps", "image", "text", "scale", "loss_div",
+                 "grad_coef", "x_op", "y_all", "inv_x", "inv_y", "stats", "lse_row", "lse_col", "scal", "ws", "peer",
+                 "grad_out", "d_image", "d_text", "d_scale", "out_dtype", "cstruct", "cpeer", "group")
+
+    def __init__(self):
+        for k in self.__slots__:
+            setattr(self, k, None)
+
+
+def _align(n, a=256):
+    return (n + a - 1) // a * a
+
+
+class PeerContext:
+    """Peer-mapped (symmetric) memory of one (local batch, width, group) between the ranks of one NVLink domain.  All of
+    it is double-buffered by call parity (a buffer is rewritten two calls after it was read, see peer_allgather_kernel):
+
+      text_src  [2][b, d] bf16     this rank's text operand rows, pulled by every peer (gather_features, loss.py:20-64)
+      stats_src [2][8] fp32        its operand statistics, pulled with them
+      col_src   [2][3, N] fp32     column statistics of this rank's block, pulled by every peer
+      slots     [2][W][b, d] fp32  slot w is written over NVLink by the gradient GEMM of rank w (the reduce-scatter of
+                                   the text gradient, i.e. the backward of loss.py:50-51)
+      flags     [3][8] uint32      one epoch word per peer and purpose (gather, statistics, gradient)
+    """
 
     def __init__(self, b, d, rank, world, group, dev):
         import torch.distributed._symmetric_memory as symm     # not importable on builds without CUDA support
         pg = group if group is not None else dist.group.WORLD
-        self.slots = symm.empty(world, b, d, dtype=torch.float32, device=dev)
-        self.slots.zero_()
-        h_acc = symm.rendezvous(self.slots, pg)
-        self.flags = symm.empty(8, dtype=torch.int32, device=dev)
-        self.flags.zero_()
-        h_flags = symm.rendezvous(self.flags, pg)
-        if h_acc.rank != rank or h_acc.world_size != world:
+        N = world * b
+        sizes = [("text", 2 * _align(b * d * 2)), ("stats", 2 * 256), ("col", 2 * _align(3 * N * 4)),
+                 ("slots", 2 * world * b * d * 4), ("flags", 256)]
+        self.off, total = {}, 0
+        for name, nbytes in sizes:
+            self.off[name] = total
+            total += _align(nbytes)
+        self.buf = symm.empty(total, dtype=torch.uint8, device=dev)
+        self.buf[self.off["flags"]:self.off["flags"] + 256].zero_()
+        h = symm.rendezvous(self.buf, pg)
+        if h.rank != rank or h.world_size != world:
             raise RuntimeError("rank / world_size of the loss do not match the process group")
-        self.rank, self.world, self.rows_per_rank, self.epoch = rank, world, b, 0
-        # this rank's slot inside every owner's buffer
-        self.slot_ptrs = (ctypes.c_void_p * world)(*[int(p) + rank * b * d * 4 for p in h_acc.buffer_ptrs])
-        self.flag_ptrs = (ctypes.c_void_p * world)(*[int(p) for p in h_flags.buffer_ptrs])
-        self._handles = (h_acc, h_flags)
+        self.rank, self.world, self.b, self.d, self.N = rank, world, b, d, N
+        self.bases = [int(p) for p in h.buffer_ptrs]
+        self._handle = h
+        self.n_fwd = self.n_bwd = 0
+        # time-outs of the peer waits land here (pinned host memory, written by the kernels, read before every call)
+        self.err = torch.zeros(4, dtype=torch.int32).pin_memory()
         torch.cuda.synchronize(dev)
-        dist.barrier(group=pg)          # every rank's buffers are zero before anyone adds or signals
+        dist.barrier(group=pg)          # every rank's flags are zero before anyone signals
+
+    def _check(self):
+        code = int(self.err[0])
+        if code:
+            raise RuntimeError(f"clipk: a wait on a peer rank timed out (code {code}): a rank died or skipped a "
+                               "collective call of the loss")
+
+    def _fill(self, half_f, half_b):
+        b, d, N, W = self.b, self.d, self.N, self.world
+        p = _lib.Peer()
+        p.world, p.rank = W, self.rank
+        o = self.off
+        for r in range(W):
+            base = self.bases[r]
+            p.text_src[r] = base + o["text"] + half_f * _align(b * d * 2)
+            p.stats_src[r] = base + o["stats"] + half_f * 256
+            p.col_src[r] = base + o["col"] + half_f * _align(3 * N * 4)
+            p.grad_slot[r] = base + o["slots"] + (half_b * W + self.rank) * b * d * 4
+            p.flags_gather[r] = base + o["flags"]
+            p.flags_stats[r] = base + o["flags"] + 32
+            p.flags_grad[r] = base + o["flags"] + 64
+        p.my_slots = self.bases[self.rank] + o["slots"] + half_b * W * b * d * 4
+        p.err = self.err.data_ptr()
+        return p
+
+    def begin_forward(self):
+        self._check()
+        self.n_fwd += 1
+        p = self._fill(self.n_fwd & 1, 0)
+        p.epoch_gather = p.epoch_stats = self.n_fwd & 0xffffffff
+        return p
+
+    def begin_backward(self):
+        self._check()
+        self.n_bwd += 1
+        p = self._fill(0, self.n_bwd & 1)
+        p.epoch_grad = self.n_bwd & 0xffffffff
+        return p
 
 
-class PeerGather:
-    """Experiment (CLIPK_PEER_GATHER=1): the all-gather of the text features by pulling from symmetric memory.  Every rank
-    copies its rows into one of two symmetric source buffers (used alternately), a flag barrier makes them visible, and ONE
-    kernel reads all ranks' rows over NVLink (clipk_peer_gather).  The barrier of call k+1 also tells that every peer has
-    finished reading the buffer of call k, so it may be overwritten in call k+2."""
-
-    def __init__(self, nbytes, rank, world, group, dev):
-        import torch.distributed._symmetric_memory as symm
-        pg = group if group is not None else dist.group.WORLD
-        self.src = symm.empty(2, nbytes, dtype=torch.uint8, device=dev)
-        h_src = symm.rendezvous(self.src, pg)
-        self.flags = symm.empty(8, dtype=torch.int32, device=dev)
-        self.flags.zero_()
-        h_flags = symm.rendezvous(self.flags, pg)
-        if h_src.rank != rank or h_src.world_size != world:
-            raise RuntimeError("rank / world_size of the loss do not match the process group")
-        self.rank, self.world, self.nbytes, self.epoch, self.calls = rank, world, nbytes, 0, 0
-        self.src_ptrs = [(ctypes.c_void_p * world)(*[int(p) + half * nbytes for p in h_src.buffer_ptrs]) for half in (0, 1)]
-        self.flag_ptrs = (ctypes.c_void_p * world)(*[int(p) for p in h_flags.buffer_ptrs])
-        self._handles = (h_src, h_flags)
-        torch.cuda.synchronize(dev)
-        dist.barrier(group=pg)
-
-    def gather(self, be, x: torch.Tensor) -> torch.Tensor:
-        half = self.calls & 1
-        self.calls += 1
-        self.src[half].view(x.dtype).view(x.shape).copy_(x)
-        be.peer_barrier(self)
-        out = torch.empty((self.world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
-        _lib.check(be.lib.clipk_peer_gather(self.src_ptrs[half], out.data_ptr(), self.nbytes, self.world, be._stream()),
-                   "clipk_peer_gather")
-        return out
-
-
-_PEER_GATHERS = {}
-
-
-def _gather_text(be, x: torch.Tensor, rank, world, group):
-    """[b, d] per rank -> [world * b, d]: NCCL all_gather_into_tensor, or (CLIPK_PEER_GATHER=1, CUDA, <= 8 ranks of one
-    NVLink domain) the pull-based gather over peer memory."""
-    x = x.contiguous()
-    nbytes = x.numel() * x.element_size()
-    if os.environ.get("CLIPK_PEER_GATHER") != "1" or _TEST_BACKEND is not None or x.device.type != "cuda" or world > 8 \
-            or nbytes % 16 != 0:
-        return _all_gather_rows(x, world, group)
-    key = (nbytes, rank, world, id(group), x.device.index)
-    pgather = _PEER_GATHERS.get(key)
-    if pgather is None:
-        pgather = _PEER_GATHERS[key] = PeerGather(nbytes, rank, world, group, x.device)
-    return pgather.gather(be, x)
-
-
-_PEER_STATES = {}
+_PEER_CONTEXTS = {}
 _PEER_DISABLED = [False]
+_MAX_PEER_CONTEXTS = 4      # shapes (train batch, eval batch, ...) that get symmetric buffers; more fall back to NCCL
 
 
-def _peer_state(b, d, rank, world, group, dev):
-    """PeerState for this shape, or None when the fused path does not apply (then NCCL reduce_scatter is used)."""
-    # CLIPK_PEER: "1" always, "0" never, unset = where it was measured faster than NCCL's reduce_scatter.  Backward of
-    # one rank at N = 32768, d = 512 (ms), gradient GEMMs alone / + NCCL reduce_scatter / fused peer stores:
-    #   8 GPUs, 2 panels of 4096 x 16384 (current panel model): 0.406 / 0.549 / 0.525  -> fused on
-    #   8 GPUs, 7 panels of 4096 x 4864 (earlier):              0.43  / 0.59  / 0.71
-    #   2 GPUs (b = 16384, second row panel adds over NVLink):  1.54  / 1.58  / 1.59   -> NCCL
-    # (an all-to-all of the row chunks + one local sum instead of the reduce_scatter: 0.576 at 8 GPUs.)
-    mode = os.environ.get("CLIPK_PEER", "auto")
-    if _PEER_DISABLED[0] or mode == "0" or _TEST_BACKEND is not None or (mode != "1" and world < 8):
+def _peer_context(b, d, rank, world, group, dev):
+    """PeerContext for this shape, or None when the collectives go through NCCL instead (CLIPK_PEER=0, no symmetric
+    memory on this system, more than 8 ranks, a local batch that is not a multiple of 128)."""
+    if _PEER_DISABLED[0] or os.environ.get("CLIPK_PEER", "1") == "0" or _TEST_BACKEND is not None:
         return None
-    if dev.type != "cuda" or world < 2 or world > 8 or b % 128 != 0:
+    if dev.type != "cuda" or world < 2 or world > _lib.MAX_PEERS or b % 128 != 0:
         return None
     key = (b, d, rank, world, id(group), dev.index)
-    st = _PEER_STATES.get(key)
-    if st is None:
+    ctx = _PEER_CONTEXTS.get(key)
+    if ctx is None:
+        if len(_PEER_CONTEXTS) >= _MAX_PEER_CONTEXTS:
+            return None
         err = None
         try:
-            st = PeerState(b, d, rank, world, group, dev)
-        except Exception as e:   # no symmetric memory on this system
-            st, err = None, e
-        # all ranks take the same path: one failure sends everyone to NCCL (first use of a shape only)
-        ok = torch.tensor([0 if st is None else 1], dtype=torch.int32, device=dev)
+            import torch.distributed._symmetric_memory  # noqa: F401
+            ok_local = 1
+        except Exception as e:          # no symmetric memory in this build
+            ok_local, err = 0, e
+        # all ranks take the same path: agree BEFORE the collective allocation, so that a rank that cannot even import
+        # the module sends everyone to NCCL instead of leaving the others inside the rendezvous
+        ok = torch.tensor([ok_local], dtype=torch.int32, device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 1:
+            try:
+                ctx = PeerContext(b, d, rank, world, group, dev)
+            except Exception as e:
+                ctx, err = None, e
+            ok = torch.tensor([0 if ctx is None else 1], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
         if int(ok.item()) == 0:
-            warnings.warn(f"clipk: peer-memory reduce unavailable ({err!r}); using NCCL reduce_scatter")
+            warnings.warn(f"clipk: peer-memory collectives unavailable ({err!r}); using NCCL")
             _PEER_DISABLED[0] = True
             return None
-        _PEER_STATES[key] = st
-    return st
+        _PEER_CONTEXTS[key] = ctx
+    return ctx
+
+
+_WORKSPACES = {}
+_LAST_STEP_STATS = [None]
+
+
+def last_forward_was_single_sweep():
+    """True / False for the most recent fused-step forward of this process (None before the first one): whether the
+    kernels took the single sweep or the exact two-sweep form (decided on the device, see fwd_bound in gemm_core.cuh).
+    Synchronises; for tests and bench.py only."""
+    st = _LAST_STEP_STATS[0]
+    if st is None:
+        return None
+    return bool(st.view(-1, _lib.STAT_WORDS)[:, 5].max().item() > 0.5)
+
+
+def _step_workspace(be, rows, cols, d, world, dev):
+    """Scratch of the fused step, shared by all calls of one shape on one stream (consumed inside each enqueue)."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream if dev.type == "cuda" else 0, rows, cols, d, world)
+    ws = _WORKSPACES.get(key)
+    if ws is None:
+        if len(_WORKSPACES) >= 8:
+            _WORKSPACES.clear()
+        ws = _WORKSPACES[key] = torch.empty(be.step_workspace_bytes(rows, cols, d, world), dtype=torch.uint8, device=dev)
+    return ws
 
 
 # ----------------------------------------------------------------------------------------------------- collectives
@@ -453,23 +509,29 @@ def _reduce_scatter_rows(x: torch.Tensor, world_size: int, group=None) -> torch.
     return out
 
 
-def _reduce_scatter_rows_a2a(be, x: torch.Tensor, world_size: int, out_dtype, group=None) -> torch.Tensor:
-    """Same result as _reduce_scatter_rows followed by a cast, as an all-to-all of the W row chunks (every rank sends
-    chunk o straight to rank o: full NVSwitch bisection, no ring) and ONE local pass that sums the W received slots and
-    casts them (clipk_reduce_slots).  Measured at 8 x B200 on the [32768, 512] fp32 gradient: see profiles/README.md."""
-    n = x.shape[0] // world_size
-    recv = torch.empty((world_size, n) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
-    dist.all_to_all_single(recv, x.contiguous(), group=group)
-    return be.sum_slots(recv, out_dtype)
-
-
 # ----------------------------------------------------------------------------------------------------- autograd
+def _autocast_bf16(dev):
+    return dev.type == "cuda" and torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16
+
+
+def _row_layout_ok(x):
+    """rows 16-byte aligned with unit inner stride: what prep_kernel reads in place"""
+    es = x.element_size()
+    return x.stride(1) == 1 and (x.stride(0) * es) % 16 == 0 and x.stride(0) >= x.shape[1] and x.data_ptr() % 16 == 0
+
+
 class FusedClipLoss(torch.autograd.Function):
-    """loss = ClipLoss(local_loss, gather_with_grad, rank, world_size).forward(I, T, s)   (loss.py:123-140)."""
+    """loss = ClipLoss(local_loss, gather_with_grad, rank, world_size).forward(I, T, s)   (loss.py:123-140).
+
+    Two routes.  The fused step (clipk_step_forward / clipk_step_backward: one enqueue per pass, collectives over peer
+    memory) takes bf16 operands - bf16 features, or fp32 features under bf16 autocast - of a width that is a multiple
+    of 64, on one GPU or on 2..8 ranks of one NVLink domain.  Everything else (fp32 / fp16 arithmetic, other widths,
+    more ranks, no symmetric memory, local_loss without gather_with_grad on several ranks) takes the general route:
+    the individual kernel entries with NCCL collectives between them."""
 
     @staticmethod
     def forward(ctx, image_features, text_features, logit_scale, local_loss, gather_with_grad, rank, world_size,
-                group):
+                group, normalize=False, eps=1e-12):
         be = _backend()
         if image_features.dim() != 2 or image_features.shape != text_features.shape:
             raise ValueError("image_features and text_features must both be [batch, dim]")
@@ -483,11 +545,67 @@ class FusedClipLoss(torch.autograd.Function):
         if in_dtype not in _FEATURE_DTYPES:
             raise TypeError(f"clipk: unsupported feature dtype {in_dtype} (bf16, fp16 and fp32 only)")
         scale = logit_scale.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+        ctx.scale_is_param = isinstance(logit_scale, torch.Tensor)
+        ctx.scale_dtype = logit_scale.dtype
+        ctx.scale_shape = logit_scale.shape
+        want_feat = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
 
+        # ---- route 1: the fused step
+        bf16_operands = in_dtype == torch.bfloat16 or (in_dtype == torch.float32 and _autocast_bf16(dev))
+        fused = bf16_operands and d_in % _K_BLOCK == 0 and (dev.type == "cuda" or _TEST_BACKEND is not None) and \
+            hasattr(be, "step_forward") and not (W > 1 and local_loss and not gather_with_grad)
+        peer = None
+        if fused and W > 1:
+            peer = _TEST_BACKEND.peer_context(b, d_in, rank, W, group) if _TEST_BACKEND is not None else \
+                _peer_context(b, d_in, rank, W, group, dev)
+            fused = peer is not None
+        if fused:
+            img, txt = image_features.detach(), text_features.detach()
+            if not _row_layout_ok(img):
+                img = img.contiguous()
+            if not _row_layout_ok(txt):
+                txt = txt.contiguous()
+            st = StepDesc()
+            st.rows, st.cols, st.d, st.world, st.rank, st.group = b, N, d_in, W, rank, group
+            st.normalize, st.eps = bool(normalize), float(eps)
+            st.image, st.text, st.scale = img, txt, scale
+            local = (W == 1) or local_loss
+            st.loss_div = 2.0 * b if local else 2.0 * N
+            # c of SURVEY App. A: 1/(2b) for W=1, local modes and global+gather_with_grad; 1/(2N) otherwise
+            st.grad_coef = 1.0 / (2.0 * b) if (local or gather_with_grad) else 1.0 / (2.0 * N)
+            produced = st.normalize or in_dtype != torch.bfloat16
+            # one fp32 allocation for everything the backward reads: lse_row | lse_col | scalars | statistics | inv norms
+            n_f = b + N + 16 + _lib.STAT_WORDS * W + (2 * b if st.normalize else 0)
+            fbuf = torch.empty(n_f, dtype=torch.float32, device=dev)
+            st.lse_row, st.lse_col = fbuf[:b], fbuf[b:b + N]
+            st.scal = fbuf[b + N:b + N + 16]
+            st.stats = fbuf[b + N + 16:b + N + 16 + _lib.STAT_WORDS * W]
+            if st.normalize:
+                st.inv_x, st.inv_y = fbuf[n_f - 2 * b:n_f - b], fbuf[n_f - b:]
+            st.x_op = torch.empty(b, d_in, dtype=torch.bfloat16, device=dev) if produced else img
+            st.y_all = torch.empty(N, d_in, dtype=torch.bfloat16, device=dev) if (produced or W > 1) else txt
+            st.ws = _step_workspace(be, b, N, d_in, W, dev)
+            st.peer = peer
+            be.step_forward(st)
+            _LAST_STEP_STATS[0] = st.stats       # tests / bench: word 5 of a rank's row tells which forward ran
+            pair = st.scal[4:6]
+            if W > 1 and not local_loss:
+                # the global (local_loss=False) loss is the same N x N problem on every rank: sum of the ranks' parts
+                dist.all_reduce(pair, op=dist.ReduceOp.SUM, group=group)
+            ctx.step = st
+            ctx.in_dtype = in_dtype
+            # the inputs themselves are saved so that autograd notices an in-place change before the backward reads them
+            ctx.save_for_backward(image_features, text_features)
+            ctx.fused = True
+            return pair[0].clone()
+
+        # ---- route 2: individual entries + NCCL
+        ctx.fused = False
+        if normalize:
+            raise RuntimeError("clipk: internal error - the general route does not normalise (see fused_normalize_clip_loss)")
         # under torch.autocast the reference's matmuls run in the autocast dtype
         feats_i, feats_t = image_features.detach(), text_features.detach()
-        if in_dtype == torch.float32 and dev.type == "cuda" and torch.is_autocast_enabled("cuda") and \
-                torch.get_autocast_dtype("cuda") == torch.bfloat16:
+        if in_dtype == torch.float32 and _autocast_bf16(dev):
             feats_i, feats_t = feats_i.to(torch.bfloat16), feats_t.to(torch.bfloat16)
         if in_dtype == torch.float16:
             # fp16 features (open_clip --precision fp16 / amp): every fp16 value is an fp32 value, so they take the
@@ -500,25 +618,15 @@ class FusedClipLoss(torch.autograd.Function):
             feats_i = torch.nn.functional.pad(feats_i, (0, d - d_in))
             feats_t = torch.nn.functional.pad(feats_t, (0, d - d_in))
 
-        t_all = _gather_text(be, feats_t, rank, W, group) if W > 1 else feats_t
+        t_all = _all_gather_rows(feats_t, W, group) if W > 1 else feats_t
         X = be.prepare(feats_i)
         Y = be.prepare(t_all)
         off = rank * b if W > 1 else 0
 
         parts = torch.empty(1, 3, N, dtype=torch.float32, device=dev)        # (max, sum, dot) of every column
         row_stats, pos, _ = be.fwd_both(X, Y, scale, off, col_out=parts[0])
-        grad_operands = None
         if W > 1:
-            if os.environ.get("CLIPK_OVERLAP") == "1" and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
-                # experiment: the backward's fp16 copies of the features are made now, on the compute stream, while
-                # NCCL gathers the column statistics on its own stream
-                gathered = torch.empty((W,) + tuple(parts.shape[1:]), dtype=parts.dtype, device=dev)
-                work = dist.all_gather_into_tensor(gathered, parts, group=group, async_op=True)
-                grad_operands = (be.prepare_grad(X), be.prepare_grad(Y))
-                work.wait()
-                parts = gathered
-            else:
-                parts = _all_gather_rows(parts, W, group)                    # [W, 3, N]
+            parts = _all_gather_rows(parts, W, group)                        # [W, 3, N]
         lse_row, lse_col, sums = be.finalize(row_stats, pos, parts, off)
 
         # sums[0:2] -> loss, sums[2:4] -> s * dloss/ds; the global (local_loss=False) loss is the same N x N problem
@@ -532,29 +640,44 @@ class FusedClipLoss(torch.autograd.Function):
             pair = pair / (2.0 * b)
         loss = pair[0]
 
-        ctx.save_for_backward(scale, lse_row, lse_col, pair)
+        ctx.save_for_backward(image_features, text_features, scale, lse_row, lse_col, pair)
         ctx.operands = (X, Y)
-        ctx.grad_operands = grad_operands
         ctx.cfg = (b, d, W, rank, off, bool(local_loss), bool(gather_with_grad), group, in_dtype, d_in)
-        ctx.scale_is_param = isinstance(logit_scale, torch.Tensor)
-        ctx.scale_dtype = logit_scale.dtype
-        ctx.scale_shape = logit_scale.shape
         return loss.clone()
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
         be = _backend()
-        scale, lse_row, lse_col, pair = ctx.saved_tensors
+        go = grad_out.detach().to(torch.float32).reshape(1)
+        if ctx.fused:
+            _ = ctx.saved_tensors            # raises if the features were modified in place since the forward
+            st = ctx.step
+            dev = st.scale.device
+            want_feat = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+            want_scale = ctx.scale_is_param and ctx.needs_input_grad[2]
+            st.grad_out = go.contiguous()
+            st.out_dtype = torch.bfloat16 if ctx.in_dtype == torch.bfloat16 else torch.float32
+            if want_feat:
+                st.d_image = torch.empty(st.rows, st.d, dtype=st.out_dtype, device=dev)
+                st.d_text = torch.empty(st.rows, st.d, dtype=st.out_dtype, device=dev)
+            st.d_scale = torch.empty(1, dtype=torch.float32, device=dev) if want_scale else None
+            if want_feat or want_scale or st.peer is not None:      # with peers every rank takes part in the barrier
+                be.step_backward(st)
+            d_scale = st.d_scale.reshape(ctx.scale_shape).to(ctx.scale_dtype) if want_scale else None
+            d_image, d_text = st.d_image, st.d_text
+            ctx.step = None
+            return d_image, d_text, d_scale, None, None, None, None, None, None, None
+
+        _, _, scale, lse_row, lse_col, pair = ctx.saved_tensors
         X, Y = ctx.operands
         b, d, W, rank, off, local_loss, gwg, group, in_dtype, d_in = ctx.cfg
-        # dtype the kernels produce directly (clipk_cast / clipk_reduce_slots write bf16 or fp32)
+        # dtype the kernels produce directly (clipk_cast writes bf16 or fp32)
         k_dtype = torch.bfloat16 if in_dtype == torch.bfloat16 else torch.float32
         N = W * b
-        go = grad_out.detach().to(torch.float32).reshape(1)
         d_image = d_text = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
-            Xg, Yg = ctx.grad_operands or (be.prepare_grad(X), be.prepare_grad(Y))
+            Xg, Yg = be.prepare_grad(X), be.prepare_grad(Y)
             local = (W == 1) or local_loss
             # c of SURVEY App. A: 1/(2b) for W=1, both local modes and global+gather_with_grad; 1/(2N) otherwise
             c_feat = 1.0 / (2.0 * b) if (local or gwg) else 1.0 / (2.0 * N)
@@ -566,24 +689,13 @@ class FusedClipLoss(torch.autograd.Function):
                 _, dY = be.bwd(X, Y, Xg, Yg, scale, off, lse_row, lse_col, 0.0, 1.0, gscale, False, True)
                 dT = _reduce_scatter_rows(dY, W, group)
             else:
-                peer = _peer_state(b, d, rank, W, group, scale.device) if W > 1 else None
-                if peer is not None:
-                    # gradient GEMM fused with the reduce-scatter: dY tiles go straight into this rank's slot at their owners
-                    be.peer_barrier(peer)            # every owner is done reading the previous contents of its slots
-                    dX = be.bwd_peer(X, Y, Xg, Yg, scale, off, lse_row, lse_col, 1.0, 1.0, gscale, peer)
-                    be.peer_barrier(peer)            # every rank's tiles have landed
-                    d_text = be.reduce_slots(peer, k_dtype)
-                    dT = None
-                else:
-                    dX, dY = be.bwd(X, Y, Xg, Yg, scale, off, lse_row, lse_col, 1.0, 1.0, gscale, True, True)
-                    dT = _reduce_scatter_rows(dY, W, group) if W > 1 else dY
+                dX, dY = be.bwd(X, Y, Xg, Yg, scale, off, lse_row, lse_col, 1.0, 1.0, gscale, True, True)
+                dT = _reduce_scatter_rows(dY, W, group) if W > 1 else dY
             if d != d_in:                         # drop the gradient columns of the zero padding
                 dX = dX[:, :d_in].contiguous()
-                dT = dT if dT is None else dT[:, :d_in].contiguous()
-                d_text = d_text if d_text is None else d_text[:, :d_in].contiguous()
+                dT = dT[:, :d_in].contiguous()
             d_image = be.cast(dX, k_dtype)
-            if dT is not None:
-                d_text = be.cast(dT, k_dtype)
+            d_text = be.cast(dT, k_dtype)
             if k_dtype != in_dtype:               # fp16 features
                 d_image, d_text = d_image.to(in_dtype), d_text.to(in_dtype)
 
@@ -591,11 +703,11 @@ class FusedClipLoss(torch.autograd.Function):
         if ctx.scale_is_param and ctx.needs_input_grad[2]:
             # pair[1] = s * dloss/ds, already normalised (and all-reduced in global mode) by the forward
             d_scale = (pair[1] * go[0] / scale[0]).reshape(ctx.scale_shape).to(ctx.scale_dtype)
-        return d_image, d_text, d_scale, None, None, None, None, None
+        return d_image, d_text, d_scale, None, None, None, None, None, None, None
 
 
 def fused_clip_loss(image_features, text_features, logit_scale, local_loss=False, gather_with_grad=False, rank=0,
-                    world_size=1, group=None):
+                    world_size=1, group=None, normalize=False, eps=1e-12):
     if not isinstance(logit_scale, torch.Tensor):
         logit_scale = torch.tensor(float(logit_scale), dtype=torch.float32, device=image_features.device)
     if image_features.dim() == 2 and image_features.shape[0] == 0 and image_features.shape == text_features.shape:
@@ -603,7 +715,7 @@ def fused_clip_loss(image_features, text_features, logit_scale, local_loss=False
         # (loss.py:135-138); nothing to launch
         return (image_features.sum() + text_features.sum()).float() * logit_scale.float() * float("nan")
     return FusedClipLoss.apply(image_features, text_features, logit_scale, local_loss, gather_with_grad, rank,
-                               world_size, group)
+                               world_size, group, normalize, eps)
 
 
 # ----------------------------------------------------------------------------------------------------- opt-in: normalise + loss
@@ -624,11 +736,28 @@ class _Normalize(torch.autograd.Function):
         return _backend().normalize_bwd(g.to(y.dtype), y, inv, ctx.eps), None
 
 
+def _fused_step_applies(x, world_size, local_loss, gather_with_grad):
+    dev = x.device
+    return x.dim() == 2 and (x.dtype == torch.bfloat16 or (x.dtype == torch.float32 and _autocast_bf16(dev))) and \
+        x.shape[1] % _K_BLOCK == 0 and x.shape[0] > 0 and (dev.type == "cuda" or _TEST_BACKEND is not None) and \
+        (world_size == 1 or (not (local_loss and not gather_with_grad) and world_size <= _lib.MAX_PEERS and
+                             x.shape[0] % 128 == 0 and os.environ.get("CLIPK_PEER", "1") != "0" and not _PEER_DISABLED[0]))
+
+
 def fused_normalize_clip_loss(raw_image_features, raw_text_features, logit_scale, local_loss=False,
                               gather_with_grad=False, rank=0, world_size=1, group=None, eps=1e-12):
     """ClipLoss of the L2-normalised embeddings, taking the RAW tower outputs: what `model.py:216,231` followed by
     `loss.py:123-140` computes, with gradients with respect to the raw embeddings.  Opt-in - the drop-in ClipLoss does
-    not normalise, exactly like the reference's (point 2)."""
+    not normalise, exactly like the reference's (point 2).
+
+    With bf16 operands the normalisation lives in the load path of the step: the pass that produces the operands
+    (prep_kernel) normalises, rounds to bf16 and takes the statistics in one sweep over the rows, and the pass that casts
+    the gradients (finish_grad_kernel) applies the Jacobian - no standalone normalise / cast / norm kernels.  Other
+    dtypes compose the row-wise kernels of clipk_normalize_fwd / _bwd with the loss."""
+    if _fused_step_applies(raw_image_features, world_size, local_loss, gather_with_grad) and \
+            raw_image_features.shape == raw_text_features.shape and raw_image_features.dtype == raw_text_features.dtype:
+        return fused_clip_loss(raw_image_features, raw_text_features, logit_scale, local_loss, gather_with_grad, rank,
+                               world_size, group, normalize=True, eps=eps)
     image_features = _Normalize.apply(raw_image_features, eps)
     text_features = _Normalize.apply(raw_text_features, eps)
     return fused_clip_loss(image_features, text_features, logit_scale, local_loss, gather_with_grad, rank, world_size,

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <atomic>
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/clipk.h"
@@ -16,6 +17,23 @@ namespace clipk {
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};   // kernels launched by this library (clipk_launch_count)
+
+// Optional per-kernel timing (clipk_profile_begin / clipk_profile_end, used by bench.py for the roofline of the dominant
+// kernel): while it is on, every launch of this library is followed by an event on its stream; the time between two
+// consecutive events is attributed to the kernel launched in between.  One stream, one thread at a time.
+struct ProfEntry { const char* name; cudaEvent_t ev; };
+static std::vector<ProfEntry> g_prof;
+static std::atomic<int> g_prof_on{0};
+static void count_launch(const char* name, cudaStream_t st) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (g_prof_on.load(std::memory_order_relaxed)) {
+        cudaEvent_t ev;
+        if (cudaEventCreate(&ev) == cudaSuccess) {
+            cudaEventRecord(ev, st);
+            g_prof.push_back(ProfEntry{name, ev});
+        }
+    }
+}
 
 static int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -169,18 +187,24 @@ __global__ void finalize_kernel(const float* __restrict__ row_max, const float* 
                                 const float* __restrict__ cmax, const float* __restrict__ csum,
                                 const float* __restrict__ cdot, int nparts, long long stride, int cols,
                                 long long diag_offset, float* __restrict__ lse_row, float* __restrict__ lse_col,
-                                float* __restrict__ sums) {
+                                float* __restrict__ sums, int* __restrict__ mm, float loss_div) {
+    // mm != null (clipk_step_forward): sums is the step's scalar block - [0..3] the sums, [4..5] receive (CE sums) /
+    // loss_div and (dscale sums) / loss_div from the last block to finish, [6] is its ticket, mm = ints [8..9]
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
+    int lo = 0x7fffffff, hi = int(0x80000000);       // min / max LSE of this thread (ordered ints), for grad_prep_kernel
     if (i < cols) {
         float lse, e;
         merge_col(cmax, csum, cdot, nparts, stride, i, &lse, &e);
         lse_col[i] = lse;
+        lo = hi = float_to_ordered(lse);
     }
     if (i < rows) {
         const float rs = row_sum[i];
         const float lr = row_max[i] + logf(rs);
         lse_row[i] = lr;
+        lo = min(lo, float_to_ordered(lr));
+        hi = max(hi, float_to_ordered(lr));
         const float p = pos[i];
         v[0] = lr - p;
         v[2] = row_dot[i] / rs - p;
@@ -194,6 +218,17 @@ __global__ void finalize_kernel(const float* __restrict__ row_max, const float* 
     }
     __shared__ float sh[4][32];
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (mm) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+        }
+        if (l == 0) {
+            atomicMin(mm, lo);
+            atomicMax(mm + 1, hi);
+        }
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
 #pragma unroll
@@ -209,15 +244,19 @@ __global__ void finalize_kernel(const float* __restrict__ row_max, const float* 
             for (int off = 16; off >= 1; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
             if (l == 0) atomicAdd(sums + k, x);
         }
+        if (mm && l == 0) {
+            __threadfence();
+            const unsigned int ticket = atomicAdd(reinterpret_cast<unsigned int*>(sums) + 6, 1u);
+            if (ticket == gridDim.x - 1) {
+                __threadfence();
+                sums[4] = (__ldcg(sums) + __ldcg(sums + 1)) / loss_div;
+                sums[5] = (__ldcg(sums + 2) + __ldcg(sums + 3)) / loss_div;
+            }
+        }
     }
 }
 
 // ---- backward preparation: one reference for every exponential of this backward (see grad_chunk PATH 0)
-__device__ __forceinline__ int float_to_ordered(float f) {
-    const int i = __float_as_int(f);
-    return i >= 0 ? i : i ^ 0x7fffffff;
-}
-__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 
 // mm[0] = min, mm[1] = max (ordered-int encoding) over both LSE vectors
 __global__ void lse_minmax_kernel(const float* __restrict__ a, int na, const float* __restrict__ b, int nb, int* mm) {
@@ -430,56 +469,267 @@ __global__ void normalize_bwd_kernel(const T* __restrict__ g, long long ldg, con
 }
 
 // ---- forward sweep helpers
-// out[which] = max over rows of |row|^2 as float bits (non-negative floats order like unsigned ints); one warp per row,
-// 16-byte loads, d % 8 == 0.  Both operands in one launch: blocks [0, bx) take X, the rest take Y.  amax (optional,
-// two floats) receives max |element| of X and of Y - what clipk_to_f16 needs for its scale, so that the backward does
-// not have to read the features once more just for that.
-__global__ void norm2_max_kernel(const __nv_bfloat16* __restrict__ X, long long rows_x, long long ldx,
-                                 const __nv_bfloat16* __restrict__ Y, long long rows_y, long long ldy, int d8, int bx,
-                                 unsigned int* __restrict__ out, unsigned int* __restrict__ amax) {
-    const bool second = int(blockIdx.x) >= bx;
-    const __nv_bfloat16* src = second ? Y : X;
-    const long long rows = second ? rows_y : rows_x, ld = second ? ldy : ldx;
-    const int nb = second ? int(gridDim.x) - bx : bx, b = second ? int(blockIdx.x) - bx : int(blockIdx.x);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-    float best = 0.f, am = 0.f;
-    for (long long r = (long long)b * wpb + warp; r < rows; r += (long long)nb * wpb) {
-        float acc = 0.f;
-        for (int k = lane; k < d8; k += 32) {
-            float v[8];
-            load8(src + r * ld + (long long)k * 8, v);
+// Operand preparation: ONE pass over the rows of both feature matrices (open_clip/model.py:216,231 + the casts that
+// precede loss.py:112-119) that leaves
+//   * the statistics the kernels steer by (OperandStats, gemm_core.cuh): max |x_i|^2 and max |y_j|^2 (bound of the single
+//     sweep), max |element| of both (scale of the fp16 copies the gradient GEMMs read), min_i x_i . y_i over the positive
+//     pairs (keeps the single sweep at large logit scales);
+//   * optionally the bf16 operands themselves: L2-normalised rows (NORMALIZE, with 1 / max(|row|, eps) per row for the
+//     Jacobian in the backward) and / or the cast of fp32 inputs, the text rows going straight into the buffer the
+//     all-gather reads.  Statistics are those of the values the tensor cores will see (after rounding to bf16).
+// One warp per row pair (x_i, y_i); the partner of x_i in the dot product is y row pair_off + i.
+struct PrepArgs {
+    const void* x; const void* y;
+    long long rows_x, rows_y, ldx, ldy;
+    int d8;                        // d / 8
+    long long pair_off;
+    __nv_bfloat16* x_out; __nv_bfloat16* y_out;    // null = operand not written (bf16 input used in place)
+    long long ldxo, ldyo;
+    float* inv_x; float* inv_y;    // NORMALIZE
+    float eps;
+    float* stats;                  // this rank's row of the statistics (accumulated with atomics: zeroed before, word 4 = +large)
+    float* reset;                  // 8 floats + 2 ints of accumulators of LATER kernels of the step, reset here (null = none)
+};
+
+template <typename T>
+__device__ __forceinline__ void load8_as_bf16(const T* p, float scale, float (&v)[8]) {
+    load8(p, v);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                acc = fmaf(v[j], v[j], acc);
-                const float a = fabsf(v[j]);
-                if (a < CUDART_INF_F) am = fmaxf(am, a);     // as amax_kernel: Inf / NaN do not set the scale
+    for (int j = 0; j < 8; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j] * scale));
+}
+
+template <typename T, bool NORMALIZE>
+__global__ void prep_kernel(const PrepArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const T* X = static_cast<const T*>(a.x);
+    const T* Y = static_cast<const T*>(a.y);
+    const long long nmax = a.rows_x > a.rows_y ? a.rows_x : a.rows_y;
+    // bf16 inputs used as they are need no rounding; everything else is rounded to the bf16 value the MMA will read
+    constexpr bool ROUND = NORMALIZE || !std::is_same<T, __nv_bfloat16>::value;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.reset) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a.reset[k] = 0.f;
+        reinterpret_cast<int*>(a.reset)[8] = 0x7f7f7f7f;          // min LSE (ordered int), see finalize_kernel
+        reinterpret_cast<int*>(a.reset)[9] = int(0x80808080);     // max LSE
+    }
+    float best_x = 0.f, best_y = 0.f, am_x = 0.f, am_y = 0.f, min_pos = CUDART_INF_F;
+    bool bad = false;
+    for (long long i = (long long)blockIdx.x * wpb + warp; i < nmax; i += (long long)gridDim.x * wpb) {
+        const bool hx = i < a.rows_x, hy = i < a.rows_y;
+        const long long j = a.pair_off + i;
+        const bool hp = hx && j >= 0 && j < a.rows_y;
+        const T* xr = X + i * a.ldx;
+        const T* yr = Y + i * a.ldy;
+        const T* pr = Y + j * a.ldy;
+        float sx = 1.f, sy = 1.f;
+        if (NORMALIZE) {
+            float ssx = 0.f, ssy = 0.f;
+            for (int k = lane; k < a.d8; k += 32) {
+                float v[8];
+                if (hx) { load8(xr + (long long)k * 8, v);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) ssx = fmaf(v[q], v[q], ssx); }
+                if (hy) { load8(yr + (long long)k * 8, v);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) ssy = fmaf(v[q], v[q], ssy); }
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                ssx += __shfl_xor_sync(0xffffffffu, ssx, off);
+                ssy += __shfl_xor_sync(0xffffffffu, ssy, off);
+            }
+            sx = 1.f / fmaxf(sqrtf(ssx), a.eps);
+            sy = 1.f / fmaxf(sqrtf(ssy), a.eps);
+            if (lane == 0) {
+                if (hx) a.inv_x[i] = sx;
+                if (hy) a.inv_y[i] = sy;
+            }
+        }
+        float nx = 0.f, ny = 0.f, dot = 0.f;
+        for (int k = lane; k < a.d8; k += 32) {
+            float vx[8], vy[8], vp[8];
+            if (hx) {
+                if (ROUND) load8_as_bf16(xr + (long long)k * 8, sx, vx); else load8(xr + (long long)k * 8, vx);
+                if (a.x_out) store8(a.x_out + i * a.ldxo + (long long)k * 8, vx);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    nx = fmaf(vx[q], vx[q], nx);
+                    const float m = fabsf(vx[q]);
+                    if (m < CUDART_INF_F) am_x = fmaxf(am_x, m);
+                }
+            }
+            if (hy) {
+                if (ROUND) load8_as_bf16(yr + (long long)k * 8, sy, vy); else load8(yr + (long long)k * 8, vy);
+                if (a.y_out) store8(a.y_out + i * a.ldyo + (long long)k * 8, vy);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    ny = fmaf(vy[q], vy[q], ny);
+                    const float m = fabsf(vy[q]);
+                    if (m < CUDART_INF_F) am_y = fmaxf(am_y, m);
+                }
+            }
+            if (hp) {
+                if (j == i) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) dot = fmaf(vx[q], vy[q], dot);
+                } else {            // never with NORMALIZE (the host requires pair_off == 0 there)
+                    if (ROUND) load8_as_bf16(pr + (long long)k * 8, 1.f, vp); else load8(pr + (long long)k * 8, vp);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) dot = fmaf(vx[q], vp[q], dot);
+                }
             }
         }
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-        // NaN / Inf propagate into the bound, which then fails its test (exact mode)
-        best = (acc > best || !(acc == acc)) ? acc : best;
+        for (int off = 16; off >= 1; off >>= 1) {
+            nx += __shfl_xor_sync(0xffffffffu, nx, off);
+            ny += __shfl_xor_sync(0xffffffffu, ny, off);
+            dot += __shfl_xor_sync(0xffffffffu, dot, off);
+        }
+        // NaN / Inf propagate into the bound, which then fails its tests (exact mode)
+        if (hx) { bad = bad || !(nx == nx); best_x = fmaxf(best_x, nx); }
+        if (hy) { bad = bad || !(ny == ny); best_y = fmaxf(best_y, ny); }
+        if (hp) min_pos = fminf(min_pos, dot);
     }
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, off));
-    __shared__ float sh[32], sha[32];
-    if (lane == 0) { sh[warp] = best; sha[warp] = am; }
+    for (int off = 16; off >= 1; off >>= 1) {
+        am_x = fmaxf(am_x, __shfl_xor_sync(0xffffffffu, am_x, off));
+        am_y = fmaxf(am_y, __shfl_xor_sync(0xffffffffu, am_y, off));
+    }
+    __shared__ float sh[5][32];
+    __shared__ int shbad;
+    if (threadIdx.x == 0) shbad = 0;
+    __syncthreads();
+    if (lane == 0) {
+        sh[0][warp] = best_x; sh[1][warp] = best_y; sh[2][warp] = am_x; sh[3][warp] = am_y; sh[4][warp] = min_pos;
+        if (bad) shbad = 1;
+    }
     __syncthreads();
     if (warp == 0) {
-        float v = lane < wpb ? sh[lane] : 0.f;
-        float a = lane < wpb ? sha[lane] : 0.f;
-        bool bad = !(v == v);
+        float v[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) v[k] = lane < wpb ? sh[k][lane] : (k == 4 ? CUDART_INF_F : 0.f);
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
-            const float o = __shfl_xor_sync(0xffffffffu, v, off);
-            bad = bad || !(o == o);
-            v = fmaxf(v, o);
-            a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, off));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = fmaxf(v[k], __shfl_xor_sync(0xffffffffu, v[k], off));
+            v[4] = fminf(v[4], __shfl_xor_sync(0xffffffffu, v[4], off));
         }
-        bad = __any_sync(0xffffffffu, bad);
         if (lane == 0) {
-            atomicMax(out + (second ? 1 : 0), bad ? 0x7f800000u : __float_as_uint(v));
-            if (amax && a > 0.f) atomicMax(amax + (second ? 1 : 0), __float_as_uint(a));
+            unsigned int* su = reinterpret_cast<unsigned int*>(a.stats);
+            const bool isbad = shbad != 0;
+            atomicMax(su + 0, isbad ? 0x7f800000u : __float_as_uint(v[0]));
+            atomicMax(su + 1, isbad ? 0x7f800000u : __float_as_uint(v[1]));
+            if (v[2] > 0.f) atomicMax(su + 2, __float_as_uint(v[2]));
+            if (v[3] > 0.f) atomicMax(su + 3, __float_as_uint(v[3]));
+            atomicMin(reinterpret_cast<int*>(a.stats) + 4, float_to_ordered(v[4]));
+        }
+    }
+}
+
+// Both fp16 copies the gradient GEMMs read, in one launch: Xg = fp16(X * 2^ex) for this rank's rows, Yg = fp16(Y * 2^ey)
+// for all gathered rows; exact for bf16 sources (8 significant bits fit in 11).  The scales come from the statistics:
+// max |x_ij| of this rank's row of the table, max |y_ij| over every row of it.  inv_out[0 / 1] = 2^-ex / 2^-ey.
+__device__ __forceinline__ float f16_scale_of(float amax) {
+    if (!(amax > 0.f && amax < CUDART_INF_F)) return 1.f;
+    int ex = 0;
+    frexpf(amax, &ex);                 // amax = m * 2^ex, m in [0.5, 1)
+    int e = 14 - ex;
+    e = e > 120 ? 120 : (e < -120 ? -120 : e);
+    return ldexpf(1.f, e);
+}
+__global__ void to_f16_pair_kernel(const __nv_bfloat16* __restrict__ X, long long rows_x, long long ldx, __half* __restrict__ Xg,
+                                   const __nv_bfloat16* __restrict__ Y, long long rows_y, long long ldy, __half* __restrict__ Yg,
+                                   long long d, long long dpad, const float* __restrict__ stats, int nstat, int stats_rank,
+                                   float* __restrict__ inv_out) {
+    float ay = 0.f;
+    for (int r = 0; r < nstat; ++r) ay = fmaxf(ay, __ldg(stats + r * STAT_WORDS + 3));
+    const float sx = f16_scale_of(__ldg(stats + stats_rank * STAT_WORDS + 2)), sy = f16_scale_of(ay);
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx == 0) { inv_out[0] = 1.f / sx; inv_out[1] = 1.f / sy; }
+    const long long dp8 = dpad / 8;
+    if (idx >= (rows_x + rows_y) * dp8) return;
+    const bool second = idx >= rows_x * dp8;
+    const long long t = second ? idx - rows_x * dp8 : idx;
+    const long long r = t / dp8, k = (t - r * dp8) * 8;
+    const __nv_bfloat16* src = (second ? Y + r * ldy : X + r * ldx) + k;
+    const float scale = second ? sy : sx;
+    float v[8];
+    if (k < d) {
+        load8(src, v);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    }
+    uint32_t hi[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) hi[j] = ptx::pack_f16x2(v[2 * j] * scale, v[2 * j + 1] * scale);
+    __half* o = (second ? Yg : Xg) + r * dpad + k;
+    *reinterpret_cast<uint4*>(o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+}
+
+// Last pass of the backward, one warp per row of either gradient: sum the per-source slots of the fused reduce-scatter
+// (text gradient), apply the Jacobian of the L2 normalisation when the forward normalised (dx = (g - y (y . g)) / |x|,
+// with y the operand row), cast to the dtype of the inputs.  Replaces clipk_cast, clipk_reduce_slots and
+// clipk_normalize_bwd of the unfused path.  Thread 0 also finishes dlogit_scale = go * (s dloss/ds) / s.
+struct FinishArgs {
+    const float* gx; long long rows_x;             // [rows_x, d] fp32 image gradient (null = skip)
+    const float* gy; long long rows_y;             // [slots][rows_y, d] fp32 text gradient (null = skip)
+    int slots; long long slot_stride;              // elements between slots
+    int d8;
+    const __nv_bfloat16* xn; const __nv_bfloat16* yn;   // operand rows for the Jacobian (null = no normalisation)
+    long long ldxn, ldyn;
+    const float* inv_x; const float* inv_y;
+    float eps;
+    void* out_x; void* out_y; int out_dtype;       // CLIPK_BF16 or CLIPK_F32, [rows, d] contiguous
+    const float* pair; const float* go; const float* scale; float* dscale;   // dscale: null = skip
+};
+__global__ void finish_grad_kernel(const FinishArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.dscale) a.dscale[0] = a.pair[1] * a.go[0] / a.scale[0];
+    const long long rx = a.gx ? a.rows_x : 0, ry = a.gy ? a.rows_y : 0;
+    const long long d = (long long)a.d8 * 8;
+    for (long long t = (long long)blockIdx.x * wpb + warp; t < rx + ry; t += (long long)gridDim.x * wpb) {
+        const bool second = t >= rx;
+        const long long r = second ? t - rx : t;
+        const float* g = (second ? a.gy : a.gx) + r * d;
+        const int slots = second ? a.slots : 1;
+        const __nv_bfloat16* yn = second ? a.yn : a.xn;
+        const long long ldn = second ? a.ldyn : a.ldxn;
+        auto load_g = [&](int k, float (&v)[8]) {
+            load8(g + (long long)k * 8, v);
+            for (int w = 1; w < slots; ++w) {
+                float u[8];
+                load8(g + (long long)w * a.slot_stride + (long long)k * 8, u);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] += u[q];
+            }
+        };
+        float dot = 0.f, inv = 1.f;
+        if (yn) {
+            for (int k = lane; k < a.d8; k += 32) {
+                float v[8], y[8];
+                load_g(k, v);
+                load8(yn + r * ldn + (long long)k * 8, y);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) dot = fmaf(v[q], y[q], dot);
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+            inv = (second ? a.inv_y : a.inv_x)[r];
+            if (inv >= 1.f / a.eps * 0.999999f) dot = 0.f;      // |x| < eps: y = x / eps, a plain scaling
+        }
+        void* out = second ? a.out_y : a.out_x;
+        for (int k = lane; k < a.d8; k += 32) {
+            float v[8];
+            load_g(k, v);
+            if (yn) {
+                float y[8];
+                load8(yn + r * ldn + (long long)k * 8, y);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = (v[q] - y[q] * dot) * inv;
+            }
+            if (a.out_dtype == CLIPK_BF16) store8(static_cast<__nv_bfloat16*>(out) + r * d + (long long)k * 8, v);
+            else store8(static_cast<float*>(out) + r * d + (long long)k * 8, v);
         }
     }
 }
@@ -518,6 +768,7 @@ __global__ void fwd_merge_kernel(const FwdArgs a0, const FwdArgs a1, int m_block
     if (sl == 0 && i < rows) merge_parts(a0.part_max, a0.part_sum, a0.part_dot, nparts_of(a0, i), rows, i, row_out, rows);
     float u;
     const bool single = fwd_bound(a0, &u);      // uniform over the grid
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a0.mode_out) *a0.mode_out = single ? 1.f : 0.f;
     if (single) {
         float L = 0.f, D = 0.f;
         if (i < cols)
@@ -676,34 +927,87 @@ __global__ void distill_grad_kernel(const float* __restrict__ S, const float* __
     G[(size_t)blockIdx.y * ldg + j] = __float2half_rn(16384.f * v);
 }
 
-// All-gather by pulling: chunk o of dst <- rank o's (peer-mapped) source buffer, all ranks' chunks in one launch so that
-// the loads from the `world` peers are in flight together (NVSwitch gives every pair its full link).  16-byte units.
-struct PeerSrc {
-    const uint4* p[MAX_PEERS];
+// ---- data-parallel ranks of one NVLink domain: flags, barrier and all-gather over peer-mapped (symmetric) memory --------
+// Every rank owns an array of MAX_PEERS flag words per purpose, mapped into all peers.  Rank r publishes epoch e to rank
+// t by storing e into word [r] of t's array (release at system scope, after everything the stream did before); t waits
+// until word [r] of its own array has reached e.  Epochs only grow (compared modulo 2^32), flags are never reset.
+struct PeerPtrs {
+    void* p[MAX_PEERS];
 };
-__global__ void peer_gather_kernel(const __grid_constant__ PeerSrc src, uint4* __restrict__ dst, long long n16) {
-    // blockIdx.y = source rank; the pointer table stays in parameter space (__grid_constant__), no local copy
-    const uint4* __restrict__ from = src.p[blockIdx.y];
-    uint4* __restrict__ to = dst + (long long)blockIdx.y * n16;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) to[i] = from[i];
+__device__ __forceinline__ void peer_signal(unsigned int* flag, unsigned int epoch) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+}
+// A wait gives up after ~20 s (a peer died, or skipped the collective call) and leaves `code` in *err - a word in
+// pinned host memory the host side checks before its next call - instead of hanging the GPU.
+__device__ __forceinline__ bool peer_wait(const unsigned int* flag, unsigned int epoch, int* err, int code) {
+    unsigned long long t0 = 0;
+    unsigned int spins = 0;
+    for (;;) {
+        unsigned int v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (int(v - epoch) >= 0) return true;
+        if ((++spins & 0xfffu) == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 20000000000ull) {
+                if (err) { *reinterpret_cast<volatile int*>(err) = code; __threadfence_system(); }
+                return false;
+            }
+        }
+    }
 }
 
-// Barrier between the ranks of one NVLink domain through peer-mapped flags: thread t publishes `epoch` in slot
-// [rank] of rank t's flag array (after everything this stream did before became visible system-wide), then waits
-// until rank t has published the same epoch here.  Epochs only grow, so the flags are never reset.
-struct PeerFlags {
-    unsigned int* flags[MAX_PEERS];   // flags[t] = rank t's array of MAX_PEERS words, peer-mapped
-};
-__global__ void peer_barrier_kernel(const PeerFlags pf, int rank, int world, unsigned int epoch) {
+__global__ void peer_barrier_kernel(const __grid_constant__ PeerPtrs flags, const int rank, const int world, const unsigned int epoch, int* const err) {
     const int t = threadIdx.x;
     if (t < world && t != rank) {
-        __threadfence_system();
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pf.flags[t] + rank), "r"(epoch) : "memory");
-        unsigned int v;
-        do {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(pf.flags[rank] + t) : "memory");
-        } while (v < epoch);
+        peer_signal(static_cast<unsigned int*>(flags.p[t]) + rank, epoch);
+        peer_wait(static_cast<const unsigned int*>(flags.p[rank]) + t, epoch, err, 2);
+    }
+}
+
+// All-gather by pulling, flags included: chunk o of dst <- rank o's source buffer, for a main buffer and an optional small
+// side buffer (the operand statistics travel with the text features).  Block (0, 0) first tells every peer that this
+// rank's sources are complete (they were written by earlier kernels of this stream); the blocks of column o then wait
+// for rank o's flag and copy with 16-byte loads, all sources in flight together (NVSwitch gives every pair its full
+// link).  Peer data is read with ld.cv: a line of the same address cached by an earlier pull must not be served.
+// A source buffer may be rewritten two calls later: before its owner got there it has waited, in the call in
+// between, for a flag every reader published after finishing this pull.
+struct GatherArgs {
+    PeerPtrs src0; long long n16_0; uint4* dst0;
+    PeerPtrs src1; long long n16_1; uint4* dst1;
+    PeerPtrs flags;
+    int rank, world;
+    unsigned int epoch;
+    int* err;
+};
+__global__ void peer_allgather_kernel(const __grid_constant__ GatherArgs a) {
+    const int o = blockIdx.y;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && int(threadIdx.x) < a.world && int(threadIdx.x) != a.rank)
+        peer_signal(static_cast<unsigned int*>(a.flags.p[threadIdx.x]) + a.rank, a.epoch);
+    const bool remote = o != a.rank;
+    if (remote) {
+        if (threadIdx.x == 0) peer_wait(static_cast<const unsigned int*>(a.flags.p[a.rank]) + o, a.epoch, a.err, 1);
+        __syncthreads();
+    }
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    {
+        const uint4* __restrict__ from = static_cast<const uint4*>(a.src0.p[o]);
+        uint4* __restrict__ to = a.dst0 + (long long)o * a.n16_0;
+        long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + 3 * stride < a.n16_0; i += 4 * stride) {      // four loads in flight per thread
+            uint4 v0, v1, v2, v3;
+            if (remote) { v0 = __ldcv(from + i); v1 = __ldcv(from + i + stride); v2 = __ldcv(from + i + 2 * stride); v3 = __ldcv(from + i + 3 * stride); }
+            else { v0 = from[i]; v1 = from[i + stride]; v2 = from[i + 2 * stride]; v3 = from[i + 3 * stride]; }
+            to[i] = v0; to[i + stride] = v1; to[i + 2 * stride] = v2; to[i + 3 * stride] = v3;
+        }
+        for (; i < a.n16_0; i += stride) to[i] = remote ? __ldcv(from + i) : from[i];
+    }
+    if (blockIdx.x == 0 && a.n16_1 > 0) {
+        const uint4* __restrict__ from = static_cast<const uint4*>(a.src1.p[o]);
+        uint4* __restrict__ to = a.dst1 + (long long)o * a.n16_1;
+        for (long long i = threadIdx.x; i < a.n16_1; i += blockDim.x) to[i] = remote ? __ldcv(from + i) : from[i];
     }
 }
 
@@ -753,59 +1057,6 @@ constexpr int MAX_PARTS = MAX_SPLIT * PARTS_PER_UNIT;
 // blocks of 256, fully L2 resident, 56 panels) 3.13 ms; 134-179 MB (32 x 32 blocks, 16 panels, two tiles per CTA pair in
 // the gradient-GEMM launch) 2.82 ms - the panel no longer fits the 126 MB L2 entirely and part of it streams through
 // HBM, but the per-launch fill / drain is paid 16 instead of 56 times, which is worth more.
-static int use_persistent() {
-    static int v = [] { const char* e = getenv("CLIPK_PERSISTENT"); return e ? atoi(e) : 0; }();
-    return v;
-}
-// Experiment (CLIPK_BWD_STREAMS=2, default 1): the recompute sweep of panel p+1 runs on a library-owned side stream
-// against the gradient GEMMs of panel p on the caller's stream, with two G buffers, so that the tail of one launch is
-// filled by the head of the other.  The side stream is forked from and joined to the caller's stream with events (legal
-// under stream capture).  One caller per device at a time in this mode: the events are per device.
-static int bwd_streams() {
-    static int v = [] { const char* e = getenv("CLIPK_BWD_STREAMS"); return e ? atoi(e) : 1; }();
-    return v;
-}
-struct SideStream {
-    cudaStream_t s = nullptr;
-    cudaEvent_t start = nullptr, ready[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
-    int ok = 0;
-};
-static SideStream g_side[64];
-static std::mutex g_side_mu;
-static int side_stream(SideStream** out) {
-    int dev = 0;
-    CK_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) return fail(CLIPK_EINVAL, "device index %d out of range", dev);
-    std::lock_guard<std::mutex> lk(g_side_mu);
-    SideStream& ss = g_side[dev];
-    if (!ss.ok) {
-        CK_CUDA(cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking));
-        CK_CUDA(cudaEventCreateWithFlags(&ss.start, cudaEventDisableTiming));
-        for (int i = 0; i < 2; ++i) {
-            CK_CUDA(cudaEventCreateWithFlags(&ss.ready[i], cudaEventDisableTiming));
-            CK_CUDA(cudaEventCreateWithFlags(&ss.freed[i], cudaEventDisableTiming));
-        }
-        ss.ok = 1;
-    }
-    *out = &ss;
-    return CLIPK_OK;
-}
-static int dbg_flags() {
-    static int v = [] { const char* e = getenv("CLIPK_DBG"); return e ? atoi(e) : 0; }();
-    return v;
-}
-static long long* g_trace = nullptr;   // set by clipk_debug_set_trace (experiments only)
-// the dataflow backward keeps THREE panels alive (written / waiting / read): 3 x 32 MB still fits the 126 MB L2
-static long long df_panel_bytes() {
-    static long long v = [] {
-        const char* e = getenv("CLIPK_DF_PANEL_MB");
-        long long mb = e ? atoll(e) : 32;
-        if (mb < 4) mb = 4;
-        if (mb > 1024) mb = 1024;
-        return mb << 20;
-    }();
-    return v;
-}
 static long long panel_bytes() {
     static long long v = [] {
         const char* e = getenv("CLIPK_PANEL_MB");
@@ -908,7 +1159,7 @@ static void choose_panel(int rows, int cols, int d, int gplanes, int sms, long l
 
 // Launch with a thread-block cluster of two CTAs (the tcgen05 cta_group::2 pair).
 template <typename... Args>
-static int launch_clustered(void (*kfn)(Args...), dim3 grid, dim3 cluster, int smem, cudaStream_t st, Args... args) {
+static int launch_clustered(const char* name, void (*kfn)(Args...), dim3 grid, dim3 cluster, int smem, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(NUM_THREADS);
@@ -924,9 +1175,9 @@ static int launch_clustered(void (*kfn)(Args...), dim3 grid, dim3 cluster, int s
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = (dbg_flags() & 32) ? 1 : 2;
+    cfg.numAttrs = 2;
     CK_CUDA(cudaLaunchKernelEx(&cfg, kfn, args...));
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    count_launch(name, st);
     return CLIPK_OK;
 }
 
@@ -942,11 +1193,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
     if (attr_err != cudaSuccess) return fail(int(attr_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
     KArgs aa = a;
-    aa.dbg = dbg_flags();
-    aa.trace = g_trace;
-    aa.trace_on = 1;
     aa.f16 = F16;
-    return launch_clustered(kfn, dim3(2 * m_pairs, units), dim3(2, 1, 1), smem, st, ta, tb, tc, aa);
+    return launch_clustered(MODE == MODE_STATS ? "gemm_kernel<STATS>" : MODE == MODE_GRAD ? "gemm_kernel<GRAD>" : "gemm_kernel<OUT>", kfn, dim3(2 * m_pairs, units), dim3(2, 1, 1), smem, st, ta, tb, tc, aa);
 }
 
 // jobs0 / jobs1 are counted in PAIRS (256 x 256 output tiles)
@@ -960,11 +1208,8 @@ static int launch_pair(const CUtensorMap& ta0, const CUtensorMap& tb0, const CUt
     std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
     if (attr_err != cudaSuccess) return fail(int(attr_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
     KArgs b0 = a0, b1 = a1;
-    b0.dbg = b1.dbg = dbg_flags();
-    b0.trace = g_trace;
-    b0.trace_on = 1;
     b0.f16 = b1.f16 = 1;
-    return launch_clustered(kfn, dim3(2 * (jobs0 + jobs1)), dim3(2, 1, 1), smem, st, ta0, tb0, tc0, b0, ta1, tb1, tc1, b1,
+    return launch_clustered("gemm_pair_kernel", kfn, dim3(2 * (jobs0 + jobs1)), dim3(2, 1, 1), smem, st, ta0, tb0, tc0, b0, ta1, tb1, tc1, b1,
                             jobs0, peers);
 }
 
@@ -989,107 +1234,6 @@ static void set_segments(KArgs& a, int planes, int k_extent, long long a_plane, 
         }
 }
 
-// ---- work plan of the dataflow backward (see bwd_dataflow_kernel) ----------------------------------------------
-// Per panel q the virtual cluster v = (cluster + shift[q]) % n runs the gradient-GEMM jobs v, v + n, ... and the
-// recompute tiles [start[q][v], start[q][v + 1]).  Work is counted in K blocks (64 wide): a recompute tile costs its
-// K blocks plus `tile_extra` (its epilogue is the expensive one), a job costs its K blocks; every cluster gets the
-// same total, so clusters with a long job (or any job) recompute fewer tiles.  The shift rotates the roles from
-// panel to panel.  The plan depends only on the shapes: it is built once per shape on the host and kept on the device.
-struct BwdPlanDev {
-    int* shift;
-    int* start;
-    unsigned char* owner;
-};
-struct BwdPlanKey {
-    int dev, rows, cols, d, rp, cp, nt, want_dx, want_dy, s_kb, g_nseg, n_clusters, tile_extra;
-    bool operator==(const BwdPlanKey& o) const { return memcmp(this, &o, sizeof(*this)) == 0; }
-};
-struct BwdPlanEntry {
-    BwdPlanKey key;
-    BwdPlanDev dev;
-    void* block;
-};
-static std::mutex g_plan_mu;
-static BwdPlanEntry g_plans[64];
-static int g_nplans = 0;
-
-static int tile_extra_cost() {
-    static int v = [] { const char* e = getenv("CLIPK_TILE_EXTRA"); return e ? atoi(e) : 3; }();
-    return v;
-}
-
-static int get_bwd_plan(const BwdP& P, int n_clusters, const BwdPlanDev** out) {
-    BwdPlanKey key;
-    memset(&key, 0, sizeof(key));
-    CK_CUDA(cudaGetDevice(&key.dev));
-    key.rows = P.rows; key.cols = P.cols; key.d = P.d; key.rp = P.rp; key.cp = P.cp; key.nt = P.nt;
-    key.want_dx = P.want_dx; key.want_dy = P.want_dy; key.s_kb = P.s_nseg * P.s_kb_per_seg; key.g_nseg = P.g_nseg;
-    key.n_clusters = n_clusters; key.tile_extra = tile_extra_cost();
-    std::lock_guard<std::mutex> lk(g_plan_mu);
-    for (int i = 0; i < g_nplans; ++i)
-        if (g_plans[i].key == key) { *out = &g_plans[i].dev; return CLIPK_OK; }
-    if (g_nplans == 64) {
-        // shapes keep changing: drop every cached plan (no kernel may still be reading them)
-        CK_CUDA(cudaDeviceSynchronize());
-        for (int i = 0; i < g_nplans; ++i) cudaFree(g_plans[i].block);
-        g_nplans = 0;
-    }
-    const int n = n_clusters, n_panels = P.n_rp * P.n_cp, max_tiles = P.max_tiles;
-    const size_t n_int = size_t(n_panels) + size_t(n_panels) * 2 * n;
-    const size_t bytes = n_int * 4 + size_t(n_panels) * max_tiles;
-    std::vector<unsigned char> host(bytes, 0);
-    int* shift = reinterpret_cast<int*>(host.data());
-    int* start = shift + n_panels;            // [q][cluster] = {first tile, end tile}
-    unsigned char* owner = host.data() + n_int * 4;
-    // A cluster's sequence is G(0) G(1) O(0) G(2) O(1) ...: what has to take equally long on every cluster is the
-    // phase G(q) followed by O(q - 1).
-    std::vector<double> prev_work(n, 0.0), work(n);
-    for (int q = 0; q < n_panels; ++q) {
-        const int ri = q / P.n_cp, ci = q - ri * P.n_cp;
-        const int nr = std::min(P.rp, P.rows - ri * P.rp), nc = std::min(P.cp, P.cols - ci * P.cp);
-        const int m_pairs = cdiv(nr, 2 * BM), n_tiles = cdiv(nc, BN), tiles = m_pairs * n_tiles;
-        const int jobs0 = P.want_dx ? m_pairs * P.nt : 0, jobs1 = P.want_dy ? cdiv(nc, 2 * BM) * P.nt : 0;
-        const double k0 = double(P.g_nseg) * cdiv(nc, BK), k1 = double(P.g_nseg) * cdiv(nr, BK);
-        const double tile_cost = double(key.s_kb + key.tile_extra);
-        shift[q] = int((long long)q * 17 % n);
-        double total = tiles * tile_cost;
-        for (int c = 0; c < n; ++c) total += prev_work[c];
-        const double target = total / n;
-        double cap_total = 0;
-        for (int c = 0; c < n; ++c) cap_total += std::max(0.0, target - prev_work[c]);
-        int* st = start + size_t(q) * 2 * n;
-        double prefix = 0;
-        int f = 0;
-        for (int i = 0; i < n; ++i) {
-            const int c = (i + shift[q]) % n;     // rotate which clusters get the first rows of the panel
-            prefix += std::max(0.0, target - prev_work[c]);
-            int f1 = cap_total > 0 ? int(tiles * (prefix / cap_total) + 0.5) : int((long long)tiles * (i + 1) / n);
-            if (i == n - 1) f1 = tiles;
-            if (f1 < f) f1 = f;
-            st[2 * c] = f; st[2 * c + 1] = f1;
-            for (int t = f; t < f1; ++t) owner[size_t(q) * max_tiles + t] = (unsigned char)c;
-            f = f1;
-        }
-        for (int c = 0; c < n; ++c) {
-            const int v = (c + shift[q]) % n;
-            work[c] = 0;
-            for (int j = v; j < jobs0 + jobs1; j += n) work[c] += (j < jobs0) ? k0 : k1;
-        }
-        prev_work = work;
-    }
-    void* block = nullptr;
-    CK_CUDA(cudaMalloc(&block, bytes));
-    cudaError_t e = cudaMemcpy(block, host.data(), bytes, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { cudaFree(block); return fail(int(e), "plan upload: %s", cudaGetErrorString(e)); }
-    BwdPlanEntry& en = g_plans[g_nplans++];
-    en.key = key; en.block = block;
-    en.dev.shift = static_cast<int*>(block);
-    en.dev.start = en.dev.shift + n_panels;
-    en.dev.owner = static_cast<unsigned char*>(block) + n_int * 4;
-    *out = &en.dev;
-    return CLIPK_OK;
-}
-
 static int check_common(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype) {
     if (!X || !Y) return fail(CLIPK_EINVAL, "null operand pointer");
     if (rows <= 0 || cols <= 0 || d <= 0) return fail(CLIPK_EINVAL, "rows, cols and d must be positive (got %d, %d, %d)", rows, cols, d);
@@ -1111,11 +1255,8 @@ static int launch_grad_sweep(const CUtensorMap& ta, const CUtensorMap& tb, const
     std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
     if (attr_err != cudaSuccess) return fail(int(attr_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
     KArgs aa = a;
-    aa.dbg = dbg_flags();
-    aa.trace = g_trace;
-    aa.trace_on = 1;
     aa.f16 = F16;
-    return launch_clustered(kfn, dim3(2 * n_clusters), dim3(2, 1, 1), smem, st, ta, tb, tc, aa, g);
+    return launch_clustered("grad_sweep_kernel", kfn, dim3(2 * n_clusters), dim3(2, 1, 1), smem, st, ta, tb, tc, aa, g);
 }
 
 // ---- host helpers of clipk_fwd_both
@@ -1149,7 +1290,7 @@ int launch_fwd_sweep(const CUtensorMap& ta, const CUtensorMap& tb, const FwdArgs
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
     if (attr_err != cudaSuccess) return fail(int(attr_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-    return launch_clustered(kfn, dim3(2 * n_clusters), dim3(2, 1, 1), smem, st, ta, tb, a);
+    return launch_clustered("fwd_sweep_kernel", kfn, dim3(2 * n_clusters), dim3(2, 1, 1), smem, st, ta, tb, a);
 }
 
 }  // namespace clipk
@@ -1208,18 +1349,18 @@ static int to_f16_impl(const void* src, int src_dtype, long long rows, long long
         const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(src);
         if (!amax) {
             amax_kernel<<<rblocks, 256, 0, st>>>(p, rows, d / 8, ld_src, bits);
-            g_launches.fetch_add(1, std::memory_order_relaxed);
+            count_launch("amax_kernel", st);
         }
         to_f16_kernel<<<cdiv(n, 256), 256, 0, st>>>(p, out, rows, d, ld_src, dpad, planes, scale_io);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
+        count_launch("to_f16_kernel", st);
     } else {
         const float* p = static_cast<const float*>(src);
         if (!amax) {
             amax_kernel<<<rblocks, 256, 0, st>>>(p, rows, d / 8, ld_src, bits);
-            g_launches.fetch_add(1, std::memory_order_relaxed);
+            count_launch("amax_kernel", st);
         }
         to_f16_kernel<<<cdiv(n, 256), 256, 0, st>>>(p, out, rows, d, ld_src, dpad, planes, scale_io);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
+        count_launch("to_f16_kernel", st);
     }
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
@@ -1270,7 +1411,7 @@ int clipk_fwd_stats(const void* X, const void* Y, int rows, int cols, int d, lon
     if (rc) return rc;
     merge_row_parts_kernel<<<cdiv(rows, 256), 256, 0, st>>>(a.part_max, a.part_sum, a.part_dot, units * PARTS_PER_UNIT,
                                                             rows, row_max, row_sum, row_dot);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    count_launch("merge_row_parts_kernel", st);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
 }
@@ -1284,53 +1425,41 @@ size_t clipk_fwd_both_workspace_bytes(int rows, int cols, int d, int dtype) {
     return one > two ? one : two;
 }
 
-int clipk_fwd_both(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
-                   const float* x_inv_scale, const float* y_inv_scale, const float* logit_scale, long long diag_offset,
-                   float* row_stats, float* pos_logit, float* col_stats, float* amax_xy, int exact, void* workspace,
-                   size_t workspace_bytes, void* stream) {
-    int rc = check_common(X, Y, rows, cols, d, ldx, ldy, dtype);
-    if (rc) return rc;
-    if (!logit_scale || !row_stats || !col_stats || !workspace) return fail(CLIPK_EINVAL, "null pointer argument");
-    if (workspace_bytes < clipk_fwd_both_workspace_bytes(rows, cols, d, dtype)) return fail(CLIPK_EWORKSPACE, "workspace too small");
-    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail(CLIPK_EINVAL, "workspace must be 256-byte aligned");
-    DevInfo di;
-    if ((rc = device_info(&di))) return rc;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int planes = planes_of(dtype);
+// launch of prep_kernel over (X rows, Y rows); stats must be this rank's row of the table (it is reset here)
+static int launch_prep(const PrepArgs& a, int src_dtype, int normalize, int sms, cudaStream_t st) {
+    CK_CUDA(cudaMemsetAsync(a.stats, 0, STAT_WORDS * sizeof(float), st));
+    CK_CUDA(cudaMemsetAsync(a.stats + 4, 0x7f, sizeof(float), st));          // min positive: a huge (ordered) value
+    const long long nmax = a.rows_x > a.rows_y ? a.rows_x : a.rows_y;
+    const int wpb = 8;
+    const int blocks = int(std::max<long long>(1, std::min<long long>(cdiv(nmax, wpb), 4LL * sms)));
+    if (src_dtype == CLIPK_BF16) {
+        if (normalize) prep_kernel<__nv_bfloat16, true><<<blocks, wpb * 32, 0, st>>>(a);
+        else prep_kernel<__nv_bfloat16, false><<<blocks, wpb * 32, 0, st>>>(a);
+    } else {
+        if (normalize) prep_kernel<float, true><<<blocks, wpb * 32, 0, st>>>(a);
+        else prep_kernel<float, false><<<blocks, wpb * 32, 0, st>>>(a);
+    }
+    count_launch("prep_kernel", st);
+    CK_CUDA(cudaGetLastError());
+    return CLIPK_OK;
+}
+
+// The sweeps + merge of the forward for one-plane operands (bf16 / fp16): row statistics [3, rows], positives [rows] and
+// this block's column statistics [3, cols].  stats = operand statistics table (null: no bound, exact mode).
+static int fwd_sweeps(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
+                      const float* x_inv_scale, const float* y_inv_scale, const float* logit_scale, long long diag_offset,
+                      float* row_stats, float* pos_logit, float* col_stats, const float* stats, int nstat, int stats_rank,
+                      int use_minpos, int exact, void* workspace, const DevInfo& di, cudaStream_t st) {
+    int rc;
     const long long dpad = round_up(d, BK);
     const int num_kb = cdiv(d, BK);
-    if (amax_xy) CK_CUDA(cudaMemsetAsync(amax_xy, 0xff, 2 * sizeof(float), static_cast<cudaStream_t>(stream)));   // NaN = not computed
-    if (planes != 1 || (dbg_flags() & 512)) {
-        // split-precision operands (fp32 inputs): two streaming sweeps
-        char* ws = static_cast<char*>(workspace);
-        const size_t w0 = clipk_fwd_workspace_bytes(rows, cols, d, dtype);
-        rc = clipk_fwd_stats(X, Y, rows, cols, d, ldx, ldy, dtype, x_inv_scale, y_inv_scale, logit_scale, diag_offset,
-                             row_stats, row_stats + rows, row_stats + 2 * (size_t)rows, pos_logit, ws, w0, stream);
-        if (rc) return rc;
-        return clipk_fwd_stats(Y, X, cols, rows, d, ldy, ldx, dtype, y_inv_scale, x_inv_scale, logit_scale, -(1LL << 40),
-                               col_stats, col_stats + cols, col_stats + 2 * (size_t)cols, nullptr, ws + round_up((long long)w0, 256),
-                               workspace_bytes - size_t(round_up((long long)w0, 256)), stream);
-    }
     const long long kext = (dtype == CLIPK_BF16) ? d : dpad;
     const int n_clusters = di.sms / 2;
     const FwdCarve cv = fwd_carve(rows, cols);
     char* ws = static_cast<char*>(workspace);
-    unsigned int* norm2 = reinterpret_cast<unsigned int*>(ws + cv.norm2);
     float* parts0 = reinterpret_cast<float*>(ws + cv.parts0);
     float* parts1 = reinterpret_cast<float*>(ws + cv.parts1);
     float* colparts = reinterpret_cast<float*>(ws + cv.colparts);
-    const bool bounded = (dtype == CLIPK_BF16) && !(dbg_flags() & 16384);
-    if (bounded) {
-        CK_CUDA(cudaMemsetAsync(norm2, 0, 2 * sizeof(unsigned int), st));
-        if (amax_xy) CK_CUDA(cudaMemsetAsync(amax_xy, 0, 2 * sizeof(float), st));
-        const int wpb = 8;
-        const int bx = std::max(1, std::min(cdiv(rows, wpb), 2 * di.sms)), by = std::max(1, std::min(cdiv(cols, wpb), 2 * di.sms));
-        norm2_max_kernel<<<bx + by, wpb * 32, 0, st>>>(static_cast<const __nv_bfloat16*>(X), rows, ldx,
-                                                        static_cast<const __nv_bfloat16*>(Y), cols, ldy, d / 8, bx, norm2,
-                                                        reinterpret_cast<unsigned int*>(amax_xy));
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        CK_CUDA(cudaGetLastError());
-    }
     CUtensorMap tx_a, ty_b, ty_a, tx_b;
     if ((rc = tmap_kmajor(&tx_a, X, rows, kext, ldx, BM))) return rc;
     if ((rc = tmap_kmajor(&ty_b, Y, cols, kext, ldy, BN / 2))) return rc;
@@ -1341,14 +1470,15 @@ int clipk_fwd_both(const void* X, const void* Y, int rows, int cols, int d, long
     a0.M = rows; a0.N = cols; a0.num_kb = num_kb;
     a0.n_tiles = cdiv(cols, BN); a0.m_pairs = cdiv(rows, 2 * BM);
     a0.n_clusters = int(std::min<long long>(n_clusters, (long long)a0.m_pairs * a0.n_tiles));
-    a0.pass = 0; a0.force_exact = (bounded && !exact) ? 0 : 1;
-    a0.scale = logit_scale; a0.xs = x_inv_scale; a0.ys = y_inv_scale; a0.norm2 = norm2;
+    a0.pass = 0; a0.force_exact = (stats && !exact) ? 0 : 1;
+    a0.scale = logit_scale; a0.xs = x_inv_scale; a0.ys = y_inv_scale;
+    a0.stats = stats; a0.nstat = nstat; a0.stats_rank = stats_rank; a0.use_minpos = (use_minpos && pos_logit) ? 1 : 0;
+    a0.mode_out = stats ? const_cast<float*>(stats) + stats_rank * STAT_WORDS + 5 : nullptr;
     a0.diag_offset = pos_logit ? diag_offset : -(1LL << 40);
     const size_t pstride0 = size_t(sweep_parts_bound(rows)) * PARTS_PER_UNIT * rows;
     a0.part_max = parts0; a0.part_sum = parts0 + pstride0; a0.part_dot = parts0 + 2 * pstride0;
     a0.pos = pos_logit;
     a0.colpart_sum = colparts; a0.colpart_dot = colparts + size_t(cv.m_blocks) * cv.ldc; a0.ldc = cv.ldc;
-    a0.trace = g_trace; a0.dbg = dbg_flags();
 
     FwdArgs a1 = a0;
     a1.M = cols; a1.N = rows;
@@ -1371,9 +1501,51 @@ int clipk_fwd_both(const void* X, const void* Y, int rows, int cols, int d, long
     }
     const int n = rows > cols ? rows : cols;
     fwd_merge_kernel<<<cdiv(n, 32), 256, 0, st>>>(a0, a1, cv.m_blocks, row_stats, col_stats);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    count_launch("fwd_merge_kernel", st);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
+}
+
+int clipk_fwd_both(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
+                   const float* x_inv_scale, const float* y_inv_scale, const float* logit_scale, long long diag_offset,
+                   float* row_stats, float* pos_logit, float* col_stats, float* amax_xy, int exact, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+    int rc = check_common(X, Y, rows, cols, d, ldx, ldy, dtype);
+    if (rc) return rc;
+    if (!logit_scale || !row_stats || !col_stats || !workspace) return fail(CLIPK_EINVAL, "null pointer argument");
+    if (workspace_bytes < clipk_fwd_both_workspace_bytes(rows, cols, d, dtype)) return fail(CLIPK_EWORKSPACE, "workspace too small");
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail(CLIPK_EINVAL, "workspace must be 256-byte aligned");
+    DevInfo di;
+    if ((rc = device_info(&di))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int planes = planes_of(dtype);
+    if (amax_xy) CK_CUDA(cudaMemsetAsync(amax_xy, 0xff, 2 * sizeof(float), st));   // NaN = not computed
+    if (planes != 1) {
+        // split-precision operands (fp32 inputs): two streaming sweeps
+        char* ws = static_cast<char*>(workspace);
+        const size_t w0 = clipk_fwd_workspace_bytes(rows, cols, d, dtype);
+        rc = clipk_fwd_stats(X, Y, rows, cols, d, ldx, ldy, dtype, x_inv_scale, y_inv_scale, logit_scale, diag_offset,
+                             row_stats, row_stats + rows, row_stats + 2 * (size_t)rows, pos_logit, ws, w0, stream);
+        if (rc) return rc;
+        return clipk_fwd_stats(Y, X, cols, rows, d, ldy, ldx, dtype, y_inv_scale, x_inv_scale, logit_scale, -(1LL << 40),
+                               col_stats, col_stats + cols, col_stats + 2 * (size_t)cols, nullptr, ws + round_up((long long)w0, 256),
+                               workspace_bytes - size_t(round_up((long long)w0, 256)), stream);
+    }
+    float* stats = nullptr;
+    if (dtype == CLIPK_BF16) {
+        // statistics of both operands in one pass; the positives' bound only when every column's positive is one of
+        // this call's rows, i.e. when the block is the whole problem (rows == cols, diagonal positives)
+        stats = reinterpret_cast<float*>(static_cast<char*>(workspace) + fwd_carve(rows, cols).norm2);
+        PrepArgs pa{};
+        pa.x = X; pa.y = Y; pa.rows_x = rows; pa.rows_y = cols; pa.ldx = ldx; pa.ldy = ldy; pa.d8 = d / 8;
+        pa.pair_off = pos_logit ? diag_offset : (1LL << 40);
+        pa.stats = stats;
+        if ((rc = launch_prep(pa, CLIPK_BF16, 0, di.sms, st))) return rc;
+        if (amax_xy) CK_CUDA(cudaMemcpyAsync(amax_xy, stats + 2, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    const int use_minpos = (pos_logit && rows == cols && diag_offset == 0) ? 1 : 0;
+    return fwd_sweeps(X, Y, rows, cols, d, ldx, ldy, dtype, x_inv_scale, y_inv_scale, logit_scale, diag_offset, row_stats,
+                      pos_logit, col_stats, stats, 1, 0, use_minpos, exact, workspace, di, st);
 }
 
 int clipk_finalize(const float* row_max, const float* row_sum, const float* row_dot, const float* pos_logit, int rows,
@@ -1393,18 +1565,16 @@ int clipk_finalize(const float* row_max, const float* row_sum, const float* row_
     const int n = rows > cols ? rows : cols;
     finalize_kernel<<<cdiv(n, 256), 256, 0, st>>>(row_max, row_sum, row_dot, pos_logit, rows, col_max_parts, col_sum_parts,
                                                   col_dot_parts, nparts, part_stride, cols, diag_offset, lse_row, lse_col,
-                                                  sums);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+                                                  sums, nullptr, 1.f);
+    count_launch("finalize_kernel", st);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
 }
 
 size_t clipk_bwd_workspace_bytes(int rows, int cols, int d, int g_dtype) {
     if (rows <= 0 || cols <= 0 || d <= 0) return 0;
-    // G panels (one of panel_bytes() for the per-panel path, three of df_panel_bytes() for the dataflow path), slack for their padding, the reference vectors, and the per-tile / per-panel counters of the dataflow schedule
-    const size_t counters = (size_t(cdiv(rows, 2 * BM)) + 64) * (size_t(cdiv(cols, BN)) + 64) * 2 * sizeof(int);
-    const size_t panels = std::max(size_t(2) * size_t(panel_bytes()), size_t(3) * size_t(df_panel_bytes()));
-    return panels + size_t(4) * 1024 * 1024 + (size_t(rows) + size_t(cols)) * sizeof(float) + counters + 4096;
+    // one G panel of panel_bytes(), slack for its padding, and the reference vectors of the recompute
+    return size_t(panel_bytes()) + size_t(4) * 1024 * 1024 + (size_t(rows) + size_t(cols)) * sizeof(float) + 4096;
 }
 
 static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
@@ -1412,7 +1582,10 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
                     long long ldyg, int g_dtype, const float* xg_inv_scale, const float* yg_inv_scale,
                     const float* logit_scale, long long diag_offset, const float* lse_row, const float* lse_col,
                     float alpha, float beta, const float* gscale, float* dX_acc, float* dY_acc, void* const* dY_peer_acc,
-                    int world, int rows_per_rank, void* workspace, size_t workspace_bytes, void* stream) {
+                    int world, int rows_per_rank, void* workspace, size_t workspace_bytes, void* stream,
+                    const int* mm_ready = nullptr, float coef = 1.f) {
+    // mm_ready: min / max of both LSE vectors (ordered ints) already computed by the forward (clipk_step_forward);
+    // coef: constant factor on both gradients next to the device scalar *gscale
     int rc = check_common(X, Y, rows, cols, d, ldx, ldy, dtype);
     if (rc) return rc;
     PeerOut peers;
@@ -1423,7 +1596,6 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
         if (rows_per_rank <= 0 || rows_per_rank % BM != 0 || (long long)rows_per_rank * world != cols)
             return fail(CLIPK_EUNSUPPORTED, "peer output needs cols == world * rows_per_rank and rows_per_rank %% 128 == 0");
         if (!dX_acc || dY_acc) return fail(CLIPK_EINVAL, "peer output: dX_acc is required and dY_acc must be NULL");
-        if (use_persistent()) return fail(CLIPK_EUNSUPPORTED, "peer output is not available in the dataflow backward");
         for (int o = 0; o < world; ++o) {
             if (!dY_peer_acc[o]) return fail(CLIPK_EINVAL, "null peer accumulator %d", o);
             if ((rc = tmap_out_f32(&peers.map[o], static_cast<const float*>(dY_peer_acc[o]), rows_per_rank, d, d))) return rc;
@@ -1448,134 +1620,35 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
     const long long kext = (dtype == CLIPK_BF16) ? d : planes * dpad;   // inner extent of X / Y rows
     const long long gext = gplanes * dpad;                              // inner extent of Xg / Yg rows
     long long rp_max, cp_max;
-    choose_panel(rows, cols, d, gplanes, di.sms, use_persistent() ? df_panel_bytes() : panel_bytes(), &rp_max, &cp_max);
+    choose_panel(rows, cols, d, gplanes, di.sms, panel_bytes(), &rp_max, &cp_max);
     const int ncp = int(cp_max);                        // panel width (multiple of BN) = G plane stride
     const int ldg = gplanes * ncp;
     if ((unsigned long long)round_up(rp_max, 2 * BM) * ldg * 2 > workspace_bytes) return fail(CLIPK_EWORKSPACE, "panel does not fit the workspace");
     __half* G = static_cast<__half*>(workspace);
-    if (use_persistent()) {
-        // ---- one dataflow launch over all panels (see bwd_dataflow_kernel)
-        auto kfn = bwd_dataflow_kernel;
-        constexpr int smem = smem_bytes_of(MODE_GRAD);
-        static std::once_flag once;
-        static cudaError_t attr_err = cudaSuccess;
-        static int max_clusters = 0;
-        std::call_once(once, [&] {
-            attr_err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (attr_err != cudaSuccess) return;
-            cudaLaunchConfig_t q{};
-            q.gridDim = dim3(2 * di.sms); q.blockDim = dim3(NUM_THREADS); q.dynamicSmemBytes = smem;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            q.attrs = at; q.numAttrs = 1;
-            attr_err = cudaOccupancyMaxActiveClusters(&max_clusters, kfn, &q);
-        });
-        if (attr_err != cudaSuccess) return fail(int(attr_err), "dataflow backward setup: %s", cudaGetErrorString(attr_err));
-        const int n_clusters = max_clusters < di.sms / 2 ? max_clusters : di.sms / 2;
-        if (n_clusters < 1 || n_clusters > 255) return fail(CLIPK_EUNSUPPORTED, "the dataflow backward needs 1..255 co-resident CTA pairs");
-
-        BwdP P{};
-        P.rows = rows; P.cols = cols; P.d = d; P.diag_offset = diag_offset;
-        P.rp = int(rp_max); P.cp = int(cp_max);
-        P.n_rp = cdiv(rows, rp_max); P.n_cp = cdiv(cols, cp_max);
-        P.nt = cdiv(d, BN);
-        P.want_dx = dX_acc != nullptr; P.want_dy = dY_acc != nullptr;
-        P.s_f16 = is_f16(dtype) ? 1 : 0;
-        {
-            KArgs t{};
-            set_segments(t, planes, d, dpad, dpad);
-            P.s_nseg = t.nseg; P.s_kb_per_seg = t.kb_per_seg;
-            for (int i = 0; i < 3; ++i) { P.s_a_off[i] = t.a_off[i]; P.s_b_off[i] = t.b_off[i]; }
-            set_segments(t, gplanes, 64, ncp, dpad);
-            P.g_nseg = t.nseg;
-            for (int i = 0; i < 3; ++i) { P.g_a_off[i] = t.a_off[i]; P.g_b_off[i] = t.b_off[i]; }
-        }
-        const int n_panels = P.n_rp * P.n_cp;
-        P.max_tiles = cdiv(P.rp, 2 * BM) * cdiv(P.cp, BN);
-        const BwdPlanDev* plan = nullptr;
-        if ((rc = get_bwd_plan(P, n_clusters, &plan))) return rc;
-        P.plan_shift = plan->shift; P.plan_start = plan->start; P.plan_owner = plan->owner;
-
-        // workspace: three G buffers | avec | bvec | gref[4] | minmax[2] | out_done[n_panels] | done[n_clusters]
-        const int gbuf_rows = int(round_up(rp_max, 2 * BM));
-        P.gbuf_rows = gbuf_rows;
-        const size_t g2_bytes = size_t(round_up((long long)3 * gbuf_rows * ldg * 2, 256));
-        float* avec2 = reinterpret_cast<float*>(static_cast<char*>(workspace) + g2_bytes);
-        float* bvec2 = avec2 + round_up(rows, 64);
-        float* gref2 = bvec2 + round_up(cols, 64);
-        int* mm2 = reinterpret_cast<int*>(gref2 + 4);
-        unsigned int* out_done = reinterpret_cast<unsigned int*>(mm2 + 4);
-        unsigned int* done = out_done + round_up(n_panels, 4);
-        const size_t ctl_words = size_t(round_up(n_panels, 4)) + size_t(round_up(n_clusters, 4));
-        const size_t need = g2_bytes + (round_up(rows, 64) + round_up(cols, 64) + 8) * sizeof(float) + ctl_words * 4;
-        if (need > workspace_bytes) return fail(CLIPK_EWORKSPACE, "workspace too small for three G panels, the reference vectors and the flags (%zu > %zu)", need, workspace_bytes);
-        P.out_done = out_done; P.done = done;
-        CK_CUDA(cudaMemsetAsync(mm2, 0x7f, sizeof(int), st));
-        CK_CUDA(cudaMemsetAsync(mm2 + 1, 0x80, sizeof(int), st));
-        CK_CUDA(cudaMemsetAsync(out_done, 0, ctl_words * 4, st));
-        if (dX_acc) CK_CUDA(cudaMemsetAsync(dX_acc, 0, size_t(rows) * d * sizeof(float), st));
-        if (dY_acc) CK_CUDA(cudaMemsetAsync(dY_acc, 0, size_t(cols) * d * sizeof(float), st));
-        {
-            const int n = rows + cols;
-            int blocks = cdiv(n, 256);
-            if (blocks > 4 * di.sms) blocks = 4 * di.sms;
-            lse_minmax_kernel<<<blocks, 256, 0, st>>>(lse_row, rows, lse_col, cols, mm2);
-            g_launches.fetch_add(1, std::memory_order_relaxed);
-            const int m = rows > cols ? rows : cols;
-            grad_prep_kernel<<<cdiv(m, 256), 256, 0, st>>>(lse_row, rows, lse_col, cols, mm2, avec2, bvec2, gref2);
-            g_launches.fetch_add(1, std::memory_order_relaxed);
-            CK_CUDA(cudaGetLastError());
-        }
-        CUtensorMap tmX, tmY, tmGst, tmGk, tmGmn, tmYg, tmXg, tmDX, tmDY;
-        if ((rc = tmap_kmajor(&tmX, X, rows, kext, ldx, BM))) return rc;
-        if ((rc = tmap_kmajor(&tmY, Y, cols, kext, ldy, BN / 2))) return rc;
-        if ((rc = tmap_g_store(&tmGst, G, 3 * gbuf_rows, ldg, ldg))) return rc;
-        if ((rc = tmap_kmajor(&tmGk, G, 3 * gbuf_rows, ldg, ldg, BM))) return rc;
-        if ((rc = tmap_mnmajor(&tmGmn, G, ldg, 3 * gbuf_rows, ldg))) return rc;
-        if ((rc = tmap_mnmajor(&tmYg, Yg, gext, cols, ldyg))) return rc;
-        if ((rc = tmap_mnmajor(&tmXg, Xg, gext, rows, ldxg))) return rc;
-        // a skipped gradient still needs a valid descriptor: point it at the other output
-        float* dx_ptr = dX_acc ? dX_acc : dY_acc;
-        float* dy_ptr = dY_acc ? dY_acc : dX_acc;
-        if ((rc = tmap_out_f32(&tmDX, dx_ptr, dX_acc ? rows : cols, d, d))) return rc;
-        if ((rc = tmap_out_f32(&tmDY, dy_ptr, dY_acc ? cols : rows, d, d))) return rc;
-
-        if (getenv("CLIPK_VERBOSE")) fprintf(stderr, "[clipk] dataflow bwd rows=%d cols=%d rp=%lld cp=%lld ldg=%d gbuf_rows=%d panels=%d clusters=%d\n", rows, cols, rp_max, cp_max, ldg, gbuf_rows, n_panels, n_clusters);
-        P.xg_inv = xg_inv_scale; P.yg_inv = yg_inv_scale;
-        KArgs& b = P.base;
-        b.scale = logit_scale; b.xs = x_inv_scale; b.ys = y_inv_scale;
-        b.lse_row = lse_row; b.lse_col = lse_col; b.avec = avec2; b.bvec = bvec2; b.gref = gref2;
-        b.alpha = alpha; b.beta = beta;
-        b.g_planes = gplanes; b.g_plane_stride = ncp; b.ldg = ldg;
-        b.oscale0 = logit_scale; b.oscale1 = gscale; b.oconst = 1.f / 16384.f;
-        b.tiles_per_unit = 1; b.dbg = dbg_flags(); b.trace = g_trace;
-        return launch_clustered(kfn, dim3(2 * n_clusters), dim3(2, 1, 1), smem, st, tmX, tmY, tmGst, tmGk, tmGmn, tmYg,
-                                tmXg, tmDX, tmDY, P);
-    }
     // after the panel(s): avec[rows], bvec[cols], gref[2], minmax[2]
     const size_t g_bytes = size_t(round_up(round_up(rp_max, 2 * BM) * ldg * 2, 256));
-    const bool two_streams = bwd_streams() == 2;
-    const int n_gbuf = two_streams ? 2 : 1;
+    const int n_gbuf = 1;
     float* avec = reinterpret_cast<float*>(static_cast<char*>(workspace) + n_gbuf * g_bytes);
     float* bvec = avec + round_up(rows, 64);
     float* gref = bvec + round_up(cols, 64);
     int* mm = reinterpret_cast<int*>(gref + 4);
     if (n_gbuf * g_bytes + (round_up(rows, 64) + round_up(cols, 64) + 8) * sizeof(float) > workspace_bytes)
         return fail(CLIPK_EWORKSPACE, "workspace too small for the panel and the reference vectors");
-    SideStream* side = nullptr;
-    if (two_streams && (rc = side_stream(&side))) return rc;
-    CK_CUDA(cudaMemsetAsync(mm, 0x7f, sizeof(int), st));
-    CK_CUDA(cudaMemsetAsync(mm + 1, 0x80, sizeof(int), st));
     {
-        const int n = rows + cols;
-        int blocks = cdiv(n, 256);
-        if (blocks > 4 * di.sms) blocks = 4 * di.sms;
-        lse_minmax_kernel<<<blocks, 256, 0, st>>>(lse_row, rows, lse_col, cols, mm);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
+        const int* mm_src = mm_ready;
+        if (!mm_src) {
+            CK_CUDA(cudaMemsetAsync(mm, 0x7f, sizeof(int), st));
+            CK_CUDA(cudaMemsetAsync(mm + 1, 0x80, sizeof(int), st));
+            const int n = rows + cols;
+            int blocks = cdiv(n, 256);
+            if (blocks > 4 * di.sms) blocks = 4 * di.sms;
+            lse_minmax_kernel<<<blocks, 256, 0, st>>>(lse_row, rows, lse_col, cols, mm);
+            count_launch("lse_minmax_kernel", st);
+            mm_src = mm;
+        }
         const int m = rows > cols ? rows : cols;
-        grad_prep_kernel<<<cdiv(m, 256), 256, 0, st>>>(lse_row, rows, lse_col, cols, mm, avec, bvec, gref);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
+        grad_prep_kernel<<<cdiv(m, 256), 256, 0, st>>>(lse_row, rows, lse_col, cols, mm_src, avec, bvec, gref);
+        count_launch("grad_prep_kernel", st);
         CK_CUDA(cudaGetLastError());
     }
     const size_t esz = 2;
@@ -1585,21 +1658,12 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
     const char* Ygb = static_cast<const char*>(Yg);
     const int nt = cdiv(d, BN);
 
-    if (two_streams) {
-        // fork: the side stream starts after everything enqueued so far (grad_prep's vectors, the caller's inputs)
-        CK_CUDA(cudaEventRecord(side->start, st));
-        CK_CUDA(cudaStreamWaitEvent(side->s, side->start, 0));
-    }
-    int panel = 0;
     for (long long r0 = 0; r0 < rows; r0 += rp_max) {
         const int nr = int(rows - r0 < rp_max ? rows - r0 : rp_max);
-        for (long long c0 = 0; c0 < cols; c0 += cp_max, ++panel) {
+        for (long long c0 = 0; c0 < cols; c0 += cp_max) {
             const int nc = int(cols - c0 < cp_max ? cols - c0 : cp_max);
-            const int gb = two_streams ? (panel & 1) : 0;
-            __half* const Gp = reinterpret_cast<__half*>(static_cast<char*>(workspace) + gb * g_bytes);
-            const cudaStream_t sg = two_streams ? side->s : st;      // stream of the recompute sweep
-            // buffer gb was last read by the gradient GEMMs of panel - 2
-            if (two_streams && panel >= 2) CK_CUDA(cudaStreamWaitEvent(side->s, side->freed[gb], 0));
+            __half* const Gp = G;
+            const cudaStream_t sg = st;
             // ---- recompute S on the panel, write G (fp16, x 2^14)
             {
                 CUtensorMap ta, tb, tc;
@@ -1619,7 +1683,7 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
                 a.alpha = alpha; a.beta = beta;
                 a.avec = avec + r0; a.bvec = bvec + c0; a.gref = gref;
                 a.G = Gp; a.ldg = ldg; a.g_planes = gplanes; a.g_plane_stride = ncp;
-                if (planes == 1 && gplanes == 1 && a.num_kb <= ARES_KB && !(dbg_flags() & 512)) {
+                if (planes == 1 && gplanes == 1 && a.num_kb <= ARES_KB) {
                     // rows of X resident in shared memory, persistent over the panel (see grad_sweep_kernel)
                     SweepGeom g{};
                     g.num_kb = a.num_kb; g.n_tiles = a.n_tiles; g.m_pairs = m_pairs;
@@ -1633,10 +1697,6 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
                 }
                 if (rc) return rc;
             }
-            if (two_streams) {
-                CK_CUDA(cudaEventRecord(side->ready[gb], side->s));
-                CK_CUDA(cudaStreamWaitEvent(st, side->ready[gb], 0));
-            }
             // ---- job 0: dX[r0:r0+nr, :] (+)= G[nr, nc] * Yg[c0:c0+nc, :]      (A K-major, B MN-major, fp16 x fp16)
             // ---- job 1: dY[c0:c0+nc, :] (+)= G^T[nc, nr] * Xg[r0:r0+nr, :]    (A MN-major, B MN-major, fp16 x fp16)
             CUtensorMap ta0, tb0, tc0, ta1, tb1, tc1;
@@ -1649,7 +1709,7 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
                 a0.M = nr; a0.N = d; a0.n_tiles = nt; a0.tiles_per_unit = 1; a0.a_mn = 0; a0.b_mn = 1;
                 set_segments(a0, gplanes, nc, ncp, dpad);
                 a0.out = dX_acc + r0 * d; a0.ldo = d; a0.accumulate = (c0 > 0);
-                a0.oscale0 = logit_scale; a0.oscale1 = gscale; a0.oscale2 = yg_inv_scale; a0.oconst = 1.f / 16384.f;
+                a0.oscale0 = logit_scale; a0.oscale1 = gscale; a0.oscale2 = yg_inv_scale; a0.oconst = coef / 16384.f;
                 jobs0 = cdiv(nr, 2 * BM) * nt;
             }
             if (dY_acc) {
@@ -1660,7 +1720,7 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
                 set_segments(a1, gplanes, nr, ncp, dpad);
                 a1.out = dY_acc + c0 * d; a1.ldo = d; a1.accumulate = (r0 > 0);
                 if (peers.world) a1.c_row_off = int(c0);   // global dY row of the panel (owner = row / rows_per_rank)
-                a1.oscale0 = logit_scale; a1.oscale1 = gscale; a1.oscale2 = xg_inv_scale; a1.oconst = 1.f / 16384.f;
+                a1.oscale0 = logit_scale; a1.oscale1 = gscale; a1.oscale2 = xg_inv_scale; a1.oconst = coef / 16384.f;
                 jobs1 = cdiv(nc, 2 * BM) * nt;
             }
             // One job (256 x 256 output tile, full K of the panel) per CTA pair.  A stream-K split of the K blocks over
@@ -1670,7 +1730,6 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
             else if (dX_acc) rc = launch_gemm<MODE_OUT, 1>(ta0, tb0, tc0, a0, nt, cdiv(nr, 2 * BM), st);
             else rc = launch_gemm<MODE_OUT, 1>(ta1, tb1, tc1, a1, nt, cdiv(nc, 2 * BM), st);
             if (rc) return rc;
-            if (two_streams) CK_CUDA(cudaEventRecord(side->freed[gb], st));
         }
     }
     return CLIPK_OK;
@@ -1725,7 +1784,7 @@ int clipk_normalize_fwd(const void* x, int dtype, long long rows, long long d, l
     else
         normalize_fwd_kernel<<<cdiv(rows, wpb), wpb * 32, 0, st>>>(static_cast<const float*>(x), rows, int(d / 8), ldx,
                                                                     static_cast<float*>(y), ldy, inv_norm, eps);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    count_launch("normalize_fwd_kernel", st);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
 }
@@ -1747,7 +1806,7 @@ int clipk_normalize_bwd(const void* g, long long ldg, const void* y, long long l
     else
         normalize_bwd_kernel<<<cdiv(rows, wpb), wpb * 32, 0, st>>>(static_cast<const float*>(g), ldg, static_cast<const float*>(y),
                                                                     ldy, inv_norm, rows, int(d / 8), static_cast<float*>(dx), ldd, eps);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    count_launch("normalize_bwd_kernel", st);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
 }
@@ -1758,7 +1817,7 @@ int clipk_reduce_slots(const float* src, long long n, int world, void* dst, int 
         return fail(CLIPK_EUNSUPPORTED, "n must be a multiple of 4 and the pointers 16-byte aligned");
     if (dtype != CLIPK_BF16 && dtype != CLIPK_F32) return fail(CLIPK_EUNSUPPORTED, "dtype %d", dtype);
     reduce_slots_kernel<<<cdiv(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, n, world, dst, dtype);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    count_launch("reduce_slots_kernel", static_cast<cudaStream_t>(stream));
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
 }
@@ -1774,7 +1833,7 @@ int clipk_rank_count(const float* S, int rows, int cols, long long ld, const lon
     if (rows == 0) return CLIPK_OK;
     rank_count_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(S, ld, cols, target, diag_offset, row0, greater,
                                                                            ties_before);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    count_launch("rank_count_kernel", static_cast<cudaStream_t>(stream));
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
 }
@@ -1791,10 +1850,10 @@ int clipk_distill_cross(const float* S, const float* T, int rows, int cols, long
     if (rows == 0) return CLIPK_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     distill_row_cross_kernel<<<rows, 256, 0, st>>>(S, T, ld, cols, s_mul, t_mul, t_lse_row, row0, row_cross);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    count_launch("distill_row_cross_kernel", st);
     CK_CUDA(cudaGetLastError());
     distill_col_cross_kernel<<<cdiv(cols, 32), 256, 0, st>>>(S, T, rows, cols, ld, s_mul, t_mul, t_lse_col, col_part);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    count_launch("distill_col_cross_kernel", st);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
 }
@@ -1811,55 +1870,298 @@ int clipk_distill_grad(const float* S, const float* T, int rows, int cols, long 
     if (rows == 0) return CLIPK_OK;
     distill_grad_kernel<<<dim3(cdiv(cols, 256), rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         S, T, cols, ld, s_mul, t_mul, s_lse_row, t_lse_row, row0, s_lse_col, t_lse_col, static_cast<__half*>(G), ldg);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    count_launch("distill_grad_kernel", static_cast<cudaStream_t>(stream));
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
 }
 
-int clipk_peer_gather(void* const* peer_src, void* dst, long long bytes_per_rank, int world, void* stream) {
-    if (!peer_src || !dst || bytes_per_rank <= 0 || world < 1 || world > MAX_PEERS) return fail(CLIPK_EINVAL, "bad argument");
-    if (bytes_per_rank % 16 != 0 || (reinterpret_cast<uintptr_t>(dst) & 15) != 0)
-        return fail(CLIPK_EINVAL, "bytes_per_rank must be a multiple of 16 and dst 16-byte aligned");
-    DevInfo di;
-    int rc = device_info(&di);
-    if (rc) return rc;
-    PeerSrc ps;
-    memset(&ps, 0, sizeof(ps));
-    for (int o = 0; o < world; ++o) {
-        if (!peer_src[o] || (reinterpret_cast<uintptr_t>(peer_src[o]) & 15) != 0) return fail(CLIPK_EINVAL, "source %d null or misaligned", o);
-        ps.p[o] = static_cast<const uint4*>(peer_src[o]);
-    }
-    const long long n16 = bytes_per_rank / 16;
-    long long blocks = cdiv(n16, 256);
-    const long long cap = cdiv(8LL * di.sms, world);     // ~8 blocks per SM over all sources
-    if (blocks > cap) blocks = cap;
-    peer_gather_kernel<<<dim3(unsigned(blocks), unsigned(world)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        ps, static_cast<uint4*>(dst), n16);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    CK_CUDA(cudaGetLastError());
-    return CLIPK_OK;
-}
-
-int clipk_peer_barrier(void* const* peer_flags, int rank, int world, unsigned int epoch, void* stream) {
+int clipk_peer_barrier(void* const* peer_flags, int rank, int world, unsigned int epoch, int* err, void* stream) {
     if (!peer_flags || world < 1 || world > MAX_PEERS || rank < 0 || rank >= world) return fail(CLIPK_EINVAL, "bad argument");
     DevInfo di;
     int rc = device_info(&di);
     if (rc) return rc;
-    PeerFlags pf;
+    PeerPtrs pf;
     memset(&pf, 0, sizeof(pf));
     for (int t = 0; t < world; ++t) {
         if (!peer_flags[t]) return fail(CLIPK_EINVAL, "null flag array %d", t);
-        pf.flags[t] = static_cast<unsigned int*>(peer_flags[t]);
+        pf.p[t] = peer_flags[t];
     }
-    peer_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pf, rank, world, epoch);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    peer_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pf, rank, world, epoch, err);
+    count_launch("peer_barrier_kernel", static_cast<cudaStream_t>(stream));
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
 }
 
-// Experiments only: device buffer of 3*64 int64 that CTA (0,0) of every following launch fills with clock64 stamps.
-int clipk_debug_set_trace(long long* device_buffer) {
-    g_trace = device_buffer;
+// ---- the whole step (see include/clipk.h) ----------------------------------------------------------------------------
+namespace {
+struct StepCarve {
+    size_t fwd, row_stats, pos, col_local, col_all;          // forward phase
+    size_t xg, yg, inv2, dx, dy, bwd;                        // backward phase (overlays the forward's scratch)
+    size_t total;
+};
+StepCarve step_carve(int rows, int cols, int d, int world) {
+    StepCarve c{};
+    auto take = [](size_t& off, size_t bytes) { const size_t o = off; off = size_t(round_up((long long)(off + bytes), 256)); return o; };
+    size_t f = 0;
+    c.fwd = take(f, fwd_carve(rows, cols).total);
+    c.row_stats = take(f, size_t(3) * rows * sizeof(float));
+    c.pos = take(f, size_t(rows) * sizeof(float));
+    c.col_local = take(f, size_t(3) * cols * sizeof(float));
+    c.col_all = take(f, world > 1 ? size_t(world) * 3 * cols * sizeof(float) : 0);
+    const size_t dpad = size_t(round_up(d, BK));
+    size_t b = 0;
+    c.xg = take(b, size_t(rows) * dpad * 2);
+    c.yg = take(b, size_t(cols) * dpad * 2);
+    c.inv2 = take(b, 256);
+    c.dx = take(b, size_t(rows) * d * sizeof(float));
+    c.dy = take(b, world > 1 ? 0 : size_t(cols) * d * sizeof(float));
+    c.bwd = take(b, clipk_bwd_workspace_bytes(rows, cols, d, CLIPK_F16));
+    c.total = (f > b ? f : b) + 256;
+    return c;
+}
+int step_check(const clipk_step* p, int* world, int* rank) {
+    if (!p) return fail(CLIPK_EINVAL, "null step");
+    const int W = p->peer ? p->peer->world : 1, r = p->peer ? p->peer->rank : 0;
+    if (W < 1 || W > MAX_PEERS || r < 0 || r >= W) return fail(CLIPK_EINVAL, "world %d / rank %d out of range", W, r);
+    if (p->rows <= 0 || p->d <= 0 || (long long)p->rows * W != p->cols) return fail(CLIPK_EINVAL, "cols must be world * rows");
+    if (p->d % BK != 0) return fail(CLIPK_EUNSUPPORTED, "d = %d is not a multiple of 64", p->d);
+    if (W > 1 && p->rows % BM != 0) return fail(CLIPK_EUNSUPPORTED, "with peers the local batch must be a multiple of 128");
+    if (p->src_dtype != CLIPK_BF16 && p->src_dtype != CLIPK_F32) return fail(CLIPK_EUNSUPPORTED, "src_dtype %d", p->src_dtype);
+    if (!p->image || !p->text || !p->logit_scale || !p->x_op || !p->y_all || !p->stats || !p->lse_row || !p->lse_col ||
+        !p->scal || !p->workspace)
+        return fail(CLIPK_EINVAL, "null pointer argument");
+    if (p->normalize && (!p->inv_x || !p->inv_y)) return fail(CLIPK_EINVAL, "normalize needs inv_x and inv_y");
+    const bool produced = p->normalize || p->src_dtype != CLIPK_BF16;
+    if (produced && (p->x_op == p->image || p->y_all == p->text)) return fail(CLIPK_EINVAL, "x_op / y_all must be separate buffers when the operands are produced");
+    if (!produced && p->x_op != p->image) return fail(CLIPK_EINVAL, "x_op must alias image when nothing is produced");
+    if (W == 1 && !produced && p->y_all != p->text) return fail(CLIPK_EINVAL, "y_all must alias text when nothing is produced or gathered");
+    const int es = p->src_dtype == CLIPK_BF16 ? 2 : 4;
+    if (p->ld_image < p->d || p->ld_text < p->d || (p->ld_image * es) % 16 != 0 || (p->ld_text * es) % 16 != 0 ||
+        (reinterpret_cast<uintptr_t>(p->image) & 15) != 0 || (reinterpret_cast<uintptr_t>(p->text) & 15) != 0)
+        return fail(CLIPK_EINVAL, "input rows must be 16-byte aligned and at least d wide");
+    if ((reinterpret_cast<uintptr_t>(p->workspace) & 255) != 0) return fail(CLIPK_EINVAL, "workspace must be 256-byte aligned");
+    if (p->workspace_bytes < step_carve(p->rows, p->cols, p->d, W).total) return fail(CLIPK_EWORKSPACE, "workspace too small");
+    if (!(p->loss_div > 0.f)) return fail(CLIPK_EINVAL, "loss_div must be positive");
+    *world = W; *rank = r;
+    return CLIPK_OK;
+}
+int launch_allgather(const GatherArgs& g, int sms, cudaStream_t st) {
+    // enough 16-byte loads in flight to cover the NVLink round trip at full rate: ~160 blocks of 256 threads x 4 loads
+    long long bx = cdiv(g.n16_0, 256 * 4);
+    const long long want = std::max(4, 160 / g.world);
+    if (bx > want) bx = want;
+    if (bx < 1) bx = 1;
+    (void)sms;
+    peer_allgather_kernel<<<dim3(unsigned(bx), unsigned(g.world)), 256, 0, st>>>(g);
+    count_launch("peer_allgather_kernel", st);
+    CK_CUDA(cudaGetLastError());
+    return CLIPK_OK;
+}
+}  // namespace
+
+size_t clipk_step_workspace_bytes(const clipk_step* p) {
+    if (!p || p->rows <= 0 || p->cols <= 0 || p->d <= 0) return 0;
+    return step_carve(p->rows, p->cols, p->d, p->peer ? p->peer->world : 1).total;
+}
+
+int clipk_step_forward(const clipk_step* p) {
+    int W = 1, rank = 0, rc;
+    if ((rc = step_check(p, &W, &rank))) return rc;
+    DevInfo di;
+    if ((rc = device_info(&di))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(p->stream);
+    const clipk_peer* pr = p->peer;
+    const int rows = p->rows, cols = p->cols, d = p->d;
+    const StepCarve cv = step_carve(rows, cols, d, W);
+    char* ws = static_cast<char*>(p->workspace);
+    float* row_stats = reinterpret_cast<float*>(ws + cv.row_stats);
+    float* pos = reinterpret_cast<float*>(ws + cv.pos);
+    float* col_local = (W > 1) ? static_cast<float*>(pr->col_src[rank]) : reinterpret_cast<float*>(ws + cv.col_local);
+    float* col_all = (W > 1) ? reinterpret_cast<float*>(ws + cv.col_all) : col_local;
+
+    // 1. one pass over the local rows: operands, statistics; resets the accumulators of finalize
+    float* my_stats = (W > 1) ? static_cast<float*>(pr->stats_src[rank]) : p->stats;
+    PrepArgs pa{};
+    pa.x = p->image; pa.y = p->text; pa.rows_x = rows; pa.rows_y = rows; pa.ldx = p->ld_image; pa.ldy = p->ld_text;
+    pa.d8 = d / 8; pa.pair_off = 0;
+    pa.x_out = (p->x_op != p->image) ? static_cast<__nv_bfloat16*>(p->x_op) : nullptr;
+    if (W > 1) pa.y_out = static_cast<__nv_bfloat16*>(pr->text_src[rank]);
+    else pa.y_out = (p->y_all != p->text) ? static_cast<__nv_bfloat16*>(p->y_all) : nullptr;
+    pa.ldxo = d; pa.ldyo = d;
+    pa.inv_x = p->inv_x; pa.inv_y = p->inv_y; pa.eps = p->eps;
+    pa.stats = my_stats; pa.reset = p->scal;
+    if ((rc = launch_prep(pa, p->src_dtype, p->normalize, di.sms, st))) return rc;
+
+    // 2. all-gather of the text operand rows and of the statistics (gather_features, loss.py:20-64)
+    if (W > 1) {
+        GatherArgs g{};
+        for (int o = 0; o < W; ++o) {
+            if (!pr->text_src[o] || !pr->stats_src[o] || !pr->flags_gather[o]) return fail(CLIPK_EINVAL, "null peer pointer %d", o);
+            g.src0.p[o] = pr->text_src[o]; g.src1.p[o] = pr->stats_src[o]; g.flags.p[o] = pr->flags_gather[o];
+        }
+        g.n16_0 = (long long)rows * d * 2 / 16; g.dst0 = static_cast<uint4*>(p->y_all);
+        g.n16_1 = STAT_WORDS * sizeof(float) / 16; g.dst1 = reinterpret_cast<uint4*>(p->stats);
+        g.rank = rank; g.world = W; g.epoch = pr->epoch_gather; g.err = pr->err;
+        if ((rc = launch_allgather(g, di.sms, st))) return rc;
+    }
+
+    // 3. single-sweep forward over the [rows, cols] block + merge
+    const long long off = (long long)rank * rows;
+    if ((rc = fwd_sweeps(p->x_op, p->y_all, rows, cols, d, d == 0 ? 0 : (p->x_op == p->image ? p->ld_image : d),
+                         (W == 1 && p->y_all == p->text) ? p->ld_text : d, CLIPK_BF16, nullptr, nullptr, p->logit_scale, off,
+                         row_stats, pos, col_local, p->stats, W, rank, 1, 0, ws + cv.fwd, di, st)))
+        return rc;
+
+    // 4. the column statistics of every rank's block
+    if (W > 1) {
+        GatherArgs g{};
+        for (int o = 0; o < W; ++o) {
+            if (!pr->col_src[o] || !pr->flags_stats[o]) return fail(CLIPK_EINVAL, "null peer pointer %d", o);
+            g.src0.p[o] = pr->col_src[o]; g.flags.p[o] = pr->flags_stats[o];
+        }
+        g.n16_0 = (long long)3 * cols * sizeof(float) / 16; g.dst0 = reinterpret_cast<uint4*>(col_all);
+        g.n16_1 = 0;
+        g.rank = rank; g.world = W; g.epoch = pr->epoch_stats; g.err = pr->err;
+        if ((rc = launch_allgather(g, di.sms, st))) return rc;
+    }
+
+    // 5. log-sum-exps, cross-entropy sums, loss
+    const int n = rows > cols ? rows : cols;
+    finalize_kernel<<<cdiv(n, 256), 256, 0, st>>>(row_stats, row_stats + rows, row_stats + 2 * (size_t)rows, pos, rows, col_all,
+                                                  col_all + cols, col_all + 2 * (size_t)cols, W, (long long)3 * cols, cols, off,
+                                                  p->lse_row, p->lse_col, p->scal, reinterpret_cast<int*>(p->scal) + 8,
+                                                  p->loss_div);
+    count_launch("finalize_kernel", st);
+    CK_CUDA(cudaGetLastError());
+    return CLIPK_OK;
+}
+
+int clipk_step_backward(const clipk_step* p) {
+    int W = 1, rank = 0, rc;
+    if ((rc = step_check(p, &W, &rank))) return rc;
+    if (!p->grad_out) return fail(CLIPK_EINVAL, "null grad_out");
+    if (p->out_dtype != CLIPK_BF16 && p->out_dtype != CLIPK_F32) return fail(CLIPK_EUNSUPPORTED, "out_dtype %d", p->out_dtype);
+    DevInfo di;
+    if ((rc = device_info(&di))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(p->stream);
+    const clipk_peer* pr = p->peer;
+    const int rows = p->rows, cols = p->cols, d = p->d;
+    const StepCarve cv = step_carve(rows, cols, d, W);
+    char* ws = static_cast<char*>(p->workspace);
+    const long long ldx = (p->x_op == p->image) ? p->ld_image : d;
+    const long long ldy = (W == 1 && p->y_all == p->text) ? p->ld_text : d;
+    const long long off = (long long)rank * rows;
+    const bool want_feat = p->d_image || p->d_text;
+    if (want_feat) {
+        if (!p->d_image || !p->d_text) return fail(CLIPK_EINVAL, "d_image and d_text must be given together");
+        // 1. exact fp16 copies of both operands for the gradient GEMMs
+        __half* Xg = reinterpret_cast<__half*>(ws + cv.xg);
+        __half* Yg = reinterpret_cast<__half*>(ws + cv.yg);
+        float* inv2 = reinterpret_cast<float*>(ws + cv.inv2);
+        const long long dpad = round_up(d, BK);
+        const long long n8 = ((long long)rows + cols) * (dpad / 8);
+        to_f16_pair_kernel<<<cdiv(n8, 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(p->x_op), rows, ldx, Xg,
+                                                          static_cast<const __nv_bfloat16*>(p->y_all), cols, ldy, Yg, d, dpad,
+                                                          p->stats, W, rank, inv2);
+        count_launch("to_f16_pair_kernel", st);
+        CK_CUDA(cudaGetLastError());
+        // 2. recompute + gradient GEMMs, panel by panel; with peers the dY tiles go straight to their owners
+        float* dX = reinterpret_cast<float*>(ws + cv.dx);
+        float* dY = (W > 1) ? nullptr : reinterpret_cast<float*>(ws + cv.dy);
+        void* slots[MAX_PEERS];
+        if (W > 1)
+            for (int o = 0; o < W; ++o) {
+                if (!pr->grad_slot[o] || !pr->flags_grad[o]) return fail(CLIPK_EINVAL, "null peer pointer %d", o);
+                slots[o] = pr->grad_slot[o];
+            }
+        if ((rc = bwd_impl(p->x_op, p->y_all, rows, cols, d, ldx, ldy, CLIPK_BF16, nullptr, nullptr, Xg, Yg, dpad, dpad, CLIPK_F16,
+                           inv2, inv2 + 1, p->logit_scale, off, p->lse_row, p->lse_col, 1.f, 1.f, p->grad_out, dX, dY,
+                           W > 1 ? slots : nullptr, W, rows, ws + cv.bwd, clipk_bwd_workspace_bytes(rows, cols, d, CLIPK_F16),
+                           p->stream, reinterpret_cast<const int*>(p->scal) + 8, p->grad_coef)))
+            return rc;
+        // 3. every rank's tiles have landed in the slots this rank owns
+        if (W > 1) {
+            PeerPtrs pf;
+            memset(&pf, 0, sizeof(pf));
+            for (int o = 0; o < W; ++o) pf.p[o] = pr->flags_grad[o];
+            peer_barrier_kernel<<<1, 32, 0, st>>>(pf, rank, W, pr->epoch_grad, pr->err);
+            count_launch("peer_barrier_kernel", st);
+            CK_CUDA(cudaGetLastError());
+        }
+        // 4. slots -> text gradient, Jacobian of the normalisation, cast, dlogit_scale
+        FinishArgs fa{};
+        fa.gx = dX; fa.rows_x = rows;
+        fa.gy = (W > 1) ? pr->my_slots : dY; fa.rows_y = rows;
+        fa.slots = W; fa.slot_stride = (long long)rows * d;
+        fa.d8 = d / 8;
+        if (p->normalize) {
+            fa.xn = static_cast<const __nv_bfloat16*>(p->x_op); fa.ldxn = ldx;
+            // this rank's own rows of the gathered text operand
+            fa.yn = static_cast<const __nv_bfloat16*>(p->y_all) + off * ldy; fa.ldyn = ldy;
+            fa.inv_x = p->inv_x; fa.inv_y = p->inv_y; fa.eps = p->eps;
+        }
+        fa.out_x = p->d_image; fa.out_y = p->d_text; fa.out_dtype = p->out_dtype;
+        fa.pair = p->scal + 4; fa.go = p->grad_out; fa.scale = p->logit_scale; fa.dscale = p->d_scale;
+        const int wpb = 8;
+        const int blocks = int(std::max<long long>(1, std::min<long long>(cdiv(2LL * rows, wpb), 8LL * di.sms)));
+        finish_grad_kernel<<<blocks, wpb * 32, 0, st>>>(fa);
+        count_launch("finish_grad_kernel", st);
+        CK_CUDA(cudaGetLastError());
+    } else if (p->d_scale) {
+        FinishArgs fa{};
+        fa.pair = p->scal + 4; fa.go = p->grad_out; fa.scale = p->logit_scale; fa.dscale = p->d_scale;
+        finish_grad_kernel<<<1, 32, 0, st>>>(fa);
+        count_launch("finish_grad_kernel", st);
+        CK_CUDA(cudaGetLastError());
+    }
+    return CLIPK_OK;
+}
+
+int clipk_bwd_panel(int rows, int cols, int d, long long* panel_rows, long long* panel_cols) {
+    if (rows <= 0 || cols <= 0 || d <= 0 || !panel_rows || !panel_cols) return fail(CLIPK_EINVAL, "bad argument");
+    DevInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    choose_panel(rows, cols, d, 1, di.sms, panel_bytes(), panel_rows, panel_cols);
+    return CLIPK_OK;
+}
+
+int clipk_profile_begin(void* stream) {
+    if (g_prof_on.load()) return fail(CLIPK_EINVAL, "profile already running");
+    for (ProfEntry& e : g_prof) cudaEventDestroy(e.ev);
+    g_prof.clear();
+    cudaEvent_t ev;
+    CK_CUDA(cudaEventCreate(&ev));
+    CK_CUDA(cudaEventRecord(ev, static_cast<cudaStream_t>(stream)));
+    g_prof.push_back(ProfEntry{"", ev});
+    g_prof_on.store(1);
+    return CLIPK_OK;
+}
+
+int clipk_profile_end(char* out, size_t out_bytes) {
+    if (!g_prof_on.load()) return fail(CLIPK_EINVAL, "no profile running");
+    g_prof_on.store(0);
+    if (!out || out_bytes < 64) return fail(CLIPK_EINVAL, "output buffer too small");
+    if (!g_prof.empty()) CK_CUDA(cudaEventSynchronize(g_prof.back().ev));
+    struct Agg { const char* name; int n; double ms; };
+    std::vector<Agg> agg;
+    for (size_t i = 1; i < g_prof.size(); ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_prof[i - 1].ev, g_prof[i].ev) != cudaSuccess) ms = 0.f;
+        bool found = false;
+        for (Agg& a : agg)
+            if (strcmp(a.name, g_prof[i].name) == 0) { a.n += 1; a.ms += ms; found = true; break; }
+        if (!found) agg.push_back(Agg{g_prof[i].name, 1, ms});
+    }
+    size_t off = 0;
+    out[0] = 0;
+    for (const Agg& a : agg) {
+        const int w = snprintf(out + off, out_bytes - off, "%s:%d:%.6f;", a.name, a.n, a.ms);
+        if (w < 0 || size_t(w) >= out_bytes - off) break;
+        off += size_t(w);
+    }
+    for (ProfEntry& e : g_prof) cudaEventDestroy(e.ev);
+    g_prof.clear();
     return CLIPK_OK;
 }
 
@@ -1869,7 +2171,7 @@ int clipk_debug_tmem_layout(int* out, void* stream) {
     int rc = device_info(&di);
     if (rc) return rc;
     tmem_layout_kernel<<<1, 128, 0, static_cast<cudaStream_t>(stream)>>>(out);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    count_launch("tmem_layout_kernel", static_cast<cudaStream_t>(stream));
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
 }
@@ -1879,7 +2181,7 @@ int clipk_cast(const float* src, void* dst, long long n, int dtype, void* stream
     if (dtype != CLIPK_BF16 && dtype != CLIPK_F32) return fail(CLIPK_EUNSUPPORTED, "dtype %d", dtype);
     if (n == 0) return CLIPK_OK;
     cast_kernel<<<cdiv(cdiv(n, 4), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, n, dtype);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    count_launch("cast_kernel", static_cast<cudaStream_t>(stream));
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
 }

@@ -52,7 +52,6 @@ __host__ __device__ constexpr int smem_bytes_of(int mode) {
     return 1024 /*align slack*/ + stages_of(mode) * STAGE_BYTES + 256 + MISC_BYTES + (mode == 0 ? 0 : STG_TOTAL);
 }
 constexpr int PARTS_PER_UNIT = 2;            // each 128-column half of a tile keeps its own row statistics
-constexpr int TRACE_N = 512;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 
@@ -100,9 +99,6 @@ struct KArgs {
     const float* oscale1;
     const float* oscale2;
     float oconst;
-    long long* trace;          // optional clock64 trace (nullptr in production): [3 roles][TRACE_N] stamps of one CTA
-    int trace_on;              // set by the kernel for the CTA that records
-    int dbg;                   // CLIPK_DBG experiment bits: 1 = skip epilogue math+staging, 2 = skip TMA stores, 4 = skip tile barriers
 };
 
 // ---------------------------------------------------------------------------------------------------- epilogues
@@ -246,15 +242,7 @@ struct Pipe {
     uint32_t ph = 0;    // its phase
     int it = 0;         // tiles processed so far (MMA / epilogue): accumulator stage = it & 1
     int stg_use = 0;    // TMA stores issued so far by this epilogue warp
-    int tr = 0;         // clock64 stamps recorded so far by this role (experiments)
 };
-
-// experiments: stamp number p.tr of `role` (0 producer, 1 MMA, 2 first epilogue warp)
-__device__ __forceinline__ void trace_stamp(const KArgs& args, Pipe& p, int role) {
-    // trace_on: 1 = CTA (0, 0) of the grid records (set by the host), 2 = this CTA records (set by the kernel)
-    if (args.trace && (args.trace_on == 2 || (args.trace_on == 1 && blockIdx.x == 0 && blockIdx.y == 0)) && p.tr < TRACE_N)
-        args.trace[role * TRACE_N + p.tr++] = clock64();
-}
 
 // Shared memory: A region (A_BYTES) | NB B stages | epilogue staging | barriers.  The streaming kernels use one A slot
 // per stage (A_BYTES = STAGES * A_STAGE_BYTES, NB = STAGES); the A-resident forward keeps all K blocks of its rows.
@@ -358,55 +346,11 @@ template <int STAGES>
 __device__ __forceinline__ void produce_unit(const Cta& c, Pipe& p, const CUtensorMap* tmA, const CUtensorMap* tmB,
                                              const KArgs& args, int m_blk, int t0, int t1) {
     for (int t = t0; t < t1; ++t) {
-        trace_stamp(args, p, 0);
         for (int kb = 0; kb < args.num_kb; ++kb) {
             const int seg = kb / args.kb_per_seg;
             load_kblock<STAGES>(c, p, tmA, tmB, args, m_blk, t, seg, kb - seg * args.kb_per_seg);
         }
-        trace_stamp(args, p, 0);
     }
-}
-
-// spin until a counter written by other CTAs reaches `target`; what they stored before (also through TMA) is then
-// visible to this thread's following TMA loads / stores
-__device__ __forceinline__ void flag_wait(const unsigned int* flag, unsigned int target) {
-    unsigned int v;
-    do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-    } while (v < target);
-    asm volatile("fence.proxy.async;" ::: "memory");
-}
-// publish: this thread's completed bulk stores (cp.async.bulk.wait_group done) and generic stores, then count
-__device__ __forceinline__ void flag_signal(unsigned int* flag) {
-    asm volatile("fence.proxy.async;" ::: "memory");
-    __threadfence();
-    atomicAdd(flag, 1u);
-}
-
-// Gradient-GEMM job of the dataflow backward: the K extent is made of `nkt` 256-wide pieces, piece i being one G tile
-// written by cluster owner[i * fstride].  Before the first load that touches a tile its owner must have published the
-// panel (done[owner] >= target); `seen` remembers the owners already checked for this panel.
-template <int STAGES>
-__device__ __forceinline__ void produce_job(const Cta& c, Pipe& p, const CUtensorMap* tmA, const CUtensorMap* tmB,
-                                            const KArgs& args, int m_blk, int t, int nkt, const unsigned int* done,
-                                            const unsigned char* owner, int fstride, unsigned int target,
-                                            unsigned long long (&seen)[4]) {
-    constexpr int KB_PER_TILE = BN / BK;
-    trace_stamp(args, p, 0);
-    for (int seg = 0; seg < args.nseg; ++seg) {
-        for (int i = 0; i < nkt; ++i) {
-            if (seg == 0 && target) {
-                const int o = owner[i * fstride];
-                if (!((seen[o >> 6] >> (o & 63)) & 1ull)) {
-                    flag_wait(done + o, target);
-                    seen[o >> 6] |= 1ull << (o & 63);
-                }
-            }
-            const int kb1 = min(args.kb_per_seg, (i + 1) * KB_PER_TILE);
-            for (int kb = i * KB_PER_TILE; kb < kb1; ++kb) load_kblock<STAGES>(c, p, tmA, tmB, args, m_blk, t, seg, kb);
-        }
-    }
-    trace_stamp(args, p, 0);
 }
 
 // ------------------------------------------------------------------ MMA issuer (one lane of warp 1, leader CTA only)
@@ -423,15 +367,12 @@ __device__ __forceinline__ void mma_unit(const Cta& c, Pipe& p, const KArgs& arg
     for (int t = 0; t < ntiles; ++t, ++p.it) {
         const int a = p.it & 1;
         const uint32_t aph = (p.it >> 1) & 1;
-        trace_stamp(args, p, 1);
         ptx::mbar_wait(c.bar_tempty + 8 * a, aph ^ 1);
         ptx::tc_fence_after();
-        trace_stamp(args, p, 1);
         const uint32_t d_tmem = c.tmem_base + a * BN;
         for (int kb = 0; kb < args.num_kb; ++kb) {
             ptx::mbar_wait(c.bar_full + 8 * p.s, p.ph);
             ptx::tc_fence_after();
-            if (kb == 0) trace_stamp(args, p, 1);
             const uint32_t a_src = c.sA + p.s * A_STAGE_BYTES;
             const uint32_t b_src = c.sB + p.s * B_STAGE_BYTES;
 #pragma unroll
@@ -443,7 +384,6 @@ __device__ __forceinline__ void mma_unit(const Cta& c, Pipe& p, const KArgs& arg
             if (++p.s == STAGES) { p.s = 0; p.ph ^= 1; }
         }
         ptx::mma_commit_pair(c.bar_tfull + 8 * a);
-        trace_stamp(args, p, 1);
     }
 }
 
@@ -451,8 +391,7 @@ __device__ __forceinline__ void mma_unit(const Cta& c, Pipe& p, const KArgs& arg
 // STATS and OUT tiles (the recompute tiles have their own epilogue below)
 template <int MODE>
 __device__ __forceinline__ void epilogue_unit(const Cta& c, Pipe& p, const CUtensorMap* tmC, const KArgs& args, int m_blk,
-                                              int unit, int t0, int t1, unsigned int* done_ctr = nullptr,
-                                              int row_shift = 0) {
+                                              int unit, int t0, int t1, int row_shift = 0) {
     static_assert(MODE == MODE_STATS || MODE == MODE_OUT, "GRAD tiles go through grad_epilogue_unit");
     const int warp = c.warp, lane = c.lane;
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
@@ -476,23 +415,16 @@ __device__ __forceinline__ void epilogue_unit(const Cta& c, Pipe& p, const CUten
         if (args.oscale2) oscale *= __ldg(args.oscale2);
     }
     StatsState st{-CUDART_INF_F, 0.f, 0.f, 0.f, false};
-    auto TR = [&]() {
-        if (warp == 2 && lane == 0) trace_stamp(args, p, 2);
-    };
     const uint32_t stg0 = c.sStg + (warp - 2) * 2 * STG_BYTES;   // this warp's two staging buffers
-    const int dbg = args.dbg, accumulate = args.accumulate, ncols = args.N;
+    const int accumulate = args.accumulate, ncols = args.N;
     const int c_col_off = args.c_col_off, c_row_off = args.c_row_off + row_shift;   // row_shift: output row of a peer slot
 
     for (int t = t0; t < t1; ++t, ++p.it) {
         const int a = p.it & 1;
         const uint32_t aph = (p.it >> 1) & 1;
         const int n0 = t * BN;
-        TR();
         ptx::mbar_wait(c.bar_tfull + 8 * a, aph);
         ptx::tc_fence_after();
-        TR();
-        // dataflow backward: every MMA of this job has completed, so nothing reads its G panel any more
-        if (MODE == MODE_OUT && done_ctr && warp == 2 && lane == 0 && c.leader) atomicAdd(done_ctr, 1u);
         const uint32_t taddr = c.tmem_base + a * BN + half * (BN / 2) + (uint32_t(q * 32) << 16);
         // edge tile: contains positives (diagonal entries) of this CTA's rows, or columns beyond N
         const long long d_lo = args.diag_offset + (long long)m_blk * BM;
@@ -503,7 +435,6 @@ __device__ __forceinline__ void epilogue_unit(const Cta& c, Pipe& p, const CUten
 
         auto process = [&](const uint32_t (&r)[32], int cidx) {
             const int col0 = colh + cidx * 32;
-            if (dbg & 1) return;
             if (MODE == MODE_STATS) {
                 if (edge) stats_chunk<true>(r, sc, col0, ncols, dcol, st);
                 else stats_chunk<false>(r, sc, col0, ncols, dcol, st);
@@ -521,7 +452,7 @@ __device__ __forceinline__ void epilogue_unit(const Cta& c, Pipe& p, const CUten
                 ptx::fence_proxy_async_smem();
                 __syncwarp();
                 ++p.stg_use;
-                if (lane == 0 && !(dbg & 2)) {
+                if (lane == 0) {
                     // the tensor map clips rows and columns beyond the output matrix
                     if (accumulate) ptx::tma_reduce_add_2d(tmC, stg, c_col_off + col0, c_row_off + row0);
                     else ptx::tma_store_2d(tmC, stg, c_col_off + col0, c_row_off + row0);
@@ -547,9 +478,7 @@ __device__ __forceinline__ void epilogue_unit(const Cta& c, Pipe& p, const CUten
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_leader(c.bar_tempty + 8 * a);
-        TR();
         process(rb, 3);
-        TR();
     }
 
     if (MODE == MODE_STATS) {
@@ -592,20 +521,16 @@ __device__ __forceinline__ void grad_epilogue_unit(const Cta& c, Pipe& p, const 
     const float Ai = row_ok ? ga * __ldg(args.avec + row) : 0.f;
     const float* __restrict__ bvec = args.bvec;
     const float* __restrict__ lse_col = args.lse_col;
-    const int dbg = args.dbg, ncols = args.N, plane_stride = args.g_plane_stride;
+    const int ncols = args.N, plane_stride = args.g_plane_stride;
     const int c_col_off = args.c_col_off, c_row_off = args.c_row_off + m_blk * BM + q * 32;
     const long long d_lo = args.diag_offset + (long long)m_blk * BM;
     const uint32_t stg0 = c.sStg + (warp - 2) * NBUF * STG_BYTES;   // this warp's staging buffer(s)
-    auto TR = [&]() {
-        if (warp == 2 && lane == 0) trace_stamp(args, p, 2);
-    };
 
     for (int t = t0; t < t1; ++t, ++p.it) {
         const int a = p.it & 1;
         const uint32_t aph = (p.it >> 1) & 1;
         const int n0 = t * BN;
         const int colh = n0 + half * (BN / 2);          // first column of this warp's half tile
-        TR();
         if (lane < 4 && t + 1 < t1) {
             // pull the B_j / LSE values of this warp's half of the NEXT tile (512 B) into L1 ahead of their use
             const int cn = colh + BN + lane * 32;
@@ -616,14 +541,12 @@ __device__ __forceinline__ void grad_epilogue_unit(const Cta& c, Pipe& p, const 
         }
         ptx::mbar_wait(c.bar_tfull + 8 * a, aph);
         ptx::tc_fence_after();
-        TR();
         const uint32_t taddr = c.tmem_base + a * BN + half * (BN / 2) + (uint32_t(q * 32) << 16);
         // edge tile: contains positives (diagonal entries) of this CTA's rows, or columns beyond N
         const bool exact = !fast || ((d_lo + BM - 1 >= n0) && (d_lo < (long long)n0 + BN)) || (n0 + BN > ncols);
 
         uint32_t stg = 0, stg_lo = 0;
         auto piece = [&](const uint32_t (&r)[16], int pi) {
-            if (dbg & 1) return;
             const int col0 = colh + pi * 16;
             if (NBUF == 1) {
                 // half buffers of 32 columns: two pieces each
@@ -639,7 +562,7 @@ __device__ __forceinline__ void grad_epilogue_unit(const Cta& c, Pipe& p, const 
                 if (pi & 1) {
                     ptx::fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0 && !(dbg & 2)) {
+                    if (lane == 0) {
                         ptx::tma_store_2d(tmC, stg, c_col_off + col0 - 16, c_row_off);
                         ptx::tma_store_commit();
                     }
@@ -665,7 +588,7 @@ __device__ __forceinline__ void grad_epilogue_unit(const Cta& c, Pipe& p, const 
             if ((pi & 3) == 3) {
                 ptx::fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0 && !(dbg & 2)) {
+                if (lane == 0) {
                     ptx::tma_store_2d(tmC, stg, c_col_off + col0 - 48, c_row_off);
                     if (TWO_PLANES) ptx::tma_store_2d(tmC, stg_lo, c_col_off + plane_stride + col0 - 48, c_row_off);
                     ptx::tma_store_commit();
@@ -689,12 +612,10 @@ __device__ __forceinline__ void grad_epilogue_unit(const Cta& c, Pipe& p, const 
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive_leader(c.bar_tempty + 8 * a);
-                TR();
             }
             piece(rb, pi + 1);
             if (pi + 2 < 8) ptx::tmem_ld_wait();
         }
-        TR();
     }
 }
 
@@ -773,6 +694,7 @@ __host__ __device__ constexpr int smem_bytes_fwd(bool ares = true) {
 }
 constexpr float FWD_SAFE_U = 96.f;               // -2u - 24 + FWD_REF_SHIFT >= -126
 constexpr float FWD_REF_SHIFT = 90.f;            // reference c = u - 90: uses the overflow headroom of fp32 as well
+constexpr float FWD_POS_MARGIN = 175.f;          // rule (b) of fwd_bound: 90 + 102 - 17 (terms of up to 2^17 rows may flush)
 
 struct FwdArgs {
     int M, N;                  // rows of A (X), rows of B (Y)
@@ -784,7 +706,11 @@ struct FwdArgs {
     const float* scale;
     const float* xs;           // dequant scalars of the operands (null = 1)
     const float* ys;
-    const unsigned int* norm2; // [2] max |x_i|^2, max |y_j|^2 as float bits (only read when !force_exact)
+    const float* stats;        // [nstat][STAT_WORDS] operand statistics (one row per data-parallel rank, see OperandStats);
+    int nstat;                 //   only read when !force_exact
+    int stats_rank;            // row of THIS rank: its max |x_i|^2 bounds the rows of the block, every row's max |y_j|^2 the columns
+    int use_minpos;            // the positives' lower bound covers every row and column of the problem (see fwd_bound)
+    float* mode_out;           // word [5] of this rank's statistics row: 1 = single sweep taken, 0 = exact two-sweep form
     long long diag_offset;
     float* part_max;           // [max parts * 2][M]; part = cluster - first cluster that touches the row pair
     float* part_sum;
@@ -793,18 +719,49 @@ struct FwdArgs {
     float* colpart_sum;        // [2 * m_pairs][ldc]   (pass 0, single sweep)
     float* colpart_dot;
     int ldc;
-    long long* trace;
-    int dbg;
 };
 
-// the reference c of the single sweep (log2 units) and whether the single sweep is allowed; identical in every
-// thread of every CTA of both launches and of the merge kernel
+// Operand statistics, one row of STAT_WORDS floats per rank, filled by prep_kernel (clipk.cu):
+//   [0] max_i |x_i|^2   [1] max_j |y_j|^2   [2] max |x_ij|   [3] max |y_ij|      (bit patterns of non-negative floats;
+//                                                                                  +Inf bits when a NaN / Inf was seen)
+//   [4] min_i x_i . y_i over the rank's positive pairs, as an order-preserving int (see float_to_ordered)
+//   [5] written by fwd_merge_kernel: 1 when the forward took the single sweep, 0 for the exact two-sweep form
+constexpr int STAT_WORDS = 8;
+__host__ __device__ __forceinline__ int float_to_ordered(float f) {
+#ifdef __CUDA_ARCH__
+    const int i = __float_as_int(f);
+#else
+    int i; memcpy(&i, &f, 4);
+#endif
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+// The reference c of the single sweep (log2 units) and whether the single sweep is allowed; identical in every thread of
+// every CTA of both launches and of the merge kernel.  With u >= |v| for every logit v (from the row norms) and
+// c = u - 90 nothing overflows.  What must not happen is that the terms that matter for some row or column flush to
+// zero: the sweep is allowed when
+//   (a) u <= 96: every logit lies within 192 of any possible maximum, or
+//   (b) every row and every column is known to hold a logit >= u - 175: its own positive.  min_i x_i . y_i over ALL
+//       pairs of the problem (all ranks) is part of the statistics; with it a trained model at logit_scale = 100
+//       (u = 144 for unit vectors) keeps the single sweep as long as no positive pair has a cosine below -0.21.
+//       A column's partial sum on a rank that holds none of its large terms may then lose terms below 2^-126 * 2^c:
+//       at least 2^85 times smaller than the column's positive, i.e. below fp32 resolution even summed over 2^20 rows.
 __device__ __forceinline__ bool fwd_bound(const FwdArgs& a, float* c_out) {
     if (a.force_exact) { *c_out = 0.f; return false; }
-    const float nx2 = __uint_as_float(a.norm2[0]), ny2 = __uint_as_float(a.norm2[1]);
-    const float u = fabsf(__ldg(a.scale)) * sqrtf(nx2) * sqrtf(ny2) * (LOG2E * 1.001f);
+    float ny2 = 0.f, minpos = CUDART_INF_F;
+    for (int r = 0; r < a.nstat; ++r) {
+        const float* st = a.stats + r * STAT_WORDS;
+        ny2 = fmaxf(ny2, __ldg(st + 1));
+        minpos = fminf(minpos, ordered_to_float(__float_as_int(__ldg(st + 4))));
+    }
+    const float nx2 = __ldg(a.stats + a.stats_rank * STAT_WORDS);
+    const float s = __ldg(a.scale);
+    const float u = fabsf(s) * sqrtf(nx2) * sqrtf(ny2) * (LOG2E * 1.001f);
     *c_out = u - FWD_REF_SHIFT;
-    return u <= FWD_SAFE_U;     // false for NaN / Inf
+    const bool by_norm = u <= FWD_SAFE_U;                                     // false for NaN / Inf
+    const bool by_pos = a.use_minpos && s > 0.f && u < 1e30f && s * LOG2E * minpos >= u - FWD_POS_MARGIN;
+    return by_norm || by_pos;
 }
 
 // one 16-lane half-chunk (2 rows x 8 columns per thread) of the single sweep
@@ -965,8 +922,7 @@ fwd_sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             KArgs ka{};
             ka.M = args.M; ka.N = args.N; ka.scale = args.scale; ka.xs = args.xs; ka.ys = args.ys;
             ka.diag_offset = args.diag_offset; ka.part_max = args.part_max; ka.part_sum = args.part_sum;
-            ka.part_dot = args.part_dot; ka.pos = args.pos; ka.dbg = args.dbg; ka.trace = args.trace;
-            ka.trace_on = (blockIdx.x == 0) ? 2 : 0;
+            ka.part_dot = args.part_dot; ka.pos = args.pos;
             SweepWalk w(geom, cluster, n_clusters);
             SweepUnit un;
             while (w.next(un)) {
@@ -986,11 +942,6 @@ fwd_sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const float sc = s_nat * LOG2E;
             const int ncols = args.N, M = args.M;
             float* const pos = args.pos;
-            KArgs ktr{};
-            ktr.trace = args.trace; ktr.trace_on = (blockIdx.x == 0) ? 2 : 0;
-            auto TR = [&]() {
-                if (warp == 2 && lane == 0) trace_stamp(ktr, p, 2);
-            };
             // column of the chunk this lane owns after the butterfly, and its slot in the column buffer
             const int own_col = 8 * (g >> 1) + cq + (g & 1);
             SweepWalk w(geom, cluster, n_clusters);
@@ -1008,17 +959,14 @@ fwd_sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const uint32_t aph = (p.it >> 1) & 1;
                     const int n0 = t * BN;
                     const int colh = n0 + half * (BN / 2);
-                    TR();
                     ptx::mbar_wait(c.bar_tfull + 8 * a, aph);
                     ptx::tc_fence_after();
-                    TR();
                     const uint32_t taddr = c.tmem_base + a * BN + half * (BN / 2) + (uint32_t(q * 32) << 16);
                     const bool edge = row_edge || (n0 + BN > ncols) ||
                                       (pos && (d_lo + BM - 1 >= n0) && (d_lo < (long long)n0 + BN));
                     const uint32_t cbuf = colbuf + uint32_t(((((t & 1) * 2 + half) * 4 + q) * 128) * 8);
                     float cs[8], cd[8];
                     auto half_chunk = [&](const uint32_t (&r)[16], int hc) {
-                        if (args.dbg & 1) return;
                         const int h = hc & 1, chunk = hc >> 1;
                         const int col0 = colh + chunk * 32 + cq;
                         const int r0 = rbase + 16 * h + g, r1 = r0 + 8;
@@ -1064,7 +1012,6 @@ fwd_sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             ptx::tc_fence_before();
                             __syncwarp();
                             if (lane == 0) ptx::mbar_arrive_leader(c.bar_tempty + 8 * a);
-                            TR();
                         }
                         half_chunk(rb, hc + 1);
                         if (hc + 2 < 8) ptx::tmem_ld_wait();
@@ -1081,13 +1028,12 @@ fwd_sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "r"(src + qq * 128 * 8));
                             S += x; D += y;
                         }
-                        if (!(args.dbg & 1)) {
+                        {
                             const size_t o = (size_t)m_blk * args.ldc + colh + idx;
                             args.colpart_sum[o] = S;
                             args.colpart_dot[o] = D;
                         }
                     }
-                    TR();
                 }
                 // row statistics of the item: merge the 4 lanes that share the rows, lane (lane & 3) == 0 writes
 #pragma unroll
@@ -1200,216 +1146,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     } else if (c.warp == 1) {
         if (c.lane == 0 && c.leader) mma_unit<STAGES>(c, p, args, 1);
     } else {
-        epilogue_unit<MODE_OUT>(c, p, tmC, args, m_blk, t0, t0, t0 + 1, nullptr, row_shift);
+        epilogue_unit<MODE_OUT>(c, p, tmC, args, m_blk, t0, t0, t0 + 1, row_shift);
         epilogue_drain(c);
     }
-    cta_teardown(c);
-}
-
-// ---------------------------------------------------------------------------------------------------- dataflow backward
-// ONE launch for the whole backward, one CTA pair per SM pair, no grid-wide barrier.  The [rows x cols] block is cut
-// into panels (rp x cp, both multiples of 256); the fp16 G of panel q lives in L2-sized buffer q % 3.  Every pair
-// walks the sequence  G(0) G(1) O(0) G(2) O(1) G(3) O(2) ...  where G(q) is its share of the recompute tiles of panel
-// q and O(q) its gradient-GEMM job(s) on panel q, back to back through one set of smem / TMEM pipelines - so the
-// epilogue of one item overlaps the MMAs of the next across item types.  Dependencies:
-//   * after G(q) the epilogue warps of a CTA wait for their bulk stores, meet at a named barrier, and ONE thread
-//     publishes with a gpu-scope fence: done[cluster] += 1 (2 per panel and pair).  This costs several microseconds
-//     (store completion + fence) but runs while the MMA thread is already inside O(q - 1), whose epilogue is far away;
-//   * the TMA producer of O(q) checks done[owner] >= 2 (q + 1) for the owners of the G tiles behind its K extent.
-//     They were produced a whole G stretch earlier, so the check normally passes at once;
-//   * a job counts itself done (out_done[q] += 1) once its last MMA has completed; the first G store of panel q + 3
-//     (same buffer) waits until all jobs of panel q are done - two phases of slack.
-// Every pair executes the items in the same global order and every dependency points backwards in it, so with all pairs
-// co-resident the schedule cannot deadlock.  The share of recompute tiles of a pair is weighted by the length of the
-// job it runs in the same phase (plan computed on the host, see get_bwd_plan), which evens out the phases.
-struct BwdP {
-    int rows, cols, d;
-    long long diag_offset;
-    int rp, cp, n_rp, n_cp;      // panel extents and counts
-    int nt;                      // 256-wide tiles of d (output tiles of the gradient GEMMs per 256 rows)
-    int gbuf_rows;               // rows of one G buffer (multiple of 256); buffer b starts at row b * gbuf_rows
-    int want_dx, want_dy;
-    int s_f16;                   // operand format of the recompute GEMM
-    int s_nseg, s_kb_per_seg, s_a_off[3], s_b_off[3];       // K segments of the recompute GEMM
-    int g_nseg, g_a_off[3], g_b_off[3];                     // plane pairs of the gradient GEMMs (K extent varies per panel)
-    // plan (read only): shift[q] (cluster c runs jobs v, v + n, ... with v = (c + shift[q]) % n); start[q][c] = {first,
-    // end} recompute tile of cluster c; owner[q][tile] = cluster that recomputes the tile
-    const int* plan_shift;
-    const int* plan_start;
-    const unsigned char* plan_owner;
-    int max_tiles;               // stride of the per-panel tile arrays
-    unsigned int* done;          // [n_clusters] panels published per cluster (x 2 CTAs), zero at launch
-    unsigned int* out_done;      // [n_panels], zero at launch
-    const float* xg_inv;         // dequant scalars of the fp16 feature copies used by the gradient GEMMs (null = 1)
-    const float* yg_inv;
-    KArgs base;                  // everything that does not depend on the panel
-};
-
-// geometry of panel q
-struct Panel { int r0, c0, nr, nc, ri, ci; };
-__device__ __forceinline__ Panel panel_of(const BwdP& P, int q) {
-    Panel x;
-    x.ri = q / P.n_cp;
-    x.ci = q - x.ri * P.n_cp;
-    x.r0 = x.ri * P.rp;
-    x.c0 = x.ci * P.cp;
-    x.nr = min(P.rp, P.rows - x.r0);
-    x.nc = min(P.cp, P.cols - x.c0);
-    return x;
-}
-__device__ __forceinline__ int cdiv_d(int a, int b) { return (a + b - 1) / b; }
-__device__ __forceinline__ int jobs_of(const BwdP& P, const Panel& x) {
-    return (P.want_dx ? cdiv_d(x.nr, 2 * BM) * P.nt : 0) + (P.want_dy ? cdiv_d(x.nc, 2 * BM) * P.nt : 0);
-}
-
-// recompute (GRAD) unit of panel q: row pair m_pair, column tiles [t0, t1)
-__device__ __forceinline__ void make_grad_args(const BwdP& P, int q, KArgs& a) {
-    const Panel x = panel_of(P, q);
-    a = P.base;
-    a.M = x.nr; a.N = x.nc;
-    a.nseg = P.s_nseg; a.kb_per_seg = P.s_kb_per_seg; a.num_kb = P.s_nseg * P.s_kb_per_seg;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { a.a_off[i] = P.s_a_off[i]; a.b_off[i] = P.s_b_off[i]; }
-    a.a_mn = 0; a.b_mn = 0; a.f16 = P.s_f16;
-    a.a_outer_off = x.r0; a.b_outer_off = x.c0;
-    a.n_tiles = cdiv_d(x.nc, BN);
-    a.diag_offset = P.diag_offset + x.r0 - x.c0;
-    a.lse_row = P.base.lse_row + x.r0; a.lse_col = P.base.lse_col + x.c0;
-    a.avec = P.base.avec + x.r0; a.bvec = P.base.bvec + x.c0;
-    a.c_col_off = 0; a.c_row_off = (q % 3) * P.gbuf_rows;
-}
-// gradient-GEMM job of panel q: which = 0: dX[r0.., :] (+)= G * Yg[c0.., :]; which = 1: dY[c0.., :] (+)= G^T * Xg[r0.., :]
-__device__ __forceinline__ void make_out_args(const BwdP& P, int q, int which, KArgs& a) {
-    const Panel x = panel_of(P, q);
-    a = P.base;
-    const int kext = which == 0 ? x.nc : x.nr;
-    a.M = which == 0 ? x.nr : x.nc;
-    a.N = P.d;
-    a.nseg = P.g_nseg; a.kb_per_seg = cdiv_d(kext, BK); a.num_kb = a.nseg * a.kb_per_seg;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { a.a_off[i] = P.g_a_off[i]; a.b_off[i] = P.g_b_off[i]; }
-    a.a_mn = which; a.b_mn = 1; a.f16 = 1;
-    // A = G: K-major rows of the buffer (job 0) or its transpose, K = buffer rows (job 1); B = features, K = their rows
-    a.a_outer_off = (q % 3) * P.gbuf_rows;
-    a.b_outer_off = which == 0 ? x.c0 : x.r0;
-    a.n_tiles = P.nt;
-    a.c_col_off = 0; a.c_row_off = which == 0 ? x.r0 : x.c0;
-    // jobs of different panels that hit the same output rows are not ordered against each other: every job adds
-    // (TMA reduce) into an accumulator the host zeroed before the launch
-    a.accumulate = 1;
-    a.oscale2 = which == 0 ? P.yg_inv : P.xg_inv;   // dequant of the feature operand: Yg for dX, Xg for dY
-}
-
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-bwd_dataflow_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
-                    const __grid_constant__ CUtensorMap tmGst, const __grid_constant__ CUtensorMap tmGk,
-                    const __grid_constant__ CUtensorMap tmGmn, const __grid_constant__ CUtensorMap tmYg,
-                    const __grid_constant__ CUtensorMap tmXg, const __grid_constant__ CUtensorMap tmDX,
-                    const __grid_constant__ CUtensorMap tmDY, const BwdP P) {
-    constexpr int STAGES = stages_of(MODE_GRAD);
-    static_assert(stages_of(MODE_GRAD) == stages_of(MODE_OUT), "GRAD and OUT share one shared-memory layout");
-    const Cta c = cta_setup<STAGES, STG_TOTAL>();
-    const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-    const int n_panels = P.n_rp * P.n_cp;
-    constexpr unsigned int kTileDone = 2 * NUM_EPI_WARPS;   // epilogue warps of both CTAs
-    Pipe p;
-    if (c.warp == 0 && c.lane == 0) {
-        ptx::prefetch_tmap(&tmX); ptx::prefetch_tmap(&tmY); ptx::prefetch_tmap(&tmGk); ptx::prefetch_tmap(&tmGmn);
-        ptx::prefetch_tmap(&tmYg); ptx::prefetch_tmap(&tmXg);
-    }
-    const bool active = (c.warp == 0 && c.lane == 0) || (c.warp == 1 && c.lane == 0 && c.leader) || c.warp >= 2;
-    // experiments (CLIPK_DBG & 1024): the MMA thread of every pair stamps globaltimer at [cluster][panel][0..3] =
-    // panel start, recompute tiles issued, job start, job issued
-    const bool gt = P.base.trace && (P.base.dbg & 1024) && c.warp == 1;
-    auto GT = [&](int q, int k) {
-        if (gt) {
-            long long t;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            P.base.trace[((size_t)cluster * n_panels + q) * 4 + k] = t;
-        }
-    };
-
-    if (active) {
-        for (int q = 0; q <= n_panels; ++q) {
-            if (q < n_panels) GT(q, 0);
-            // ---- G(q): recompute tiles [f0, f1) of panel q (flat index = row pair * n_tiles + column tile)
-            if (q < n_panels) {
-                const Panel x = panel_of(P, q);
-                const int n_tiles = cdiv_d(x.nc, BN);
-                int f0 = __ldg(P.plan_start + ((size_t)q * n_clusters + cluster) * 2);
-                const int f1 = __ldg(P.plan_start + ((size_t)q * n_clusters + cluster) * 2 + 1);
-                if (f0 < f1 && !(P.base.dbg & 128)) {
-                    KArgs a;
-                    make_grad_args(P, q, a);
-                    a.trace_on = (blockIdx.x == 0 && !(P.base.dbg & 1024)) ? 2 : 0;
-                    if (c.warp >= 2 && q >= 3 && !(P.base.dbg & 64)) {
-                        // buffer q % 3 was last read by the jobs of panel q - 3
-                        if (c.lane == 0) flag_wait(P.out_done + (q - 3), (unsigned int)jobs_of(P, panel_of(P, q - 3)));
-                        __syncwarp();
-                    }
-                    while (f0 < f1) {
-                        const int m_pair = f0 / n_tiles;
-                        const int t0 = f0 - m_pair * n_tiles;
-                        const int t1 = min(n_tiles, t0 + (f1 - f0));
-                        const int m_blk = 2 * m_pair + int(c.cta_rank);
-                        if (c.warp == 0) {
-                            produce_unit<STAGES>(c, p, &tmX, &tmY, a, m_blk, t0, t1);
-                        } else if (c.warp == 1) {
-                            mma_unit<STAGES>(c, p, a, t1 - t0);
-                        } else {
-                            if (a.g_planes == 2) grad_epilogue_unit<true>(c, p, &tmGst, a, m_blk, t0, t1);
-                            else grad_epilogue_unit<false>(c, p, &tmGst, a, m_blk, t0, t1);
-                        }
-                        f0 += t1 - t0;
-                    }
-                }
-                if (c.warp >= 2) {
-                    // publish panel q of this CTA (also when it had no tiles: the counters advance in lockstep)
-                    epilogue_drain_complete(c);
-                    ptx::named_bar_sync(3, NUM_EPI_WARPS * 32);
-                    if (c.warp == 2 && c.lane == 0) flag_signal(P.done + cluster);
-                }
-                GT(q, 1);
-            }
-            // ---- O(q - 1): gradient-GEMM jobs v, v + n, ... of the previous panel
-            if (q >= 1 && !(P.base.dbg & 64)) {
-                const int qo = q - 1;
-                const Panel x = panel_of(P, qo);
-                const int m_pairs = cdiv_d(x.nr, 2 * BM), n_tiles = cdiv_d(x.nc, BN);
-                const int v = (cluster + __ldg(P.plan_shift + qo)) % n_clusters;
-                const unsigned char* own_q = P.plan_owner + (size_t)qo * P.max_tiles;
-                const int jobs0 = P.want_dx ? m_pairs * P.nt : 0;
-                const int jobs1 = P.want_dy ? cdiv_d(x.nc, 2 * BM) * P.nt : 0;
-                unsigned long long seen[4] = {0ull, 0ull, 0ull, 0ull};
-                for (int j = v; j < jobs0 + jobs1; j += n_clusters) {
-                    const int which = j < jobs0 ? 0 : 1;
-                    const int k = which == 0 ? j : j - jobs0;
-                    KArgs a;
-                    make_out_args(P, qo, which, a);
-                    a.trace_on = (blockIdx.x == 0 && !(P.base.dbg & 1024)) ? 2 : 0;
-                    GT(qo, 2);
-                    const int blk = k / P.nt;          // 256-row block of the panel (dX) or 256-column block (dY)
-                    const int m_blk = 2 * blk + int(c.cta_rank);
-                    const int t = k - blk * P.nt;
-                    if (c.warp == 0) {
-                        const unsigned int target = (P.base.dbg & 128) ? 0u : 2u * (unsigned int)(qo + 1);
-                        if (which == 0)
-                            produce_job<STAGES>(c, p, &tmGk, &tmYg, a, m_blk, t, n_tiles, P.done, own_q + blk * n_tiles, 1,
-                                                target, seen);
-                        else
-                            produce_job<STAGES>(c, p, &tmGmn, &tmXg, a, m_blk, t, m_pairs, P.done, own_q + blk, n_tiles,
-                                                target, seen);
-                    } else if (c.warp == 1) {
-                        mma_unit<STAGES>(c, p, a, 1);
-                    } else {
-                        epilogue_unit<MODE_OUT>(c, p, which == 0 ? &tmDX : &tmDY, a, m_blk, t, t, t + 1, P.out_done + qo);
-                    }
-                    GT(qo, 3);
-                }
-            }
-        }
-    }
-    if (c.warp >= 2) epilogue_drain(c);
     cta_teardown(c);
 }
 

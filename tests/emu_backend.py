@@ -69,6 +69,84 @@ class EmuBackend:
         dY = (G.T @ X.data).float() if want_dy else None
         return dX, dY
 
+    # ---- the fused step (clipk_step_forward / clipk_step_backward); the peer-memory collectives become gloo ones
+    class _Peer:
+        pass
+
+    def peer_context(self, b, d, rank, world, group):
+        return self._Peer()
+
+    def step_workspace_bytes(self, rows, cols, d, world):
+        return 256
+
+    def step_forward(self, st):
+        import torch.distributed as dist
+        W, b, N, rank = st.world, st.rows, st.cols, st.rank
+        x, y = st.image.double(), st.text.double()
+        if st.normalize:
+            ix = 1.0 / x.norm(dim=-1).clamp_min(st.eps)
+            iy = 1.0 / y.norm(dim=-1).clamp_min(st.eps)
+            st.inv_x.copy_(ix.float())
+            st.inv_y.copy_(iy.float())
+            x, y = x * ix[:, None], y * iy[:, None]
+        xb, yb = x.to(torch.bfloat16), y.to(torch.bfloat16)
+        if st.x_op is not st.image:
+            st.x_op.copy_(xb)
+        if W > 1:
+            parts = [torch.empty(b, st.d, dtype=torch.float32) for _ in range(W)]
+            dist.all_gather(parts, yb.float(), group=st.group)
+            st.y_all.copy_(torch.cat(parts).to(torch.bfloat16))
+        elif st.y_all is not st.text:
+            st.y_all.copy_(yb)
+        X, Y = st.x_op.double(), st.y_all.double()
+        s, off = float(st.scale[0]), rank * b
+        S = s * X @ Y.T
+        idx = torch.arange(b)
+        pos = S[idx, idx + off]
+        lse_row = torch.logsumexp(S, dim=1)
+        e_row = (torch.softmax(S, dim=1) * S).sum(1)
+        cm = S.max(dim=0).values
+        ce = torch.exp(S - cm[None, :])
+        col = torch.stack((cm, ce.sum(0), (ce * S).sum(0)))
+        if W > 1:
+            cols = [torch.empty_like(col) for _ in range(W)]
+            dist.all_gather(cols, col, group=st.group)
+            cp = torch.stack(cols)
+        else:
+            cp = col[None]
+        M = cp[:, 0].max(dim=0).values
+        w = torch.exp(cp[:, 0] - M)
+        L, Tt = (cp[:, 1] * w).sum(0), (cp[:, 2] * w).sum(0)
+        lse_col, e_col = M + L.log(), Tt / L
+        st.lse_row.copy_(lse_row.float())
+        st.lse_col.copy_(lse_col.float())
+        sums = ((lse_row - pos).sum(), (lse_col[idx + off] - pos).sum(), (e_row - pos).sum(), (e_col[idx + off] - pos).sum())
+        st.scal[4] = float(sums[0] + sums[1]) / st.loss_div
+        st.scal[5] = float(sums[2] + sums[3]) / st.loss_div
+
+    def step_backward(self, st):
+        import torch.distributed as dist
+        W, b, rank = st.world, st.rows, st.rank
+        s, go, off = float(st.scale[0]), float(st.grad_out[0]), rank * b
+        if st.d_scale is not None:
+            st.d_scale[0] = float(st.scal[5]) * go / s
+        if st.d_image is None:
+            return
+        X, Y = st.x_op.double(), st.y_all.double()
+        S = s * X @ Y.T
+        G = torch.exp(S - st.lse_row.double()[:, None]) + torch.exp(S - st.lse_col.double()[None, :])
+        G[torch.arange(b), torch.arange(b) + off] -= 2.0
+        G = G * (s * go * st.grad_coef)
+        dX, dY = G @ Y, G.T @ X
+        if W > 1:
+            dist.all_reduce(dY, group=st.group)
+        dT = dY[off:off + b]
+        if st.normalize:
+            for g, yn, inv in ((dX, X, st.inv_x.double()), (dT, Y[off:off + b], st.inv_y.double())):
+                g.copy_((g - yn * (g * yn).sum(-1, keepdim=True)) * inv[:, None])
+        st.d_image.copy_(dX.to(st.d_image.dtype))
+        st.d_text.copy_(dT.to(st.d_text.dtype))
+
     def normalize_fwd(self, x, eps):
         n = x.double().norm(dim=-1, keepdim=True).clamp_min(eps)
         return (x.double() / n).to(x.dtype), (1.0 / n.squeeze(-1)).float()

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name                 # dlsym resolves it
     assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
-    assert lib.clipk_version() == 1
+    assert lib.clipk_version() == 2
 
 
 def test_abi_reports_errors_without_a_gpu():
@@ -226,18 +226,84 @@ def test_fused_normalize_entry_host_logic():
         ops.set_backend_for_testing(None)
 
 
+@pytest.mark.parametrize("normalize", [False, True])
+def test_fused_step_route_host_logic(normalize):
+    """bf16 features of a width that is a multiple of 64 take the fused step (clipk_step_forward / _backward): buffers,
+    coefficients, saved state and the label cache, with the two entries emulated on the CPU."""
+    from clipk import ClipLoss, ops, fused_normalize_clip_loss
+    from oracle import cliploss_oracle as O
+    from tests.emu_backend import EmuBackend
+    be = EmuBackend()
+    calls = []
+    fwd, bwd = be.step_forward, be.step_backward
+    be.step_forward = lambda st: (calls.append("f"), fwd(st))[1]
+    be.step_backward = lambda st: (calls.append("b"), bwd(st))[1]
+    ops.set_backend_for_testing(be)
+    try:
+        g = torch.Generator().manual_seed(11)
+        raw_i, raw_t = torch.randn(48, 128, generator=g) * 1.7, torch.randn(48, 128, generator=g) * 0.6
+        if not normalize:
+            raw_i, raw_t = torch.nn.functional.normalize(raw_i, dim=-1), torch.nn.functional.normalize(raw_t, dim=-1)
+        I = raw_i.bfloat16().requires_grad_(True)
+        T = raw_t.bfloat16().requires_grad_(True)
+        s = torch.tensor(9.0, requires_grad=True)
+        mod = ClipLoss(cache_labels=True)
+        loss = fused_normalize_clip_loss(I, T, s) if normalize else mod(I, T, s)
+        (loss * 1.5).backward()
+        assert calls == ["f", "b"]
+        assert loss.dtype == torch.float32 and I.grad.dtype == torch.bfloat16 and s.grad.shape == s.shape
+        if not normalize:
+            assert mod.prev_num_logits == 48 and torch.equal(mod.labels[I.device], torch.arange(48))
+        # reference: the oracle on the operand values (normalised in fp64, rounded to bf16), chained through the Jacobian
+        x64, t64 = I.detach().double(), T.detach().double()
+        if normalize:
+            xn, tn = x64 / x64.norm(dim=-1, keepdim=True), t64 / t64.norm(dim=-1, keepdim=True)
+        else:
+            xn, tn = x64, t64
+        xo, to = xn.bfloat16().double().numpy(), tn.bfloat16().double().numpy()
+        ref = O.clip_loss_single(xo, to, 9.0, grad_output=1.5)
+        dI, dT = torch.from_numpy(ref.d_image), torch.from_numpy(ref.d_text)
+        if normalize:
+            for gr, y, x in ((dI, torch.from_numpy(xo), x64), (dT, torch.from_numpy(to), t64)):
+                gr.copy_((gr - y * (gr * y).sum(-1, keepdim=True)) / x.norm(dim=-1, keepdim=True))
+        assert abs(loss.item() - ref.loss) <= 1e-5 * ref.loss
+        assert (I.grad.double() - dI).norm() <= 8e-3 * dI.norm() and (T.grad.double() - dT).norm() <= 8e-3 * dT.norm()
+        assert abs(s.grad.item() - ref.d_scale) <= 1e-5 * abs(ref.d_scale)
+    finally:
+        ops.set_backend_for_testing(None)
+
+
+def test_in_place_change_of_the_features_is_detected():
+    """The features are read again by the backward (in place, no copy): autograd must notice a modification in between."""
+    from clipk import ClipLoss, ops
+    from tests.emu_backend import EmuBackend
+    ops.set_backend_for_testing(EmuBackend())
+    try:
+        base = torch.nn.functional.normalize(torch.randn(16, 64), dim=-1).bfloat16().requires_grad_(True)
+        I = base * 1.0                      # non-leaf, so that it may be modified in place
+        T = torch.nn.functional.normalize(torch.randn(16, 64), dim=-1).bfloat16().requires_grad_(True)
+        loss = ClipLoss()(I, T, torch.tensor(5.0))
+        I.mul_(2.0)
+        with pytest.raises(RuntimeError, match="modified by an inplace operation"):
+            loss.backward()
+    finally:
+        ops.set_backend_for_testing(None)
+
+
 def test_bench_reference_arm_prints_one_json_line():
     """`bench.py --impl reference` (the CPU arm the driver runs next to the GPU arm): exactly one JSON line on stdout
     with the contract's keys; here with a tiny sample so that it takes seconds."""
     import json, subprocess, sys
     env = dict(os.environ, OMP_NUM_THREADS="2")
     code = ("import sys; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0'];"
-            "import runpy, bench; bench.CPU_SAMPLE_BATCH = 512; bench.main()")
+            "import runpy, bench; bench.CPU_SAMPLE_BATCH = 512; bench.CPU_ARM_BUDGET_S = 0.0; bench.main()")
     out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, out.stdout
     j = json.loads(lines[0])
     assert j["impl"] == "reference" and j["unit"] == "samples/s" and j["higher_is_better"] is True
-    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
+    # the reference module itself when baseline/_ref holds it (the build container, the GPU box), else the oracle's port
+    assert j["cpu_baseline"]["kind"] in ("reference", "port") and j["cpu_baseline"]["cores"] >= 1
+    assert j["cpu_baseline"]["sample_batch"] == 512 and j["cpu_baseline"]["extrapolated"] is True
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0 and j["value"] > 0

@@ -186,18 +186,74 @@ def test_odd_widths_and_fp16_across_ranks():
                 assert abs(float(o["d_scale"]) - g.d_scale) <= 1e-5 * max(abs(g.d_scale), 1 / 11.0)
 
 
-def test_overlap_switch_gives_the_same_results(monkeypatch):
-    """CLIPK_OVERLAP=1 (fp16 copies for the backward made under the asynchronous gather of the column statistics) is a
-    reordering only: same losses and gradients as the default path on two ranks."""
+def test_fused_step_route_across_ranks():
+    """bf16 features with d % 64 == 0 take the fused step on several ranks as well (here with the peer-memory collectives
+    of the two entries emulated by gloo ones): coefficients of the modes, global-loss all-reduce, rank offsets."""
     from oracle import cliploss_oracle as O
-    cases = [(10, 64, "float32", True, True), (8, 64, "bfloat16", False, True)]
-    outs = {}
-    for flag in ("0", "1"):
-        monkeypatch.setenv("CLIPK_OVERLAP", flag)            # inherited by the spawned ranks
-        with tempfile.TemporaryDirectory() as tmp:
-            mp.spawn(_odd_worker, args=(2, tmp, cases), nprocs=2, join=True)
-            outs[flag] = [[dict(np.load(f"{tmp}/odd{i}_{r}.npz")) for r in range(2)] for i in range(len(cases))]
-    for i in range(len(cases)):
-        for r in range(2):
-            for k in ("loss", "d_image", "d_text", "d_scale"):
-                assert np.array_equal(outs["0"][i][r][k], outs["1"][i][r][k]), (i, r, k)
+    cases = [(12, 64, "bfloat16", True, True), (8, 128, "bfloat16", False, True), (8, 64, "bfloat16", False, False),
+             (8, 64, "bfloat16", True, False)]          # the last one (local, no gather_with_grad) takes the general route
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(_odd_worker, args=(2, tmp, cases), nprocs=2, join=True)
+        for i, (b, d, dtype, ll, gwg) in enumerate(cases):
+            outs = [dict(np.load(f"{tmp}/odd{i}_{r}.npz")) for r in range(2)]
+            ref = O.clip_loss_world([o["image"] for o in outs], [o["text"] for o in outs], 11.0, ll, gwg)
+            for r in range(2):
+                o, g = outs[r], ref[r]
+                assert abs(float(o["loss"]) - g.loss) <= 1e-5 * abs(g.loss), (i, r)
+                for k, want in (("d_image", g.d_image), ("d_text", g.d_text)):
+                    assert np.linalg.norm(o[k] - want) <= 8e-3 * np.linalg.norm(want), (i, r, k)
+                assert abs(float(o["d_scale"]) - g.d_scale) <= 1e-5 * max(abs(g.d_scale), 1 / 11.0)
+
+
+def _pipeline_worker(rank, world, tmp):
+    import sys
+    import types
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "megatron-clip_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from clipk import ops
+    from clipk.megatron_adapter import make_loss_func
+    from oracle import cliploss_oracle as O
+    from tests.emu_backend import EmuBackend
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", init_method=f"file://{tmp}/store", rank=rank, world_size=world)
+    ops.set_backend_for_testing(EmuBackend())
+    # 4 ranks = 2 pipeline stages x 2 data-parallel ranks; only the LAST stage (ranks 2, 3) computes the loss
+    dp_groups = [dist.new_group([0, 1]), dist.new_group([2, 3])]
+    my_dp = dp_groups[rank // 2]
+    # what `from megatron.core import mpu` would give the adapter
+    mpu = types.ModuleType("megatron.core.mpu")
+    mpu.get_data_parallel_group = lambda: my_dp
+    core = types.ModuleType("megatron.core")
+    core.mpu = mpu
+    meg = types.ModuleType("megatron")
+    meg.core = core
+    sys.modules.update({"megatron": meg, "megatron.core": core, "megatron.core.mpu": mpu})
+    if rank >= 2:
+        x, t = O.synthetic_features(10, 32, seed=5, rank=rank - 2)
+        I, T = torch.from_numpy(x).requires_grad_(True), torch.from_numpy(t).requires_grad_(True)
+        # group=None: the adapter must find Megatron's data-parallel group by itself; a WORLD collective would hang
+        # here, because ranks 0 and 1 never call loss_func
+        loss, avg = make_loss_func(logit_scale=7.0, data_parallel=True)(T, I)
+        loss.backward()
+        np.savez(f"{tmp}/pp{rank}.npz", loss=loss.detach().numpy(), avg=avg["loss"].numpy(), image=x, text=t,
+                 d_image=I.grad.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_megatron_adapter_defaults_to_the_data_parallel_group():
+    """pretrain_CLIP.py's loss_func averages over mpu.get_data_parallel_group() (megatron/utils.py:96-105) and, with
+    pipeline parallelism, runs on the last stage only.  make_loss_func(group=None) must use that group - not WORLD - for
+    the gather, the reduce-scatter and the logged average: ranks of the other stage never enter a collective."""
+    from oracle import cliploss_oracle as O
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(_pipeline_worker, args=(4, tmp), nprocs=4, join=True)
+        outs = [dict(np.load(f"{tmp}/pp{r}.npz")) for r in (2, 3)]
+    ref = O.clip_loss_world([o["image"] for o in outs], [o["text"] for o in outs], 7.0, True, True)
+    mean = 0.5 * (ref[0].loss + ref[1].loss)
+    for o, g in zip(outs, ref):
+        assert abs(float(o["loss"]) - g.loss) <= 1e-5 * abs(g.loss)
+        assert abs(float(o["avg"]) - mean) <= 1e-5 * abs(mean)
+        assert np.linalg.norm(o["d_image"] - g.d_image) <= 1e-5 * np.linalg.norm(g.d_image)

@@ -73,7 +73,7 @@ def test_two_gpus_match_reference_goldens(path):
 
 
 @pytest.mark.parametrize("ll,gwg", [(True, True), (True, False), (False, True), (False, False)])
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_bf16_modes_against_oracle(world, ll, gwg):
     _need(world)
     from oracle import cliploss_oracle as O
@@ -93,44 +93,80 @@ def _steps_worker(rank, world, tmp, case):
         if p not in sys.path:
             sys.path.insert(0, p)
     import torch.distributed as dist
-    os.environ["CLIPK_PEER"] = "1"     # the fused path is opt-in (NCCL reduce_scatter is faster at 8 GPUs today)
+    for k, v in case.get("env", {}).items():
+        os.environ[k] = v
     from clipk import ClipLoss, ops
     from oracle import cliploss_oracle as O
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", init_method=f"file://{tmp}/store", rank=rank, world_size=world,
                             device_id=torch.device("cuda", rank))
-    mod = ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True, rank=rank, world_size=world)
+    mod = ClipLoss(local_loss=case.get("ll", True), gather_with_grad=True, cache_labels=True, rank=rank, world_size=world)
     out = {}
     for step in range(case["steps"]):
         x, t = O.synthetic_features(case["b"], case["d"], seed=100 + step, rank=rank)
         I = torch.from_numpy(x).cuda().bfloat16().requires_grad_(True)
         T = torch.from_numpy(t).cuda().bfloat16().requires_grad_(True)
-        S = torch.tensor(1 / 0.07, device="cuda", requires_grad=True)
-        mod(I, T, S).backward()
+        S = torch.tensor(case.get("s", 1 / 0.07), device="cuda", requires_grad=True)
+        if step == 1:
+            with torch.no_grad():           # a forward without a backward in between (validation): epochs stay in step
+                mod(I, T, S)
+        loss = mod(I, T, S)
+        loss.backward()
+        out[f"loss{step}"] = np.array(loss.item())
+        out[f"d_scale{step}"] = np.array(S.grad.item())
         out[f"d_image{step}"] = I.grad.float().cpu().numpy()
         out[f"d_text{step}"] = T.grad.float().cpu().numpy()
         out[f"image{step}"] = I.detach().float().cpu().numpy()
         out[f"text{step}"] = T.detach().float().cpu().numpy()
     torch.cuda.synchronize()
-    out["peer_used"] = np.array(len(ops._PEER_STATES))
+    out["peer_used"] = np.array(len(ops._PEER_CONTEXTS))
+    out["single"] = np.array(1 if ops.last_forward_was_single_sweep() else 0)
     np.savez(f"{tmp}/out{rank}.npz", **out)
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_peer_reduce_over_consecutive_steps():
-    """The fused gradient-GEMM + reduce-scatter path (dY tiles added into the owners' peer-mapped accumulators) over
-    several steps with different inputs: the accumulators are zeroed, filled and read in the right order."""
-    _need(2)
+def _check_steps(world, case, single=None):
     import torch.multiprocessing as mp
     from oracle import cliploss_oracle as O
-    world, case = 2, {"b": 384, "d": 128, "steps": 3}
     with tempfile.TemporaryDirectory() as tmp:
         mp.spawn(_steps_worker, args=(world, tmp, case), nprocs=world, join=True)
         outs = [dict(np.load(f"{tmp}/out{r}.npz")) for r in range(world)]
-    assert all(int(o["peer_used"]) == 1 for o in outs), "peer-memory path was not taken"
+    assert all(int(o["peer_used"]) == 1 for o in outs), "the peer-memory path was not taken"
+    if single is not None:
+        assert all(int(o["single"]) == int(single) for o in outs)
+    s = case.get("s", 1 / 0.07)
     for step in range(case["steps"]):
-        ref = O.clip_loss_world([o[f"image{step}"] for o in outs], [o[f"text{step}"] for o in outs], 1 / 0.07, True, True)
+        ref = O.clip_loss_world([o[f"image{step}"] for o in outs], [o[f"text{step}"] for o in outs], s,
+                                case.get("ll", True), True)
         for r in range(world):
-            assert rel(outs[r][f"d_image{step}"], ref[r].d_image) <= 2e-3
-            assert rel(outs[r][f"d_text{step}"], ref[r].d_text) <= 2e-3
+            o, g = outs[r], ref[r]
+            assert abs(float(o[f"loss{step}"]) - g.loss) <= 2e-3 * abs(g.loss), (step, r)
+            assert rel(o[f"d_image{step}"], g.d_image) <= 2e-3, (step, r, rel(o[f"d_image{step}"], g.d_image))
+            assert rel(o[f"d_text{step}"], g.d_text) <= 2e-3, (step, r, rel(o[f"d_text{step}"], g.d_text))
+            assert abs(float(o[f"d_scale{step}"]) - g.d_scale) <= 2e-3 * max(abs(g.d_scale), 1 / s), (step, r)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_peer_memory_step_over_consecutive_steps(world):
+    """The fused step between ranks - text rows and statistics pulled from peer memory, column statistics pulled, dY tiles
+    stored straight into their owners' slots, flag barriers - over several steps with different inputs and a forward
+    without a backward in between: the double-buffered sources / slots and the epochs stay consistent."""
+    _need(world)
+    _check_steps(world, {"b": 384, "d": 128, "steps": 4}, single=True)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_peer_memory_step_with_several_row_panels(world):
+    """A local batch that needs several row panels of the softmax gradient (8 MB panel budget): the dY tiles of the later
+    row panels are ADDED into the owners' slots over NVLink."""
+    _need(world)
+    _check_steps(world, {"b": 1536, "d": 256, "steps": 2, "env": {"CLIPK_PANEL_MB": "8"}})
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_peer_memory_step_global_loss_at_scale_100(world):
+    """local_loss=False (the loss all-reduced over the ranks) at the clamp logit_scale = 100: the positives' bound travels
+    with the gathered statistics, every rank keeps the single sweep."""
+    _need(world)
+    _check_steps(world, {"b": 640, "d": 256, "steps": 2, "ll": False, "s": 100.0}, single=True)

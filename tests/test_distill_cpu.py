@@ -56,7 +56,7 @@ def test_panel_path_host_logic(n, d, dt, panel_bytes, emu):
 
 
 def test_distill_class_switch(emu, monkeypatch):
-    """DistillClipLoss takes the panel path only when asked to (CLIPK_FUSED_DISTILL=1) and only for calls it covers;
+    """DistillClipLoss takes the panel path (the default; CLIPK_FUSED_DISTILL=0 switches it off) only for calls it covers;
     both paths return the reference's tuple / dictionary."""
     from clipk import DistillClipLoss, distill
     g = torch.Generator().manual_seed(1)

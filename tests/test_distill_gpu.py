@@ -1,17 +1,11 @@
-"""Panel-based distillation term on the real kernels against the oracle.  PENDING: written in a session that had no GPU
-time left, so it has not run on a B200 yet - the module is opt-in (CLIPK_FUSED_DISTILL=1) and these tests only run with
-CLIPK_TEST_PENDING=1.  First thing to do with a GPU: run them, then drop the gate and make the path the default."""
-import os
-
+"""Panel-based distillation term (clipk/distill.py) on the real kernels against the oracle."""
 import numpy as np
 import pytest
 import torch
 
 from oracle import cliploss_oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("CLIPK_TEST_PENDING") != "1",
-                                 reason="GPU validation of clipk/distill.py pending; set CLIPK_TEST_PENDING=1 to run")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("n,d,dt,panel_bytes", [(700, 256, 512, 256 << 20), (1000, 128, 128, 1 << 20), (333, 100, 64, 1)])
@@ -35,11 +29,11 @@ def test_panel_distill_term_against_oracle(n, d, dt, panel_bytes):
 
 def test_distill_class_on_the_panel_path(monkeypatch):
     from clipk import DistillClipLoss
-    monkeypatch.setenv("CLIPK_FUSED_DISTILL", "1")
+    monkeypatch.delenv("CLIPK_FUSED_DISTILL", raising=False)         # the panel path is the default for bf16 features
     g = torch.Generator().manual_seed(5)
     f = [torch.nn.functional.normalize(torch.randn(512, 256, generator=g), dim=-1).bfloat16().cuda() for _ in range(4)]
     s, ts = torch.tensor(1 / 0.07, device="cuda"), torch.tensor(30.0, device="cuda")
     con, dis = DistillClipLoss()(f[0], f[1], s, f[2], f[3], ts)
-    monkeypatch.delenv("CLIPK_FUSED_DISTILL")
+    monkeypatch.setenv("CLIPK_FUSED_DISTILL", "0")
     con0, dis0 = DistillClipLoss()(*(x.float() for x in f[:2]), s, *(x.float() for x in f[2:]), ts)
     assert abs(con.item() - con0.item()) <= 1e-4 * con0.item() and abs(dis.item() - dis0.item()) <= 1e-4 * dis0.item()
