@@ -257,3 +257,56 @@ def test_megatron_adapter_defaults_to_the_data_parallel_group():
         assert abs(float(o["loss"]) - g.loss) <= 1e-5 * abs(g.loss)
         assert abs(float(o["avg"]) - mean) <= 1e-5 * abs(mean)
         assert np.linalg.norm(o["d_image"] - g.d_image) <= 1e-5 * np.linalg.norm(g.d_image)
+
+
+def _ddp_worker(rank, world, tmp, feat_dtype):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "megatron-clip_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    from clipk import ClipLoss, ops
+    from tests.ddp_towers import Towers, global_batch
+    from tests.emu_backend import EmuBackend
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", init_method=f"file://{tmp}/store", rank=rank, world_size=world)
+    ops.set_backend_for_testing(EmuBackend())
+    torch.manual_seed(0)
+    model = Towers(24, 16, 64, getattr(torch, feat_dtype))
+    ddp = DDP(model, static_graph=True)
+    loss_mod = ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True, rank=rank, world_size=world)
+    b = 6
+    out = {}
+    for it in range(3):                 # static_graph changes DDP's behaviour from the second iteration on
+        images, texts = global_batch(world * b, 24, 16, seed=10 + it)
+        model.zero_grad()
+        i, t, s = ddp(images[rank * b:(rank + 1) * b], texts[rank * b:(rank + 1) * b])
+        loss = loss_mod(i, t, s)
+        (loss * 64.0).backward()        # an upstream factor, as AMP's GradScaler applies (training/train.py:58-62)
+        out[f"loss{it}"] = loss.detach().numpy()
+        for k, p in model.named_parameters():
+            out[f"{k}@{it}"] = (p.grad / 64.0).numpy()
+    np.savez(f"{tmp}/ddp{rank}.npz", **out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("feat_dtype,tol", [("float32", 2e-5), ("bfloat16", 2e-2)])
+def test_ddp_static_graph_towers_get_the_single_process_gradient(feat_dtype, tol):
+    """SURVEY 7 parity matrix: DDP(static_graph=True)-wrapped towers + the loss's own collectives, upstream gradient scale.
+    fp32 features take the general route, bf16 features (width 64) the fused step; both with the kernels emulated."""
+    from tests.ddp_towers import Towers, global_batch, reference_grads
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(_ddp_worker, args=(2, tmp, feat_dtype), nprocs=2, join=True)
+        outs = [dict(np.load(f"{tmp}/ddp{r}.npz")) for r in range(2)]
+    torch.manual_seed(0)
+    model = Towers(24, 16, 64, getattr(torch, feat_dtype))
+    for it in range(3):
+        images, texts = global_batch(12, 24, 16, seed=10 + it)
+        loss, grads = reference_grads(model, images, texts)
+        assert abs(0.5 * (float(outs[0][f"loss{it}"]) + float(outs[1][f"loss{it}"])) - loss) <= tol * abs(loss)
+        for k, g in grads.items():
+            for r in range(2):
+                got = torch.from_numpy(outs[r][f"{k}@{it}"])
+                assert (got - g).norm() <= tol * g.norm().clamp_min(1e-3), (it, k, r, float((got - g).norm()), float(g.norm()))

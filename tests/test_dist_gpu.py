@@ -170,3 +170,66 @@ def test_peer_memory_step_global_loss_at_scale_100(world):
     with the gathered statistics, every rank keeps the single sweep."""
     _need(world)
     _check_steps(world, {"b": 640, "d": 256, "steps": 2, "ll": False, "s": 100.0}, single=True)
+
+
+def _ddp_worker(rank, world, tmp):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "megatron-clip_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    from clipk import ClipLoss, ops
+    from tests.ddp_towers import Towers, global_batch
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"file://{tmp}/store", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    torch.manual_seed(0)
+    model = Towers(96, 48, 128, torch.bfloat16).cuda()
+    ddp = DDP(model, device_ids=[rank], static_graph=True)
+    loss_mod = ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True, rank=rank, world_size=world)
+    scaler = torch.amp.GradScaler("cuda", init_scale=1024.0)
+    opt = torch.optim.SGD(model.parameters(), lr=0.0)
+    out = {}
+    for it, b in enumerate((256, 256, 384)):        # the last one: cache_labels with a changed num_logits
+        images, texts = global_batch(world * b, 96, 48, seed=20 + it)
+        opt.zero_grad()
+        i, t, s = ddp(images[rank * b:(rank + 1) * b].cuda(), texts[rank * b:(rank + 1) * b].cuda())
+        loss = loss_mod(i, t, s)
+        scaler.scale(loss).backward()               # training/train.py:58-62
+        scaler.unscale_(opt)
+        assert loss_mod.prev_num_logits == b and torch.equal(loss_mod.labels[i.device], torch.arange(b, device=i.device) + b * rank)
+        out[f"loss{it}"] = np.array(loss.item())
+        for k, p in model.named_parameters():
+            out[f"{k}@{it}"] = p.grad.float().cpu().numpy()
+        scaler.step(opt)
+        scaler.update()
+    out["peer_used"] = np.array(len(ops._PEER_CONTEXTS))
+    np.savez(f"{tmp}/ddp{rank}.npz", **out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ddp_static_graph_towers_with_grad_scaler():
+    """SURVEY 7 parity matrix on real kernels: DDP(static_graph=True) towers, torch.amp.GradScaler upstream gradient,
+    cache_labels across a change of the batch size; two ranks over NCCL + peer memory.  Every rank must end with the
+    gradient a single process gets on the global batch with the reference's formula in fp32."""
+    _need(2)
+    import torch.multiprocessing as mp
+    from tests.ddp_towers import Towers, global_batch, reference_grads
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(_ddp_worker, args=(2, tmp), nprocs=2, join=True)
+        outs = [dict(np.load(f"{tmp}/ddp{r}.npz")) for r in range(2)]
+    assert all(int(o["peer_used"]) == 2 for o in outs)          # two shapes (b = 256, 384), both on peer memory
+    torch.manual_seed(0)
+    model = Towers(96, 48, 128, torch.bfloat16).cuda()
+    for it, b in enumerate((256, 256, 384)):
+        images, texts = global_batch(2 * b, 96, 48, seed=20 + it)
+        loss, grads = reference_grads(model, images.cuda(), texts.cuda())
+        assert abs(0.5 * (float(outs[0][f"loss{it}"]) + float(outs[1][f"loss{it}"])) - loss) <= 2e-3 * abs(loss)
+        for k, g in grads.items():
+            for r in range(2):
+                got = torch.from_numpy(outs[r][f"{k}@{it}"]).cuda()
+                # bf16 features and bf16 feature gradients on both sides of the loss
+                assert (got - g).norm() <= 1e-2 * g.norm().clamp_min(1e-4), (it, k, r, float((got - g).norm()), float(g.norm()))
