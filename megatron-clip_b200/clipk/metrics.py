@@ -63,6 +63,40 @@ def target_ranks(queries: torch.Tensor, keys: torch.Tensor, target: torch.Tensor
     return greater.long() + ties.long()
 
 
+def logits_panels(image_features: torch.Tensor, text_features: torch.Tensor, logit_scale=1.0, panel_bytes: int = PANEL_BYTES):
+    """Tile view of ClipLoss.get_logits (reference loss.py:104-121) for callers that need the logits themselves but not
+    all at once: yields (row0, panel) with panel = logit_scale * image_features[row0:row0 + n] @ text_features.T as an
+    fp32 [n, cols] tensor made on the tcgen05 mainloop (clipk_gemm16).  The SAME buffer is reused for every panel
+    (<= panel_bytes): consume or copy it before advancing.  No autograd (the differentiable consumers - the loss and the
+    distillation term - never need the logits in memory)."""
+    if image_features.dim() != 2 or text_features.dim() != 2 or image_features.shape[1] != text_features.shape[1]:
+        raise ValueError("image_features and text_features must be [rows, dim] and [cols, dim]")
+    if image_features.dtype != text_features.dtype:
+        raise TypeError("image_features and text_features must have the same dtype")
+    rows, cols = image_features.shape[0], text_features.shape[0]
+    if rows == 0 or cols == 0:
+        return
+    be = ops._backend()
+    dev = image_features.device
+    cols4 = (cols + 3) // 4 * 4
+    keys = text_features.detach()
+    if cols4 != cols:
+        keys = torch.nn.functional.pad(keys, (0, 0, 0, cols4 - cols))
+    Q, K = be.dense_operand(image_features.detach()), be.dense_operand(keys)
+    # fp32 / fp16 operands are held as scaled fp16 planes: the product carries both power-of-two scales
+    mul = float(logit_scale) if not isinstance(logit_scale, torch.Tensor) else logit_scale.detach().float().to(dev)
+    if getattr(Q, "keep", None) is not None:
+        mul = mul * Q.keep.inv_scale * K.keep.inv_scale
+    per = min(max(256, panel_bytes // (4 * cols4) // 256 * 256), rows)
+    panel = torch.empty(per, cols4, dtype=torch.float32, device=dev)
+    for r0 in range(0, rows, per):
+        n = min(per, rows - r0)
+        be.logits_panel(Q, K, r0, n, panel)
+        view = panel[:n, :cols]
+        view.mul_(mul)
+        yield r0, view
+
+
 def _signed(features, logit_scale):
     """A positive logit_scale does not change any order; a negative one reverses it, zero makes every entry tie."""
     s = float(logit_scale)
