@@ -187,9 +187,11 @@ __global__ void finalize_kernel(const float* __restrict__ row_max, const float* 
                                 const float* __restrict__ cmax, const float* __restrict__ csum,
                                 const float* __restrict__ cdot, int nparts, long long stride, int cols,
                                 long long diag_offset, float* __restrict__ lse_row, float* __restrict__ lse_col,
-                                float* __restrict__ sums, int* __restrict__ mm, float loss_div) {
+                                float* __restrict__ sums, int* __restrict__ mm, float loss_div, float* __restrict__ gvec) {
     // mm != null (clipk_step_forward): sums is the step's scalar block - [0..3] the sums, [4..5] receive (CE sums) /
-    // loss_div and (dscale sums) / loss_div from the last block to finish, [6] is its ticket, mm = ints [8..9]
+    // loss_div and (dscale sums) / loss_div from the last block to finish, [6] is its ticket, mm = ints [8..9].
+    // gvec != null: that last block also writes what grad_prep_kernel would (avec | bvec | gref, see there) - the
+    // backward then starts with its first recompute sweep
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     int lo = 0x7fffffff, hi = int(0x80000000);       // min / max LSE of this thread (ordered ints), for grad_prep_kernel
@@ -244,15 +246,33 @@ __global__ void finalize_kernel(const float* __restrict__ row_max, const float* 
             for (int off = 16; off >= 1; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
             if (l == 0) atomicAdd(sums + k, x);
         }
-        if (mm && l == 0) {
+    }
+    if (!mm) return;
+    __shared__ int last_block;
+    __syncthreads();                                  // every warp's lse stores and atomics are issued
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int ticket = atomicAdd(reinterpret_cast<unsigned int*>(sums) + 6, 1u);
+        last_block = (ticket == gridDim.x - 1);
+        if (last_block) {
             __threadfence();
-            const unsigned int ticket = atomicAdd(reinterpret_cast<unsigned int*>(sums) + 6, 1u);
-            if (ticket == gridDim.x - 1) {
-                __threadfence();
-                sums[4] = (__ldcg(sums) + __ldcg(sums + 1)) / loss_div;
-                sums[5] = (__ldcg(sums + 2) + __ldcg(sums + 3)) / loss_div;
-            }
+            sums[4] = (__ldcg(sums) + __ldcg(sums + 1)) / loss_div;
+            sums[5] = (__ldcg(sums + 2) + __ldcg(sums + 3)) / loss_div;
         }
+    }
+    __syncthreads();
+    if (last_block && gvec) {
+        __threadfence();
+        const float lo_l = ordered_to_float(__ldcg(mm)) * LOG2E, hi_l = ordered_to_float(__ldcg(mm + 1)) * LOG2E;
+        float* avec = gvec;
+        float* bvec = gvec + (rows + 63) / 64 * 64;
+        float* gref = bvec + (cols + 63) / 64 * 64;
+        if (threadIdx.x == 0) {
+            gref[0] = lo_l;
+            gref[1] = (hi_l - lo_l <= 100.f && lo_l > -CUDART_INF_F && hi_l < CUDART_INF_F) ? 1.f : 0.f;
+        }
+        for (int k = threadIdx.x; k < rows; k += blockDim.x) avec[k] = exp2f(lo_l - __ldcg(lse_row + k) * LOG2E);
+        for (int k = threadIdx.x; k < cols; k += blockDim.x) bvec[k] = exp2f(lo_l - __ldcg(lse_col + k) * LOG2E);
     }
 }
 
@@ -487,7 +507,7 @@ struct PrepArgs {
     long long ldxo, ldyo;
     float* inv_x; float* inv_y;    // NORMALIZE
     float eps;
-    float* stats;                  // this rank's row of the statistics (accumulated with atomics: zeroed before, word 4 = +large)
+    float* stats;                  // this rank's row of the statistics (accumulated with atomics: zeroed before)
     float* reset;                  // 8 floats + 2 ints of accumulators of LATER kernels of the step, reset here (null = none)
 };
 
@@ -621,7 +641,9 @@ __global__ void prep_kernel(const PrepArgs a) {
             atomicMax(su + 1, isbad ? 0x7f800000u : __float_as_uint(v[1]));
             if (v[2] > 0.f) atomicMax(su + 2, __float_as_uint(v[2]));
             if (v[3] > 0.f) atomicMax(su + 3, __float_as_uint(v[3]));
-            atomicMin(reinterpret_cast<int*>(a.stats) + 4, float_to_ordered(v[4]));
+            // min over the positives as a max over an order-reversing unsigned code (0 = "no pair seen" is its identity,
+            // so that one memset of zeros initialises the whole row); decoded by stat_min_pos (gemm_core.cuh)
+            atomicMax(su + 4, ~unsigned(float_to_ordered(v[4]) ^ 0x80000000));
         }
     }
 }
@@ -981,10 +1003,15 @@ struct GatherArgs {
     int rank, world;
     unsigned int epoch;
     int* err;
+    int do_signal;        // 0: the flags were already published by peer_signal_kernel (work was put in between)
 };
+__global__ void peer_signal_kernel(const __grid_constant__ PeerPtrs flags, const int rank, const int world, const unsigned int epoch) {
+    const int t = threadIdx.x;
+    if (t < world && t != rank) peer_signal(static_cast<unsigned int*>(flags.p[t]) + rank, epoch);
+}
 __global__ void peer_allgather_kernel(const __grid_constant__ GatherArgs a) {
     const int o = blockIdx.y;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && int(threadIdx.x) < a.world && int(threadIdx.x) != a.rank)
+    if (a.do_signal && blockIdx.x == 0 && blockIdx.y == 0 && int(threadIdx.x) < a.world && int(threadIdx.x) != a.rank)
         peer_signal(static_cast<unsigned int*>(a.flags.p[threadIdx.x]) + a.rank, a.epoch);
     const bool remote = o != a.rank;
     if (remote) {
@@ -1428,7 +1455,6 @@ size_t clipk_fwd_both_workspace_bytes(int rows, int cols, int d, int dtype) {
 // launch of prep_kernel over (X rows, Y rows); stats must be this rank's row of the table (it is reset here)
 static int launch_prep(const PrepArgs& a, int src_dtype, int normalize, int sms, cudaStream_t st) {
     CK_CUDA(cudaMemsetAsync(a.stats, 0, STAT_WORDS * sizeof(float), st));
-    CK_CUDA(cudaMemsetAsync(a.stats + 4, 0x7f, sizeof(float), st));          // min positive: a huge (ordered) value
     const long long nmax = a.rows_x > a.rows_y ? a.rows_x : a.rows_y;
     const int wpb = 8;
     const int blocks = int(std::max<long long>(1, std::min<long long>(cdiv(nmax, wpb), 4LL * sms)));
@@ -1565,7 +1591,7 @@ int clipk_finalize(const float* row_max, const float* row_sum, const float* row_
     const int n = rows > cols ? rows : cols;
     finalize_kernel<<<cdiv(n, 256), 256, 0, st>>>(row_max, row_sum, row_dot, pos_logit, rows, col_max_parts, col_sum_parts,
                                                   col_dot_parts, nparts, part_stride, cols, diag_offset, lse_row, lse_col,
-                                                  sums, nullptr, 1.f);
+                                                  sums, nullptr, 1.f, nullptr);
     count_launch("finalize_kernel", st);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
@@ -1583,8 +1609,9 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
                     const float* logit_scale, long long diag_offset, const float* lse_row, const float* lse_col,
                     float alpha, float beta, const float* gscale, float* dX_acc, float* dY_acc, void* const* dY_peer_acc,
                     int world, int rows_per_rank, void* workspace, size_t workspace_bytes, void* stream,
-                    const int* mm_ready = nullptr, float coef = 1.f) {
+                    const int* mm_ready = nullptr, float coef = 1.f, const float* gvec_ready = nullptr) {
     // mm_ready: min / max of both LSE vectors (ordered ints) already computed by the forward (clipk_step_forward);
+    // gvec_ready: avec | bvec | gref already written by its finalize kernel (then nothing is prepared here);
     // coef: constant factor on both gradients next to the device scalar *gscale
     int rc = check_common(X, Y, rows, cols, d, ldx, ldy, dtype);
     if (rc) return rc;
@@ -1634,7 +1661,11 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
     int* mm = reinterpret_cast<int*>(gref + 4);
     if (n_gbuf * g_bytes + (round_up(rows, 64) + round_up(cols, 64) + 8) * sizeof(float) > workspace_bytes)
         return fail(CLIPK_EWORKSPACE, "workspace too small for the panel and the reference vectors");
-    {
+    if (gvec_ready) {
+        avec = const_cast<float*>(gvec_ready);
+        bvec = avec + round_up(rows, 64);
+        gref = bvec + round_up(cols, 64);
+    } else {
         const int* mm_src = mm_ready;
         if (!mm_src) {
             CK_CUDA(cudaMemsetAsync(mm, 0x7f, sizeof(int), st));
@@ -1723,9 +1754,13 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
                 a1.oscale0 = logit_scale; a1.oscale1 = gscale; a1.oscale2 = xg_inv_scale; a1.oconst = coef / 16384.f;
                 jobs1 = cdiv(nc, 2 * BM) * nt;
             }
-            // One job (256 x 256 output tile, full K of the panel) per CTA pair.  A stream-K split of the K blocks over
-            // all 74 pairs was measured SLOWER (2.94 vs 2.73 ms per backward at N = 32768): the step runs at the 1 kW
-            // power cap, so evening out the MMAs buys nothing and the extra partial-tile reduces cost energy.
+            // One job (256 x 256 output tile, full K of the panel) per CTA pair, dispatched in order by the hardware.
+            // Measured alternatives, all SLOWER although they even out the MMAs per SM pair - the tensor kernels run at
+            // the power limit (SM clocks 1.55-1.65 GHz under ncu even for a single launch), so idle pairs lend their
+            // budget to the busy ones and extra partial tiles cost energy: a stream-K split over the 74 pairs (round 1:
+            // 2.94 vs 2.73 ms per backward at N = 32768); a persistent kernel walking a longest-first schedule with the
+            // epilogue of one item under the MMAs of the next, unsplit / dX in pieces of 64 or 32 K blocks / both
+            // outputs in pieces (round 2, profiles/r02c_scheduled_pair_kernel_ab.log: 1.97-2.13 vs 1.81 ms per step).
             if (dX_acc && dY_acc) rc = launch_pair(ta0, tb0, tc0, a0, jobs0, ta1, tb1, tc1, a1, jobs1, peers, st);
             else if (dX_acc) rc = launch_gemm<MODE_OUT, 1>(ta0, tb0, tc0, a0, nt, cdiv(nr, 2 * BM), st);
             else rc = launch_gemm<MODE_OUT, 1>(ta1, tb1, tc1, a1, nt, cdiv(nc, 2 * BM), st);
@@ -1910,9 +1945,8 @@ StepCarve step_carve(int rows, int cols, int d, int world) {
     c.col_all = take(f, world > 1 ? size_t(world) * 3 * cols * sizeof(float) : 0);
     const size_t dpad = size_t(round_up(d, BK));
     size_t b = 0;
-    c.xg = take(b, size_t(rows) * dpad * 2);
-    c.yg = take(b, size_t(cols) * dpad * 2);
-    c.inv2 = take(b, 256);
+    c.xg = take(b, (size_t(rows) + cols) * dpad * 2 + 256);      // Xg | Yg | dequant scalars, one block (step_to_f16)
+    c.yg = c.inv2 = c.xg;
     c.dx = take(b, size_t(rows) * d * sizeof(float));
     c.dy = take(b, world > 1 ? 0 : size_t(cols) * d * sizeof(float));
     c.bwd = take(b, clipk_bwd_workspace_bytes(rows, cols, d, CLIPK_F16));
@@ -1959,6 +1993,24 @@ int launch_allgather(const GatherArgs& g, int sms, cudaStream_t st) {
 }
 }  // namespace
 
+// exact fp16 copies of both operands for the gradient GEMMs: buf = Xg [rows, d] | Yg [cols, d] | 64 floats (2 dequant scalars)
+static int step_to_f16(const clipk_step* p, int W, int rank, __half* buf, cudaStream_t st) {
+    const int rows = p->rows, cols = p->cols, d = p->d;
+    const long long ldx = (p->x_op == p->image) ? p->ld_image : d;
+    const long long ldy = (W == 1 && p->y_all == p->text) ? p->ld_text : d;
+    const long long dpad = round_up(d, BK);
+    __half* Xg = buf;
+    __half* Yg = buf + (size_t)rows * dpad;
+    float* inv2 = reinterpret_cast<float*>(Yg + (size_t)cols * dpad);
+    const long long n8 = ((long long)rows + cols) * (dpad / 8);
+    to_f16_pair_kernel<<<cdiv(n8, 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(p->x_op), rows, ldx, Xg,
+                                                      static_cast<const __nv_bfloat16*>(p->y_all), cols, ldy, Yg, d, dpad,
+                                                      p->stats, W, rank, inv2);
+    count_launch("to_f16_pair_kernel", st);
+    CK_CUDA(cudaGetLastError());
+    return CLIPK_OK;
+}
+
 size_t clipk_step_workspace_bytes(const clipk_step* p) {
     if (!p || p->rows <= 0 || p->cols <= 0 || p->d <= 0) return 0;
     return step_carve(p->rows, p->cols, p->d, p->peer ? p->peer->world : 1).total;
@@ -2001,7 +2053,7 @@ int clipk_step_forward(const clipk_step* p) {
         }
         g.n16_0 = (long long)rows * d * 2 / 16; g.dst0 = static_cast<uint4*>(p->y_all);
         g.n16_1 = STAT_WORDS * sizeof(float) / 16; g.dst1 = reinterpret_cast<uint4*>(p->stats);
-        g.rank = rank; g.world = W; g.epoch = pr->epoch_gather; g.err = pr->err;
+        g.rank = rank; g.world = W; g.epoch = pr->epoch_gather; g.err = pr->err; g.do_signal = 1;
         if ((rc = launch_allgather(g, di.sms, st))) return rc;
     }
 
@@ -2021,7 +2073,15 @@ int clipk_step_forward(const clipk_step* p) {
         }
         g.n16_0 = (long long)3 * cols * sizeof(float) / 16; g.dst0 = reinterpret_cast<uint4*>(col_all);
         g.n16_1 = 0;
-        g.rank = rank; g.world = W; g.epoch = pr->epoch_stats; g.err = pr->err;
+        g.rank = rank; g.world = W; g.epoch = pr->epoch_stats; g.err = pr->err; g.do_signal = 1;
+        if (p->g16) {
+            // tell the peers first, then do the backward's operand conversion while their statistics are on the way
+            peer_signal_kernel<<<1, 32, 0, st>>>(g.flags, rank, W, pr->epoch_stats);
+            count_launch("peer_signal_kernel", st);
+            CK_CUDA(cudaGetLastError());
+            g.do_signal = 0;
+            if ((rc = step_to_f16(p, W, rank, static_cast<__half*>(p->g16), st))) return rc;
+        }
         if ((rc = launch_allgather(g, di.sms, st))) return rc;
     }
 
@@ -2030,7 +2090,7 @@ int clipk_step_forward(const clipk_step* p) {
     finalize_kernel<<<cdiv(n, 256), 256, 0, st>>>(row_stats, row_stats + rows, row_stats + 2 * (size_t)rows, pos, rows, col_all,
                                                   col_all + cols, col_all + 2 * (size_t)cols, W, (long long)3 * cols, cols, off,
                                                   p->lse_row, p->lse_col, p->scal, reinterpret_cast<int*>(p->scal) + 8,
-                                                  p->loss_div);
+                                                  p->loss_div, p->gvec);
     count_launch("finalize_kernel", st);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
@@ -2054,17 +2114,14 @@ int clipk_step_backward(const clipk_step* p) {
     const bool want_feat = p->d_image || p->d_text;
     if (want_feat) {
         if (!p->d_image || !p->d_text) return fail(CLIPK_EINVAL, "d_image and d_text must be given together");
-        // 1. exact fp16 copies of both operands for the gradient GEMMs
-        __half* Xg = reinterpret_cast<__half*>(ws + cv.xg);
-        __half* Yg = reinterpret_cast<__half*>(ws + cv.yg);
-        float* inv2 = reinterpret_cast<float*>(ws + cv.inv2);
+        // 1. exact fp16 copies of both operands for the gradient GEMMs (already made by the forward when it had a wait
+        //    to fill, see clipk_step_forward)
         const long long dpad = round_up(d, BK);
-        const long long n8 = ((long long)rows + cols) * (dpad / 8);
-        to_f16_pair_kernel<<<cdiv(n8, 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(p->x_op), rows, ldx, Xg,
-                                                          static_cast<const __nv_bfloat16*>(p->y_all), cols, ldy, Yg, d, dpad,
-                                                          p->stats, W, rank, inv2);
-        count_launch("to_f16_pair_kernel", st);
-        CK_CUDA(cudaGetLastError());
+        __half* g16 = p->g16 ? static_cast<__half*>(p->g16) : reinterpret_cast<__half*>(ws + cv.xg);
+        if (!(p->g16 && W > 1) && (rc = step_to_f16(p, W, rank, g16, st))) return rc;
+        __half* Xg = g16;
+        __half* Yg = g16 + (size_t)rows * dpad;
+        float* inv2 = reinterpret_cast<float*>(Yg + (size_t)cols * dpad);
         // 2. recompute + gradient GEMMs, panel by panel; with peers the dY tiles go straight to their owners
         float* dX = reinterpret_cast<float*>(ws + cv.dx);
         float* dY = (W > 1) ? nullptr : reinterpret_cast<float*>(ws + cv.dy);
@@ -2077,7 +2134,7 @@ int clipk_step_backward(const clipk_step* p) {
         if ((rc = bwd_impl(p->x_op, p->y_all, rows, cols, d, ldx, ldy, CLIPK_BF16, nullptr, nullptr, Xg, Yg, dpad, dpad, CLIPK_F16,
                            inv2, inv2 + 1, p->logit_scale, off, p->lse_row, p->lse_col, 1.f, 1.f, p->grad_out, dX, dY,
                            W > 1 ? slots : nullptr, W, rows, ws + cv.bwd, clipk_bwd_workspace_bytes(rows, cols, d, CLIPK_F16),
-                           p->stream, reinterpret_cast<const int*>(p->scal) + 8, p->grad_coef)))
+                           p->stream, reinterpret_cast<const int*>(p->scal) + 8, p->grad_coef, p->gvec)))
             return rc;
         // 3. every rank's tiles have landed in the slots this rank owns
         if (W > 1) {

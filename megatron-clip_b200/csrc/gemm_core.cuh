@@ -357,6 +357,7 @@ __device__ __forceinline__ void produce_unit(const Cta& c, Pipe& p, const CUtens
 template <int STAGES>
 __device__ __forceinline__ void mma_unit(const Cta& c, Pipe& p, const KArgs& args, int ntiles) {
     const int a_mn = args.a_mn, b_mn = args.b_mn;
+    const int num_kb = args.num_kb;
     const uint32_t idesc = ptx::make_idesc_16bit(2 * BM, BN, a_mn, b_mn, /*a_is_bf16=*/!args.f16, /*b_is_bf16=*/!args.f16);
     // K-major SW128: 8-row groups 1024 B apart (SBO); MN-major SW128: 64-wide MN blocks 8192 B apart (LBO),
     // 8-row K groups 1024 B apart (SBO).
@@ -370,7 +371,7 @@ __device__ __forceinline__ void mma_unit(const Cta& c, Pipe& p, const KArgs& arg
         ptx::mbar_wait(c.bar_tempty + 8 * a, aph ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = c.tmem_base + a * BN;
-        for (int kb = 0; kb < args.num_kb; ++kb) {
+        for (int kb = 0; kb < num_kb; ++kb) {
             ptx::mbar_wait(c.bar_full + 8 * p.s, p.ph);
             ptx::tc_fence_after();
             const uint32_t a_src = c.sA + p.s * A_STAGE_BYTES;
@@ -724,7 +725,8 @@ struct FwdArgs {
 // Operand statistics, one row of STAT_WORDS floats per rank, filled by prep_kernel (clipk.cu):
 //   [0] max_i |x_i|^2   [1] max_j |y_j|^2   [2] max |x_ij|   [3] max |y_ij|      (bit patterns of non-negative floats;
 //                                                                                  +Inf bits when a NaN / Inf was seen)
-//   [4] min_i x_i . y_i over the rank's positive pairs, as an order-preserving int (see float_to_ordered)
+//   [4] min_i x_i . y_i over the rank's positive pairs, as an order-REVERSING unsigned code whose maximum is taken
+//       (0 = no pair seen; decoded by stat_min_pos)
 //   [5] written by fwd_merge_kernel: 1 when the forward took the single sweep, 0 for the exact two-sweep form
 constexpr int STAT_WORDS = 8;
 __host__ __device__ __forceinline__ int float_to_ordered(float f) {
@@ -736,6 +738,12 @@ __host__ __device__ __forceinline__ int float_to_ordered(float f) {
     return i >= 0 ? i : i ^ 0x7fffffff;
 }
 __device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__device__ __forceinline__ float stat_min_pos(float word) {
+    const unsigned int u = __float_as_uint(word);
+    if (u == 0u) return CUDART_INF_F;                 // no positive pair was seen
+    return ordered_to_float(int((~u) ^ 0x80000000u));
+}
 
 // The reference c of the single sweep (log2 units) and whether the single sweep is allowed; identical in every thread of
 // every CTA of both launches and of the merge kernel.  With u >= |v| for every logit v (from the row norms) and
@@ -753,7 +761,7 @@ __device__ __forceinline__ bool fwd_bound(const FwdArgs& a, float* c_out) {
     for (int r = 0; r < a.nstat; ++r) {
         const float* st = a.stats + r * STAT_WORDS;
         ny2 = fmaxf(ny2, __ldg(st + 1));
-        minpos = fminf(minpos, ordered_to_float(__float_as_int(__ldg(st + 4))));
+        minpos = fminf(minpos, stat_min_pos(__ldg(st + 4)));
     }
     const float nx2 = __ldg(a.stats + a.stats_rank * STAT_WORDS);
     const float s = __ldg(a.scale);

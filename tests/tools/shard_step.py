@@ -29,3 +29,18 @@ for _ in range(reps):
     dX, dY = be.bwd(X, Y, Xg, Yg, sc, 0, lse_row, lse_col, 1.0, 1.0, gs, True, True)
 torch.cuda.synchronize()
 print("ok", float(sums[0]), float(dX.abs().sum()), float(dY.abs().sum()))
+if os.environ.get("SHARD_TIME"):
+    def ev(fn, n=10):
+        fn(); fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n * 1e3
+    parts = torch.empty(1, 3, cols, dtype=torch.float32, device="cuda")
+    t_f = ev(lambda: be.fwd_both(X, Y, sc, 0, col_out=parts[0]))
+    t_b = ev(lambda: be.bwd(X, Y, Xg, Yg, sc, 0, lse_row, lse_col, 1.0, 1.0, gs, True, True))
+    print(f"timing us: fwd_both {t_f:.1f}  bwd {t_b:.1f}")
