@@ -60,6 +60,15 @@ static std::mutex g_dev_mu;
 static int device_info(DevInfo* out) {
     int dev = 0;
     CK_CUDA(cudaGetDevice(&dev));
+    // The driver-API tensor-map encoder needs the device's primary context CURRENT on the calling thread.  PyTorch's
+    // autograd worker threads only have the device selected: until the first runtime call that touches the context
+    // (a launch, a memset) cuTensorMapEncodeTiled fails there with CUDA_ERROR_INVALID_CONTEXT.  Bind it once per thread
+    // and device.
+    static thread_local int bound_dev = -1;
+    if (bound_dev != dev) {
+        CK_CUDA(cudaFree(nullptr));
+        bound_dev = dev;
+    }
     if (dev < 0 || dev >= 64) return fail(CLIPK_EINVAL, "device index %d out of range", dev);
     std::lock_guard<std::mutex> lk(g_dev_mu);
     if (!g_dev[dev].queried) {
