@@ -212,8 +212,6 @@ typedef struct clipk_step {
     float* lse_row; float* lse_col;     /* [rows], [cols]                                                              */
     float* scal;                        /* 16 floats: [0..3] CE / dscale sums, [4] loss, [5] s * dloss/ds, [8..9] LSE   */
                                         /* min / max (ints)                                                            */
-    float* gvec;                        /* round_up(rows, 64) + round_up(cols, 64) + 4 floats: per-row / per-column    */
-                                        /* factors of the recompute, written by the forward (NULL: no backward follows) */
     void* g16;                          /* [rows + cols, d] fp16 + 64 floats: the operands' fp16 copies for the gradient */
                                         /* GEMMs.  world > 1: made by the forward while it waits for the peers' column  */
                                         /* statistics (NULL: the backward makes them in its workspace)                  */

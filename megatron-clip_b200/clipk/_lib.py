@@ -72,7 +72,7 @@ class Step(ctypes.Structure):
                 ("image", _vp), ("text", _vp), ("ld_image", _ll), ("ld_text", _ll), ("logit_scale", _vp),
                 ("loss_div", _f), ("grad_coef", _f),
                 ("x_op", _vp), ("y_all", _vp), ("inv_x", _vp), ("inv_y", _vp), ("stats", _vp), ("lse_row", _vp),
-                ("lse_col", _vp), ("scal", _vp), ("gvec", _vp), ("g16", _vp),
+                ("lse_col", _vp), ("scal", _vp), ("g16", _vp),
                 ("grad_out", _vp), ("d_image", _vp), ("d_text", _vp), ("d_scale", _vp), ("out_dtype", _i),
                 ("peer", ctypes.POINTER(Peer)), ("workspace", _vp), ("workspace_bytes", _sz), ("stream", _vp)]
 

@@ -195,7 +195,7 @@ class CudaBackend:
             c.inv_x, c.inv_y = _ptr(st.inv_x), _ptr(st.inv_y)
             c.stats, c.lse_row, c.lse_col, c.scal = (st.stats.data_ptr(), st.lse_row.data_ptr(), st.lse_col.data_ptr(),
                                                      st.scal.data_ptr())
-            c.gvec, c.g16 = _ptr(st.gvec), _ptr(st.g16)
+            c.g16 = _ptr(st.g16)
             c.workspace, c.workspace_bytes = st.ws.data_ptr(), st.ws.numel()
         c.stream = self._stream()
         return c
@@ -340,7 +340,7 @@ def gpu_launches() -> int:
 class StepDesc:
     """Everything one loss evaluation holds between its forward and its backward (mirrors struct clipk_step)."""
     __slots__ = ("rows", "cols", "d", "world", "rank", "normalize", "eps", "image", "text", "scale", "loss_div",
-                 "grad_coef", "x_op", "y_all", "inv_x", "inv_y", "stats", "lse_row", "lse_col", "scal", "gvec", "g16", "ws",
+                 "grad_coef", "x_op", "y_all", "inv_x", "inv_y", "stats", "lse_row", "lse_col", "scal", "g16", "ws",
                  "peer",
                  "grad_out", "d_image", "d_text", "d_scale", "out_dtype", "cstruct", "cpeer", "group")
 
@@ -576,10 +576,8 @@ class FusedClipLoss(torch.autograd.Function):
             # c of SURVEY App. A: 1/(2b) for W=1, local modes and global+gather_with_grad; 1/(2N) otherwise
             st.grad_coef = 1.0 / (2.0 * b) if (local or gather_with_grad) else 1.0 / (2.0 * N)
             produced = st.normalize or in_dtype != torch.bfloat16
-            # one fp32 allocation for everything the backward reads: lse_row | lse_col | scalars | statistics | inv norms |
-            # the recompute's per-row / per-column factors (only when a feature gradient will be asked for)
-            n_g = (_round_up(b, 64) + _round_up(N, 64) + 4) if want_feat else 0
-            n_f = b + N + 16 + _lib.STAT_WORDS * W + (2 * b if st.normalize else 0) + n_g
+            # one fp32 allocation for everything the backward reads: lse_row | lse_col | scalars | statistics | inv norms
+            n_f = b + N + 16 + _lib.STAT_WORDS * W + (2 * b if st.normalize else 0)
             fbuf = torch.empty(n_f, dtype=torch.float32, device=dev)
             st.lse_row, st.lse_col = fbuf[:b], fbuf[b:b + N]
             st.scal = fbuf[b + N:b + N + 16]
@@ -589,12 +587,10 @@ class FusedClipLoss(torch.autograd.Function):
             if st.normalize:
                 st.inv_x, st.inv_y = fbuf[o:o + b], fbuf[o + b:o + 2 * b]
                 o += 2 * b
-            if want_feat:
-                st.gvec = fbuf[o:o + n_g]
-                if W > 1:
-                    # fp16 copies of the operands for the gradient GEMMs: made in the forward, under the wait for the
-                    # peers' column statistics
-                    st.g16 = torch.empty((b + N) * d_in * 2 + 256, dtype=torch.uint8, device=dev)
+            if want_feat and W > 1:
+                # fp16 copies of the operands for the gradient GEMMs: made in the forward, under the wait for the
+                # peers' column statistics
+                st.g16 = torch.empty((b + N) * d_in * 2 + 256, dtype=torch.uint8, device=dev)
             st.x_op = torch.empty(b, d_in, dtype=torch.bfloat16, device=dev) if produced else img
             st.y_all = torch.empty(N, d_in, dtype=torch.bfloat16, device=dev) if (produced or W > 1) else txt
             st.ws = _step_workspace(be, b, N, d_in, W, dev)

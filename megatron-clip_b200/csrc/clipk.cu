@@ -196,11 +196,11 @@ __global__ void finalize_kernel(const float* __restrict__ row_max, const float* 
                                 const float* __restrict__ cmax, const float* __restrict__ csum,
                                 const float* __restrict__ cdot, int nparts, long long stride, int cols,
                                 long long diag_offset, float* __restrict__ lse_row, float* __restrict__ lse_col,
-                                float* __restrict__ sums, int* __restrict__ mm, float loss_div, float* __restrict__ gvec) {
+                                float* __restrict__ sums, int* __restrict__ mm, float loss_div) {
     // mm != null (clipk_step_forward): sums is the step's scalar block - [0..3] the sums, [4..5] receive (CE sums) /
     // loss_div and (dscale sums) / loss_div from the last block to finish, [6] is its ticket, mm = ints [8..9].
-    // gvec != null: that last block also writes what grad_prep_kernel would (avec | bvec | gref, see there) - the
-    // backward then starts with its first recompute sweep
+    // (one block preparing the recompute's per-row / per-column factors here as well was measured: +37 us for 40K
+    //  entries - they stay with grad_prep_kernel in the backward)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     int lo = 0x7fffffff, hi = int(0x80000000);       // min / max LSE of this thread (ordered ints), for grad_prep_kernel
@@ -236,8 +236,8 @@ __global__ void finalize_kernel(const float* __restrict__ row_max, const float* 
             hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, off));
         }
         if (l == 0) {
-            atomicMin(mm, lo);
-            atomicMax(mm + 1, hi);
+            if (lo < __ldcg(mm)) atomicMin(mm, lo);
+            if (hi > __ldcg(mm + 1)) atomicMax(mm + 1, hi);
         }
     }
 #pragma unroll
@@ -270,19 +270,6 @@ __global__ void finalize_kernel(const float* __restrict__ row_max, const float* 
         }
     }
     __syncthreads();
-    if (last_block && gvec) {
-        __threadfence();
-        const float lo_l = ordered_to_float(__ldcg(mm)) * LOG2E, hi_l = ordered_to_float(__ldcg(mm + 1)) * LOG2E;
-        float* avec = gvec;
-        float* bvec = gvec + (rows + 63) / 64 * 64;
-        float* gref = bvec + (cols + 63) / 64 * 64;
-        if (threadIdx.x == 0) {
-            gref[0] = lo_l;
-            gref[1] = (hi_l - lo_l <= 100.f && lo_l > -CUDART_INF_F && hi_l < CUDART_INF_F) ? 1.f : 0.f;
-        }
-        for (int k = threadIdx.x; k < rows; k += blockDim.x) avec[k] = exp2f(lo_l - __ldcg(lse_row + k) * LOG2E);
-        for (int k = threadIdx.x; k < cols; k += blockDim.x) bvec[k] = exp2f(lo_l - __ldcg(lse_col + k) * LOG2E);
-    }
 }
 
 // ---- backward preparation: one reference for every exponential of this backward (see grad_chunk PATH 0)
@@ -646,13 +633,17 @@ __global__ void prep_kernel(const PrepArgs a) {
         if (lane == 0) {
             unsigned int* su = reinterpret_cast<unsigned int*>(a.stats);
             const bool isbad = shbad != 0;
-            atomicMax(su + 0, isbad ? 0x7f800000u : __float_as_uint(v[0]));
-            atomicMax(su + 1, isbad ? 0x7f800000u : __float_as_uint(v[1]));
-            if (v[2] > 0.f) atomicMax(su + 2, __float_as_uint(v[2]));
-            if (v[3] > 0.f) atomicMax(su + 3, __float_as_uint(v[3]));
+            // hundreds of blocks hit the same five words: look first, only a block that raises a maximum pays for an atomic
+            auto bump = [](unsigned int* addr, unsigned int val) {
+                if (val > __ldcg(addr)) atomicMax(addr, val);
+            };
+            bump(su + 0, isbad ? 0x7f800000u : __float_as_uint(v[0]));
+            bump(su + 1, isbad ? 0x7f800000u : __float_as_uint(v[1]));
+            bump(su + 2, __float_as_uint(v[2]));
+            bump(su + 3, __float_as_uint(v[3]));
             // min over the positives as a max over an order-reversing unsigned code (0 = "no pair seen" is its identity,
             // so that one memset of zeros initialises the whole row); decoded by stat_min_pos (gemm_core.cuh)
-            atomicMax(su + 4, ~unsigned(float_to_ordered(v[4]) ^ 0x80000000));
+            bump(su + 4, ~unsigned(float_to_ordered(v[4]) ^ 0x80000000));
         }
     }
 }
@@ -1126,10 +1117,11 @@ static int choose_split(int m_pairs, int n_tiles, int sms) {
 // the gradient GEMMs at 0.45 us per K block with the jobs list-scheduled, in launch order, over the CTA pairs.
 // The choice depends only on the shape and is cached.
 struct PanelKey {
-    int rows, cols, d, gplanes, sms;
+    int rows, cols, d, gplanes, sms, one_row_panel;
     long long budget;
     bool operator==(const PanelKey& o) const {
-        return rows == o.rows && cols == o.cols && d == o.d && gplanes == o.gplanes && sms == o.sms && budget == o.budget;
+        return rows == o.rows && cols == o.cols && d == o.d && gplanes == o.gplanes && sms == o.sms && budget == o.budget &&
+               one_row_panel == o.one_row_panel;
     }
 };
 struct PanelChoice { PanelKey key; long long rp, cp; };
@@ -1153,8 +1145,11 @@ static double panel_cost_us(int rb, int cb, int nt, int s_kb, int g_nseg, int pa
     return grad + pair;
 }
 
-static void choose_panel(int rows, int cols, int d, int gplanes, int sms, long long budget, long long* rp_out, long long* cp_out) {
-    const PanelKey key{rows, cols, d, gplanes, sms, budget};
+// one_row_panel: prefer splits that keep all rows in ONE panel (fused reduce-scatter: the dY tiles of the first row panel
+// are plain stores into the owners' slots, those of later row panels reduce-adds, ~3x slower over NVLink)
+static void choose_panel(int rows, int cols, int d, int gplanes, int sms, long long budget, long long* rp_out, long long* cp_out,
+                         int one_row_panel = 0) {
+    const PanelKey key{rows, cols, d, gplanes, sms, one_row_panel, budget};
     {
         std::lock_guard<std::mutex> lk(g_panel_mu);
         for (const PanelChoice& c : g_panel_cache)
@@ -1168,7 +1163,9 @@ static void choose_panel(int rows, int cols, int d, int gplanes, int sms, long l
     double best = 1e300;
     int best_rb = 1, best_cb = 1;
     int last_rb = 0;
-    for (int nr = 1; nr <= R; ++nr) {
+    // a single row panel must leave room for at least one 256-column block
+    const bool single_rows = one_row_panel && (long long)R * 4 * BM * BM * 2 * gplanes <= budget;
+    for (int nr = 1; nr <= (single_rows ? 1 : R); ++nr) {
         const int rb = cdiv(R, nr);
         if (rb == last_rb) continue;
         last_rb = rb;
@@ -1600,7 +1597,7 @@ int clipk_finalize(const float* row_max, const float* row_sum, const float* row_
     const int n = rows > cols ? rows : cols;
     finalize_kernel<<<cdiv(n, 256), 256, 0, st>>>(row_max, row_sum, row_dot, pos_logit, rows, col_max_parts, col_sum_parts,
                                                   col_dot_parts, nparts, part_stride, cols, diag_offset, lse_row, lse_col,
-                                                  sums, nullptr, 1.f, nullptr);
+                                                  sums, nullptr, 1.f);
     count_launch("finalize_kernel", st);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
@@ -1618,9 +1615,8 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
                     const float* logit_scale, long long diag_offset, const float* lse_row, const float* lse_col,
                     float alpha, float beta, const float* gscale, float* dX_acc, float* dY_acc, void* const* dY_peer_acc,
                     int world, int rows_per_rank, void* workspace, size_t workspace_bytes, void* stream,
-                    const int* mm_ready = nullptr, float coef = 1.f, const float* gvec_ready = nullptr) {
+                    const int* mm_ready = nullptr, float coef = 1.f) {
     // mm_ready: min / max of both LSE vectors (ordered ints) already computed by the forward (clipk_step_forward);
-    // gvec_ready: avec | bvec | gref already written by its finalize kernel (then nothing is prepared here);
     // coef: constant factor on both gradients next to the device scalar *gscale
     int rc = check_common(X, Y, rows, cols, d, ldx, ldy, dtype);
     if (rc) return rc;
@@ -1656,7 +1652,7 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
     const long long kext = (dtype == CLIPK_BF16) ? d : planes * dpad;   // inner extent of X / Y rows
     const long long gext = gplanes * dpad;                              // inner extent of Xg / Yg rows
     long long rp_max, cp_max;
-    choose_panel(rows, cols, d, gplanes, di.sms, panel_bytes(), &rp_max, &cp_max);
+    choose_panel(rows, cols, d, gplanes, di.sms, panel_bytes(), &rp_max, &cp_max, peers.world > 0 ? 1 : 0);
     const int ncp = int(cp_max);                        // panel width (multiple of BN) = G plane stride
     const int ldg = gplanes * ncp;
     if ((unsigned long long)round_up(rp_max, 2 * BM) * ldg * 2 > workspace_bytes) return fail(CLIPK_EWORKSPACE, "panel does not fit the workspace");
@@ -1670,11 +1666,7 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
     int* mm = reinterpret_cast<int*>(gref + 4);
     if (n_gbuf * g_bytes + (round_up(rows, 64) + round_up(cols, 64) + 8) * sizeof(float) > workspace_bytes)
         return fail(CLIPK_EWORKSPACE, "workspace too small for the panel and the reference vectors");
-    if (gvec_ready) {
-        avec = const_cast<float*>(gvec_ready);
-        bvec = avec + round_up(rows, 64);
-        gref = bvec + round_up(cols, 64);
-    } else {
+    {
         const int* mm_src = mm_ready;
         if (!mm_src) {
             CK_CUDA(cudaMemsetAsync(mm, 0x7f, sizeof(int), st));
@@ -2099,7 +2091,7 @@ int clipk_step_forward(const clipk_step* p) {
     finalize_kernel<<<cdiv(n, 256), 256, 0, st>>>(row_stats, row_stats + rows, row_stats + 2 * (size_t)rows, pos, rows, col_all,
                                                   col_all + cols, col_all + 2 * (size_t)cols, W, (long long)3 * cols, cols, off,
                                                   p->lse_row, p->lse_col, p->scal, reinterpret_cast<int*>(p->scal) + 8,
-                                                  p->loss_div, p->gvec);
+                                                  p->loss_div);
     count_launch("finalize_kernel", st);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
@@ -2143,7 +2135,7 @@ int clipk_step_backward(const clipk_step* p) {
         if ((rc = bwd_impl(p->x_op, p->y_all, rows, cols, d, ldx, ldy, CLIPK_BF16, nullptr, nullptr, Xg, Yg, dpad, dpad, CLIPK_F16,
                            inv2, inv2 + 1, p->logit_scale, off, p->lse_row, p->lse_col, 1.f, 1.f, p->grad_out, dX, dY,
                            W > 1 ? slots : nullptr, W, rows, ws + cv.bwd, clipk_bwd_workspace_bytes(rows, cols, d, CLIPK_F16),
-                           p->stream, reinterpret_cast<const int*>(p->scal) + 8, p->grad_coef, p->gvec)))
+                           p->stream, reinterpret_cast<const int*>(p->scal) + 8, p->grad_coef)))
             return rc;
         // 3. every rank's tiles have landed in the slots this rank owns
         if (W > 1) {

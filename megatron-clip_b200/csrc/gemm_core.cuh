@@ -906,17 +906,19 @@ template <int F16, bool ARES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fwd_sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FwdArgs args) {
     constexpr int STAGES = FWD_STAGES;
-    const Cta c = cta_setup<STAGES, COLBUF_BYTES, (ARES ? ARES_KB : STAGES) * A_STAGE_BYTES>();
-    const uint32_t colbuf = c.sStg;
     float u = 0.f;
     const bool safe = fwd_bound(args, &u);
+    // the launch of the swapped pass has nothing to do when the single sweep is taken: leave before any barrier, TMEM or
+    // cluster state exists (uniform over the grid; the statistics it read were complete before the first launch began)
+    if (safe && args.pass == 1) return;
+    const Cta c = cta_setup<STAGES, COLBUF_BYTES, (ARES ? ARES_KB : STAGES) * A_STAGE_BYTES>();
+    const uint32_t colbuf = c.sStg;
     const bool single = safe && args.pass == 0;
-    const bool skip = safe && args.pass == 1;
     const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     Pipe p;
     const SweepGeom geom{args.num_kb, args.n_tiles, args.m_pairs};
     const long long total_tiles = (long long)args.m_pairs * args.n_tiles;
-    if (!skip) {
+    {
         if (c.warp == 0) {
             if (c.lane == 0) {
                 ptx::prefetch_tmap(&tmA);
