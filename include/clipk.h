@@ -132,32 +132,6 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
               float alpha, float beta, const float* gscale, float* dX_acc, float* dY_acc, void* workspace,
               size_t workspace_bytes, void* stream);
 
-/* ---- backward fused with the reduce-scatter of the text gradient (data-parallel ranks of one NVLink domain) ----
- * clipk_bwd_peer is clipk_bwd with the dY output replaced by memory of ALL ranks: the rows of dY belong to their home
- * ranks (rank o owns global rows [o * rows_per_rank, +rows_per_rank), cols == world * rows_per_rank,
- * rows_per_rank % 128 == 0, world <= 8).  Every owner holds `world` slots [rows_per_rank, d] fp32, one per source
- * rank; dY_peer_slot[o] is THIS rank's slot in owner o's memory - a peer-mapped device pointer for remote owners (e.g.
- * from torch.distributed._symmetric_memory) - and every dY tile is written there by TMA while later tiles are still
- * being multiplied; the CTAs do not wait for the remote writes.  The owner then sums its slots (clipk_reduce_slots).
- * This replaces torch.distributed.nn.all_gather's backward (a reduce_scatter of the [cols, d] gradient, loss.py:35-36)
- * and its 4 * cols * d byte input.  dY_peer_slot is a HOST array of `world` device pointers.
- * Protocol (caller): clipk_peer_barrier (every owner is done reading the previous contents of its slots);
- * clipk_bwd_peer on every rank; clipk_peer_barrier; clipk_reduce_slots on every owner.
- * clipk_peer_barrier: barrier between the ranks through peer-mapped flag words (peer_flags[t] = device pointer to
- * rank t's array of 8 uint32, zero at start; HOST array of `world` pointers).  `epoch` must grow by one per call and be
- * the same on all ranks.  Everything the stream did before the barrier is visible to the peers after it.  A wait that
- * lasts longer than ~20 s (a peer died or skipped the call) gives up and stores 2 into *err (a word of pinned host
- * memory, may be NULL) instead of hanging the device.
- * clipk_reduce_slots: dst[i] = (dtype) sum over w < world of src[w * n + i]   (dtype CLIPK_BF16 or CLIPK_F32). */
-int clipk_bwd_peer(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
-                   const float* x_inv_scale, const float* y_inv_scale, const void* Xg, const void* Yg, long long ldxg,
-                   long long ldyg, int g_dtype, const float* xg_inv_scale, const float* yg_inv_scale,
-                   const float* logit_scale, long long diag_offset, const float* lse_row, const float* lse_col,
-                   float alpha, float beta, const float* gscale, float* dX_acc, void* const* dY_peer_slot, int world,
-                   int rows_per_rank, void* workspace, size_t workspace_bytes, void* stream);
-int clipk_reduce_slots(const float* src, long long n, int world, void* dst, int dtype, void* stream);
-int clipk_peer_barrier(void* const* peer_flags, int rank, int world, unsigned int epoch, int* err, void* stream);
-
 /* ---- the whole loss step in two calls ---------------------------------------------------------------------------------
  * clipk_step_forward / clipk_step_backward run everything ClipLoss.forward (loss.py:123-140) and its autograd do on one
  * rank - including, between the ranks of one NVLink domain, gather_features (loss.py:20-64) and the backward of its

@@ -37,10 +37,6 @@ PROTOTYPES = {
     "clipk_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "clipk_bwd": (_i, [_vp, _vp, _i, _i, _i, _ll, _ll, _i, _vp, _vp, _vp, _vp, _ll, _ll, _i, _vp, _vp,
                        _vp, _ll, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "clipk_bwd_peer": (_i, [_vp, _vp, _i, _i, _i, _ll, _ll, _i, _vp, _vp, _vp, _vp, _ll, _ll, _i, _vp, _vp,
-                            _vp, _ll, _vp, _vp, _f, _f, _vp, _vp, ctypes.POINTER(ctypes.c_void_p), _i, _i, _vp, _sz, _vp]),
-    "clipk_reduce_slots": (_i, [_vp, _ll, _i, _vp, _i, _vp]),
-    "clipk_peer_barrier": (_i, [ctypes.POINTER(ctypes.c_void_p), _i, _i, ctypes.c_uint, _vp, _vp]),
     "clipk_normalize_fwd": (_i, [_vp, _i, _ll, _ll, _ll, _vp, _ll, _vp, _f, _vp]),
     "clipk_normalize_bwd": (_i, [_vp, _ll, _vp, _ll, _vp, _i, _ll, _ll, _vp, _ll, _f, _vp]),
     "clipk_cast": (_i, [_vp, _vp, _ll, _i, _vp]),

@@ -562,7 +562,8 @@ __global__ void prep_kernel(const PrepArgs a) {
             }
         }
         float nx = 0.f, ny = 0.f, dot = 0.f;
-        for (int k = lane; k < a.d8; k += 32) {
+#pragma unroll 2
+        for (int k = lane; k < a.d8; k += 32) {          // two iterations' loads in flight (d = 512: the whole row pair)
             float vx[8], vy[8], vp[8];
             if (hx) {
                 if (ROUND) load8_as_bf16(xr + (long long)k * 8, sx, vx); else load8(xr + (long long)k * 8, vx);
@@ -691,8 +692,8 @@ __global__ void to_f16_pair_kernel(const __nv_bfloat16* __restrict__ X, long lon
 
 // Last pass of the backward, one warp per row of either gradient: sum the per-source slots of the fused reduce-scatter
 // (text gradient), apply the Jacobian of the L2 normalisation when the forward normalised (dx = (g - y (y . g)) / |x|,
-// with y the operand row), cast to the dtype of the inputs.  Replaces clipk_cast, clipk_reduce_slots and
-// clipk_normalize_bwd of the unfused path.  Thread 0 also finishes dlogit_scale = go * (s dloss/ds) / s.
+// with y the operand row), cast to the dtype of the inputs.  Replaces clipk_cast and clipk_normalize_bwd of the
+// unfused path and the separate slot sum of round 1.  Thread 0 also finishes dlogit_scale = go * (s dloss/ds) / s.
 struct FinishArgs {
     const float* gx; long long rows_x;             // [rows_x, d] fp32 image gradient (null = skip)
     const float* gy; long long rows_y;             // [slots][rows_y, d] fp32 text gradient (null = skip)
@@ -810,22 +811,6 @@ __global__ void fwd_merge_kernel(const FwdArgs a0, const FwdArgs a1, int m_block
     } else if (sl == 0 && i < cols) {
         merge_parts(a1.part_max, a1.part_sum, a1.part_dot, nparts_of(a1, i), cols, i, col_out, cols);
     }
-}
-
-// dst[i] = (dtype) sum_w src[w * n + i]: the owner's sum over the per-source slots of the fused reduce-scatter
-__global__ void reduce_slots_kernel(const float* __restrict__ src, long long n, int world, void* __restrict__ dst, int dtype) {
-    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i >= n) return;
-    float4 acc = *reinterpret_cast<const float4*>(src + i);
-    for (int w = 1; w < world; ++w) {
-        const float4 v = *reinterpret_cast<const float4*>(src + (size_t)w * n + i);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    }
-    if (dtype == CLIPK_BF16)
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(dst) + i) =
-            make_uint2(ptx::pack_bf16x2(acc.x, acc.y), ptx::pack_bf16x2(acc.z, acc.w));
-    else
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + i) = acc;
 }
 
 // Rank of the target column in every row of a materialised fp32 logits panel (evaluation side: retrieval ranks of
@@ -1782,18 +1767,6 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
                     dY_acc, nullptr, 0, 0, workspace, workspace_bytes, stream);
 }
 
-int clipk_bwd_peer(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
-                   const float* x_inv_scale, const float* y_inv_scale, const void* Xg, const void* Yg, long long ldxg,
-                   long long ldyg, int g_dtype, const float* xg_inv_scale, const float* yg_inv_scale,
-                   const float* logit_scale, long long diag_offset, const float* lse_row, const float* lse_col,
-                   float alpha, float beta, const float* gscale, float* dX_acc, void* const* dY_peer_acc, int world,
-                   int rows_per_rank, void* workspace, size_t workspace_bytes, void* stream) {
-    if (!dY_peer_acc) return fail(CLIPK_EINVAL, "null peer accumulator table");
-    return bwd_impl(X, Y, rows, cols, d, ldx, ldy, dtype, x_inv_scale, y_inv_scale, Xg, Yg, ldxg, ldyg, g_dtype,
-                    xg_inv_scale, yg_inv_scale, logit_scale, diag_offset, lse_row, lse_col, alpha, beta, gscale, dX_acc,
-                    nullptr, dY_peer_acc, world, rows_per_rank, workspace, workspace_bytes, stream);
-}
-
 static int normalize_check(const void* a, const void* b, int dtype, long long rows, long long d, long long lda, long long ldb) {
     if (!a || !b || rows <= 0 || d <= 0) return fail(CLIPK_EINVAL, "bad argument");
     if (dtype != CLIPK_BF16 && dtype != CLIPK_F32) return fail(CLIPK_EUNSUPPORTED, "dtype %d", dtype);
@@ -1847,17 +1820,6 @@ int clipk_normalize_bwd(const void* g, long long ldg, const void* y, long long l
     return CLIPK_OK;
 }
 
-int clipk_reduce_slots(const float* src, long long n, int world, void* dst, int dtype, void* stream) {
-    if (!src || !dst || n <= 0 || world < 1) return fail(CLIPK_EINVAL, "bad argument");
-    if (n % 4 != 0 || (reinterpret_cast<uintptr_t>(src) & 15) != 0 || (reinterpret_cast<uintptr_t>(dst) & 15) != 0)
-        return fail(CLIPK_EUNSUPPORTED, "n must be a multiple of 4 and the pointers 16-byte aligned");
-    if (dtype != CLIPK_BF16 && dtype != CLIPK_F32) return fail(CLIPK_EUNSUPPORTED, "dtype %d", dtype);
-    reduce_slots_kernel<<<cdiv(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, n, world, dst, dtype);
-    count_launch("reduce_slots_kernel", static_cast<cudaStream_t>(stream));
-    CK_CUDA(cudaGetLastError());
-    return CLIPK_OK;
-}
-
 int clipk_rank_count(const float* S, int rows, int cols, long long ld, const long long* target, long long diag_offset,
                      long long row0, int* greater, int* ties_before, void* stream) {
     if (!S || !greater || rows < 0 || cols <= 0 || row0 < 0) return fail(CLIPK_EINVAL, "bad argument");
@@ -1907,23 +1869,6 @@ int clipk_distill_grad(const float* S, const float* T, int rows, int cols, long 
     distill_grad_kernel<<<dim3(cdiv(cols, 256), rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         S, T, cols, ld, s_mul, t_mul, s_lse_row, t_lse_row, row0, s_lse_col, t_lse_col, static_cast<__half*>(G), ldg);
     count_launch("distill_grad_kernel", static_cast<cudaStream_t>(stream));
-    CK_CUDA(cudaGetLastError());
-    return CLIPK_OK;
-}
-
-int clipk_peer_barrier(void* const* peer_flags, int rank, int world, unsigned int epoch, int* err, void* stream) {
-    if (!peer_flags || world < 1 || world > MAX_PEERS || rank < 0 || rank >= world) return fail(CLIPK_EINVAL, "bad argument");
-    DevInfo di;
-    int rc = device_info(&di);
-    if (rc) return rc;
-    PeerPtrs pf;
-    memset(&pf, 0, sizeof(pf));
-    for (int t = 0; t < world; ++t) {
-        if (!peer_flags[t]) return fail(CLIPK_EINVAL, "null flag array %d", t);
-        pf.p[t] = peer_flags[t];
-    }
-    peer_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pf, rank, world, epoch, err);
-    count_launch("peer_barrier_kernel", static_cast<cudaStream_t>(stream));
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
 }
