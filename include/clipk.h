@@ -123,14 +123,18 @@ int clipk_finalize(const float* row_max, const float* row_sum, const float* row_
  *   dY_acc [cols, d] = logit_scale * gscale * G^T * Xg        (NULL to skip; the caller reduce-scatters it)
  * Per panel: one launch recomputes and writes G, one launch runs the dX tiles and the dY tiles together.
  * gscale is a device scalar = grad_output / (2 * num_logits).  dX_acc and dY_acc are overwritten.
+ * split_row_col = 1: dX is built from alpha (P_row - Id) alone and dY from beta (P_col - Id) alone, from ONE recompute
+ * that writes the two parts as two planes of the panel - the gradients of local_loss=True, gather_with_grad=False
+ * (loss.py:53-56: the gathered tensors carry no gradient, so dI sees only the image->text softmax and dT only the
+ * text->image one).  One-plane (CLIPK_F16) gradient operands only.
  */
 size_t clipk_bwd_workspace_bytes(int rows, int cols, int d, int g_dtype);
 int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
               const float* x_inv_scale, const float* y_inv_scale, const void* Xg, const void* Yg, long long ldxg,
               long long ldyg, int g_dtype, const float* xg_inv_scale, const float* yg_inv_scale,
               const float* logit_scale, long long diag_offset, const float* lse_row, const float* lse_col,
-              float alpha, float beta, const float* gscale, float* dX_acc, float* dY_acc, void* workspace,
-              size_t workspace_bytes, void* stream);
+              float alpha, float beta, int split_row_col, const float* gscale, float* dX_acc, float* dY_acc,
+              void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- the whole loss step in two calls ---------------------------------------------------------------------------------
  * clipk_step_forward / clipk_step_backward run everything ClipLoss.forward (loss.py:123-140) and its autograd do on one
@@ -178,6 +182,8 @@ typedef struct clipk_step {
     float loss_div;                     /* loss = (CE sums) / loss_div: 2b (single, local) or 2N (global, then summed  */
                                         /* over the ranks by the caller)                                               */
     float grad_coef;                    /* feature gradients = grad_out * grad_coef * d(CE sums): 1/2b or 1/2N         */
+    int grad_split;                     /* 1: local_loss without gather_with_grad - dI from the row softmax only, dT   */
+                                        /* from the column softmax only (see clipk_bwd's split_row_col)               */
     /* buffers that live from the forward to the backward (caller-allocated, one set per call) */
     void* x_op;                         /* [rows, d] bf16 image operand; == image when nothing has to be produced      */
     void* y_all;                        /* [cols, d] bf16 gathered text operand; == text under the same condition      */

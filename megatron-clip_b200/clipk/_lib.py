@@ -36,7 +36,7 @@ PROTOTYPES = {
     "clipk_finalize": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _ll, _i, _ll, _vp, _vp, _vp, _vp]),
     "clipk_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "clipk_bwd": (_i, [_vp, _vp, _i, _i, _i, _ll, _ll, _i, _vp, _vp, _vp, _vp, _ll, _ll, _i, _vp, _vp,
-                       _vp, _ll, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
+                       _vp, _ll, _vp, _vp, _f, _f, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "clipk_normalize_fwd": (_i, [_vp, _i, _ll, _ll, _ll, _vp, _ll, _vp, _f, _vp]),
     "clipk_normalize_bwd": (_i, [_vp, _ll, _vp, _ll, _vp, _i, _ll, _ll, _vp, _ll, _f, _vp]),
     "clipk_cast": (_i, [_vp, _vp, _ll, _i, _vp]),
@@ -66,7 +66,7 @@ class Step(ctypes.Structure):
     """struct clipk_step (include/clipk.h)."""
     _fields_ = [("rows", _i), ("cols", _i), ("d", _i), ("src_dtype", _i), ("normalize", _i), ("eps", _f),
                 ("image", _vp), ("text", _vp), ("ld_image", _ll), ("ld_text", _ll), ("logit_scale", _vp),
-                ("loss_div", _f), ("grad_coef", _f),
+                ("loss_div", _f), ("grad_coef", _f), ("grad_split", _i),
                 ("x_op", _vp), ("y_all", _vp), ("inv_x", _vp), ("inv_y", _vp), ("stats", _vp), ("lse_row", _vp),
                 ("lse_col", _vp), ("scal", _vp), ("g16", _vp),
                 ("grad_out", _vp), ("d_image", _vp), ("d_text", _vp), ("d_scale", _vp), ("out_dtype", _i),

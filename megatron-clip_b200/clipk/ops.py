@@ -164,7 +164,8 @@ class CudaBackend:
         return lse_row, lse_col, sums
 
     def bwd(self, X: Operand, Y: Operand, Xg: Operand, Yg: Operand, scale, diag_offset, lse_row, lse_col, alpha,
-            beta, gscale, want_dx, want_dy):
+            beta, gscale, want_dx, want_dy, split=False):
+        """split: dX from alpha (P_row - Id) only, dY from beta (P_col - Id) only, one recompute (clipk_bwd)"""
         dev = X.data.device
         rows, cols, d = X.rows, Y.rows, X.d
         dX = torch.empty(rows, d, dtype=torch.float32, device=dev) if want_dx else None
@@ -174,7 +175,7 @@ class CudaBackend:
         _lib.check(self.lib.clipk_bwd(X.data.data_ptr(), Y.data.data_ptr(), rows, cols, d, X.ld, Y.ld, X.dtype,
                                       X.inv_ptr(), Y.inv_ptr(), Xg.data.data_ptr(), Yg.data.data_ptr(), Xg.ld, Yg.ld,
                                       Xg.dtype, Xg.inv_ptr(), Yg.inv_ptr(), scale.data_ptr(), diag_offset,
-                                      lse_row.data_ptr(), lse_col.data_ptr(), float(alpha), float(beta),
+                                      lse_row.data_ptr(), lse_col.data_ptr(), float(alpha), float(beta), 1 if split else 0,
                                       gscale.data_ptr(), _ptr(dX), _ptr(dY), ws.data_ptr(), nbytes, self._stream()),
                    "clipk_bwd")
         return dX, dY
@@ -190,7 +191,7 @@ class CudaBackend:
             c.image, c.text = st.image.data_ptr(), st.text.data_ptr()
             c.ld_image, c.ld_text = st.image.stride(0), st.text.stride(0)
             c.logit_scale = st.scale.data_ptr()
-            c.loss_div, c.grad_coef = float(st.loss_div), float(st.grad_coef)
+            c.loss_div, c.grad_coef, c.grad_split = float(st.loss_div), float(st.grad_coef), int(bool(st.grad_split))
             c.x_op, c.y_all = st.x_op.data_ptr(), st.y_all.data_ptr()
             c.inv_x, c.inv_y = _ptr(st.inv_x), _ptr(st.inv_y)
             c.stats, c.lse_row, c.lse_col, c.scal = (st.stats.data_ptr(), st.lse_row.data_ptr(), st.lse_col.data_ptr(),
@@ -340,7 +341,7 @@ def gpu_launches() -> int:
 class StepDesc:
     """Everything one loss evaluation holds between its forward and its backward (mirrors struct clipk_step)."""
     __slots__ = ("rows", "cols", "d", "world", "rank", "normalize", "eps", "image", "text", "scale", "loss_div",
-                 "grad_coef", "x_op", "y_all", "inv_x", "inv_y", "stats", "lse_row", "lse_col", "scal", "g16", "ws",
+                 "grad_coef", "grad_split", "x_op", "y_all", "inv_x", "inv_y", "stats", "lse_row", "lse_col", "scal", "g16", "ws",
                  "peer",
                  "grad_out", "d_image", "d_text", "d_scale", "out_dtype", "cstruct", "cpeer", "group")
 
@@ -555,7 +556,7 @@ class FusedClipLoss(torch.autograd.Function):
         # ---- route 1: the fused step
         bf16_operands = in_dtype == torch.bfloat16 or (in_dtype == torch.float32 and _autocast_bf16(dev))
         fused = bf16_operands and d_in % _K_BLOCK == 0 and (dev.type == "cuda" or _TEST_BACKEND is not None) and \
-            hasattr(be, "step_forward") and not (W > 1 and local_loss and not gather_with_grad)
+            hasattr(be, "step_forward")
         peer = None
         if fused and W > 1:
             peer = _TEST_BACKEND.peer_context(b, d_in, rank, W, group) if _TEST_BACKEND is not None else \
@@ -575,6 +576,9 @@ class FusedClipLoss(torch.autograd.Function):
             st.loss_div = 2.0 * b if local else 2.0 * N
             # c of SURVEY App. A: 1/(2b) for W=1, local modes and global+gather_with_grad; 1/(2N) otherwise
             st.grad_coef = 1.0 / (2.0 * b) if (local or gather_with_grad) else 1.0 / (2.0 * N)
+            # loss.py:53-56 with local_loss: the gathered tensors carry no gradient, so dI sees only the image->text
+            # softmax and dT only the text->image one - two planes of one recompute
+            st.grad_split = W > 1 and bool(local_loss) and not gather_with_grad
             produced = st.normalize or in_dtype != torch.bfloat16
             # one fp32 allocation for everything the backward reads: lse_row | lse_col | scalars | statistics | inv norms
             n_f = b + N + 16 + _lib.STAT_WORDS * W + (2 * b if st.normalize else 0)
@@ -693,9 +697,13 @@ class FusedClipLoss(torch.autograd.Function):
             gscale = (go * c_feat).contiguous()
             if W > 1 and local_loss and not gwg:
                 # loss.py:53-56 with local_loss: gathered tensors carry no gradient, so dI sees only the image->text
-                # softmax and dT only the text->image one.
-                dX, _ = be.bwd(X, Y, Xg, Yg, scale, off, lse_row, lse_col, 1.0, 0.0, gscale, True, False)
-                _, dY = be.bwd(X, Y, Xg, Yg, scale, off, lse_row, lse_col, 0.0, 1.0, gscale, False, True)
+                # softmax and dT only the text->image one: one recompute with the two parts in two planes of the
+                # panel (one-plane operands), else (fp32 arithmetic: the planes are taken by [hi | lo]) two passes
+                if getattr(Xg, "dtype", None) == _lib.F16 or _TEST_BACKEND is not None:
+                    dX, dY = be.bwd(X, Y, Xg, Yg, scale, off, lse_row, lse_col, 1.0, 1.0, gscale, True, True, split=True)
+                else:
+                    dX, _ = be.bwd(X, Y, Xg, Yg, scale, off, lse_row, lse_col, 1.0, 0.0, gscale, True, False)
+                    _, dY = be.bwd(X, Y, Xg, Yg, scale, off, lse_row, lse_col, 0.0, 1.0, gscale, False, True)
                 dT = _reduce_scatter_rows(dY, W, group)
             else:
                 dX, dY = be.bwd(X, Y, Xg, Yg, scale, off, lse_row, lse_col, 1.0, 1.0, gscale, True, True)
@@ -749,8 +757,8 @@ def _fused_step_applies(x, world_size, local_loss, gather_with_grad):
     dev = x.device
     return x.dim() == 2 and (x.dtype == torch.bfloat16 or (x.dtype == torch.float32 and _autocast_bf16(dev))) and \
         x.shape[1] % _K_BLOCK == 0 and x.shape[0] > 0 and (dev.type == "cuda" or _TEST_BACKEND is not None) and \
-        (world_size == 1 or (not (local_loss and not gather_with_grad) and world_size <= _lib.MAX_PEERS and
-                             x.shape[0] % 128 == 0 and os.environ.get("CLIPK_PEER", "1") != "0" and not _PEER_DISABLED[0]))
+        (world_size == 1 or (world_size <= _lib.MAX_PEERS and x.shape[0] % 128 == 0 and
+                             os.environ.get("CLIPK_PEER", "1") != "0" and not _PEER_DISABLED[0]))
 
 
 def fused_normalize_clip_loss(raw_image_features, raw_text_features, logit_scale, local_loss=False,

@@ -1600,9 +1600,12 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
                     const float* logit_scale, long long diag_offset, const float* lse_row, const float* lse_col,
                     float alpha, float beta, const float* gscale, float* dX_acc, float* dY_acc, void* const* dY_peer_acc,
                     int world, int rows_per_rank, void* workspace, size_t workspace_bytes, void* stream,
-                    const int* mm_ready = nullptr, float coef = 1.f) {
+                    const int* mm_ready = nullptr, float coef = 1.f, int split_row_col = 0) {
     // mm_ready: min / max of both LSE vectors (ordered ints) already computed by the forward (clipk_step_forward);
-    // coef: constant factor on both gradients next to the device scalar *gscale
+    // coef: constant factor on both gradients next to the device scalar *gscale;
+    // split_row_col: dX is built from alpha (P_row - Id) only and dY from beta (P_col - Id) only - the gradients of
+    // local_loss without gather_with_grad (loss.py:53-56: the gathered tensors carry no gradient) - from ONE recompute
+    // that writes the two parts as two planes of the panel (one-plane fp16 operands only)
     int rc = check_common(X, Y, rows, cols, d, ldx, ldy, dtype);
     if (rc) return rc;
     PeerOut peers;
@@ -1632,10 +1635,12 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
     const int planes = planes_of(dtype);                // S-GEMM operand planes
-    const int gplanes = planes_of(g_dtype);             // planes of G and of the gradient-GEMM features
+    const int fplanes = planes_of(g_dtype);             // planes of the gradient-GEMM features
+    if (split_row_col && fplanes != 1) return fail(CLIPK_EUNSUPPORTED, "split_row_col needs one-plane (CLIPK_F16) gradient operands");
+    const int gplanes = split_row_col ? 2 : fplanes;    // planes of G: [hi | lo] with two-plane features, [row | col] when split
     const long long dpad = round_up(d, BK);
     const long long kext = (dtype == CLIPK_BF16) ? d : planes * dpad;   // inner extent of X / Y rows
-    const long long gext = gplanes * dpad;                              // inner extent of Xg / Yg rows
+    const long long gext = fplanes * dpad;                              // inner extent of Xg / Yg rows
     long long rp_max, cp_max;
     choose_panel(rows, cols, d, gplanes, di.sms, panel_bytes(), &rp_max, &cp_max, peers.world > 0 ? 1 : 0);
     const int ncp = int(cp_max);                        // panel width (multiple of BN) = G plane stride
@@ -1699,7 +1704,7 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
                 a.lse_row = lse_row + r0; a.lse_col = lse_col + c0;
                 a.alpha = alpha; a.beta = beta;
                 a.avec = avec + r0; a.bvec = bvec + c0; a.gref = gref;
-                a.G = Gp; a.ldg = ldg; a.g_planes = gplanes; a.g_plane_stride = ncp;
+                a.G = Gp; a.ldg = ldg; a.g_planes = gplanes; a.g_plane_stride = ncp; a.g_split = split_row_col ? 1 : 0;
                 if (planes == 1 && gplanes == 1 && a.num_kb <= ARES_KB) {
                     // rows of X resident in shared memory, persistent over the panel (see grad_sweep_kernel)
                     SweepGeom g{};
@@ -1720,11 +1725,12 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
             KArgs a0{}, a1{};
             int jobs0 = 0, jobs1 = 0;
             if (dX_acc) {
-                if ((rc = tmap_kmajor(&ta0, Gp, nr, gplanes == 2 ? ldg : nc, ldg, BM))) return rc;
+                // dX reads plane 0 of a split panel (the row part); [hi | lo] panels are read across both planes
+                if ((rc = tmap_kmajor(&ta0, Gp, nr, fplanes == 2 ? ldg : nc, ldg, BM))) return rc;
                 if ((rc = tmap_mnmajor(&tb0, Ygb + c0 * ldyg * esz, gext, nc, ldyg))) return rc;
                 if ((rc = tmap_out_f32(&tc0, dX_acc + r0 * d, nr, d, d))) return rc;
                 a0.M = nr; a0.N = d; a0.n_tiles = nt; a0.tiles_per_unit = 1; a0.a_mn = 0; a0.b_mn = 1;
-                set_segments(a0, gplanes, nc, ncp, dpad);
+                set_segments(a0, fplanes, nc, ncp, dpad);
                 a0.out = dX_acc + r0 * d; a0.ldo = d; a0.accumulate = (c0 > 0);
                 a0.oscale0 = logit_scale; a0.oscale1 = gscale; a0.oscale2 = yg_inv_scale; a0.oconst = coef / 16384.f;
                 jobs0 = cdiv(nr, 2 * BM) * nt;
@@ -1734,7 +1740,8 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
                 if ((rc = tmap_mnmajor(&tb1, Xgb + r0 * ldxg * esz, gext, nr, ldxg))) return rc;
                 if ((rc = tmap_out_f32(&tc1, peers.world ? dY_acc : dY_acc + c0 * d, peers.world ? peers.rows_per_rank : nc, d, d))) return rc;
                 a1.M = nc; a1.N = d; a1.n_tiles = nt; a1.tiles_per_unit = 1; a1.a_mn = 1; a1.b_mn = 1;
-                set_segments(a1, gplanes, nr, ncp, dpad);
+                set_segments(a1, fplanes, nr, ncp, dpad);
+                if (split_row_col) a1.a_off[0] = ncp;       // dY reads plane 1 (the column part)
                 a1.out = dY_acc + c0 * d; a1.ldo = d; a1.accumulate = (r0 > 0);
                 if (peers.world) a1.c_row_off = int(c0);   // global dY row of the panel (owner = row / rows_per_rank)
                 a1.oscale0 = logit_scale; a1.oscale1 = gscale; a1.oscale2 = xg_inv_scale; a1.oconst = coef / 16384.f;
@@ -1760,11 +1767,11 @@ int clipk_bwd(const void* X, const void* Y, int rows, int cols, int d, long long
               const float* x_inv_scale, const float* y_inv_scale, const void* Xg, const void* Yg, long long ldxg,
               long long ldyg, int g_dtype, const float* xg_inv_scale, const float* yg_inv_scale,
               const float* logit_scale, long long diag_offset, const float* lse_row, const float* lse_col,
-              float alpha, float beta, const float* gscale, float* dX_acc, float* dY_acc, void* workspace,
+              float alpha, float beta, int split_row_col, const float* gscale, float* dX_acc, float* dY_acc, void* workspace,
               size_t workspace_bytes, void* stream) {
     return bwd_impl(X, Y, rows, cols, d, ldx, ldy, dtype, x_inv_scale, y_inv_scale, Xg, Yg, ldxg, ldyg, g_dtype,
                     xg_inv_scale, yg_inv_scale, logit_scale, diag_offset, lse_row, lse_col, alpha, beta, gscale, dX_acc,
-                    dY_acc, nullptr, 0, 0, workspace, workspace_bytes, stream);
+                    dY_acc, nullptr, 0, 0, workspace, workspace_bytes, stream, nullptr, 1.f, split_row_col);
 }
 
 static int normalize_check(const void* a, const void* b, int dtype, long long rows, long long d, long long lda, long long ldb) {
@@ -2080,7 +2087,7 @@ int clipk_step_backward(const clipk_step* p) {
         if ((rc = bwd_impl(p->x_op, p->y_all, rows, cols, d, ldx, ldy, CLIPK_BF16, nullptr, nullptr, Xg, Yg, dpad, dpad, CLIPK_F16,
                            inv2, inv2 + 1, p->logit_scale, off, p->lse_row, p->lse_col, 1.f, 1.f, p->grad_out, dX, dY,
                            W > 1 ? slots : nullptr, W, rows, ws + cv.bwd, clipk_bwd_workspace_bytes(rows, cols, d, CLIPK_F16),
-                           p->stream, reinterpret_cast<const int*>(p->scal) + 8, p->grad_coef)))
+                           p->stream, reinterpret_cast<const int*>(p->scal) + 8, p->grad_coef, p->grad_split)))
             return rc;
         // 3. every rank's tiles have landed in the slots this rank owns
         if (W > 1) {

@@ -89,8 +89,11 @@ struct KArgs {
     float alpha, beta;
     __half* G;                 // panel of G * 2^14 in fp16, row-major, rows padded to BM and ldg to BN
     int ldg;
-    int g_planes;              // 1, or 2 (G split into hi/lo fp16 planes, g_plane_stride columns apart)
+    int g_planes;              // 1, or 2 (G split into two fp16 planes, g_plane_stride columns apart)
     int g_plane_stride;
+    int g_split;               // meaning of the two planes: 0 = [hi | lo] of one G (22 bits, fp32 features);
+                               // 1 = [alpha (P_row - Id) | beta (P_col - Id)]: dX reads the first, dY the second
+                               // (local_loss without gather_with_grad, loss.py:53-56)
     // OUT
     float* out;
     int ldo;
@@ -197,6 +200,47 @@ __device__ __forceinline__ void grad16_exact(const uint32_t (&r)[16], float sc, 
         if (k == didx) { pr -= 1.f; pc -= 1.f; }
         g[k] = inside ? ga * pr + gb * pc : 0.f;
     }
+}
+// the same two, with the row part alpha (P_row - Id) and the column part beta (P_col - Id) kept apart (g_split)
+__device__ __forceinline__ void grad16_fast2(const uint32_t (&r)[16], float sc, float cref, float Ai, float gb,
+                                             const float* __restrict__ bv, float (&gr)[16], float (&gc)[16]) {
+    float4 l4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) l4[j] = __ldg(reinterpret_cast<const float4*>(bv) + j);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const float e = ptx::ex2(fmaf(__uint_as_float(r[k]), sc, -cref));
+        const float b = (k & 3) == 0 ? l4[k >> 2].x : (k & 3) == 1 ? l4[k >> 2].y : (k & 3) == 2 ? l4[k >> 2].z : l4[k >> 2].w;
+        gr[k] = e * Ai;
+        gc[k] = e * (gb * b);
+    }
+}
+__device__ __forceinline__ void grad16_exact2(const uint32_t (&r)[16], float sc, float Lr, float ga, float gb,
+                                              const float* __restrict__ lse_col, int col0, int ncols, long long dcol,
+                                              float (&gr)[16], float (&gc)[16]) {
+    const int didx = (dcol >= col0 && dcol < (long long)col0 + 16) ? int(dcol - col0) : -1;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const bool inside = col0 + k < ncols;
+        const float lc = inside ? __ldg(lse_col + k) * LOG2E : CUDART_INF_F;
+        const float v = __uint_as_float(r[k]) * sc;
+        float pr = ptx::ex2(v - Lr), pc = ptx::ex2(v - lc);
+        if (k == didx) { pr -= 1.f; pc -= 1.f; }
+        gr[k] = inside ? ga * pr : 0.f;
+        gc[k] = inside ? gb * pc : 0.f;
+    }
+}
+__device__ __forceinline__ void grad16_store2(const float (&gr)[16], const float (&gc)[16], uint32_t stg, uint32_t stg2, int lane,
+                                              int piece0) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pk[k] = ptx::pack_f16x2(gr[2 * k], gr[2 * k + 1]);
+    st_shared_v4(stg_addr(stg, lane, piece0), pk[0], pk[1], pk[2], pk[3]);
+    st_shared_v4(stg_addr(stg, lane, piece0 + 1), pk[4], pk[5], pk[6], pk[7]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pk[k] = ptx::pack_f16x2(gc[2 * k], gc[2 * k + 1]);
+    st_shared_v4(stg_addr(stg2, lane, piece0), pk[0], pk[1], pk[2], pk[3]);
+    st_shared_v4(stg_addr(stg2, lane, piece0 + 1), pk[4], pk[5], pk[6], pk[7]);
 }
 // g[16] -> fp16, into 16-byte pieces [piece0, piece0 + 2) of this row's line of the staging buffer(s): 128-byte rows
 // in SWIZZLE_128B order, or (DENSE64) plain 64-byte rows - the half-size buffers of the A-resident recompute kernel,
@@ -499,10 +543,11 @@ __device__ __forceinline__ void epilogue_unit(const Cta& c, Pipe& p, const CUten
 // NBUF = 4 KB of staging per warp: 2 (two 64-column buffers, one fills while the other leaves; both planes of a
 // two-plane G) or 1 (the A-resident recompute kernel, whose shared memory goes to the resident rows: its 4 KB are two
 // dense 32-column half buffers, written and stored alternately through a non-swizzled tensor map).
-template <bool TWO_PLANES, int NBUF = 2>
+template <bool TWO_PLANES, int NBUF = 2, bool SPLIT = false>
 __device__ __forceinline__ void grad_epilogue_unit(const Cta& c, Pipe& p, const CUtensorMap* tmC, const KArgs& args,
                                                    int m_blk, int t0, int t1) {
     static_assert(NBUF == 2 || !TWO_PLANES, "a two-plane G needs both staging buffers");
+    static_assert(TWO_PLANES || !SPLIT, "the row / column split is a two-plane layout");
     const int warp = c.warp, lane = c.lane;
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
@@ -582,10 +627,17 @@ __device__ __forceinline__ void grad_epilogue_unit(const Cta& c, Pipe& p, const 
                 stg = stg0 + (p.stg_use & 1) * STG_BYTES;
                 stg_lo = stg0 + ((p.stg_use + 1) & 1) * STG_BYTES;
             }
-            float g[16];
-            if (exact) grad16_exact(r, sc, Lr, ga, gb, lse_col + col0, col0, ncols, dcol, g);
-            else grad16_fast(r, sc, cref, Ai, gb, bvec + col0, g);
-            grad16_store<TWO_PLANES>(g, stg, stg_lo, lane, (pi & 3) * 2);
+            if (SPLIT) {
+                float gr[16], gc[16];
+                if (exact) grad16_exact2(r, sc, Lr, ga, gb, lse_col + col0, col0, ncols, dcol, gr, gc);
+                else grad16_fast2(r, sc, cref, Ai, gb, bvec + col0, gr, gc);
+                grad16_store2(gr, gc, stg, stg_lo, lane, (pi & 3) * 2);
+            } else {
+                float g[16];
+                if (exact) grad16_exact(r, sc, Lr, ga, gb, lse_col + col0, col0, ncols, dcol, g);
+                else grad16_fast(r, sc, cref, Ai, gb, bvec + col0, g);
+                grad16_store<TWO_PLANES>(g, stg, stg_lo, lane, (pi & 3) * 2);
+            }
             if ((pi & 3) == 3) {
                 ptx::fence_proxy_async_smem();
                 __syncwarp();
@@ -655,7 +707,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (c.lane == 0 && c.leader) mma_unit<STAGES>(c, p, args, t1 - t0);
     } else {
         if (MODE == MODE_GRAD) {
-            if (args.g_planes == 2) grad_epilogue_unit<true>(c, p, &tmC, args, m_blk, t0, t1);
+            if (args.g_planes == 2 && args.g_split) grad_epilogue_unit<true, 2, true>(c, p, &tmC, args, m_blk, t0, t1);
+            else if (args.g_planes == 2) grad_epilogue_unit<true>(c, p, &tmC, args, m_blk, t0, t1);
             else grad_epilogue_unit<false>(c, p, &tmC, args, m_blk, t0, t1);
         } else {
             epilogue_unit<MODE == MODE_GRAD ? MODE_OUT : MODE>(c, p, &tmC, args, m_blk, unit, t0, t1);

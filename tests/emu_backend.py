@@ -57,16 +57,18 @@ class EmuBackend:
                             (e_col[idx] - p).sum()))
         return lse_row.float(), lse_col.float(), sums.float()
 
-    def bwd(self, X, Y, Xg, Yg, scale, diag_offset, lse_row, lse_col, alpha, beta, gscale, want_dx, want_dy):
+    def bwd(self, X, Y, Xg, Yg, scale, diag_offset, lse_row, lse_col, alpha, beta, gscale, want_dx, want_dy, split=False):
         s = float(scale[0])
         S = s * X.data @ Y.data.T
         Pr = torch.exp(S - lse_row.double()[:, None])
         Pc = torch.exp(S - lse_col.double()[None, :])
         eye = torch.zeros_like(S)
         eye[torch.arange(X.rows), torch.arange(X.rows) + diag_offset] = 1.0
-        G = s * float(gscale[0]) * (alpha * (Pr - eye) + beta * (Pc - eye))
-        dX = (G @ Y.data).float() if want_dx else None
-        dY = (G.T @ X.data).float() if want_dy else None
+        k = s * float(gscale[0])
+        Gx = k * alpha * (Pr - eye) if split else k * (alpha * (Pr - eye) + beta * (Pc - eye))
+        Gy = k * beta * (Pc - eye) if split else Gx
+        dX = (Gx @ Y.data).float() if want_dx else None
+        dY = (Gy.T @ X.data).float() if want_dy else None
         return dX, dY
 
     # ---- the fused step (clipk_step_forward / clipk_step_backward); the peer-memory collectives become gloo ones
@@ -134,10 +136,12 @@ class EmuBackend:
             return
         X, Y = st.x_op.double(), st.y_all.double()
         S = s * X @ Y.T
-        G = torch.exp(S - st.lse_row.double()[:, None]) + torch.exp(S - st.lse_col.double()[None, :])
-        G[torch.arange(b), torch.arange(b) + off] -= 2.0
-        G = G * (s * go * st.grad_coef)
-        dX, dY = G @ Y, G.T @ X
+        Pr, Pc = torch.exp(S - st.lse_row.double()[:, None]), torch.exp(S - st.lse_col.double()[None, :])
+        Pr[torch.arange(b), torch.arange(b) + off] -= 1.0
+        Pc[torch.arange(b), torch.arange(b) + off] -= 1.0
+        k = s * go * st.grad_coef
+        Gx, Gy = (k * Pr, k * Pc) if st.grad_split else (k * (Pr + Pc),) * 2
+        dX, dY = Gx @ Y, Gy.T @ X
         if W > 1:
             dist.all_reduce(dY, group=st.group)
         dT = dY[off:off + b]

@@ -191,7 +191,7 @@ def test_fused_step_route_across_ranks():
     of the two entries emulated by gloo ones): coefficients of the modes, global-loss all-reduce, rank offsets."""
     from oracle import cliploss_oracle as O
     cases = [(12, 64, "bfloat16", True, True), (8, 128, "bfloat16", False, True), (8, 64, "bfloat16", False, False),
-             (8, 64, "bfloat16", True, False)]          # the last one (local, no gather_with_grad) takes the general route
+             (8, 64, "bfloat16", True, False)]          # the last one: dI / dT from different softmaxes (two-plane recompute)
     with tempfile.TemporaryDirectory() as tmp:
         mp.spawn(_odd_worker, args=(2, tmp, cases), nprocs=2, join=True)
         for i, (b, d, dtype, ll, gwg) in enumerate(cases):

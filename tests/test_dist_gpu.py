@@ -233,3 +233,60 @@ def test_ddp_static_graph_towers_with_grad_scaler():
                 got = torch.from_numpy(outs[r][f"{k}@{it}"]).cuda()
                 # bf16 features and bf16 feature gradients on both sides of the loss
                 assert (got - g).norm() <= 1e-2 * g.norm().clamp_min(1e-4), (it, k, r, float((got - g).norm()), float(g.norm()))
+
+
+def _shell_worker(rank, world, tmp, paths):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "megatron-clip_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    from clipk import loss as L
+    from tests.test_shells_cpu import load
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"file://{tmp}/store", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    for i, path in enumerate(paths):
+        z, W, ranks = load(path)
+        g = ranks[rank]
+        I = torch.from_numpy(g["image"]).cuda().requires_grad_(True)          # fp64, as the goldens were made
+        T = torch.from_numpy(g["text"]).cuda().requires_grad_(True)
+        s = torch.tensor(float(z["scale"]), dtype=torch.float64, device="cuda", requires_grad=True)
+        ll, gwg = bool(z["local_loss"]), bool(z["gather_with_grad"])
+        wi, wt = torch.from_numpy(g["w_image"]).cuda(), torch.from_numpy(g["w_text"]).cuda()
+        if str(z["what"]) == "gather":
+            a, b = L.gather_features(I, T, ll, gwg, rank, world)
+        else:
+            a, b = L.ClipLoss(local_loss=ll, gather_with_grad=gwg, rank=rank, world_size=world).get_logits(I, T, s)
+        f = (a * wi).sum() + (b * wt).sum()
+        if f.requires_grad:
+            f.backward()
+        zero = lambda x: np.zeros(tuple(x.shape)) if x.grad is None else x.grad.cpu().numpy()
+        np.savez(f"{tmp}/shell{i}_{rank}.npz", a=a.detach().cpu().numpy(), b=b.detach().cpu().numpy(), g_d_image=zero(I),
+                 g_d_text=zero(T), g_d_scale=zero(s))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_features_and_get_logits_over_nccl():
+    """The public gather_features (reference loss.py:20-64: values AND which gradient reaches which rank in the four
+    modes) and the materialising ClipLoss.get_logits (loss.py:104-121) on two GPUs over NCCL, against outputs of the
+    unmodified reference (tests/golden/shells, made under gloo in fp64)."""
+    _need(2)
+    import glob
+    import torch.multiprocessing as mp
+    from tests.test_shells_cpu import SHELLS, load
+    paths = sorted(glob.glob(os.path.join(SHELLS, "gather_w2_*.npz")) + glob.glob(os.path.join(SHELLS, "logits_w2_*.npz")))
+    assert len(paths) == 8
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(_shell_worker, args=(2, tmp, paths), nprocs=2, join=True)
+        for i, path in enumerate(paths):
+            z, W, ranks = load(path)
+            names = ("all_image", "all_text") if str(z["what"]) == "gather" else ("per_image", "per_text")
+            for r in range(2):
+                o, g = dict(np.load(f"{tmp}/shell{i}_{r}.npz")), ranks[r]
+                for mine, ref in (("a", names[0]), ("b", names[1]), ("g_d_image", "g_d_image"), ("g_d_text", "g_d_text"),
+                                  ("g_d_scale", "g_d_scale")):
+                    if ref in g:
+                        assert np.allclose(o[mine], g[ref], rtol=1e-9, atol=1e-11), (os.path.basename(path), r, ref)

@@ -418,3 +418,28 @@ def test_rank_block_at_baseline_sizes(name, b, N, d, rank):
     assert r(dY[cj], ref_dY) <= 2e-3, ("dY", r(dY[cj], ref_dY))
     lhs, rhs = (Xf * dX).double().sum().item(), (Yf * dY).double().sum().item()
     assert abs(lhs - rhs) <= 2e-3 * max(abs(lhs), abs(rhs)), (lhs, rhs)
+
+
+@pytest.mark.parametrize("rows,cols,d,off", [(1024, 4096, 256, 1024), (700, 2100, 512, 0), (512, 1536, 768, 512)])
+def test_split_row_col_backward_equals_two_passes(rows, cols, d, off):
+    """clipk_bwd's split_row_col (local_loss without gather_with_grad, loss.py:53-56): dX from the row softmax and dY from
+    the column softmax out of ONE recompute with two planes, against the two single-softmax passes it replaces."""
+    from clipk import ops
+    be = ops._backend()
+    x, _ = O.synthetic_features(rows, d, seed=11)
+    _, t = O.synthetic_features(cols, d, seed=12)
+    X = be.prepare(torch.from_numpy(x).cuda().bfloat16())
+    Y = be.prepare(torch.from_numpy(t).cuda().bfloat16())
+    sc = torch.tensor([1 / 0.07], device="cuda")
+    parts = torch.empty(1, 3, cols, dtype=torch.float32, device="cuda")
+    rs, pos, _ = be.fwd_both(X, Y, sc, off, col_out=parts[0])
+    lse_row, lse_col, _ = be.finalize(rs, pos, parts, off)
+    Xg, Yg = be.prepare_grad(X), be.prepare_grad(Y)
+    gs = torch.tensor([1.0 / (2 * rows)], device="cuda")
+    dX1, _ = be.bwd(X, Y, Xg, Yg, sc, off, lse_row, lse_col, 1.0, 0.0, gs, True, False)
+    _, dY1 = be.bwd(X, Y, Xg, Yg, sc, off, lse_row, lse_col, 0.0, 1.0, gs, False, True)
+    dX2, dY2 = be.bwd(X, Y, Xg, Yg, sc, off, lse_row, lse_col, 1.0, 1.0, gs, True, True, split=True)
+    torch.cuda.synchronize()
+    # same fp16 G entries, same fp16 operands: only the summation order inside the tensor core may differ
+    assert rel(dX2.cpu().numpy(), dX1.cpu().numpy()) <= 2e-6 and rel(dY2.cpu().numpy(), dY1.cpu().numpy()) <= 2e-6
+    assert float(dX1.abs().sum()) > 0 and float(dY1.abs().sum()) > 0
