@@ -243,16 +243,19 @@ __device__ __forceinline__ void grad16_store2(const float (&gr)[16], const float
     st_shared_v4(stg_addr(stg2, lane, piece0 + 1), pk[4], pk[5], pk[6], pk[7]);
 }
 // g[16] -> fp16, into 16-byte pieces [piece0, piece0 + 2) of this row's line of the staging buffer(s): 128-byte rows
-// in SWIZZLE_128B order, or (DENSE64) plain 64-byte rows - the half-size buffers of the A-resident recompute kernel,
-// whose 16 stores per tile and warp do not care about the 4-way bank conflict of that layout
+// in SWIZZLE_128B order, or (DENSE64) 64-byte rows in SWIZZLE_64B order - the half-size buffers of the A-resident
+// recompute kernel
 template <bool TWO_PLANES, bool DENSE64 = false>
 __device__ __forceinline__ void grad16_store(const float (&g)[16], uint32_t stg, uint32_t stg_lo, int lane, int piece0) {
     uint32_t pk[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) pk[k] = ptx::pack_f16x2(g[2 * k], g[2 * k + 1]);
     if (DENSE64) {
-        st_shared_v4(stg + lane * 64 + piece0 * 16, pk[0], pk[1], pk[2], pk[3]);
-        st_shared_v4(stg + lane * 64 + piece0 * 16 + 16, pk[4], pk[5], pk[6], pk[7]);
+        // 64-byte rows in SWIZZLE_64B order: the 16-byte chunk index is XORed with bits 7..8 of the address = (row / 2) % 4,
+        // so the 32 lanes of one store cover all 32 banks four times instead of 8 banks sixteen times
+        const int sw = (lane >> 1) & 3;
+        st_shared_v4(stg + lane * 64 + ((piece0 ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+        st_shared_v4(stg + lane * 64 + (((piece0 + 1) ^ sw) << 4), pk[4], pk[5], pk[6], pk[7]);
         return;
     }
     st_shared_v4(stg_addr(stg, lane, piece0), pk[0], pk[1], pk[2], pk[3]);
@@ -542,7 +545,7 @@ __device__ __forceinline__ void epilogue_unit(const Cta& c, Pipe& p, const CUten
 // 168 a 10-warp CTA allows; four pieces (64 columns = 128 B of fp16 per row) fill one staging buffer = one TMA store.
 // NBUF = 4 KB of staging per warp: 2 (two 64-column buffers, one fills while the other leaves; both planes of a
 // two-plane G) or 1 (the A-resident recompute kernel, whose shared memory goes to the resident rows: its 4 KB are two
-// dense 32-column half buffers, written and stored alternately through a non-swizzled tensor map).
+// 32-column half buffers of 64-byte rows, written and stored alternately through a SWIZZLE_64B tensor map).
 template <bool TWO_PLANES, int NBUF = 2, bool SPLIT = false>
 __device__ __forceinline__ void grad_epilogue_unit(const Cta& c, Pipe& p, const CUtensorMap* tmC, const KArgs& args,
                                                    int m_blk, int t0, int t1) {
@@ -1179,12 +1182,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                  const __grid_constant__ CUtensorMap tmC0, const KArgs args0,
                  const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
-                 const __grid_constant__ CUtensorMap tmC1, const KArgs args1, const int jobs0,
-                 const __grid_constant__ PeerOut peers) {
+                 const __grid_constant__ CUtensorMap tmC1, const KArgs args1, const int jobs0, const int jobs1,
+                 const int dy_first, const __grid_constant__ PeerOut peers) {
     constexpr int STAGES = stages_of(MODE_OUT);
     const Cta c = cta_setup<STAGES, STG_TOTAL>();
-    const int j = blockIdx.x >> 1;   // cluster (2, 1, 1): one job per CTA pair = a 256 x 256 output tile
-    const bool first = j < jobs0;
+    // cluster (2, 1, 1): one job per CTA pair = a 256 x 256 output tile.  The hardware dispatches the pairs in index
+    // order, so the kind with the LONGER jobs goes first (longest-first keeps the tail short); when those are the dY
+    // jobs their stores - the ones that cross NVLink in the fused reduce-scatter - also drain under the dX jobs
+    const int jj = blockIdx.x >> 1;
+    const bool first = dy_first ? (jj >= jobs1) : (jj < jobs0);
+    const int j = dy_first ? (first ? jj - jobs1 : jj + jobs0) : jj;     // index in the [dX jobs | dY jobs] numbering
     const KArgs& args = first ? args0 : args1;
     const CUtensorMap* tmA = first ? &tmA0 : &tmA1;
     const CUtensorMap* tmB = first ? &tmB0 : &tmB1;
