@@ -201,7 +201,9 @@ typedef struct clipk_step {
     float* d_scale;                     /* device scalar (NULL = not wanted)                                           */
     int out_dtype;                      /* CLIPK_BF16 or CLIPK_F32                                                     */
     const clipk_peer* peer;             /* NULL when world == 1                                                        */
-    void* workspace; size_t workspace_bytes;        /* scratch, may be shared by all calls of one shape               */
+    void* workspace; size_t workspace_bytes;        /* scratch, may be shared by all calls of one shape on one stream; */
+                                                    /* its first 256 bytes must be ZERO when it is created (a ticket   */
+                                                    /* that every forward returns to zero)                             */
     void* stream;
 } clipk_step;
 size_t clipk_step_workspace_bytes(const clipk_step* step);

@@ -493,6 +493,7 @@ def _step_workspace(be, rows, cols, d, world, dev):
         if len(_WORKSPACES) >= 8:
             _WORKSPACES.clear()
         ws = _WORKSPACES[key] = torch.empty(be.step_workspace_bytes(rows, cols, d, world), dtype=torch.uint8, device=dev)
+        ws[:256].zero_()        # the operand pass's ticket: zero at creation, returned to zero by every forward
     return ws
 
 

@@ -506,7 +506,14 @@ struct PrepArgs {
     long long ldxo, ldyo;
     float* inv_x; float* inv_y;    // NORMALIZE
     float eps;
-    float* stats;                  // this rank's row of the statistics (accumulated with atomics: zeroed before)
+    float* stats;                  // this rank's row of the statistics
+    // How the blocks' partial results meet.  ticket == null: atomics on `stats`, which the launcher zeroes first
+    // (cudaMemsetAsync: a separate operation on the stream, ~10-30 us of engine switching around a 5 us kernel).
+    // ticket != null (the fused step, whose scratch lives across calls): every block leaves its five values in
+    // partials[block], takes a ticket, and the LAST block reduces them, writes `stats` and puts the ticket back to 0 -
+    // no memset, no atomics on the statistics.  *ticket must be 0 when the scratch is created.
+    unsigned int* ticket;
+    float* partials;               // [gridDim.x][8]
     float* reset;                  // 8 floats + 2 ints of accumulators of LATER kernels of the step, reset here (null = none)
 };
 
@@ -625,6 +632,7 @@ __global__ void prep_kernel(const PrepArgs a) {
     }
     __syncthreads();
     if (warp == 0) {
+        bool last = false;
         float v[5];
 #pragma unroll
         for (int k = 0; k < 5; ++k) v[k] = lane < wpb ? sh[k][lane] : (k == 4 ? CUDART_INF_F : 0.f);
@@ -637,17 +645,44 @@ __global__ void prep_kernel(const PrepArgs a) {
         if (lane == 0) {
             unsigned int* su = reinterpret_cast<unsigned int*>(a.stats);
             const bool isbad = shbad != 0;
-            // hundreds of blocks hit the same five words: look first, only a block that raises a maximum pays for an atomic
-            auto bump = [](unsigned int* addr, unsigned int val) {
-                if (val > __ldcg(addr)) atomicMax(addr, val);
-            };
-            bump(su + 0, isbad ? 0x7f800000u : __float_as_uint(v[0]));
-            bump(su + 1, isbad ? 0x7f800000u : __float_as_uint(v[1]));
-            bump(su + 2, __float_as_uint(v[2]));
-            bump(su + 3, __float_as_uint(v[3]));
-            // min over the positives as a max over an order-reversing unsigned code (0 = "no pair seen" is its identity,
-            // so that one memset of zeros initialises the whole row); decoded by stat_min_pos (gemm_core.cuh)
-            bump(su + 4, ~unsigned(float_to_ordered(v[4]) ^ 0x80000000));
+            const unsigned int mine[5] = {isbad ? 0x7f800000u : __float_as_uint(v[0]), isbad ? 0x7f800000u : __float_as_uint(v[1]),
+                                          __float_as_uint(v[2]), __float_as_uint(v[3]),
+                                          // min over the positives as a max over an order-reversing unsigned code (0 = "no
+                                          // pair seen" is its identity); decoded by stat_min_pos (gemm_core.cuh)
+                                          ~unsigned(float_to_ordered(v[4]) ^ 0x80000000)};
+            if (!a.ticket) {
+                // hundreds of blocks hit the same five words: look first, only a block that raises a maximum pays for an atomic
+#pragma unroll
+                for (int k = 0; k < 5; ++k)
+                    if (mine[k] > __ldcg(su + k)) atomicMax(su + k, mine[k]);
+            } else {
+                unsigned int* part = reinterpret_cast<unsigned int*>(a.partials) + (size_t)blockIdx.x * 8;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) part[k] = mine[k];
+                __threadfence();
+                last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+            }
+        }
+        last = __shfl_sync(0xffffffffu, last ? 1 : 0, 0) != 0;
+        if (last) {
+            // the last block to finish: reduce every block's five values (all of them are maxima)
+            __threadfence();
+            unsigned int best[5] = {0u, 0u, 0u, 0u, 0u};
+            const unsigned int* all = reinterpret_cast<const unsigned int*>(a.partials);
+            for (unsigned int b = lane; b < gridDim.x; b += 32)
+#pragma unroll
+                for (int k = 0; k < 5; ++k) best[k] = max(best[k], __ldcg(all + (size_t)b * 8 + k));
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+                for (int k = 0; k < 5; ++k) best[k] = max(best[k], __shfl_xor_sync(0xffffffffu, best[k], off));
+            if (lane == 0) {
+                unsigned int* su = reinterpret_cast<unsigned int*>(a.stats);
+#pragma unroll
+                for (int k = 0; k < 5; ++k) su[k] = best[k];
+                su[5] = su[6] = su[7] = 0u;
+                *a.ticket = 0u;
+            }
         }
     }
 }
@@ -1455,11 +1490,12 @@ size_t clipk_fwd_both_workspace_bytes(int rows, int cols, int d, int dtype) {
 }
 
 // launch of prep_kernel over (X rows, Y rows); stats must be this rank's row of the table (it is reset here)
+constexpr int PREP_MAX_BLOCKS = 1024;        // bound of the partials array of the ticket path
 static int launch_prep(const PrepArgs& a, int src_dtype, int normalize, int sms, cudaStream_t st) {
-    CK_CUDA(cudaMemsetAsync(a.stats, 0, STAT_WORDS * sizeof(float), st));
+    if (!a.ticket) CK_CUDA(cudaMemsetAsync(a.stats, 0, STAT_WORDS * sizeof(float), st));
     const long long nmax = a.rows_x > a.rows_y ? a.rows_x : a.rows_y;
     const int wpb = 8;
-    const int blocks = int(std::max<long long>(1, std::min<long long>(cdiv(nmax, wpb), 4LL * sms)));
+    const int blocks = int(std::max<long long>(1, std::min<long long>(cdiv(nmax, wpb), std::min<long long>(4LL * sms, PREP_MAX_BLOCKS))));
     if (src_dtype == CLIPK_BF16) {
         if (normalize) prep_kernel<__nv_bfloat16, true><<<blocks, wpb * 32, 0, st>>>(a);
         else prep_kernel<__nv_bfloat16, false><<<blocks, wpb * 32, 0, st>>>(a);
@@ -1894,6 +1930,7 @@ int clipk_distill_grad(const float* S, const float* T, int rows, int cols, long 
 // ---- the whole step (see include/clipk.h) ----------------------------------------------------------------------------
 namespace {
 struct StepCarve {
+    size_t ticket, partials;                                 // persistent across calls: prep's ticket (0 at creation)
     size_t fwd, row_stats, pos, col_local, col_all;          // forward phase
     size_t xg, yg, inv2, dx, dy, bwd;                        // backward phase (overlays the forward's scratch)
     size_t total;
@@ -1901,14 +1938,17 @@ struct StepCarve {
 StepCarve step_carve(int rows, int cols, int d, int world) {
     StepCarve c{};
     auto take = [](size_t& off, size_t bytes) { const size_t o = off; off = size_t(round_up((long long)(off + bytes), 256)); return o; };
-    size_t f = 0;
+    size_t head = 0;
+    c.ticket = take(head, 256);
+    c.partials = take(head, size_t(PREP_MAX_BLOCKS) * 8 * sizeof(float));
+    size_t f = head;
     c.fwd = take(f, fwd_carve(rows, cols).total);
     c.row_stats = take(f, size_t(3) * rows * sizeof(float));
     c.pos = take(f, size_t(rows) * sizeof(float));
     c.col_local = take(f, size_t(3) * cols * sizeof(float));
     c.col_all = take(f, world > 1 ? size_t(world) * 3 * cols * sizeof(float) : 0);
     const size_t dpad = size_t(round_up(d, BK));
-    size_t b = 0;
+    size_t b = head;
     c.xg = take(b, (size_t(rows) + cols) * dpad * 2 + 256);      // Xg | Yg | dequant scalars, one block (step_to_f16)
     c.yg = c.inv2 = c.xg;
     c.dx = take(b, size_t(rows) * d * sizeof(float));
@@ -2006,6 +2046,8 @@ int clipk_step_forward(const clipk_step* p) {
     pa.ldxo = d; pa.ldyo = d;
     pa.inv_x = p->inv_x; pa.inv_y = p->inv_y; pa.eps = p->eps;
     pa.stats = my_stats; pa.reset = p->scal;
+    pa.ticket = reinterpret_cast<unsigned int*>(ws + cv.ticket);
+    pa.partials = reinterpret_cast<float*>(ws + cv.partials);
     if ((rc = launch_prep(pa, p->src_dtype, p->normalize, di.sms, st))) return rc;
 
     // 2. all-gather of the text operand rows and of the statistics (gather_features, loss.py:20-64)
