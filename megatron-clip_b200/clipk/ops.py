@@ -611,7 +611,8 @@ class FusedClipLoss(torch.autograd.Function):
             # the inputs themselves are saved so that autograd notices an in-place change before the backward reads them
             ctx.save_for_backward(image_features, text_features)
             ctx.fused = True
-            return pair[0].clone()
+            # a 0-dim view into this evaluation's own state tensor (nothing else reads that word again): no copy kernel
+            return st.scal[4]
 
         # ---- route 2: individual entries + NCCL
         ctx.fused = False

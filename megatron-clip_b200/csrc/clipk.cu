@@ -795,12 +795,53 @@ __global__ void finish_grad_kernel(const FinishArgs a) {
     }
 }
 
+// ---- data-parallel ranks of one NVLink domain: flags, barrier and all-gather over peer-mapped (symmetric) memory --------
+// Every rank owns an array of MAX_PEERS flag words per purpose, mapped into all peers.  Rank r publishes epoch e to rank
+// t by storing e into word [r] of t's array (release at system scope, after everything the stream did before); t waits
+// until word [r] of its own array has reached e.  Epochs only grow (compared modulo 2^32), flags are never reset.
+struct PeerPtrs {
+    void* p[MAX_PEERS];
+};
+__device__ __forceinline__ void peer_signal(unsigned int* flag, unsigned int epoch) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+}
+// A wait gives up after ~20 s (a peer died, or skipped the collective call) and leaves `code` in *err - a word in
+// pinned host memory the host side checks before its next call - instead of hanging the GPU.
+__device__ __forceinline__ bool peer_wait(const unsigned int* flag, unsigned int epoch, int* err, int code) {
+    unsigned long long t0 = 0;
+    unsigned int spins = 0;
+    for (;;) {
+        unsigned int v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (int(v - epoch) >= 0) return true;
+        if ((++spins & 0xfffu) == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 20000000000ull) {
+                if (err) { *reinterpret_cast<volatile int*>(err) = code; __threadfence_system(); }
+                return false;
+            }
+        }
+    }
+}
+
+
 // rows: merge the per-item parts (max, sum, dot; log2-scaled domain) into natural-log (max, sum, dot), as
 // merge_row_parts_kernel.  columns: in single-sweep mode sum the per-row-block partial (sum, dot) of the global
 // reference u; in exact mode merge the parts the swapped launch wrote.  The mode is recomputed from the same scalars.
 // Block = 32 indices x 8 slices: the (up to hundreds of) row-block partials of a column are summed by 8 threads.
+// sig.ticket != null (fused step on several ranks): the LAST block to finish publishes the epoch flag of the statistics
+// exchange to every peer - the column statistics this kernel wrote are what they pull next - and returns the ticket to 0.
+struct MergeSignal {
+    unsigned int* ticket;
+    PeerPtrs flags;
+    int rank, world;
+    unsigned int epoch;
+};
 __global__ void fwd_merge_kernel(const FwdArgs a0, const FwdArgs a1, int m_blocks, float* __restrict__ row_out,
-                                 float* __restrict__ col_out) {
+                                 float* __restrict__ col_out, const __grid_constant__ MergeSignal sig) {
     const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;      // blockDim.x == 256
     const int i = blockIdx.x * 32 + lane;
     const int rows = a0.M, cols = a0.N;
@@ -848,6 +889,20 @@ __global__ void fwd_merge_kernel(const FwdArgs a0, const FwdArgs a1, int m_block
         }
     } else if (sl == 0 && i < cols) {
         merge_parts(a1.part_max, a1.part_sum, a1.part_dot, nparts_of(a1, i), cols, i, col_out, cols);
+    }
+    if (sig.ticket) {
+        __shared__ int last_block;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            last_block = atomicAdd(sig.ticket, 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (last_block) {
+            const int t = threadIdx.x;
+            if (t < sig.world && t != sig.rank) peer_signal(static_cast<unsigned int*>(sig.flags.p[t]) + sig.rank, sig.epoch);
+            if (t == 0) *sig.ticket = 0u;
+        }
     }
 }
 
@@ -972,38 +1027,7 @@ __global__ void distill_grad_kernel(const float* __restrict__ S, const float* __
     G[(size_t)blockIdx.y * ldg + j] = __float2half_rn(16384.f * v);
 }
 
-// ---- data-parallel ranks of one NVLink domain: flags, barrier and all-gather over peer-mapped (symmetric) memory --------
-// Every rank owns an array of MAX_PEERS flag words per purpose, mapped into all peers.  Rank r publishes epoch e to rank
-// t by storing e into word [r] of t's array (release at system scope, after everything the stream did before); t waits
-// until word [r] of its own array has reached e.  Epochs only grow (compared modulo 2^32), flags are never reset.
-struct PeerPtrs {
-    void* p[MAX_PEERS];
-};
-__device__ __forceinline__ void peer_signal(unsigned int* flag, unsigned int epoch) {
-    __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
-}
-// A wait gives up after ~20 s (a peer died, or skipped the collective call) and leaves `code` in *err - a word in
-// pinned host memory the host side checks before its next call - instead of hanging the GPU.
-__device__ __forceinline__ bool peer_wait(const unsigned int* flag, unsigned int epoch, int* err, int code) {
-    unsigned long long t0 = 0;
-    unsigned int spins = 0;
-    for (;;) {
-        unsigned int v;
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-        if (int(v - epoch) >= 0) return true;
-        if ((++spins & 0xfffu) == 0) {
-            unsigned long long t;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            if (t0 == 0) t0 = t;
-            else if (t - t0 > 20000000000ull) {
-                if (err) { *reinterpret_cast<volatile int*>(err) = code; __threadfence_system(); }
-                return false;
-            }
-        }
-    }
-}
-
+// ---- data-parallel ranks of one NVLink domain: barrier and all-gather over peer-mapped (symmetric) memory (flags: see above)
 __global__ void peer_barrier_kernel(const __grid_constant__ PeerPtrs flags, const int rank, const int world, const unsigned int epoch, int* const err) {
     const int t = threadIdx.x;
     if (t < world && t != rank) {
@@ -1026,12 +1050,8 @@ struct GatherArgs {
     int rank, world;
     unsigned int epoch;
     int* err;
-    int do_signal;        // 0: the flags were already published by peer_signal_kernel (work was put in between)
+    int do_signal;        // 0: the flags were already published by the kernel that wrote the sources (work was put in between)
 };
-__global__ void peer_signal_kernel(const __grid_constant__ PeerPtrs flags, const int rank, const int world, const unsigned int epoch) {
-    const int t = threadIdx.x;
-    if (t < world && t != rank) peer_signal(static_cast<unsigned int*>(flags.p[t]) + rank, epoch);
-}
 __global__ void peer_allgather_kernel(const __grid_constant__ GatherArgs a) {
     const int o = blockIdx.y;
     if (a.do_signal && blockIdx.x == 0 && blockIdx.y == 0 && int(threadIdx.x) < a.world && int(threadIdx.x) != a.rank)
@@ -1513,7 +1533,8 @@ static int launch_prep(const PrepArgs& a, int src_dtype, int normalize, int sms,
 static int fwd_sweeps(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
                       const float* x_inv_scale, const float* y_inv_scale, const float* logit_scale, long long diag_offset,
                       float* row_stats, float* pos_logit, float* col_stats, const float* stats, int nstat, int stats_rank,
-                      int use_minpos, int exact, void* workspace, const DevInfo& di, cudaStream_t st) {
+                      int use_minpos, int exact, void* workspace, const DevInfo& di, cudaStream_t st,
+                      const MergeSignal* signal = nullptr) {
     int rc;
     const long long dpad = round_up(d, BK);
     const int num_kb = cdiv(d, BK);
@@ -1564,7 +1585,10 @@ static int fwd_sweeps(const void* X, const void* Y, int rows, int cols, int d, l
         if ((rc = ares ? launch_fwd_sweep<0, true>(ty_a, tx_b, a1, nc1, st) : launch_fwd_sweep<0, false>(ty_a, tx_b, a1, nc1, st))) return rc;
     }
     const int n = rows > cols ? rows : cols;
-    fwd_merge_kernel<<<cdiv(n, 32), 256, 0, st>>>(a0, a1, cv.m_blocks, row_stats, col_stats);
+    MergeSignal sig;
+    memset(&sig, 0, sizeof(sig));
+    if (signal) sig = *signal;
+    fwd_merge_kernel<<<cdiv(n, 32), 256, 0, st>>>(a0, a1, cv.m_blocks, row_stats, col_stats, sig);
     count_launch("fwd_merge_kernel", st);
     CK_CUDA(cudaGetLastError());
     return CLIPK_OK;
@@ -2063,11 +2087,24 @@ int clipk_step_forward(const clipk_step* p) {
         if ((rc = launch_allgather(g, di.sms, st))) return rc;
     }
 
-    // 3. single-sweep forward over the [rows, cols] block + merge
+    // 3. single-sweep forward over the [rows, cols] block + merge.  When the backward's operand conversion is to run
+    //    under the statistics exchange, the merge kernel's last block already tells the peers that this rank's column
+    //    statistics are complete.
     const long long off = (long long)rank * rows;
-    if ((rc = fwd_sweeps(p->x_op, p->y_all, rows, cols, d, d == 0 ? 0 : (p->x_op == p->image ? p->ld_image : d),
+    const bool early_signal = W > 1 && p->g16;
+    MergeSignal sig;
+    memset(&sig, 0, sizeof(sig));
+    if (early_signal) {
+        for (int o = 0; o < W; ++o) {
+            if (!pr->flags_stats[o]) return fail(CLIPK_EINVAL, "null peer pointer %d", o);
+            sig.flags.p[o] = pr->flags_stats[o];
+        }
+        sig.ticket = reinterpret_cast<unsigned int*>(ws + cv.ticket) + 1;
+        sig.rank = rank; sig.world = W; sig.epoch = pr->epoch_stats;
+    }
+    if ((rc = fwd_sweeps(p->x_op, p->y_all, rows, cols, d, p->x_op == p->image ? p->ld_image : d,
                          (W == 1 && p->y_all == p->text) ? p->ld_text : d, CLIPK_BF16, nullptr, nullptr, p->logit_scale, off,
-                         row_stats, pos, col_local, p->stats, W, rank, 1, 0, ws + cv.fwd, di, st)))
+                         row_stats, pos, col_local, p->stats, W, rank, 1, 0, ws + cv.fwd, di, st, early_signal ? &sig : nullptr)))
         return rc;
 
     // 4. the column statistics of every rank's block
@@ -2080,11 +2117,9 @@ int clipk_step_forward(const clipk_step* p) {
         g.n16_0 = (long long)3 * cols * sizeof(float) / 16; g.dst0 = reinterpret_cast<uint4*>(col_all);
         g.n16_1 = 0;
         g.rank = rank; g.world = W; g.epoch = pr->epoch_stats; g.err = pr->err; g.do_signal = 1;
-        if (p->g16) {
-            // tell the peers first, then do the backward's operand conversion while their statistics are on the way
-            peer_signal_kernel<<<1, 32, 0, st>>>(g.flags, rank, W, pr->epoch_stats);
-            count_launch("peer_signal_kernel", st);
-            CK_CUDA(cudaGetLastError());
+        if (early_signal) {
+            // the peers were told by the merge kernel; the fp16 copies for the gradient GEMMs are made while their
+            // statistics are on the way
             g.do_signal = 0;
             if ((rc = step_to_f16(p, W, rank, static_cast<__half*>(p->g16), st))) return rc;
         }
