@@ -212,29 +212,21 @@ def test_fwd_both_matches_direct_statistics(rows, cols, d, s, off):
 
 
 def test_single_sweep_and_exact_mode_agree():
-    """Same inputs through the single sweep and through the exact two-sweep mode (forced with CLIPK_DBG=512 in a
-    subprocess): the statistics agree to fp32 rounding."""
-    import os, subprocess, sys, json
-    code = (
-        "import sys, json, torch\n"
-        "sys.path.insert(0, 'megatron-clip_b200'); sys.path.insert(0, '.')\n"
-        "from clipk import ops\n"
-        "from oracle import cliploss_oracle as O\n"
-        "x, t = O.synthetic_features(1500, 512, seed=9)\n"
-        "I = torch.from_numpy(x).cuda().bfloat16(); T = torch.from_numpy(t).cuda().bfloat16()\n"
-        "be = ops._backend(); X, Y = be.prepare(I), be.prepare(T)\n"
-        "rs, pos, cs = be.fwd_both(X, Y, torch.tensor([1 / 0.07], device='cuda'), 0)\n"
-        "torch.cuda.synchronize()\n"
-        "print(json.dumps([(rs[0] + rs[1].log()).tolist(), (cs[0] + cs[1].log()).tolist()]))\n")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    """Same inputs through the single sweep and through the exact two-sweep form (clipk_fwd_both's `exact` argument): the
+    log-sum-exps of every row and column agree to fp32 rounding."""
+    from clipk import ops
+    x, t = O.synthetic_features(1500, 512, seed=9)
+    I, T = torch.from_numpy(x).cuda().bfloat16(), torch.from_numpy(t).cuda().bfloat16()
+    be = ops._backend()
+    X, Y = be.prepare(I), be.prepare(T)
+    sc = torch.tensor([1 / 0.07], device="cuda")
     outs = []
-    for dbg in ("0", "512"):
-        env = dict(os.environ, CLIPK_DBG=dbg)
-        out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
-        assert out.returncode == 0, out.stderr[-2000:]
-        outs.append(json.loads(out.stdout.strip().splitlines()[-1]))
-    a, b = np.array(outs[0]), np.array(outs[1])
-    assert np.abs(a - b).max() <= 1e-5
+    for exact in (False, True):
+        rs, pos, cs = be.fwd_both(X, Y, sc, 0, exact=exact)
+        torch.cuda.synchronize()
+        outs.append(((rs[0] + rs[1].log()).cpu().numpy(), (cs[0] + cs[1].log()).cpu().numpy(), pos.cpu().numpy()))
+    for a, b in zip(outs[0], outs[1]):
+        assert np.abs(a - b).max() <= 1e-5
 
 
 def test_tmem_fragment_layout_hook():
