@@ -1137,6 +1137,14 @@ static long long panel_bytes() {
     }();
     return v;
 }
+// A block that fits ONE panel of up to 1.5x the budget takes it whole: a single recompute + gradient-GEMM launch instead of
+// two (8-GPU shard 4096 x 32768, 268 MB: 343 vs 358 us per backward, profiles/r02z; larger blocks keep the budget - at
+// N = 32768 on one GPU bigger panels were measured slower).
+static long long panel_budget_for(long long rows, long long cols, int gplanes) {
+    const long long whole = round_up(rows, 2 * BM) * round_up(cols, BN) * 2 * gplanes;
+    const long long budget = panel_bytes();
+    return (whole > budget && whole <= budget + budget / 2) ? whole : budget;
+}
 
 // How many CTAs share the column sweep of one 128-row block: fill the SMs in as few equal waves as possible.
 static int choose_split(int m_pairs, int n_tiles, int sms) {
@@ -1661,8 +1669,9 @@ int clipk_finalize(const float* row_max, const float* row_sum, const float* row_
 
 size_t clipk_bwd_workspace_bytes(int rows, int cols, int d, int g_dtype) {
     if (rows <= 0 || cols <= 0 || d <= 0) return 0;
-    // one G panel of panel_bytes(), slack for its padding, and the reference vectors of the recompute
-    return size_t(panel_bytes()) + size_t(4) * 1024 * 1024 + (size_t(rows) + size_t(cols)) * sizeof(float) + 4096;
+    // one G panel (two planes at most), slack for its padding, and the reference vectors of the recompute
+    const long long panel = std::max(panel_budget_for(rows, cols, 1), panel_budget_for(rows, cols, 2));
+    return size_t(panel) + size_t(4) * 1024 * 1024 + (size_t(rows) + size_t(cols)) * sizeof(float) + 4096;
 }
 
 static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, long long ldx, long long ldy, int dtype,
@@ -1713,7 +1722,7 @@ static int bwd_impl(const void* X, const void* Y, int rows, int cols, int d, lon
     const long long kext = (dtype == CLIPK_BF16) ? d : planes * dpad;   // inner extent of X / Y rows
     const long long gext = fplanes * dpad;                              // inner extent of Xg / Yg rows
     long long rp_max, cp_max;
-    choose_panel(rows, cols, d, gplanes, di.sms, panel_bytes(), &rp_max, &cp_max, peers.world > 0 ? 1 : 0);
+    choose_panel(rows, cols, d, gplanes, di.sms, panel_budget_for(rows, cols, gplanes), &rp_max, &cp_max, peers.world > 0 ? 1 : 0);
     const int ncp = int(cp_max);                        // panel width (multiple of BN) = G plane stride
     const int ldg = gplanes * ncp;
     if ((unsigned long long)round_up(rp_max, 2 * BM) * ldg * 2 > workspace_bytes) return fail(CLIPK_EWORKSPACE, "panel does not fit the workspace");
@@ -2220,7 +2229,7 @@ int clipk_bwd_panel(int rows, int cols, int d, long long* panel_rows, long long*
     DevInfo di;
     int rc = device_info(&di);
     if (rc) return rc;
-    choose_panel(rows, cols, d, 1, di.sms, panel_bytes(), panel_rows, panel_cols);
+    choose_panel(rows, cols, d, 1, di.sms, panel_budget_for(rows, cols, 1), panel_rows, panel_cols);
     return CLIPK_OK;
 }
 
