@@ -1,15 +1,19 @@
 """Host side of the fused contrastive loss: a torch.autograd.Function over the clipk C ABI.
 
-Data flow on rank r of W (b local rows, N = W*b), replacing open_CLIP/src/open_clip/loss.py:104-140:
+Data flow on rank r of W (b local rows, N = W*b), replacing open_CLIP/src/open_clip/loss.py:20-64, 104-140:
 
-  forward   T_all = all_gather(T_loc)                                  (NCCL, one contiguous [N, d] buffer)
-            row stats of  S = s * I_loc @ T_all^T   [b x N]            clipk_fwd_both: ONE sweep over the tiles feeds
-            col stats of the same block              [N]               both (two exact sweeps when logits are unbounded)
-            all_gather of the (max, sum) column pairs                  (2*N floats per rank)
-            lse_row[b], lse_col[N], cross-entropy sums                 clipk_finalize
-  backward  G = s*g*(alpha*(P_row-Id) + beta*(P_col-Id)) tile by tile; dI_loc = G @ T_all;
-            dT_partial[N, d] = G^T @ I_loc                             clipk_bwd
-            dT_loc = reduce_scatter(dT_partial)                        (NCCL)
+  forward   operand pass over the local rows (normalise / cast, statistics)      \
+            T_all = all-gather of the text operand rows                           |  fused step: ONE enqueue,
+            row AND column statistics of S = s * I_loc @ T_all^T  [b x N]         |  clipk_step_forward; between
+            from ONE sweep over the tiles (two exact sweeps when unsafe)          |  2..8 ranks every exchange is a
+            all-gather of the [3, N] column statistics                            |  pull from peer-mapped memory
+            lse_row[b], lse_col[N], loss, s * dloss/ds                            /  (PeerContext)
+  backward  G = alpha*(P_row-Id) + beta*(P_col-Id) tile by tile; dI_loc = c G @ T_all;   clipk_step_backward: the tiles of
+            dT_partial[N, d] = c G^T @ I_loc; dT_loc = sum over ranks of their parts     dT go straight to their owners
+
+Route 2 (fp32 / fp16 arithmetic, widths that are not multiples of 64, more than 8 ranks, no symmetric memory) runs the
+same mathematics through the individual entries (clipk_fwd_both, clipk_finalize, clipk_bwd, ...) with NCCL
+all_gather_into_tensor / reduce_scatter_tensor between them.
 
 The [b x N] logits are never written to HBM and I_all is never gathered.  All four (local_loss,
 gather_with_grad) modes of the reference are coefficient choices of this one pipeline.
