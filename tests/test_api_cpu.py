@@ -307,3 +307,20 @@ def test_bench_reference_arm_prints_one_json_line():
     assert j["cpu_baseline"]["kind"] in ("reference", "port") and j["cpu_baseline"]["cores"] >= 1
     assert j["cpu_baseline"]["sample_batch"] == 512 and j["cpu_baseline"]["extrapolated"] is True
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0 and j["value"] > 0
+
+
+@pytest.mark.parametrize("n,d,s", [(96, 48, 1 / 0.07), (130, 32, 100.0)])
+def test_bench_parity_checker_matches_the_oracle(n, d, s):
+    """bench.py's parity phase checks the benchmark's own shapes against `torch_fp32_reference` (chunked fp32 torch, no
+    N x N matrix held).  That checker is itself pinned here: single process, against the fp64 oracle."""
+    import bench
+    from oracle import cliploss_oracle as O
+    x, t = O.synthetic_features(n, d, seed=2)
+    I, T = torch.from_numpy(x), torch.from_numpy(t)
+    loss, dI, dT, ds = bench.torch_fp32_reference(I, T, s, 0, 1, True, True, chunk=50)
+    ref = O.clip_loss_single(x, t, s)
+    tol = 2e-5 if s < 50 else 3e-4
+    assert abs(loss - ref.loss) <= tol * abs(ref.loss)
+    assert np.linalg.norm(dI.numpy() - ref.d_image) <= tol * np.linalg.norm(ref.d_image)
+    assert np.linalg.norm(dT.numpy() - ref.d_text) <= tol * np.linalg.norm(ref.d_text)
+    assert abs(ds - ref.d_scale) <= tol * max(abs(ref.d_scale), 1 / s)
