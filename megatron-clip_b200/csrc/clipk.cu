@@ -1137,13 +1137,14 @@ static long long panel_bytes() {
     }();
     return v;
 }
-// A block that fits ONE panel of up to 1.5x the budget takes it whole: a single recompute + gradient-GEMM launch instead of
-// two (8-GPU shard 4096 x 32768, 268 MB: 343 vs 358 us per backward, profiles/r02z; larger blocks keep the budget - at
-// N = 32768 on one GPU bigger panels were measured slower).
+// A block that fits ONE panel of up to 3x the budget takes it whole: a single recompute + gradient-GEMM launch instead of
+// two or four (backward of one rank, profiles/r02z: 8-GPU shard 4096 x 32768, 268 MB: 343 vs 358 us; 4-GPU shard 8192 x
+// 32768, 537 MB: 657 vs 676 us).  Larger blocks keep the budget: on one GPU at N = 32768 the step runs at the power
+// limit and bigger panels, although their kernels add up to less, were not faster (3.73 vs 3.67 ms at 288 MB).
 static long long panel_budget_for(long long rows, long long cols, int gplanes) {
     const long long whole = round_up(rows, 2 * BM) * round_up(cols, BN) * 2 * gplanes;
     const long long budget = panel_bytes();
-    return (whole > budget && whole <= budget + budget / 2) ? whole : budget;
+    return (whole > budget && whole <= 3 * budget) ? whole : budget;
 }
 
 // How many CTAs share the column sweep of one 128-row block: fill the SMs in as few equal waves as possible.
