@@ -1122,25 +1122,29 @@ static inline long long round_up(long long a, long long b) { return (a + b - 1) 
 
 constexpr int MAX_SPLIT = 32;
 constexpr int MAX_PARTS = MAX_SPLIT * PARTS_PER_UNIT;
-// Budget of the fp16 G panel (CLIPK_PANEL_MB overrides it).  It is a constant, independent of the problem size: the
-// softmax gradient only ever exists as one panel.  Measured at N = 32768, d = 512 (B200, bwd only): 48 MB (18 x 19
-// blocks of 256, fully L2 resident, 56 panels) 3.13 ms; 134-179 MB (32 x 32 blocks, 16 panels, two tiles per CTA pair in
-// the gradient-GEMM launch) 2.82 ms - the panel no longer fits the 126 MB L2 entirely and part of it streams through
-// HBM, but the per-launch fill / drain is paid 16 instead of 56 times, which is worth more.
+// Budget of the fp16 G panel (CLIPK_PANEL_MB overrides it) - the only place a piece of the softmax gradient exists in
+// memory.  It is a constant, independent of the problem size; what it buys is fewer recompute / gradient-GEMM launch pairs
+// (each pays a fill and a drain of the persistent pipelines).  The panel streams through HBM either way - it stopped
+// fitting the 126 MB L2 at 134 MB - and the traffic (written once, read by both gradient GEMMs) does not depend on how it is
+// cut.  Measured at N = 32768, d = 512 on one B200, whole step: 48 MB panels (round 1, backward only) 3.13 vs 2.82 ms at
+// 134-179 MB; round 2, same call (profiles/r02z_panel_budget_ab_1gpu.log): 192 MB (12 panels) 3.87 / 3.78 ms, 384 MB (6)
+// 3.77, 512 MB (4) 3.66 / 3.80, the whole block as ONE 2 GiB panel 3.56 ms (3.55 in another call).
 static long long panel_bytes() {
     static long long v = [] {
         const char* e = getenv("CLIPK_PANEL_MB");
-        long long mb = e ? atoll(e) : 192;
+        long long mb = e ? atoll(e) : 768;
         if (mb < 8) mb = 8;
-        if (mb > 1024) mb = 1024;
+        if (mb > 4096) mb = 4096;
         return mb << 20;
     }();
     return v;
 }
 // A block that fits ONE panel of up to 3x the budget takes it whole: a single recompute + gradient-GEMM launch instead of
-// two or four (backward of one rank, profiles/r02z: 8-GPU shard 4096 x 32768, 268 MB: 343 vs 358 us; 4-GPU shard 8192 x
-// 32768, 537 MB: 657 vs 676 us).  Larger blocks keep the budget: on one GPU at N = 32768 the step runs at the power
-// limit and bigger panels, although their kernels add up to less, were not faster (3.73 vs 3.67 ms at 288 MB).
+// several (backward of one rank, profiles/r02z: 8-GPU shard 4096 x 32768, 268 MB: 343 vs 358 us with two panels; 4-GPU
+// shard 8192 x 32768, 537 MB: 657 vs 676 us with four; 2-GPU shard, 1 GiB: 1279 vs 1336 us with six; one GPU, 2 GiB: see
+// above).  With the default budget that covers blocks up to 2.25 GiB of fp16 G - the headline problem on 1..8 GPUs;
+// anything larger (N = 65536 on one GPU: 8 GiB; N = 163840 on eight: 6.25 GiB per rank) is cut into panels of the budget,
+// so the memory the backward needs stays bounded whatever N is.  CLIPK_PANEL_MB=192 restores round 1's small panels.
 static long long panel_budget_for(long long rows, long long cols, int gplanes) {
     const long long whole = round_up(rows, 2 * BM) * round_up(cols, BN) * 2 * gplanes;
     const long long budget = panel_bytes();

@@ -80,9 +80,30 @@ def test_odd_widths_and_fp16_features(b, d, dtype, tol):
 
 
 def test_multi_panel_rows_and_cols():
-    """More than one 4096 x 4096 G panel in both directions (accumulating gradient GEMMs)."""
-    x, t = make_inputs(4300, 64, seed=12)
-    check(x, t, 1 / 0.07, torch.bfloat16)
+    """Several G panels in both directions (8 MB budget, set before the library reads it: a fresh process): dX accumulates
+    over the column panels, dY over the row panels (TMA reduce-adds after the first panel's stores)."""
+    import json, os, subprocess, sys
+    code = (
+        "import sys, json, torch, numpy as np\n"
+        "sys.path.insert(0, 'megatron-clip_b200'); sys.path.insert(0, '.')\n"
+        "from clipk import ClipLoss\n"
+        "from oracle import cliploss_oracle as O\n"
+        "x, t = O.synthetic_features(4300, 128, seed=12)\n"
+        "I = torch.from_numpy(x).cuda().bfloat16().requires_grad_(True)\n"
+        "T = torch.from_numpy(t).cuda().bfloat16().requires_grad_(True)\n"
+        "S = torch.tensor(1 / 0.07, device='cuda', requires_grad=True)\n"
+        "loss = ClipLoss()(I, T, S); loss.backward(); torch.cuda.synchronize()\n"
+        "ref = O.clip_loss_single(I.detach().float().cpu().numpy(), T.detach().float().cpu().numpy(), 1 / 0.07)\n"
+        "r = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))\n"
+        "print(json.dumps([abs(loss.item() - ref.loss) / ref.loss, r(I.grad.float().cpu().numpy(), ref.d_image), "
+        "r(T.grad.float().cpu().numpy(), ref.d_text), abs(S.grad.item() - ref.d_scale) / max(abs(ref.d_scale), 0.07)]))\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CLIPK_PANEL_MB="8", CLIPK_VERBOSE="1")
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "panels" in out.stderr and "(1 x 1 panels" not in out.stderr, out.stderr[-500:]      # really several panels
+    errs = json.loads(out.stdout.strip().splitlines()[-1])
+    assert all(e <= 2e-3 for e in errs), errs
 
 
 @pytest.mark.parametrize("path", golden_files(world=1), ids=lambda p: p.split("/")[-1][:-4])

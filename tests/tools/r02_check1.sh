@@ -1,8 +1,8 @@
 #!/bin/bash
+# one GPU: the -m gpu suite, then the default bench line (final defaults of round 2)
 set -u
 mkdir -p gpurun_out
-echo "=== gpu suite"; timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -4
-echo "=== shard timing 8192 x 32768"; CLIPK_VERBOSE=1 SHARD_TIME=1 timeout 100 python tests/tools/shard_step.py 8192 32768 512 1 2>&1 | grep -E "timing|panel" | sort -u | tail -2
-echo "=== step timeline, 8-GPU-shard-sized single-GPU problem (4096 rows) and N = 32768"
-timeout 100 python tests/tools/step_timeline.py 4096 512 2 2>&1 | tail -45
-timeout 100 python tests/tools/step_timeline.py 32768 512 2 2>&1 | grep -v "grad_sweep\|gemm_pair" | tail -40
+echo "=== gpu suite"; timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -6
+echo "=== bench N=1 (default flags)"
+timeout 600 python bench.py > gpurun_out/bench_r2zz_n1.json 2> gpurun_out/bench_r2zz_n1.err || tail -20 gpurun_out/bench_r2zz_n1.err
+python tests/tools/show_bench.py gpurun_out/bench_r2zz_n1.json
