@@ -66,7 +66,8 @@ struct KArgs {
     int nseg, kb_per_seg;
     int a_off[3], b_off[3];
     int a_mn, b_mn;       // operand majors (1 = MN-major)
-    int f16;              // operands are fp16 (1) or bf16 (0)
+    int f16;              // operands are fp16 (1) or bf16 (0) - BOTH: an instruction descriptor with a_format != b_format
+                          // (fp16 panel x bf16 features) ends in an illegal-instruction error on sm_100a (measured, round 2)
     int a_outer_off, b_outer_off;   // added to the OUTER TMA coordinate (row of a K-major operand, K of an MN-major one)
     int c_col_off, c_row_off;       // added to the epilogue's TMA store coordinates
     int n_tiles;          // ceil(N / BN)
@@ -1168,7 +1169,7 @@ grad_sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // With peers.world > 0 every dY tile is written straight into the owner's memory through its peer-mapped address -
 // over NVLink for remote owners - into the slot reserved for THIS source rank (plain TMA stores: reductions over
 // NVLink were measured ~3x slower), and the CTA does not wait for the remote writes: they drain while the next
-// panel is being recomputed.  The owner sums its `world` slots afterwards (clipk_reduce_slots).  The separate
+// panel is being recomputed.  The owner sums its `world` slots afterwards (finish_grad_kernel).  The separate
 // reduce-scatter of loss.py's all_gather backward and its 4 * N * d byte input buffer disappear.
 constexpr int MAX_PEERS = 8;
 struct PeerOut {
