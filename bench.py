@@ -637,33 +637,64 @@ def run_clipk(args):
     bar()
 
     # ------------------------------------------------------------------ 5b. other operating points
-    def quick(cfg_name, s_val, steps=5, warmup=3):
+    def quick(cfg_name, s_val, steps=5, warmup=3, gwg=None, eager=False):
         c = CONFIGS[cfg_name]
         if c["N"] % world:
             return {"skipped": "global batch not divisible"}
         bb = c["N"] // world
+        gwg = c["gwg"] if gwg is None else gwg
         try:
             xq, tq = make(bb, c["d"], 4321)
             Iq, Tq = xq.to(dev).requires_grad_(True), tq.to(dev).requires_grad_(True)
             Sq = torch.tensor(s_val, device=dev, requires_grad=True)
-            mod = ClipLoss(local_loss=c["local"], gather_with_grad=c["gwg"], cache_labels=True, rank=rank, world_size=world)
+            mod = ClipLoss(local_loss=c["local"], gather_with_grad=gwg, cache_labels=True, rank=rank, world_size=world)
             t, _, _ = timed(make_step(mod, Iq, Tq, Sq), steps, warmup)
             f_alg = 6.0 * bb * c["N"] * c["d"]
             pk = peaks()
-            return {"ms_per_step": t, "value": c["N"] / (t * 1e-3), "unit": "samples/s", "global_batch": c["N"], "d": c["d"],
-                    "local_batch": bb, "mode": "local" if c["local"] else "global", "gather_with_grad": c["gwg"],
-                    "logit_scale": s_val, "single_sweep_forward": ops.last_forward_was_single_sweep(),
-                    "frac_of_burst_peak": f_alg / (t * 1e-3) / 1e12 / pk["tflops_burst"]}
+            out = {"ms_per_step": t, "value": c["N"] / (t * 1e-3), "unit": "samples/s", "global_batch": c["N"], "d": c["d"],
+                   "local_batch": bb, "mode": "local" if c["local"] else "global", "gather_with_grad": gwg,
+                   "logit_scale": s_val, "single_sweep_forward": ops.last_forward_was_single_sweep(),
+                   "frac_of_burst_peak": f_alg / (t * 1e-3) / 1e12 / pk["tflops_burst"]}
         except torch.OutOfMemoryError:
             torch.cuda.empty_cache()
             return {"oom": True}
+        if eager:
+            out["reference_eager"] = quick_eager(c, gwg, Iq, Tq, Sq)
+        return out
+
+    def quick_eager(c, gwg, Iq, Tq, Sq):
+        """The reference module itself on the same inputs and GPUs (an out-of-memory error is a result: SURVEY 8d)."""
+        L = load_reference_loss()
+        if L is None:
+            return {"unavailable": "baseline/_ref missing"}
+        with _Quiet():
+            ref = L.ClipLoss(local_loss=c["local"], gather_with_grad=gwg, cache_labels=True, rank=rank, world_size=world)
+
+        def fn():
+            Iq.grad = Tq.grad = Sq.grad = None
+            with _Quiet():
+                loss = ref(Iq, Tq, Sq)
+            loss.backward()
+            return loss
+        res = None
+        try:
+            torch.cuda.reset_peak_memory_stats(dev)
+            t, _, _ = timed(fn, 3, 2)
+            res = {"ms_per_step": t, "value": c["N"] / (t * 1e-3), "unit": "samples/s",
+                   "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9}
+        except torch.OutOfMemoryError:
+            pass
+        Iq.grad = Tq.grad = Sq.grad = None
+        torch.cuda.empty_cache()
+        return res if res is not None else {"oom": True}
 
     extras = {}
     if not args.skip_extras and args.config == "c2" and abs(scale_value - INIT_SCALE) < 1e-6:
         extras["c2_logit_scale_100"] = quick("c2", 100.0)
-        extras["c3_global"] = quick("c3", INIT_SCALE, steps=3, warmup=2)
+        extras["c3_global"] = quick("c3", INIT_SCALE, steps=3, warmup=2, eager=True)
+        extras["c3_global_no_gather_grad"] = quick("c3", INIT_SCALE, steps=3, warmup=2, gwg=False)
         if world == 8:
-            extras["c4"] = quick("c4", INIT_SCALE, steps=3, warmup=2)
+            extras["c4"] = quick("c4", INIT_SCALE, steps=3, warmup=2, eager=True)
 
     # nvidia-smi cannot sample faster than every ~50 ms and the timed region lasts ~0.1 s, so the sampler stays on from
     # before the timed region until the end of a short untimed continuation of the same step; `clocks` is the busier

@@ -168,15 +168,17 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 //   FAST (interior tile and the LSE spread of this backward <= 100 in log2 units): ONE ex2 per element.  With the
 //        reference c = min over all row and column LSEs,  E = 2^(v - c),  g = E * (A_i + B_j),
 //        A_i = ga * 2^(c - Lr_i) (a register), B_j = gb * 2^(c - Lc_j) (a vector prepared once per backward, read
-//        through L1 as warp-uniform float4 loads).  v <= min(Lr_i, Lc_j) and the spread bound keep every factor in
+//        through L1 as warp-uniform float4 loads, issued ONE PIECE AHEAD of their use: loaded where they are used
+//        they cost a long-scoreboard stall as long as the piece's sixteen ex2).  v <= min(Lr_i, Lc_j) and the spread bound keep every factor in
 //        fp32 range; what underflows is below 2^-126 of a probability.  MUFU runs 16 ex2/clk/SM, so two per element
 //        would cost exactly the tile's MMA time - this path halves it and needs no per-tile staging or barrier.
 //   exact (tile with positives, columns beyond N, or a wide LSE spread): two ex2 per element, exact masking.
-__device__ __forceinline__ void grad16_fast(const uint32_t (&r)[16], float sc, float cref, float Ai, float gb,
-                                            const float* __restrict__ bv, float (&g)[16]) {
-    float4 l4[4];
+__device__ __forceinline__ void grad16_load_b(const float* __restrict__ bv, float4 (&l4)[4]) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) l4[j] = __ldg(reinterpret_cast<const float4*>(bv) + j);
+}
+__device__ __forceinline__ void grad16_fast(const uint32_t (&r)[16], float sc, float cref, float Ai, float gb,
+                                            const float4 (&l4)[4], float (&g)[16]) {
     float e[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) e[k] = ptx::ex2(fmaf(__uint_as_float(r[k]), sc, -cref));
@@ -204,10 +206,7 @@ __device__ __forceinline__ void grad16_exact(const uint32_t (&r)[16], float sc, 
 }
 // the same two, with the row part alpha (P_row - Id) and the column part beta (P_col - Id) kept apart (g_split)
 __device__ __forceinline__ void grad16_fast2(const uint32_t (&r)[16], float sc, float cref, float Ai, float gb,
-                                             const float* __restrict__ bv, float (&gr)[16], float (&gc)[16]) {
-    float4 l4[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) l4[j] = __ldg(reinterpret_cast<const float4*>(bv) + j);
+                                             const float4 (&l4)[4], float (&gr)[16], float (&gc)[16]) {
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
         const float e = ptx::ex2(fmaf(__uint_as_float(r[k]), sc, -cref));
@@ -589,15 +588,21 @@ __device__ __forceinline__ void grad_epilogue_unit(const Cta& c, Pipe& p, const 
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(lse_col + cn));
             }
         }
+        // edge tile: contains positives (diagonal entries) of this CTA's rows, or columns beyond N
+        const bool exact = !fast || ((d_lo + BM - 1 >= n0) && (d_lo < (long long)n0 + BN)) || (n0 + BN > ncols);
+        // B_j of the piece in hand and of the next one (fast tiles only; the exact form reads lse_col itself); the
+        // first piece's are on their way while this warp waits for the accumulator
+        float4 bq[2][4];
+        if (!exact) grad16_load_b(bvec + colh, bq[0]);
         ptx::mbar_wait(c.bar_tfull + 8 * a, aph);
         ptx::tc_fence_after();
         const uint32_t taddr = c.tmem_base + a * BN + half * (BN / 2) + (uint32_t(q * 32) << 16);
-        // edge tile: contains positives (diagonal entries) of this CTA's rows, or columns beyond N
-        const bool exact = !fast || ((d_lo + BM - 1 >= n0) && (d_lo < (long long)n0 + BN)) || (n0 + BN > ncols);
 
         uint32_t stg = 0, stg_lo = 0;
         auto piece = [&](const uint32_t (&r)[16], int pi) {
             const int col0 = colh + pi * 16;
+            const float4 (&bcur)[4] = bq[pi & 1];
+            if (!exact && pi + 1 < 8) grad16_load_b(bvec + col0 + 16, bq[(pi + 1) & 1]);
             if (NBUF == 1) {
                 // half buffers of 32 columns: two pieces each
                 if ((pi & 1) == 0) {
@@ -607,7 +612,7 @@ __device__ __forceinline__ void grad_epilogue_unit(const Cta& c, Pipe& p, const 
                 }
                 float g[16];
                 if (exact) grad16_exact(r, sc, Lr, ga, gb, lse_col + col0, col0, ncols, dcol, g);
-                else grad16_fast(r, sc, cref, Ai, gb, bvec + col0, g);
+                else grad16_fast(r, sc, cref, Ai, gb, bcur, g);
                 grad16_store<false, true>(g, stg, 0, lane, (pi & 1) * 2);
                 if (pi & 1) {
                     ptx::fence_proxy_async_smem();
@@ -634,12 +639,12 @@ __device__ __forceinline__ void grad_epilogue_unit(const Cta& c, Pipe& p, const 
             if (SPLIT) {
                 float gr[16], gc[16];
                 if (exact) grad16_exact2(r, sc, Lr, ga, gb, lse_col + col0, col0, ncols, dcol, gr, gc);
-                else grad16_fast2(r, sc, cref, Ai, gb, bvec + col0, gr, gc);
+                else grad16_fast2(r, sc, cref, Ai, gb, bcur, gr, gc);
                 grad16_store2(gr, gc, stg, stg_lo, lane, (pi & 3) * 2);
             } else {
                 float g[16];
                 if (exact) grad16_exact(r, sc, Lr, ga, gb, lse_col + col0, col0, ncols, dcol, g);
-                else grad16_fast(r, sc, cref, Ai, gb, bvec + col0, g);
+                else grad16_fast(r, sc, cref, Ai, gb, bcur, g);
                 grad16_store<TWO_PLANES>(g, stg, stg_lo, lane, (pi & 3) * 2);
             }
             if ((pi & 3) == 3) {
