@@ -738,6 +738,7 @@ def run_clipk(args):
         ach = flops_per_launch / (k["ms_per_launch"] * 1e-3) / 1e12
         roofline.update({"kernel": f"clipk::{dom} (dX = G Y and dY = G^T X tiles of one {rp.value} x {cp.value} panel, tcgen05 "
                                    "cta_group::2 256x256x64)", "achieved": ach, "frac": ach / pk["tflops_burst"],
+                         "frac_of_sustained_peak": ach / pk["tflops_sustained"],
                          "algorithmic_flops_per_launch": flops_per_launch, "ms_per_launch": k["ms_per_launch"],
                          "share_of_step": k["share_of_profiled_step"]})
     else:
@@ -758,6 +759,8 @@ def run_clipk(args):
                               "achieved_tflops": step_tflops, "frac_of_burst_peak": step_tflops / pk["tflops_burst"],
                               "frac_of_sustained_peak": step_tflops / pk["tflops_sustained"],
                               "definition": "SURVEY 8d: F_alg = 6 b N d over t_step, per GPU"}
+    # a power-capped part: a 0.07 s timed region runs ~15 % faster than a 0.4 s one (profiles/README.md)
+    roofline["timed_region_s"] = ms * args.steps * 1e-3
     roofline["kernels"] = kern
     roofline["kernels_note"] = (f"library event profile over {prof_steps} steps of this run (an event after every launch; the "
                                 "time between consecutive events goes to the kernel launched in between)")
